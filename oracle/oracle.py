@@ -1,0 +1,183 @@
+"""ctypes loader for the CPU oracle (oracle/afb_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Never imported by the arcanefem_b200 package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libafb_oracle.so")
+
+OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN = 0, 1, 2
+FORM_COMPACT, FORM_HOST, FORM_BSR, FORM_NODEWISE = 0, 1, 2, 3
+LAYOUT_PER_BLOCK, LAYOUT_PER_ROW = 0, 1
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "afb_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_build_pattern.restype = C.c_int64
+        _lib.orc_build_pattern_host.restype = C.c_int64
+        _lib.orc_value_index.restype = C.c_int64
+    return _lib
+
+
+def _p(a, ty=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u8(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def block_size(op: int, dim: int) -> int:
+    return 1 if op == OP_POISSON else (dim if op == OP_ELASTICITY else 2)
+
+
+def lame(E: float, nu: float):
+    lam, mu = C.c_double(), C.c_double()
+    lib().orc_lame(C.c_double(E), C.c_double(nu), C.byref(lam), C.byref(mu))
+    return lam.value, mu.value
+
+
+def element_matrix(npc, dim, op, form, coords, cell_nodes, params=None):
+    b = block_size(op, dim)
+    K = np.zeros((npc * b, npc * b))
+    coords = _f64(coords)
+    cn = _i32(cell_nodes)
+    prm = _f64(params if params is not None else [0.0, 0.0])
+    rc = lib().orc_element_matrix(npc, dim, op, form, _p(prm), _p(coords), _p(cn), _p(K))
+    assert rc == 0
+    return K
+
+
+def build_pattern(npc, nb_node, cells):
+    cells = _i32(cells)
+    nb_cell = cells.shape[0]
+    rows = np.empty(nb_node + 1, dtype=np.int32)
+    nnz = lib().orc_build_pattern(npc, C.c_int32(nb_node), C.c_int64(nb_cell), _p(cells), _p(rows), None)
+    cols = np.empty(nnz, dtype=np.int32)
+    lib().orc_build_pattern(npc, C.c_int32(nb_node), C.c_int64(nb_cell), _p(cells), _p(rows), _p(cols))
+    return rows, cols
+
+
+def build_pattern_host(npc, nb_node, cells, capacity):
+    cells = _i32(cells)
+    rows = np.empty(nb_node + 1, dtype=np.int32)
+    cols = np.empty(capacity, dtype=np.int32)
+    nnz = lib().orc_build_pattern_host(npc, C.c_int32(nb_node), C.c_int64(cells.shape[0]), _p(cells), _p(rows), _p(cols), C.c_int64(capacity))
+    assert nnz >= 0
+    return rows, cols[:nnz]
+
+
+def assemble(mesh_dim, coords, cells, rows, cols, op=OP_POISSON, form=FORM_COMPACT, params=None,
+             layout=LAYOUT_PER_BLOCK, nodewise=False, is_own=None, skip_zero=False):
+    coords, cells, rows, cols = _f64(coords), _i32(cells), _i32(rows), _i32(cols)
+    npc = cells.shape[1]
+    b = block_size(op, mesh_dim)
+    vals = np.zeros(int(cols.shape[0]) * b * b)
+    prm = _f64(params if params is not None else [0.0, 0.0])
+    own = _u8(is_own)
+    nb_node = coords.shape[0]
+    if nodewise:
+        rc = lib().orc_assemble_nodewise(npc, mesh_dim, op, form, _p(prm), C.c_int32(nb_node), C.c_int64(cells.shape[0]), _p(coords), _p(cells), _p(own),
+                                         _p(rows), _p(cols), layout, _p(vals))
+    else:
+        rc = lib().orc_assemble_cellwise(npc, mesh_dim, op, form, _p(prm), C.c_int32(nb_node), C.c_int64(cells.shape[0]), _p(coords), _p(cells), _p(own),
+                                         _p(rows), _p(cols), layout, int(skip_zero), _p(vals))
+    assert rc == 0, rc
+    return vals
+
+
+def bsr_to_csr(b, rows, cols):
+    rows, cols = _i32(rows), _i32(cols)
+    nbr = rows.shape[0] - 1
+    csr_rows = np.empty(nbr * b + 1, dtype=np.int32)
+    csr_cols = np.empty(cols.shape[0] * b * b, dtype=np.int32)
+    nbc = np.empty(nbr * b, dtype=np.int32)
+    lib().orc_bsr_to_csr(C.c_int32(nbr), b, _p(rows), _p(cols), _p(csr_rows), _p(csr_cols), _p(nbc))
+    return csr_rows, csr_cols, nbc
+
+
+def csr_to_coo_rows(rows):
+    rows = _i32(rows)
+    out = np.empty(int(rows[-1]), dtype=np.int32)
+    lib().orc_csr_to_coo_rows(C.c_int32(rows.shape[0] - 1), _p(rows), _p(out))
+    return out
+
+
+def value_index(rows, cols, b, layout, dof_row, dof_col):
+    return lib().orc_value_index(_p(_i32(rows)), _p(_i32(cols)), b, layout, C.c_int32(dof_row), C.c_int32(dof_col))
+
+
+def rhs_source_cellwise(mesh_dim, coords, cells, f, signed_area=False, is_own=None, is_dirichlet=None):
+    coords, cells = _f64(coords), _i32(cells)
+    f = _f64(np.atleast_1d(f))
+    b = f.shape[0]
+    rhs = np.zeros(coords.shape[0] * b)
+    lib().orc_rhs_source_cellwise(cells.shape[1], mesh_dim, b, int(signed_area), C.c_int32(coords.shape[0]), C.c_int64(cells.shape[0]), _p(coords), _p(cells),
+                                  _p(_u8(is_own)), _p(_u8(is_dirichlet)), _p(f), _p(rhs))
+    return rhs
+
+
+def rhs_source_nodewise(mesh_dim, coords, cells, f, is_own=None):
+    coords, cells = _f64(coords), _i32(cells)
+    f = _f64(np.atleast_1d(f))
+    b = f.shape[0]
+    rhs = np.zeros(coords.shape[0] * b)
+    lib().orc_rhs_source_nodewise(cells.shape[1], mesh_dim, b, C.c_int32(coords.shape[0]), C.c_int64(cells.shape[0]), _p(coords), _p(cells), _p(_u8(is_own)), _p(f), _p(rhs))
+    return rhs
+
+
+def dirichlet_penalty(rows, cols, values, rhs, dof_ids, g, penalty, weak=False):
+    dof_ids, g = _i32(dof_ids), _f64(g)
+    rc = lib().orc_dirichlet_penalty(int(weak), C.c_double(penalty), C.c_int32(dof_ids.shape[0]), _p(dof_ids), _p(g), _p(_i32(rows)), _p(_i32(cols)), _p(values), _p(rhs))
+    assert rc == 0
+
+
+def apply_elimination(rows, cols, values, rhs, elim_info, elim_value, forced_info=None, forced_value=None, dof_is_own=None, quirk_skip_col0=True):
+    rows, cols = _i32(rows), _i32(cols)
+    lib().orc_apply_elimination(C.c_int32(rows.shape[0] - 1), _p(rows), _p(cols), _p(values), _p(rhs), _p(_u8(elim_info)), _p(_f64(elim_value)),
+                                _p(_u8(forced_info)), _p(_f64(forced_value)), _p(_u8(dof_is_own)), int(quirk_skip_col0))
+
+
+def spmv(rows, cols, values, x):
+    rows, cols = _i32(rows), _i32(cols)
+    y = np.empty(rows.shape[0] - 1)
+    lib().orc_spmv(C.c_int32(rows.shape[0] - 1), _p(rows), _p(cols), _p(_f64(values)), _p(_f64(x)), _p(y))
+    return y
+
+
+def assemble_csr_host_range(mesh_dim, coords, cells, rows, cols, values, cell_lo, cell_hi, owner_lo, owner_hi):
+    """Reference sequential CSR AddAndCompute on a sub-domain (thread-safe for disjoint owner ranges)."""
+    rc = lib().orc_assemble_csr_host_range(cells.shape[1], mesh_dim, C.c_int64(cell_lo), C.c_int64(cell_hi), C.c_int32(owner_lo), C.c_int32(owner_hi),
+                                           _p(coords), _p(cells), _p(rows), _p(cols), _p(values))
+    assert rc == 0, rc

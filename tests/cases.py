@@ -1,0 +1,81 @@
+"""The reference's own end-to-end test cases for the assembly path,
+restated as data: mesh fixture, source term, Dirichlet groups in .arc order, penalty,
+golden nodal field.  Citations: modules/testlab/inputs/Test.*.arc,
+modules/elasticity/inputs/bar.*.arc, modules/bilaplacian/inputs/direct.arc."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+POISSON_CASES = {
+    # modules/testlab/inputs/Test.L-shape.2D.csr-gpu.arc
+    "L-shape_2D": dict(mesh="L-shape.msh", f=-5.5, dirichlet=[("boundary", 0.5)], penalty=1.0e30,
+                       golden="poisson_test_ref_L-shape_2D.txt"),
+    # modules/testlab/inputs/Test.L-shape.3D.nwcsr.arc
+    "L-shape_3D": dict(mesh="L-shape-3D.msh", f=5.5, dirichlet=[("bot", 50.0), ("bc", 10.0)], penalty=1.0e30,
+                       golden="poisson_test_ref_L-shape_3D.txt"),
+    # modules/testlab/inputs/Test.circle.2D.csr.arc
+    "circle_2D": dict(mesh="circle_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], penalty=1.0e30,
+                      golden="poisson_test_ref_circle_2D.txt"),
+    # modules/testlab/inputs/Test.sphere.3D.csr-gpu.arc
+    "sphere_3D": dict(mesh="sphere_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], penalty=1.0e31,
+                      golden="poisson_test_ref_sphere_3D.txt"),
+}
+
+ELASTICITY_CASES = {
+    # modules/elasticity/inputs/bar.2D.Dirichlet.bodyForce.arc
+    "bar_2D": dict(mesh="bar.msh", E=21.0e5, nu=0.28, f=[0.0, -1.0], dirichlet=[("left", [0.0, 0.0])], penalty=1.0e30,
+                   golden="elasticity_bar.2D.Dirichlet.bodyForce.txt"),
+    # modules/elasticity/inputs/bar.3D.Dirichlet.bodyForce.arc
+    "bar_3D": dict(mesh="bar_dynamic_3D.msh", E=21.0e5, nu=0.28, f=[-1.0, 0.0, 0.0],
+                   dirichlet=[("surfaceleft", [0.0, 0.0, 0.0]), ("surfaceright", [None, 1.0, None])], penalty=1.0e30,
+                   golden="elasticity_bar.3D.Dirichlet.bodyForce.txt"),
+}
+
+# modules/bilaplacian/inputs/direct.arc
+BILAPLACIAN_CASE = dict(mesh="bilap.msh", f=-786.25, dirichlet=[("boundary", [145.5, None])], penalty=1.0e30,
+                        golden="bilaplacian_2d_test.txt")
+
+
+def load_golden(name, ncomp):
+    """'uid v0 [v1 ...]' per line -> dict uid -> values[:ncomp]"""
+    out = {}
+    with open(os.path.join(GOLDEN, name)) as f:
+        for line in f:
+            p = line.split()
+            if not p:
+                continue
+            out[int(p[0])] = np.array([float(x) for x in p[1:1 + ncomp]])
+    return out
+
+
+def dirichlet_dofs(mesh, dirichlet, b):
+    """.arc order; later groups override earlier ones (m_u is overwritten in order,
+    modules/testlab/FemModule.cc:647-677).  Returns (dof_ids, values) sorted by dof."""
+    val = {}
+    for name, v in dirichlet:
+        vs = [v] if b == 1 and not isinstance(v, (list, tuple)) else list(v)
+        for node in mesh.groups[name]:
+            for k, x in enumerate(vs):
+                if x is not None:
+                    val[int(node) * b + k] = float(x)
+    ids = np.array(sorted(val), dtype=np.int32)
+    return ids, np.array([val[i] for i in ids], dtype=np.float64)
+
+
+def compare_to_golden(mesh, u, golden, b, eps, min_value):
+    """femutils/FemUtils.cc:108-172 (checkNodeResultFile): relative eps, values below
+    min_value skipped.  Returns max relative deviation over compared entries."""
+    worst = 0.0
+    assert np.all(np.isfinite(u))
+    for lid in range(mesh.nb_node):
+        ref = golden[int(mesh.node_uid[lid])]
+        for k in range(b):
+            r, v = ref[k], u[lid * b + k]
+            if abs(r) < min_value and abs(v) < min_value:
+                continue
+            d = abs(r - v) / max(abs(r), abs(v))
+            worst = max(worst, d)
+    assert worst <= eps, f"max relative deviation {worst} > {eps}"
+    return worst

@@ -1,0 +1,36 @@
+"""Copies the reference's own fixtures for the assembly path into tests/golden/
+(meshes + golden post-solve nodal fields).  These are DATA files of the reference's
+test-suite, not source; they travel with the repo because
+/root/reference does not exist on the GPU box.  Run:  python tests/golden/make_golden.py
+"""
+import os
+import shutil
+
+REF = os.environ.get("AFB_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FILES = {
+    # meshes (Gmsh 4.1 binary)
+    "meshes/msh/L-shape.msh": "L-shape.msh",
+    "meshes/msh/L-shape-3D.msh": "L-shape-3D.msh",
+    "meshes/msh/circle_cut.msh": "circle_cut.msh",
+    "meshes/msh/sphere_cut.msh": "sphere_cut.msh",
+    "meshes/msh/porous-medium.msh": "porous-medium.msh",
+    "meshes/msh/bar.msh": "bar.msh",
+    "meshes/msh/bar_dynamic_3D.msh": "bar_dynamic_3D.msh",
+    "meshes/msh/bilap.msh": "bilap.msh",
+    # golden nodal solutions ("uid value..." per line)
+    "modules/testlab/tests/poisson_test_ref_L-shape_2D.txt": "poisson_test_ref_L-shape_2D.txt",
+    "modules/testlab/tests/poisson_test_ref_L-shape_3D.txt": "poisson_test_ref_L-shape_3D.txt",
+    "modules/testlab/tests/poisson_test_ref_circle_2D.txt": "poisson_test_ref_circle_2D.txt",
+    "modules/testlab/tests/poisson_test_ref_sphere_3D.txt": "poisson_test_ref_sphere_3D.txt",
+    "modules/elasticity/check/bar.2D.Dirichlet.bodyForce.txt": "elasticity_bar.2D.Dirichlet.bodyForce.txt",
+    "modules/elasticity/check/bar.3D.Dirichlet.bodyForce.txt": "elasticity_bar.3D.Dirichlet.bodyForce.txt",
+    "modules/bilaplacian/check/2d_test.txt": "bilaplacian_2d_test.txt",
+}
+
+if __name__ == "__main__":
+    for src, dst in FILES.items():
+        shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
+        os.chmod(os.path.join(HERE, dst), 0o644)
+        print("copied", src, "->", dst)
