@@ -1,0 +1,266 @@
+"""ctypes binding of the C ABI (include/afb200.h) — what tests/ and bench.py call.
+
+There is no CPU fallback: if libafb200.so is missing or no CUDA device is present the
+calls raise.  Device arrays are returned as raw pointers; `Context.to_host` copies them
+out and `Context.as_torch` wraps them as zero-copy torch tensors (torch is plumbing:
+device memory, streams, torch.distributed).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libafb200.so")
+
+# enums of afb200.h
+OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN = 0, 1, 2
+FORMAT_CSR, FORMAT_COO, FORMAT_BSR = 0, 1, 2
+VARIANT_CELLWISE_ATOMIC, VARIANT_NODEWISE, VARIANT_TILED_GATHER = 0, 1, 2
+LAYOUT_PER_BLOCK, LAYOUT_PER_ROW = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+FLAG_SIGNED_TRI_AREA = 1
+ELIMINATE_ROW, ELIMINATE_ROW_COLUMN = 1, 2
+(ARRAY_ROWS, ARRAY_COLUMNS, ARRAY_VALUES, ARRAY_NZ_PER_ROW, ARRAY_RHS, ARRAY_COO_ROWS, ARRAY_CSR_ROWS, ARRAY_CSR_COLUMNS,
+ ARRAY_CSR_NB_COLUMN, ARRAY_COORDS, ARRAY_CELL_NODES, ARRAY_NODE_CELL_PTR, ARRAY_NODE_CELL_LIST) = range(13)
+
+_ARRAY_DTYPE = {ARRAY_ROWS: np.int32, ARRAY_COLUMNS: np.int32, ARRAY_VALUES: np.float64, ARRAY_NZ_PER_ROW: np.int32, ARRAY_RHS: np.float64,
+                ARRAY_COO_ROWS: np.int32, ARRAY_CSR_ROWS: np.int32, ARRAY_CSR_COLUMNS: np.int32, ARRAY_CSR_NB_COLUMN: np.int32,
+                ARRAY_COORDS: np.float64, ARRAY_CELL_NODES: np.int32, ARRAY_NODE_CELL_PTR: np.int32, ARRAY_NODE_CELL_LIST: np.int32}
+
+EXPORTS = [
+    "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_mesh_generate_box",
+    "afb_build_pattern", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_set_dirichlet_nodes",
+    "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
+    "afb_apply_rhs_transformation", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
+    "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail", "afb_last_timings", "afb_launch_count",
+]
+
+
+class AfbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into arcanefem_b200/libafb200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AfbError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.afb_last_error.restype = C.c_char_p
+        _lib.afb_version.restype = C.c_char_p
+        _lib.afb_launch_count.restype = C.c_int64
+        _lib.afb_launch_count.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise AfbError(f"afb error {rc}: {lib().afb_last_error().decode()}")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    # torch tensor
+    return C.c_void_p(a.data_ptr())
+
+
+class Context:
+    """One assembly context per GPU (afb_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = C.c_void_p()
+        _check(lib().afb_create(int(device), C.byref(self._h)))
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+        self.b = 1
+
+    def close(self):
+        if self._h:
+            lib().afb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def set_stream(self, stream_ptr: int | None):
+        _check(lib().afb_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+
+    def synchronize(self):
+        _check(lib().afb_synchronize(self._h))
+
+    # -- mesh -----------------------------------------------------------------------------------
+    def set_mesh(self, dim, coords, cells, is_own=None, mem_space=MEM_HOST):
+        if mem_space == MEM_HOST:
+            coords = np.ascontiguousarray(coords, dtype=np.float64)
+            cells = np.ascontiguousarray(cells, dtype=np.int32)
+            is_own = None if is_own is None else np.ascontiguousarray(is_own, dtype=np.uint8)
+        self._keep = (coords, cells, is_own)
+        nb_node, npc = int(coords.shape[0]), int(cells.shape[1])
+        _check(lib().afb_set_mesh(self._h, int(dim), npc, C.c_int32(nb_node), C.c_int64(int(cells.shape[0])), _ptr(coords), _ptr(cells), _ptr(is_own), mem_space))
+        self.dim, self.npc, self.nb_node, self.nb_cell = dim, npc, nb_node, int(cells.shape[0])
+
+    def generate_box(self, dim, n, jitter=0.2, seed=12345, k_lo=0, k_hi=None):
+        k_hi = n if k_hi is None else k_hi
+        _check(lib().afb_mesh_generate_box(self._h, dim, n, C.c_double(jitter), C.c_uint32(seed), k_lo, k_hi))
+        info = self.mesh_info()
+        self.dim, self.npc, self.nb_node, self.nb_cell = info["dim"], info["npc"], info["nb_node"], info["nb_cell"]
+        return info
+
+    def mesh_info(self):
+        dim, npc, nbn, nbo = C.c_int(), C.c_int(), C.c_int32(), C.c_int32()
+        nbc = C.c_int64()
+        xyz, cn, own = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().afb_get_mesh(self._h, C.byref(dim), C.byref(npc), C.byref(nbn), C.byref(nbc), C.byref(nbo), C.byref(xyz), C.byref(cn), C.byref(own)))
+        return dict(dim=dim.value, npc=npc.value, nb_node=nbn.value, nb_cell=nbc.value, nb_own_node=nbo.value, xyz=xyz.value, cell_nodes=cn.value, is_own=own.value)
+
+    # -- pattern / assembly ------------------------------------------------------------------
+    def build_pattern(self, nb_dof_per_node=1):
+        nbr, nnz = C.c_int32(), C.c_int64()
+        _check(lib().afb_build_pattern(self._h, nb_dof_per_node, C.byref(nbr), C.byref(nnz)))
+        self.b, self.nb_block_row, self.nnz = nb_dof_per_node, nbr.value, nnz.value
+        return nbr.value, nnz.value
+
+    def reset_values(self):
+        _check(lib().afb_reset_values(self._h))
+
+    def assemble(self, op=OP_POISSON, params=None, fmt=FORMAT_CSR, variant=VARIANT_CELLWISE_ATOMIC, layout=LAYOUT_PER_BLOCK, flags=0):
+        prm = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        _check(lib().afb_assemble_bilinear(self._h, op, _ptr(prm), 0 if prm is None else int(prm.size), fmt, variant, layout, flags))
+        self.layout = layout
+
+    # -- rhs / dirichlet -----------------------------------------------------------------------
+    def rhs_reset(self):
+        _check(lib().afb_rhs_reset(self._h))
+
+    def rhs_source(self, f, nodewise=False, signed_tri_area=False):
+        f = np.ascontiguousarray(np.atleast_1d(f), dtype=np.float64)
+        _check(lib().afb_assemble_rhs_source(self._h, _ptr(f), int(f.size), int(nodewise), int(signed_tri_area)))
+
+    def set_dirichlet_nodes(self, node_ids):
+        ids = np.ascontiguousarray(node_ids, dtype=np.int32)
+        _check(lib().afb_set_dirichlet_nodes(self._h, C.c_int32(ids.size), _ptr(ids), MEM_HOST))
+
+    def dirichlet_penalty(self, dof_ids, g, penalty, weak=False):
+        ids = np.ascontiguousarray(dof_ids, dtype=np.int32)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        _check(lib().afb_dirichlet_penalty(self._h, int(weak), C.c_double(penalty), C.c_int32(ids.size), _ptr(ids), _ptr(g), MEM_HOST))
+
+    def set_elimination(self, kind, dof_ids, g):
+        ids = np.ascontiguousarray(dof_ids, dtype=np.int32)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        _check(lib().afb_set_elimination(self._h, kind, C.c_int32(ids.size), _ptr(ids), _ptr(g), MEM_HOST))
+
+    def set_forced_values(self, dof_ids, v):
+        ids = np.ascontiguousarray(dof_ids, dtype=np.int32)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        _check(lib().afb_set_forced_values(self._h, C.c_int32(ids.size), _ptr(ids), _ptr(v), MEM_HOST))
+
+    def clear_dirichlet(self):
+        _check(lib().afb_clear_dirichlet(self._h))
+
+    def apply_matrix_transformation(self, replicate_column0_quirk=True):
+        _check(lib().afb_apply_matrix_transformation(self._h, int(replicate_column0_quirk)))
+
+    def apply_rhs_transformation(self):
+        _check(lib().afb_apply_rhs_transformation(self._h))
+
+    # -- views -------------------------------------------------------------------------------------
+    def csr_view(self):
+        rows, nbc, cols, vals = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nb_row, nnz = C.c_int32(), C.c_int64()
+        _check(lib().afb_get_csr_view(self._h, C.byref(rows), C.byref(nbc), C.byref(cols), C.byref(vals), C.byref(nb_row), C.byref(nnz)))
+        return dict(rows=rows.value, rows_nb_column=nbc.value, columns=cols.value, values=vals.value, nb_row=nb_row.value, nnz=nnz.value)
+
+    def bsr_view(self):
+        rows, cols, vals, nzr = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nbr, b, lay = C.c_int32(), C.c_int(), C.c_int()
+        nbc = C.c_int64()
+        _check(lib().afb_get_bsr(self._h, C.byref(rows), C.byref(cols), C.byref(vals), C.byref(nzr), C.byref(nbr), C.byref(nbc), C.byref(b), C.byref(lay)))
+        return dict(rows_index=rows.value, columns=cols.value, values=vals.value, nb_nz_per_row=nzr.value, nb_block_row=nbr.value, nb_col=nbc.value,
+                    block_size=b.value, layout=lay.value)
+
+    def coo_view(self):
+        r, c, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nnz = C.c_int64()
+        _check(lib().afb_get_coo(self._h, C.byref(r), C.byref(c), C.byref(v), C.byref(nnz)))
+        return dict(rows=r.value, cols=c.value, values=v.value, nnz=nnz.value)
+
+    def rhs_view(self):
+        p = C.c_void_p()
+        n = C.c_int32()
+        _check(lib().afb_get_rhs(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def to_host(self, which, out=None):
+        nbytes = C.c_size_t()
+        _check(lib().afb_copy_to_host(self._h, which, None, C.byref(nbytes)))
+        dt = np.dtype(_ARRAY_DTYPE[which])
+        if out is None:
+            out = np.empty(nbytes.value // dt.itemsize, dtype=dt)
+        assert out.nbytes >= nbytes.value
+        _check(lib().afb_copy_to_host(self._h, which, _ptr(out), C.byref(nbytes)))
+        return out
+
+    # -- multi-GPU helpers -------------------------------------------------------------------------
+    def lookup_value_slots(self, n, dof_rows_ptr, dof_cols_ptr, slots_ptr):
+        _check(lib().afb_lookup_value_slots(self._h, C.c_int64(n), _ptr(dof_rows_ptr), _ptr(dof_cols_ptr), _ptr(slots_ptr)))
+
+    def add_values_at(self, n, slots_ptr, contrib_ptr):
+        _check(lib().afb_add_values_at(self._h, C.c_int64(n), _ptr(slots_ptr), _ptr(contrib_ptr)))
+
+    def values_tail(self, first_block_row):
+        first, nb = C.c_int64(), C.c_int64()
+        _check(lib().afb_values_tail(self._h, C.c_int32(first_block_row), C.byref(first), C.byref(nb)))
+        return first.value, nb.value
+
+    # -- instrumentation -----------------------------------------------------------------------------
+    def last_timings(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _check(lib().afb_last_timings(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(connectivity_ms=a.value, pattern_ms=b.value, assemble_ms=c.value)
+
+    def launch_count(self):
+        return int(lib().afb_launch_count(self._h))
+
+
+def as_torch(ptr: int, shape, dtype, device: int):
+    """Zero-copy torch view of a device array owned by the context."""
+    import torch
+
+    class _Holder:
+        pass
+
+    tstr = {np.dtype(np.float64): "<f8", np.dtype(np.int32): "<i4", np.dtype(np.int64): "<i8", np.dtype(np.uint8): "|u1"}[np.dtype(dtype)]
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": tuple(int(s) for s in np.atleast_1d(shape)), "typestr": tstr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device=f"cuda:{device}")

@@ -1,0 +1,504 @@
+// C ABI entry points of libafb200.so (include/afb200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "afb_internal.h"
+
+namespace afb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int check_ctx(afb_ctx* ctx)
+{
+  AFB_REQUIRE(ctx != nullptr, AFB_ERR_INVALID, "null context");
+  AFB_CUDA(cudaSetDevice(ctx->device));
+  return AFB_OK;
+}
+
+static int time_begin(afb_ctx* ctx, int phase)
+{
+  AFB_CUDA(cudaEventRecord(ctx->ev[2 * phase], ctx->stream));
+  return AFB_OK;
+}
+static int time_end(afb_ctx* ctx, int phase)
+{
+  AFB_CUDA(cudaEventRecord(ctx->ev[2 * phase + 1], ctx->stream));
+  ctx->timed[phase] = true;
+  return AFB_OK;
+}
+
+static void invalidate_pattern(afb_ctx* ctx)
+{
+  ctx->has_pattern = false;
+  ctx->assembled = false;
+  ctx->coo_rows_valid = false;
+  ctx->csr_valid = false;
+  ctx->saved_valid = false;
+  ctx->plan.valid = false;
+  ctx->has_elim = ctx->has_forced = ctx->has_rc = false;
+}
+
+// copy a host or device array into an owned device buffer
+static int upload(afb_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, int mem_space)
+{
+  if (mem_space == AFB_MEM_DEVICE) {
+    buf.alias(src, bytes);
+    return AFB_OK;
+  }
+  if (!buf.owned) buf.release();
+  AFB_TRY(buf.reserve(bytes));
+  if (bytes) AFB_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return AFB_OK;
+}
+
+// stage a small host/device id or value list on the device
+static int stage(afb_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, int mem_space, const void** dev)
+{
+  if (mem_space == AFB_MEM_DEVICE) {
+    *dev = src;
+    return AFB_OK;
+  }
+  AFB_TRY(buf.reserve(bytes));
+  if (bytes) AFB_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dev = buf.p;
+  return AFB_OK;
+}
+
+} // namespace afb
+
+using namespace afb;
+
+extern "C" {
+
+const char* afb_last_error(void) { return g_err; }
+const char* afb_version(void) { return "arcanefem_b200 0.1 (sm_100a)"; }
+
+int afb_create(int device, afb_ctx** out)
+{
+  AFB_REQUIRE(out != nullptr, AFB_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s): libafb200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return AFB_ERR_CUDA;
+  }
+  AFB_REQUIRE(device >= 0 && device < count, AFB_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  AFB_CUDA(cudaSetDevice(device));
+  afb_ctx* ctx = new afb_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  AFB_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  AFB_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  for (int i = 0; i < 6; ++i) AFB_CUDA(cudaEventCreate(&ctx->ev[i]));
+  *out = ctx;
+  return AFB_OK;
+}
+
+int afb_destroy(afb_ctx* ctx)
+{
+  if (!ctx) return AFB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,
+                     &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
+                     &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag,
+                     &ctx->plan.tile_desc, &ctx->plan.tile_rows, &ctx->plan.tile_foot, &ctx->plan.tile_cells, &ctx->plan.pair_ptr, &ctx->plan.pairs, &ctx->plan.node_tile };
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < 6; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return AFB_OK;
+}
+
+int afb_set_stream(afb_ctx* ctx, void* cuda_stream)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return AFB_OK;
+}
+
+int afb_synchronize(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AFB_OK;
+}
+
+int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cell, const double* xyz, const int32_t* cell_nodes, const uint8_t* node_is_own, int mem_space)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(dim == 2 || dim == 3, AFB_ERR_UNSUPPORTED, "BSRFormat(initialize): Only supports 2D and 3D (dim=%d)", dim);
+  AFB_REQUIRE((dim == 2 && (npc == 3 || npc == 6)) || (dim == 3 && (npc == 4 || npc == 10)), AFB_ERR_UNSUPPORTED,
+              "unsupported cell type: %d nodes per cell in dimension %d (Tri3/Tri6/Tet4/Tet10 only)", npc, dim);
+  AFB_REQUIRE(nb_node > 0 && nb_cell >= 0, AFB_ERR_INVALID, "bad mesh sizes nb_node=%d nb_cell=%lld", nb_node, (long long)nb_cell);
+  AFB_REQUIRE(xyz && (cell_nodes || nb_cell == 0), AFB_ERR_INVALID, "null mesh arrays");
+  invalidate_pattern(ctx);
+  ctx->has_mesh = false;
+  ctx->dim = dim;
+  ctx->npc = npc;
+  ctx->nb_node = nb_node;
+  ctx->nb_cell = nb_cell;
+  AFB_TRY(upload(ctx, ctx->coords, xyz, sizeof(double) * 3 * (size_t)nb_node, mem_space));
+  AFB_TRY(upload(ctx, ctx->conn, cell_nodes, sizeof(int32_t) * (size_t)npc * (size_t)nb_cell, mem_space));
+  ctx->all_own = (node_is_own == nullptr);
+  ctx->nb_own_node = nb_node;
+  if (node_is_own) AFB_TRY(upload(ctx, ctx->is_own, node_is_own, (size_t)nb_node, mem_space));
+  ctx->has_dir_nodes = false;
+  ctx->has_mesh = true;
+  AFB_TRY(time_begin(ctx, 0));
+  AFB_TRY(build_node_cells(ctx));
+  AFB_TRY(time_end(ctx, 0));
+  return AFB_OK;
+}
+
+int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi)
+{
+  AFB_TRY(check_ctx(ctx));
+  invalidate_pattern(ctx);
+  ctx->has_mesh = false;
+  if (!ctx->coords.owned) ctx->coords.release();
+  if (!ctx->conn.owned) ctx->conn.release();
+  if (!ctx->is_own.owned) ctx->is_own.release();
+  AFB_TRY(generate_box(ctx, dim, n, jitter, seed, k_lo, k_hi));
+  ctx->has_dir_nodes = false;
+  AFB_TRY(time_begin(ctx, 0));
+  AFB_TRY(build_node_cells(ctx));
+  AFB_TRY(time_end(ctx, 0));
+  return AFB_OK;
+}
+
+int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_block_row, int64_t* nb_block_nnz)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_mesh, AFB_ERR_INVALID, "afb_build_pattern: no mesh set");
+  // BSRMatrix::initialize argument checks (femutils/BSRFormat.cc:51-55)
+  AFB_REQUIRE(nb_dof_per_node >= 1 && nb_dof_per_node <= 3, AFB_ERR_INVALID, "BSRMatrix(initialize): block_size must be 1, 2 or 3 (got %d)", nb_dof_per_node);
+  invalidate_pattern(ctx);
+  ctx->b = nb_dof_per_node;
+  AFB_TRY(time_begin(ctx, 1));
+  AFB_TRY(build_pattern(ctx));
+  AFB_TRY(time_end(ctx, 1));
+  ctx->has_pattern = true;
+  if (nb_block_row) *nb_block_row = ctx->nb_node;
+  if (nb_block_nnz) *nb_block_nnz = ctx->nnz;
+  return AFB_OK;
+}
+
+int afb_reset_values(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_reset_values: no pattern");
+  AFB_CUDA(cudaMemsetAsync(ctx->values.p, 0, sizeof(double) * (size_t)ctx->nnz * ctx->b * ctx->b, ctx->stream));
+  ctx->assembled = false;
+  ctx->saved_valid = false;
+  return AFB_OK;
+}
+
+int afb_assemble_bilinear(afb_ctx* ctx, int op, const double* params, int nb_params, int format, int variant, int value_layout, int flags)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_assemble_bilinear: build the pattern first");
+  AFB_REQUIRE(format == AFB_FORMAT_CSR || format == AFB_FORMAT_COO || format == AFB_FORMAT_BSR, AFB_ERR_INVALID, "unknown matrix format %d", format);
+  AFB_REQUIRE(value_layout == AFB_LAYOUT_PER_BLOCK || value_layout == AFB_LAYOUT_PER_ROW, AFB_ERR_INVALID, "unknown value layout %d", value_layout);
+  const int need_b = op == AFB_OP_POISSON ? 1 : (op == AFB_OP_ELASTICITY ? ctx->dim : (op == AFB_OP_BILAPLACIAN ? 2 : -1));
+  AFB_REQUIRE(need_b > 0, AFB_ERR_INVALID, "unknown operator %d", op);
+  AFB_REQUIRE(need_b == ctx->b, AFB_ERR_INVALID, "operator %d needs %d dof per node, pattern was built with %d", op, need_b, ctx->b);
+  AFB_REQUIRE(op != AFB_OP_ELASTICITY || (params && nb_params >= 2), AFB_ERR_INVALID, "elasticity needs params = {lambda, mu}");
+  AFB_REQUIRE(!(ctx->b > 1 && format != AFB_FORMAT_BSR), AFB_ERR_INVALID, "CSR/COO back-ends hold one dof per node; use AFB_FORMAT_BSR for b=%d", ctx->b);
+  AFB_REQUIRE(!(ctx->assembled && ctx->layout != value_layout), AFB_ERR_INVALID, "values already hold the other layout; afb_reset_values first");
+  ctx->layout = value_layout;
+  AFB_TRY(time_begin(ctx, 2));
+  if (variant == AFB_VARIANT_TILED_GATHER) {
+    if (!ctx->plan.valid) AFB_TRY(build_tile_plan(ctx));
+    AFB_TRY(assemble_tiled(ctx, op, params, value_layout, flags));
+  }
+  else
+    AFB_TRY(assemble_bilinear(ctx, op, params, format, variant, value_layout, flags));
+  AFB_TRY(time_end(ctx, 2));
+  ctx->assembled = true;
+  return AFB_OK;
+}
+
+int afb_rhs_reset(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_rhs_reset: no pattern");
+  AFB_CUDA(cudaMemsetAsync(ctx->rhs.p, 0, sizeof(double) * (size_t)ctx->nb_node * ctx->b, ctx->stream));
+  return AFB_OK;
+}
+
+int afb_assemble_rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed_tri_area)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern && f, AFB_ERR_INVALID, "afb_assemble_rhs_source: no pattern / null source");
+  return rhs_source(ctx, f, nb_f, nodewise, signed_tri_area);
+}
+
+int afb_set_dirichlet_nodes(afb_ctx* ctx, int32_t n, const int32_t* node_ids, int mem_space)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_mesh, AFB_ERR_INVALID, "afb_set_dirichlet_nodes: no mesh");
+  AFB_TRY(ctx->dir_node.reserve((size_t)ctx->nb_node));
+  AFB_CUDA(cudaMemsetAsync(ctx->dir_node.p, 0, (size_t)ctx->nb_node, ctx->stream));
+  ctx->has_dir_nodes = false;
+  if (n <= 0 || !node_ids) return AFB_OK;
+  const void* ids = nullptr;
+  AFB_TRY(stage(ctx, ctx->tmp_ids, node_ids, sizeof(int32_t) * (size_t)n, mem_space, &ids));
+  AFB_TRY(scatter_flags(ctx, ctx->dir_node.as<uint8_t>(), nullptr, 1, n, (const int32_t*)ids, nullptr));
+  ctx->has_dir_nodes = true;
+  return AFB_OK;
+}
+
+int afb_dirichlet_penalty(afb_ctx* ctx, int weak, double penalty, int32_t n, const int32_t* dof_ids, const double* g, int mem_space)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_dirichlet_penalty: no pattern");
+  if (n <= 0) return AFB_OK;
+  const void *ids = nullptr, *vals = nullptr;
+  AFB_TRY(stage(ctx, ctx->tmp_ids, dof_ids, sizeof(int32_t) * (size_t)n, mem_space, &ids));
+  AFB_TRY(stage(ctx, ctx->tmp_vals, g, sizeof(double) * (size_t)n, mem_space, &vals));
+  return dirichlet_penalty(ctx, weak, penalty, n, (const int32_t*)ids, (const double*)vals);
+}
+
+static int ensure_dof_flags(afb_ctx* ctx, DevBuf& info, DevBuf& value, bool& has)
+{
+  if (has) return AFB_OK;
+  const size_t nb_dof = (size_t)ctx->nb_node * ctx->b;
+  AFB_TRY(info.reserve(nb_dof));
+  AFB_TRY(value.reserve(sizeof(double) * nb_dof));
+  AFB_CUDA(cudaMemsetAsync(info.p, 0, nb_dof, ctx->stream));
+  AFB_CUDA(cudaMemsetAsync(value.p, 0, sizeof(double) * nb_dof, ctx->stream));
+  has = true;
+  return AFB_OK;
+}
+
+int afb_set_elimination(afb_ctx* ctx, int type, int32_t n, const int32_t* dof_ids, const double* g, int mem_space)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_set_elimination: no pattern");
+  AFB_REQUIRE(type == AFB_ELIMINATE_ROW || type == AFB_ELIMINATE_ROW_COLUMN, AFB_ERR_INVALID, "bad elimination type %d", type);
+  if (n <= 0) return AFB_OK;
+  AFB_TRY(ensure_dof_flags(ctx, ctx->elim_info, ctx->elim_value, ctx->has_elim));
+  const void *ids = nullptr, *vals = nullptr;
+  AFB_TRY(stage(ctx, ctx->tmp_ids, dof_ids, sizeof(int32_t) * (size_t)n, mem_space, &ids));
+  AFB_TRY(stage(ctx, ctx->tmp_vals, g, sizeof(double) * (size_t)n, mem_space, &vals));
+  AFB_TRY(scatter_flags(ctx, ctx->elim_info.as<uint8_t>(), ctx->elim_value.as<double>(), (uint8_t)type, n, (const int32_t*)ids, (const double*)vals));
+  if (type == AFB_ELIMINATE_ROW_COLUMN) ctx->has_rc = true;
+  return AFB_OK;
+}
+
+int afb_set_forced_values(afb_ctx* ctx, int32_t n, const int32_t* dof_ids, const double* v, int mem_space)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_set_forced_values: no pattern");
+  if (n <= 0) return AFB_OK;
+  AFB_TRY(ensure_dof_flags(ctx, ctx->forced_info, ctx->forced_value, ctx->has_forced));
+  const void *ids = nullptr, *vals = nullptr;
+  AFB_TRY(stage(ctx, ctx->tmp_ids, dof_ids, sizeof(int32_t) * (size_t)n, mem_space, &ids));
+  AFB_TRY(stage(ctx, ctx->tmp_vals, v, sizeof(double) * (size_t)n, mem_space, &vals));
+  return scatter_flags(ctx, ctx->forced_info.as<uint8_t>(), ctx->forced_value.as<double>(), 1, n, (const int32_t*)ids, (const double*)vals);
+}
+
+int afb_clear_dirichlet(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  ctx->has_elim = ctx->has_forced = ctx->has_rc = false;
+  ctx->saved_valid = false;
+  ctx->has_dir_nodes = false;
+  return AFB_OK;
+}
+
+int afb_apply_matrix_transformation(afb_ctx* ctx, int replicate_column0_quirk)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_apply_matrix_transformation: no pattern");
+  return apply_matrix_transformation(ctx, replicate_column0_quirk);
+}
+
+int afb_apply_rhs_transformation(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_apply_rhs_transformation: no pattern");
+  return apply_rhs_transformation(ctx);
+}
+
+int afb_get_csr_view(afb_ctx* ctx, const int32_t** rows, const int32_t** rows_nb_column, const int32_t** columns, double** values, int32_t* nb_row, int64_t* nnz)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_get_csr_view: no pattern");
+  if (ctx->b == 1) {
+    if (rows) *rows = ctx->rows.as<int32_t>();
+    if (rows_nb_column) *rows_nb_column = ctx->nz_per_row.as<int32_t>();
+    if (columns) *columns = ctx->cols.as<int32_t>();
+    if (nb_row) *nb_row = ctx->nb_node;
+    if (nnz) *nnz = ctx->nnz;
+  }
+  else {
+    // "BSRFormat(toLinearSystem): Linear system was set to use CSR but is incompatible" (femutils/BSRFormat.cc:382-383)
+    AFB_REQUIRE(!ctx->assembled || ctx->layout == AFB_LAYOUT_PER_ROW, AFB_ERR_INVALID,
+                "CSR view of a b=%d matrix needs AFB_LAYOUT_PER_ROW values (does_linear_system_use_csr)", ctx->b);
+    AFB_TRY(ensure_scalar_csr(ctx));
+    if (rows) *rows = ctx->csr_rows.as<int32_t>();
+    if (rows_nb_column) *rows_nb_column = ctx->csr_nbcol.as<int32_t>();
+    if (columns) *columns = ctx->csr_cols.as<int32_t>();
+    if (nb_row) *nb_row = ctx->nb_node * ctx->b;
+    if (nnz) *nnz = ctx->nnz * ctx->b * ctx->b;
+  }
+  if (values) *values = ctx->values.as<double>();
+  return AFB_OK;
+}
+
+int afb_get_bsr(afb_ctx* ctx, const int32_t** rows_index, const int32_t** columns, double** values, const int32_t** nb_nz_per_row, int32_t* nb_block_row,
+                int64_t* nb_col, int* block_size, int* value_layout)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_get_bsr: no pattern");
+  if (rows_index) *rows_index = ctx->rows.as<int32_t>();
+  if (columns) *columns = ctx->cols.as<int32_t>();
+  if (values) *values = ctx->values.as<double>();
+  if (nb_nz_per_row) *nb_nz_per_row = ctx->nz_per_row.as<int32_t>();
+  if (nb_block_row) *nb_block_row = ctx->nb_node;
+  if (nb_col) *nb_col = ctx->nnz;
+  if (block_size) *block_size = ctx->b;
+  if (value_layout) *value_layout = ctx->layout;
+  return AFB_OK;
+}
+
+int afb_get_coo(afb_ctx* ctx, const int32_t** coo_rows, const int32_t** coo_cols, double** values, int64_t* nnz)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_get_coo: no pattern");
+  AFB_REQUIRE(ctx->b == 1, AFB_ERR_UNSUPPORTED, "COO view is defined for one dof per node");
+  AFB_TRY(ensure_coo_rows(ctx));
+  if (coo_rows) *coo_rows = ctx->coo_rows.as<int32_t>();
+  if (coo_cols) *coo_cols = ctx->cols.as<int32_t>();
+  if (values) *values = ctx->values.as<double>();
+  if (nnz) *nnz = ctx->nnz;
+  return AFB_OK;
+}
+
+int afb_get_rhs(afb_ctx* ctx, double** rhs, int32_t* nb_dof)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_get_rhs: no pattern");
+  if (rhs) *rhs = ctx->rhs.as<double>();
+  if (nb_dof) *nb_dof = ctx->nb_node * ctx->b;
+  return AFB_OK;
+}
+
+int afb_get_mesh(afb_ctx* ctx, int* dim, int* npc, int32_t* nb_node, int64_t* nb_cell, int32_t* nb_own_node, const double** xyz, const int32_t** cell_nodes,
+                 const uint8_t** node_is_own)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_mesh, AFB_ERR_INVALID, "afb_get_mesh: no mesh");
+  if (dim) *dim = ctx->dim;
+  if (npc) *npc = ctx->npc;
+  if (nb_node) *nb_node = ctx->nb_node;
+  if (nb_cell) *nb_cell = ctx->nb_cell;
+  if (nb_own_node) *nb_own_node = ctx->nb_own_node;
+  if (xyz) *xyz = ctx->coords.as<double>();
+  if (cell_nodes) *cell_nodes = ctx->conn.as<int32_t>();
+  if (node_is_own) *node_is_own = ctx->all_own ? nullptr : ctx->is_own.as<uint8_t>();
+  return AFB_OK;
+}
+
+int afb_copy_to_host(afb_ctx* ctx, int which, void* dst, size_t* bytes)
+{
+  AFB_TRY(check_ctx(ctx));
+  const void* src = nullptr;
+  size_t n = 0;
+  const int b = ctx->b;
+  const bool need_pattern = which <= AFB_ARRAY_CSR_NB_COLUMN;
+  AFB_REQUIRE(!need_pattern || ctx->has_pattern, AFB_ERR_INVALID, "afb_copy_to_host: no pattern");
+  AFB_REQUIRE(need_pattern || ctx->has_mesh, AFB_ERR_INVALID, "afb_copy_to_host: no mesh");
+  switch (which) {
+  case AFB_ARRAY_ROWS: src = ctx->rows.p; n = sizeof(int32_t) * ((size_t)ctx->nb_node + 1); break;
+  case AFB_ARRAY_COLUMNS: src = ctx->cols.p; n = sizeof(int32_t) * (size_t)ctx->nnz; break;
+  case AFB_ARRAY_VALUES: src = ctx->values.p; n = sizeof(double) * (size_t)ctx->nnz * b * b; break;
+  case AFB_ARRAY_NZ_PER_ROW: src = ctx->nz_per_row.p; n = sizeof(int32_t) * (size_t)ctx->nb_node; break;
+  case AFB_ARRAY_RHS: src = ctx->rhs.p; n = sizeof(double) * (size_t)ctx->nb_node * b; break;
+  case AFB_ARRAY_COO_ROWS:
+    AFB_TRY(ensure_coo_rows(ctx));
+    src = ctx->coo_rows.p; n = sizeof(int32_t) * (size_t)ctx->nnz; break;
+  case AFB_ARRAY_CSR_ROWS:
+    AFB_TRY(ensure_scalar_csr(ctx));
+    src = ctx->csr_rows.p; n = sizeof(int32_t) * ((size_t)ctx->nb_node * b + 1); break;
+  case AFB_ARRAY_CSR_COLUMNS:
+    AFB_TRY(ensure_scalar_csr(ctx));
+    src = ctx->csr_cols.p; n = sizeof(int32_t) * (size_t)ctx->nnz * b * b; break;
+  case AFB_ARRAY_CSR_NB_COLUMN:
+    AFB_TRY(ensure_scalar_csr(ctx));
+    src = ctx->csr_nbcol.p; n = sizeof(int32_t) * (size_t)ctx->nb_node * b; break;
+  case AFB_ARRAY_COORDS: src = ctx->coords.p; n = sizeof(double) * 3 * (size_t)ctx->nb_node; break;
+  case AFB_ARRAY_CELL_NODES: src = ctx->conn.p; n = sizeof(int32_t) * (size_t)ctx->npc * (size_t)ctx->nb_cell; break;
+  case AFB_ARRAY_NODE_CELL_PTR: src = ctx->nc_ptr.p; n = sizeof(int32_t) * ((size_t)ctx->nb_node + 1); break;
+  case AFB_ARRAY_NODE_CELL_LIST: src = ctx->nc_list.p; n = sizeof(int32_t) * (size_t)ctx->npc * (size_t)ctx->nb_cell; break;
+  default:
+    set_error("afb_copy_to_host: unknown array %d", which);
+    return AFB_ERR_INVALID;
+  }
+  if (bytes) *bytes = n;
+  if (dst && n) {
+    AFB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream));
+    AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return AFB_OK;
+}
+
+int afb_lookup_value_slots(afb_ctx* ctx, int64_t n, const int32_t* dof_rows, const int32_t* dof_cols, int64_t* slots)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_lookup_value_slots: no pattern");
+  return lookup_value_slots(ctx, n, dof_rows, dof_cols, slots);
+}
+
+int afb_add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, const double* contrib)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_add_values_at: no pattern");
+  return add_values_at(ctx, n, slots, contrib);
+}
+
+int afb_values_tail(afb_ctx* ctx, int32_t first_block_row, int64_t* first_value, int64_t* nb_values)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_values_tail: no pattern");
+  AFB_REQUIRE(first_block_row >= 0 && first_block_row <= ctx->nb_node, AFB_ERR_INVALID, "row %d out of range", first_block_row);
+  int32_t rb = 0;
+  AFB_CUDA(cudaMemcpyAsync(&rb, ctx->rows.as<int32_t>() + first_block_row, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t bb = (int64_t)ctx->b * ctx->b;
+  if (first_value) *first_value = (int64_t)rb * bb;
+  if (nb_values) *nb_values = (ctx->nnz - rb) * bb;
+  return AFB_OK;
+}
+
+int afb_last_timings(afb_ctx* ctx, float* connectivity_ms, float* pattern_ms, float* assemble_ms)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  float* out[3] = { connectivity_ms, pattern_ms, assemble_ms };
+  for (int p = 0; p < 3; ++p) {
+    if (!out[p]) continue;
+    *out[p] = -1.0f;
+    if (ctx->timed[p]) AFB_CUDA(cudaEventElapsedTime(out[p], ctx->ev[2 * p], ctx->ev[2 * p + 1]));
+  }
+  return AFB_OK;
+}
+
+int64_t afb_launch_count(afb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,188 @@
+// Internal declarations shared by the CUDA translation units of libafb200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "afb200.h"
+
+namespace afb {
+
+void set_error(const char* fmt, ...);
+
+#define AFB_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      afb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return AFB_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define AFB_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != AFB_OK) return _rc; \
+  } while (0)
+
+#define AFB_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      afb::set_error(__VA_ARGS__);    \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// Grow-only device buffer (no cudaMalloc/cudaFree in steady state: pattern rebuilds and
+// re-assemblies of the same mesh reuse their memory).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool owned = true;
+  int reserve(size_t bytes)
+  {
+    if (bytes <= cap && p) return AFB_OK;
+    if (p && owned) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    owned = true;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      p = nullptr;
+      return AFB_ERR_CUDA;
+    }
+    cap = bytes;
+    return AFB_OK;
+  }
+  void alias(const void* ext, size_t bytes)
+  {
+    if (p && owned) cudaFree(p);
+    p = const_cast<void*>(ext);
+    cap = bytes;
+    owned = false;
+  }
+  void release()
+  {
+    if (p && owned) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    owned = true;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Plan of the tiled-gather variant (built by tiles.cu from the pattern + connectivity).
+struct TilePlan {
+  bool valid = false;
+  int32_t nb_tile = 0;
+  int max_rows = 0, max_cells = 0, max_foot = 0, max_vals = 0;
+  DevBuf tile_desc;   // int32[nb_tile+1][8]
+  DevBuf tile_rows;   // int32 : owned rows of each tile (global node ids), concatenated
+  DevBuf tile_foot;   // int32 : footprint nodes (owned rows first, then halo), concatenated
+  DevBuf tile_cells;  // uint16[4] (or npc) local footprint indices per tile cell, concatenated
+  DevBuf pair_ptr;    // int32 : per owned row, start of its (cell,slots) pair list
+  DevBuf pairs;       // uint32 packed (local cell idx, a, slots...) -- see tiles.cu
+  DevBuf node_tile;   // scratch
+};
+
+} // namespace afb
+
+struct afb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+
+  // mesh
+  int dim = 0, npc = 0;
+  int32_t nb_node = 0, nb_own_node = 0;
+  int64_t nb_cell = 0;
+  bool has_mesh = false;
+  afb::DevBuf coords, conn, is_own; // double[nb_node*3], int32[nb_cell*npc], uint8[nb_node] (may be null => all owned)
+  bool all_own = true;
+  afb::DevBuf nc_ptr, nc_list;      // node -> cells (int32[nb_node+1], int32[nb_cell*npc]), ascending cell ids
+  int max_valence = 0;
+
+  // pattern
+  bool has_pattern = false;
+  int b = 1;
+  int64_t nnz = 0; // block nnz
+  afb::DevBuf rows, cols, nz_per_row, coo_rows; // int32
+  bool coo_rows_valid = false;
+  afb::DevBuf values; // double[nnz*b*b]
+  afb::DevBuf rhs;    // double[nb_node*b]
+  int layout = AFB_LAYOUT_PER_BLOCK;
+  bool assembled = false;
+  // expanded scalar CSR of a b>1 matrix (BSRMatrix::toCsr)
+  afb::DevBuf csr_rows, csr_cols, csr_nbcol;
+  bool csr_valid = false;
+
+  // Dirichlet state
+  afb::DevBuf dir_node;                     // uint8[nb_node]
+  bool has_dir_nodes = false;
+  afb::DevBuf elim_info, elim_value;        // uint8[nb_dof], double[nb_dof]
+  afb::DevBuf forced_info, forced_value;    // uint8[nb_dof], double[nb_dof]
+  bool has_elim = false, has_forced = false, has_rc = false;
+  afb::DevBuf saved_values;                 // pre-elimination copy for the RC RHS correction
+  bool saved_valid = false;
+
+  // scratch
+  afb::DevBuf tmp_i32a, tmp_i32b, tmp_scan, tmp_ids, tmp_vals, tmp_flag;
+
+  afb::TilePlan plan;
+
+  // timings
+  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  bool timed[3] = { false, false, false };
+};
+
+namespace afb {
+
+// ---- scan.cu -------------------------------------------------------------------------------
+// out[i] = sum_{j<i} in[j] for i in [0,n]; out has n+1 entries (out[n] = total). in/out may alias
+// only if identical pointers are NOT used (separate buffers required).
+int exclusive_scan_i32(afb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n);
+
+// ---- connectivity.cu -------------------------------------------------------------------------
+int build_node_cells(afb_ctx* ctx);
+int build_pattern(afb_ctx* ctx);
+
+// ---- assemble.cu -----------------------------------------------------------------------------
+int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, int variant, int layout, int flags);
+
+// ---- tiles.cu --------------------------------------------------------------------------------
+int build_tile_plan(afb_ctx* ctx);
+int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags);
+
+// ---- linear.cu (rhs, dirichlet, views) -------------------------------------------------------
+int rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed_area);
+int dirichlet_penalty(afb_ctx* ctx, int weak, double penalty, int32_t n, const int32_t* dof_ids, const double* g);
+int apply_matrix_transformation(afb_ctx* ctx, int quirk);
+int apply_rhs_transformation(afb_ctx* ctx);
+int ensure_coo_rows(afb_ctx* ctx);
+int ensure_scalar_csr(afb_ctx* ctx);
+int lookup_value_slots(afb_ctx* ctx, int64_t n, const int32_t* dof_rows, const int32_t* dof_cols, int64_t* slots);
+int add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, const double* contrib);
+int scatter_flags(afb_ctx* ctx, uint8_t* flags, double* vals, uint8_t flag, int32_t n, const int32_t* ids, const double* v);
+
+// ---- mesh_gen.cu -----------------------------------------------------------------------------
+int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi);
+
+inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+#define AFB_LAUNCH_CHECK(ctx)                                                                 \
+  do {                                                                                        \
+    (ctx)->launches++;                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      afb::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return AFB_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+} // namespace afb

@@ -1,0 +1,315 @@
+// Mesh connectivity (node -> cells) and the sparsity pattern (row_index / columns).
+//
+// Replaces, with one warp per node and no global sort:
+//   - Arcane's nodeCell connectivity view used by the node-wise back-ends
+//     (modules/testlab/NodeWiseCsrBiliAssembly.cc:179,188; femutils/BSRFormat.h:411,428);
+//   - the sort-based sparsity of the reference: pack edges -> cub radix sort of
+//     6*nbCell u64 keys -> unique-edge degree count (atomics) -> exclusive scan -> atomic
+//     column slot claim (modules/testlab/CsrGpuBiliAssembly.cc:42-207,
+//     femutils/BSRFormat.cc:799-1006) and the connectivity-based one
+//     (femutils/BSRFormat.cc:445-790, NodeWiseCsrBiliAssembly.cc:90-152).
+// Here each warp loads the cells incident to its node (<= 4 per lane in registers), and
+// extracts the distinct neighbour ids in ascending order with a warp-wide REDUX.MIN per
+// entry: degree pass -> prefix scan -> column pass.  Columns come out sorted, the
+// diagonal sits at its sorted position, the result is deterministic.
+#include "afb_internal.h"
+
+namespace afb {
+
+constexpr unsigned UMAX = 0xFFFFFFFFu;
+constexpr int WARPS_PER_BLOCK = 8;
+
+// ---------------------------------------------------------------------------------------------
+// node -> cell lists
+// ---------------------------------------------------------------------------------------------
+template <int NPC>
+__global__ void __launch_bounds__(256) k_count_node_cells(const int32_t* __restrict__ conn, int64_t nb_cell, int32_t* __restrict__ deg)
+{
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb_cell) return;
+  const int32_t* cn = conn + c * NPC;
+  if constexpr (NPC == 4) {
+    int4 v = *reinterpret_cast<const int4*>(cn);
+    atomicAdd(deg + v.x, 1); atomicAdd(deg + v.y, 1); atomicAdd(deg + v.z, 1); atomicAdd(deg + v.w, 1);
+  }
+  else {
+#pragma unroll
+    for (int i = 0; i < NPC; ++i) atomicAdd(deg + cn[i], 1);
+  }
+}
+
+template <int NPC>
+__global__ void __launch_bounds__(256) k_fill_node_cells(const int32_t* __restrict__ conn, int64_t nb_cell, const int32_t* __restrict__ ptr,
+                                                          int32_t* __restrict__ fill, int32_t* __restrict__ list)
+{
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb_cell) return;
+  const int32_t* cn = conn + c * NPC;
+#pragma unroll
+  for (int i = 0; i < NPC; ++i) {
+    int32_t n = cn[i];
+    int pos = atomicAdd(fill + n, 1);
+    list[ptr[n] + pos] = (int32_t)c;
+  }
+}
+
+// ascending extraction over K registers per lane; calls emit(count, value) for each distinct value
+template <int R, class Emit>
+__device__ __forceinline__ int warp_extract_sorted_unique(const unsigned (&cand)[R], Emit emit)
+{
+  unsigned lo = 0;
+  int count = 0;
+  while (true) {
+    unsigned m = UMAX;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      unsigned c = cand[r];
+      m = min(m, c >= lo ? c : UMAX);
+    }
+    m = __reduce_min_sync(0xffffffffu, m);
+    if (m == UMAX) break;
+    emit(count, m);
+    ++count;
+    lo = m + 1u;
+  }
+  return count;
+}
+
+template <int K>
+__device__ __forceinline__ void sort_list_regs(int32_t* list, int beg, int val, int lane)
+{
+  unsigned cand[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int idx = lane + 32 * k;
+    cand[k] = idx < val ? (unsigned)list[beg + idx] : UMAX;
+  }
+  unsigned mine = 0;
+  int count = warp_extract_sorted_unique<K>(cand, [&](int cnt, unsigned m) {
+    if ((cnt & 31) == lane) mine = m;
+    if ((cnt & 31) == 31) list[beg + (cnt & ~31) + lane] = (int32_t)mine;
+  });
+  int rem = count & 31;
+  if (lane < rem) list[beg + (count & ~31) + lane] = (int32_t)mine;
+}
+
+// Sort each node's cell list ascending (the atomic fill order is arbitrary).  Cell ids of a
+// node are distinct, so "sorted unique" == sorted.
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_sort_node_cells(const int32_t* __restrict__ ptr, int32_t* __restrict__ list, int32_t nb_node, int* __restrict__ max_valence)
+{
+  const int lane = threadIdx.x & 31;
+  int64_t node = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (node >= nb_node) return;
+  int beg = ptr[node], val = ptr[node + 1] - beg;
+  if (lane == 0 && val > *max_valence) atomicMax(max_valence, val);
+  if (val <= 1) return;
+  if (val <= 32) sort_list_regs<1>(list, beg, val, lane);
+  else if (val <= 64) sort_list_regs<2>(list, beg, val, lane);
+  else if (val <= 128) sort_list_regs<4>(list, beg, val, lane);
+  else if (val <= 256) sort_list_regs<8>(list, beg, val, lane);
+  else if (lane == 0) {
+    // pathological valence: serial insertion sort
+    for (int i = 1; i < val; ++i) {
+      int32_t x = list[beg + i];
+      int j = i - 1;
+      while (j >= 0 && list[beg + j] > x) { list[beg + j + 1] = list[beg + j]; --j; }
+      list[beg + j + 1] = x;
+    }
+  }
+}
+
+int build_node_cells(afb_ctx* ctx)
+{
+  const int64_t nb_cell = ctx->nb_cell;
+  const int32_t nb_node = ctx->nb_node;
+  const int npc = ctx->npc;
+  AFB_REQUIRE((int64_t)npc * nb_cell < 2147483647LL, AFB_ERR_OVERFLOW, "node-cell connectivity exceeds Int32 (%lld incidences)", (long long)(npc * nb_cell));
+  AFB_TRY(ctx->nc_ptr.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
+  AFB_TRY(ctx->nc_list.reserve(sizeof(int32_t) * (size_t)(npc * nb_cell)));
+  AFB_TRY(ctx->tmp_i32a.reserve(sizeof(int32_t) * ((size_t)nb_node + 2)));
+  int32_t* deg = ctx->tmp_i32a.as<int32_t>();
+  const int32_t* conn = ctx->conn.as<int32_t>();
+  AFB_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * ((size_t)nb_node + 2), ctx->stream));
+  int grid = grid_for(nb_cell, 256);
+  if (nb_cell > 0) {
+    switch (npc) {
+    case 3: k_count_node_cells<3><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
+    case 4: k_count_node_cells<4><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
+    case 6: k_count_node_cells<6><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
+    case 10: k_count_node_cells<10><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
+    }
+    AFB_LAUNCH_CHECK(ctx);
+  }
+  AFB_TRY(exclusive_scan_i32(ctx, deg, ctx->nc_ptr.as<int32_t>(), nb_node));
+  AFB_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * ((size_t)nb_node + 2), ctx->stream));
+  if (nb_cell > 0) {
+    int32_t* ptr = ctx->nc_ptr.as<int32_t>();
+    int32_t* list = ctx->nc_list.as<int32_t>();
+    switch (npc) {
+    case 3: k_fill_node_cells<3><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
+    case 4: k_fill_node_cells<4><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
+    case 6: k_fill_node_cells<6><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
+    case 10: k_fill_node_cells<10><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
+    }
+    AFB_LAUNCH_CHECK(ctx);
+    int* maxv = reinterpret_cast<int*>(deg + nb_node + 1); // zeroed above... but fill[] used deg[0..nb_node)
+    k_sort_node_cells<<<grid_for(nb_node, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(ptr, list, nb_node, maxv);
+    AFB_LAUNCH_CHECK(ctx);
+    AFB_CUDA(cudaMemcpyAsync(&ctx->max_valence, maxv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return AFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row degree / columns
+// ---------------------------------------------------------------------------------------------
+template <int NPC, int K>
+__device__ __forceinline__ void load_candidates(unsigned (&cand)[K * NPC], const int32_t* __restrict__ conn, const int32_t* __restrict__ list, int beg, int val, int lane)
+{
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int idx = lane + 32 * k;
+    if (idx < val) {
+      const int32_t* cn = conn + (int64_t)list[beg + idx] * NPC;
+      if constexpr (NPC == 4) {
+        int4 v = __ldg(reinterpret_cast<const int4*>(cn));
+        cand[k * 4 + 0] = (unsigned)v.x; cand[k * 4 + 1] = (unsigned)v.y; cand[k * 4 + 2] = (unsigned)v.z; cand[k * 4 + 3] = (unsigned)v.w;
+      }
+      else {
+#pragma unroll
+        for (int i = 0; i < NPC; ++i) cand[k * NPC + i] = (unsigned)__ldg(cn + i);
+      }
+    }
+    else {
+#pragma unroll
+      for (int i = 0; i < NPC; ++i) cand[k * NPC + i] = UMAX;
+    }
+  }
+}
+
+template <int NPC, int K, bool WRITE>
+__device__ __forceinline__ int row_unique_regs(const int32_t* __restrict__ conn, const int32_t* __restrict__ list, int beg, int val, int lane, int32_t* __restrict__ cols, int rowbeg)
+{
+  unsigned cand[K * NPC];
+  load_candidates<NPC, K>(cand, conn, list, beg, val, lane);
+  unsigned mine = 0;
+  int count = warp_extract_sorted_unique<K * NPC>(cand, [&](int cnt, unsigned m) {
+    if constexpr (WRITE) {
+      if ((cnt & 31) == lane) mine = m;
+      if ((cnt & 31) == 31) cols[rowbeg + (cnt & ~31) + lane] = (int32_t)mine;
+    }
+  });
+  if constexpr (WRITE) {
+    int rem = count & 31;
+    if (lane < rem) cols[rowbeg + (count & ~31) + lane] = (int32_t)mine;
+  }
+  return count;
+}
+
+// valence > 128: candidates are re-read (L1/L2) for every extracted entry
+template <int NPC, bool WRITE>
+__device__ __noinline__ int row_unique_slow(const int32_t* __restrict__ conn, const int32_t* __restrict__ list, int beg, int val, int lane, int32_t* __restrict__ cols, int rowbeg)
+{
+  unsigned lo = 0;
+  int count = 0;
+  while (true) {
+    unsigned m = UMAX;
+    for (int idx = lane; idx < val; idx += 32) {
+      const int32_t* cn = conn + (int64_t)list[beg + idx] * NPC;
+#pragma unroll
+      for (int i = 0; i < NPC; ++i) {
+        unsigned c = (unsigned)__ldg(cn + i);
+        m = min(m, c >= lo ? c : UMAX);
+      }
+    }
+    m = __reduce_min_sync(0xffffffffu, m);
+    if (m == UMAX) break;
+    if (WRITE && lane == 0) cols[rowbeg + count] = (int32_t)m;
+    ++count;
+    lo = m + 1u;
+  }
+  return count;
+}
+
+template <int NPC, bool WRITE>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
+k_row_unique(const int32_t* __restrict__ conn, const int32_t* __restrict__ ptr, const int32_t* __restrict__ list, int32_t nb_node,
+             int32_t* __restrict__ deg_out, const int32_t* __restrict__ rows, int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row)
+{
+  const int lane = threadIdx.x & 31;
+  int64_t node = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (node >= nb_node) return;
+  int beg = ptr[node], val = ptr[node + 1] - beg;
+  int rowbeg = 0;
+  if constexpr (WRITE) rowbeg = rows[node];
+  int count;
+  if (val == 0) { // isolated node: diagonal only
+    count = 1;
+    if (WRITE && lane == 0) cols[rowbeg] = (int32_t)node;
+  }
+  else if (val <= 32) count = row_unique_regs<NPC, 1, WRITE>(conn, list, beg, val, lane, cols, rowbeg);
+  else if (val <= 64) count = row_unique_regs<NPC, 2, WRITE>(conn, list, beg, val, lane, cols, rowbeg);
+  else if (val <= 128 && NPC <= 6) count = row_unique_regs<NPC, 4, WRITE>(conn, list, beg, val, lane, cols, rowbeg);
+  else count = row_unique_slow<NPC, WRITE>(conn, list, beg, val, lane, cols, rowbeg);
+  if (lane == 0) {
+    if constexpr (WRITE) nz_per_row[node] = count;
+    else deg_out[node] = count;
+  }
+}
+
+template <int NPC>
+static int launch_row_unique(afb_ctx* ctx, bool write, int32_t* deg)
+{
+  const int32_t nb_node = ctx->nb_node;
+  int grid = grid_for(nb_node, WARPS_PER_BLOCK);
+  const int32_t* conn = ctx->conn.as<int32_t>();
+  const int32_t* ptr = ctx->nc_ptr.as<int32_t>();
+  const int32_t* list = ctx->nc_list.as<int32_t>();
+  if (!write)
+    k_row_unique<NPC, false><<<grid, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(conn, ptr, list, nb_node, deg, nullptr, nullptr, nullptr);
+  else
+    k_row_unique<NPC, true><<<grid, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(conn, ptr, list, nb_node, nullptr, ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(),
+                                                                            ctx->nz_per_row.as<int32_t>());
+  AFB_LAUNCH_CHECK(ctx);
+  return AFB_OK;
+}
+
+static int dispatch_row_unique(afb_ctx* ctx, bool write, int32_t* deg)
+{
+  switch (ctx->npc) {
+  case 3: return launch_row_unique<3>(ctx, write, deg);
+  case 4: return launch_row_unique<4>(ctx, write, deg);
+  case 6: return launch_row_unique<6>(ctx, write, deg);
+  case 10: return launch_row_unique<10>(ctx, write, deg);
+  }
+  set_error("unsupported nodes_per_cell %d", ctx->npc);
+  return AFB_ERR_UNSUPPORTED;
+}
+
+int build_pattern(afb_ctx* ctx)
+{
+  const int32_t nb_node = ctx->nb_node;
+  AFB_TRY(ctx->tmp_i32b.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
+  AFB_TRY(ctx->rows.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
+  AFB_TRY(ctx->nz_per_row.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
+  int32_t* deg = ctx->tmp_i32b.as<int32_t>();
+  AFB_TRY(dispatch_row_unique(ctx, false, deg));
+  AFB_TRY(exclusive_scan_i32(ctx, deg, ctx->rows.as<int32_t>(), nb_node));
+  int32_t nnz32 = 0;
+  AFB_CUDA(cudaMemcpyAsync(&nnz32, ctx->rows.as<int32_t>() + nb_node, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  AFB_REQUIRE(nnz32 >= 0, AFB_ERR_OVERFLOW, "block nnz exceeds Int32");
+  ctx->nnz = nnz32;
+  const int b = ctx->b;
+  AFB_REQUIRE((int64_t)ctx->nnz * b * b < 2147483647LL, AFB_ERR_OVERFLOW,
+              "scalar nnz %lld exceeds the Int32 index space of the reference containers (femutils/BSRFormat.cc:362-364)", (long long)(ctx->nnz * b * b));
+  AFB_TRY(ctx->cols.reserve(sizeof(int32_t) * (size_t)ctx->nnz));
+  AFB_TRY(ctx->values.reserve(sizeof(double) * (size_t)ctx->nnz * b * b));
+  AFB_TRY(ctx->rhs.reserve(sizeof(double) * (size_t)nb_node * b));
+  AFB_TRY(dispatch_row_unique(ctx, true, nullptr));
+  AFB_CUDA(cudaMemsetAsync(ctx->values.p, 0, sizeof(double) * (size_t)ctx->nnz * b * b, ctx->stream));
+  AFB_CUDA(cudaMemsetAsync(ctx->rhs.p, 0, sizeof(double) * (size_t)nb_node * b, ctx->stream));
+  return AFB_OK;
+}
+
+} // namespace afb

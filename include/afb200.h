@@ -1,0 +1,279 @@
+/*
+ * afb200.h — C ABI of the B200-native bilinear-form assembly path (libafb200.so).
+ *
+ * This is the drop-in boundary for ArcaneFEM's assembly back-ends: everything between
+ * "mesh connectivity + node coordinates in" and "row/col/val (+rhs) arrays out".
+ * Plain pointers and sizes only; no C++/torch types.  Each entry point names the
+ * reference interface it replaces (paths relative to the ArcaneFEM source root).
+ * The thin C++ façade that keeps the reference's class names (CsrFormat, BSRFormat,
+ * BSRMatrix, CooFormat, CsrFormatMatrixView, DoFLinearSystem) lives in
+ * include/arcanefem_b200/ and calls only these functions.  INTEGRATION.md shows the
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns AFB_OK (0) or a negative error code; afb_last_error()
+ *     gives the thread-local message (the reference throws ARCANE_FATAL / ARCANE_THROW:
+ *     the façade converts non-zero codes into exceptions).
+ *   - one afb_ctx per GPU, used from one host thread at a time (the reference is
+ *     single-threaded per MPI rank with one RunQueue: modules/testlab/FemModule.cc:114).
+ *   - all work is stream-ordered on the context's CUDA stream (afb_set_stream lets the
+ *     host use its own stream, e.g. torch's current stream); nothing here falls back to
+ *     the CPU: a missing device or kernel failure is an error.
+ *   - the caller owns host arrays; device arrays returned by afb_get_* stay owned by the
+ *     context and remain valid until the next afb_build_pattern / afb_destroy
+ *     (same contract as DoFLinearSystem::setCSRValues: femutils/DoFLinearSystem.h:318-325).
+ *   - indices are Int32, reals are IEEE fp64, DoF id = node_lid*b + component
+ *     (femutils/FemDoFsOnNodes.cc:79-111).  Row arrays are written with nb_row+1 entries;
+ *     the first nb_row are exactly the reference's sentinel-less arrays
+ *     (femutils/CsrFormatMatrix.h:71-80, femutils/BSRFormat.h:131-134).
+ *   - columns are emitted ascending inside each row (the reference's intra-row order is
+ *     non-deterministic / connectivity-order dependent; HYPRE and PETSc accept any order).
+ */
+#ifndef AFB200_H
+#define AFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFB_API __attribute__((visibility("default")))
+
+typedef struct afb_ctx afb_ctx;
+
+enum {
+  AFB_OK = 0,
+  AFB_ERR_INVALID = -1,     /* bad argument / call order (ArgumentException in the reference)   */
+  AFB_ERR_CUDA = -2,        /* CUDA runtime or kernel failure                                    */
+  AFB_ERR_UNSUPPORTED = -3, /* NotImplementedException / NotSupportedException in the reference  */
+  AFB_ERR_OVERFLOW = -4     /* Int32 index space exceeded (femutils/BSRFormat.cc:362-364)        */
+};
+
+/* operator tag: replaces the device lambda template parameter of
+ * BSRFormat::assembleBilinear* (femutils/BSRFormat.h:218-236) */
+enum {
+  AFB_OP_POISSON = 0,    /* modules/testlab/FemModule.h:342-538, FemModule.cc:267-315, modules/poisson/ElementMatrix.h:28-118 */
+  AFB_OP_ELASTICITY = 1, /* modules/elasticity/ElementMatrix.h:41-301; params = {lambda, mu}                               */
+  AFB_OP_BILAPLACIAN = 2 /* modules/bilaplacian/ElementMatrix.h:30-47 (Tri3, 2 DoF/node)                                   */
+};
+
+/* matrix format = how entries are located during the scatter and which view is native
+ * (.arc options csr-gpu / coo-gpu / bsr; modules/testlab/Fem.axl) */
+enum {
+  AFB_FORMAT_CSR = 0, /* per-row search in [row[r], row[r+1])      : CsrGpuBiliAssembly.cc:356-366 */
+  AFB_FORMAT_COO = 1, /* binary search over the COO row array      : CooFormatMatrix.h:308-353     */
+  AFB_FORMAT_BSR = 2  /* block rows, b = dof per node              : femutils/BSRFormat.h:257-577   */
+};
+
+/* assembly variant */
+enum {
+  AFB_VARIANT_CELLWISE_ATOMIC = 0, /* thread per cell + fp64 atomics: csr-gpu / coo-gpu / bsr                       */
+  AFB_VARIANT_NODEWISE = 1,        /* thread per row, no atomics: nwcsr / bsr-atomic-free (AF-CSR_GPU / AF-BSR_GPU)  */
+  AFB_VARIANT_TILED_GATHER = 2     /* B200 path: row tiles staged in shared memory, every row written exactly once   */
+};
+
+/* BSR value layout (femutils/BSRFormat.cc:367: per-block unless the solver consumes CSR) */
+enum {
+  AFB_LAYOUT_PER_BLOCK = 0, /* begin*b*b + i*b + j                   (femutils/BSRFormat.h:292-296) */
+  AFB_LAYOUT_PER_ROW = 1    /* row[r]*b*b + b*(x + i*nz_r) + j       (femutils/BSRFormat.h:356)      */
+};
+
+enum { AFB_MEM_HOST = 0, AFB_MEM_DEVICE = 1 };
+
+/* flags for afb_assemble_bilinear */
+enum {
+  /* Tri3: use the SIGNED area like the testlab CSR/COO back-ends (modules/testlab/FemModule.h:359);
+   * default is the unsigned area of the BSR lambdas (femutils/ArcaneFemFunctionsGpu.h:76-86). */
+  AFB_FLAG_SIGNED_TRI_AREA = 1
+};
+
+/* matrix elimination type: femutils/FemUtilsGlobal.h:51-62 */
+enum { AFB_ELIMINATE_NONE = 0, AFB_ELIMINATE_ROW = 1, AFB_ELIMINATE_ROW_COLUMN = 2 };
+
+/* arrays addressable through afb_copy_to_host */
+enum {
+  AFB_ARRAY_ROWS = 0,         /* int32[nb_block_row+1]                */
+  AFB_ARRAY_COLUMNS = 1,      /* int32[nb_block_nnz]                  */
+  AFB_ARRAY_VALUES = 2,       /* double[nb_block_nnz*b*b]             */
+  AFB_ARRAY_NZ_PER_ROW = 3,   /* int32[nb_block_row]                  */
+  AFB_ARRAY_RHS = 4,          /* double[nb_block_row*b]               */
+  AFB_ARRAY_COO_ROWS = 5,     /* int32[nb_block_nnz]                  */
+  AFB_ARRAY_CSR_ROWS = 6,     /* expanded scalar CSR (b>1): int32[nb_row*b+1] */
+  AFB_ARRAY_CSR_COLUMNS = 7,  /* int32[nb_block_nnz*b*b]              */
+  AFB_ARRAY_CSR_NB_COLUMN = 8,/* int32[nb_row*b]                      */
+  AFB_ARRAY_COORDS = 9,       /* double[nb_node*3]                    */
+  AFB_ARRAY_CELL_NODES = 10,  /* int32[nb_cell*npc]                   */
+  AFB_ARRAY_NODE_CELL_PTR = 11, /* int32[nb_node+1]                   */
+  AFB_ARRAY_NODE_CELL_LIST = 12 /* int32[nb_cell*npc]                 */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+
+/* ctor of CsrFormat/BSRFormat + the RunQueue they hold (femutils/BSRFormat.cc:233-240). */
+AFB_API int afb_create(int device, afb_ctx** out);
+AFB_API int afb_destroy(afb_ctx* ctx);
+AFB_API const char* afb_last_error(void);
+AFB_API const char* afb_version(void);
+/* Use the caller's CUDA stream (cudaStream_t) for all subsequent work; NULL = own stream. */
+AFB_API int afb_set_stream(afb_ctx* ctx, void* cuda_stream);
+/* RunQueue::barrier() */
+AFB_API int afb_synchronize(afb_ctx* ctx);
+
+/* ---- mesh in -------------------------------------------------------------------------- */
+
+/*
+ * Replaces the IMesh* / UnstructuredMeshConnectivityView / VariableNodeReal3 /
+ * ItemGenericInfoListView::isOwn inputs of every back-end
+ * (modules/testlab/CsrGpuBiliAssembly.cc:330-335, femutils/BSRFormat.h:260-263).
+ * dim in {2,3}; nodes_per_cell in {3,4} (P1) or {6,10} (P2, reference node order
+ * femutils/ArcaneFemFunctions.h:3245-3262,3893-3911); xyz = AoS double[nb_node][3];
+ * cell_nodes = int32[nb_cell][npc]; node_is_own = uint8[nb_node] or NULL (all owned).
+ * Also builds the node->cell connectivity (Arcane's nodeCell view), ascending cell ids.
+ * mem_space HOST copies to the device; DEVICE keeps the caller's pointers (zero-copy).
+ */
+AFB_API int afb_set_mesh(afb_ctx* ctx, int dim, int nodes_per_cell, int32_t nb_node, int64_t nb_cell,
+                         const double* xyz, const int32_t* cell_nodes, const uint8_t* node_is_own, int mem_space);
+
+/*
+ * Synthetic structured box of SURVEY.md §8(d), generated on the device (bench + tests):
+ * [0,1]^dim, n^dim cubes, Kuhn 6-tet / 2-triangle split, node id = i+(n+1)(j+(n+1)k),
+ * deterministic interior jitter (bit-identical to arcanefem_b200/mesh.py::box_mesh).
+ * Cube layers [k_lo,k_hi) of the last axis only (domain-decomposition slab); local node
+ * numbering is owned-first: when k_lo > 0 the bottom node layer is a ghost layer owned by
+ * the lower neighbour and numbered last (node_is_own = 0).  k_lo=0,k_hi=n = whole box.
+ */
+AFB_API int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi);
+
+/* ---- sparsity --------------------------------------------------------------------------- */
+
+/*
+ * Replaces BSRFormat::initialize + computeSparsity{,Atomic,AtomicFree}
+ * (femutils/BSRFormat.cc:350-372,777-790,799-1006), FemModuleTestlab::_computeSparsity /
+ * _buildMatrix* (modules/testlab/CsrGpuBiliAssembly.cc:187-207, CsrBiliAssembly.cc:23-92,
+ * NodeWiseCsrBiliAssembly.cc:115-152, CooGpuBiliAssembly.cc:76-232) and
+ * CsrFormat/CooFormat/BSRMatrix::initialize (allocation + zero fill).
+ * Block pattern over nodes (P1: node + edge neighbours; P2: all nodes sharing a cell),
+ * nb_block_nnz = nbNode + 2*nbEdge.  Also fills nb_nz_per_row (computeNzPerRowArray,
+ * femutils/BSRFormat.cc:400-440) and zeroes values/rhs.
+ */
+AFB_API int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_block_row, int64_t* nb_block_nnz);
+
+/* ---- bilinear form ------------------------------------------------------------------------ */
+
+/* BSRFormat::resetMatrixValues / DoFLinearSystem::clearValues (values only) */
+AFB_API int afb_reset_values(afb_ctx* ctx);
+
+/*
+ * Replaces BSRFormat::assembleBilinear{Atomic,AtomicFree} (femutils/BSRFormat.h:257-577) and
+ * FemModuleTestlab::_assemble{Csr,Coo,NodeWiseCsr}...BilinearOperator{TRIA3,TETRA4}
+ * (modules/testlab/CsrGpuBiliAssembly.cc:222-374, CooGpuBiliAssembly.cc:237-352,
+ * NodeWiseCsrBiliAssembly.cc:157-297).  Adds into `values` (call afb_reset_values first for
+ * a fresh matrix).  Rows of non-owned nodes are left untouched (isOwn gate).
+ * op/params: see AFB_OP_*; format/variant/layout: see enums; flags: AFB_FLAG_*.
+ */
+AFB_API int afb_assemble_bilinear(afb_ctx* ctx, int op, const double* params, int nb_params,
+                                  int format, int variant, int value_layout, int flags);
+
+/* ---- linear form / Dirichlet ------------------------------------------------------------- */
+
+/* rhs_values.fill(0) (modules/testlab/FemModule.cc:724-725) */
+AFB_API int afb_rhs_reset(afb_ctx* ctx);
+
+/*
+ * Constant source term, b components f[0..b): rhs[dof(n,k)] += f[k]*meas/npc.
+ * nodewise=0: cell-wise with atomics, skips nodes flagged by afb_set_dirichlet_nodes
+ *   (modules/testlab/FemModule.cc:836-868,1358-1532; modules/elasticity/BodyForce.h:93-104);
+ * nodewise=1: per-node sum over incident cells, rhs = sum
+ *   (femutils/ArcaneFemFunctionsGpu.h:675-708).
+ * signed_tri_area: testlab uses the signed triangle area (FemModule.cc:1762).
+ */
+AFB_API int afb_assemble_rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed_tri_area);
+
+/* Node flags m_u_dirichlet (modules/testlab/FemModule.cc:647-677); NULL / n=0 clears. */
+AFB_API int afb_set_dirichlet_nodes(afb_ctx* ctx, int32_t n, const int32_t* node_ids, int mem_space);
+
+/*
+ * Penalty / weak penalty on a list of DoFs: A[i,i] = P (weak: += P), rhs[i] = P*g
+ * (modules/testlab/FemModule.cc:728-790,1201-1313).  Must be called after the assembly
+ * (stream order guarantees the atomics have completed).
+ */
+AFB_API int afb_dirichlet_penalty(afb_ctx* ctx, int weak, double penalty, int32_t n, const int32_t* dof_ids, const double* g, int mem_space);
+
+/* DoFLinearSystem::eliminateRow / eliminateRowColumn (femutils/DoFLinearSystem.h) on a DoF list;
+ * type = AFB_ELIMINATE_*.  DoFLinearSystem::clearValues resets them: afb_clear_dirichlet. */
+AFB_API int afb_set_elimination(afb_ctx* ctx, int type, int32_t n, const int32_t* dof_ids, const double* g, int mem_space);
+/* forced_info / forced_value (femutils/ArcaneFemFunctionsGpu.cc:54-105) */
+AFB_API int afb_set_forced_values(afb_ctx* ctx, int32_t n, const int32_t* dof_ids, const double* v, int mem_space);
+AFB_API int afb_clear_dirichlet(afb_ctx* ctx);
+
+/*
+ * CsrDoFLinearSystemImpl::applyMatrixTransformation (femutils/CsrDoFLinearSystemImpl.cc:235-242):
+ * row elimination, row+column elimination (pre-elimination values are kept for the RHS step,
+ * replacing the host OrderedRowColumnMap), forced diagonal values.  Works on the scalar CSR
+ * view (b>1 needs AFB_LAYOUT_PER_ROW).  replicate_column0_quirk != 0 reproduces the reference's
+ * `if (column_index > 0)` (CsrDoFLinearSystemImpl.cc:111), i.e. column 0 is never touched by the
+ * row+column pass.
+ */
+AFB_API int afb_apply_matrix_transformation(afb_ctx* ctx, int replicate_column0_quirk);
+/* CsrDoFLinearSystemImpl::applyRHSTransformation (:247-253): rhs[col] -= A[row,col]*g_row for
+ * RC-eliminated rows (DoFLinearSystemImplBase.cc:55-88), then rhs[row] = g_row. */
+AFB_API int afb_apply_rhs_transformation(afb_ctx* ctx);
+
+/* ---- views out (device pointers) ---------------------------------------------------------- */
+
+/*
+ * CsrFormat::view() / CSRFormatView (femutils/CsrFormatMatrixView.h:135-210), laid out as
+ * HYPRE_IJMatrixSetValues(nrows, ncols=rows_nb_column, rows, cols, values) expects
+ * (femutils/HypreDoFLinearSystem.cc:501-514).  For b>1 this is BSRMatrix::toCsr
+ * (femutils/BSRFormat.cc:110-172): rows[nb_row*b+1], col = block_col*b+k, values shared
+ * (requires AFB_LAYOUT_PER_ROW), built on the device instead of the reference's host loops.
+ */
+AFB_API int afb_get_csr_view(afb_ctx* ctx, const int32_t** rows, const int32_t** rows_nb_column, const int32_t** columns,
+                             double** values, int32_t* nb_row, int64_t* nnz);
+/* BSRMatrix arrays (femutils/BSRFormat.h:131-134) */
+AFB_API int afb_get_bsr(afb_ctx* ctx, const int32_t** rows_index, const int32_t** columns, double** values,
+                        const int32_t** nb_nz_per_row, int32_t* nb_block_row, int64_t* nb_col, int* block_size, int* value_layout);
+/* CooFormat arrays / _translateCSRToCOO (femutils/CsrFormatMatrix.cc:161-184) = the
+ * MatSetPreallocationCOOLocal(nnz, coo_rows, coo_cols) + MatSetValuesCOO(values) layout
+ * (femutils/PetscDoFLinearSystem.cc:329-345,398). */
+AFB_API int afb_get_coo(afb_ctx* ctx, const int32_t** coo_rows, const int32_t** coo_cols, double** values, int64_t* nnz);
+AFB_API int afb_get_rhs(afb_ctx* ctx, double** rhs, int32_t* nb_dof);
+/* raw mesh pointers on the device (coords, cell_nodes, node_is_own) */
+AFB_API int afb_get_mesh(afb_ctx* ctx, int* dim, int* nodes_per_cell, int32_t* nb_node, int64_t* nb_cell, int32_t* nb_own_node,
+                         const double** xyz, const int32_t** cell_nodes, const uint8_t** node_is_own);
+
+/* UVM host access of the reference (getValue, dumps, tests): synchronous copy; returns the
+ * number of bytes of the array in *bytes when dst == NULL. */
+AFB_API int afb_copy_to_host(afb_ctx* ctx, int which, void* dst, size_t* bytes);
+
+/* ---- multi-GPU support (domain decomposition) ------------------------------ */
+
+/*
+ * Slot lookup on the owner side of a ghost-row exchange: for n scalar (dof_row, dof_col)
+ * pairs (device arrays, local numbering) writes the index into `values` or -1.
+ * Replaces the role of the ghost DoF synchronisation in
+ * HypreDoFLinearSystemImpl::_computeMatrixNumeration (femutils/HypreDoFLinearSystem.cc:209-249).
+ */
+AFB_API int afb_lookup_value_slots(afb_ctx* ctx, int64_t n, const int32_t* dof_rows, const int32_t* dof_cols, int64_t* slots);
+/* values[slots[i]] += contrib[i] (unique slots per call; device arrays) */
+AFB_API int afb_add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, const double* contrib);
+/* Index of the first value of block row `first_block_row` and the number of doubles from
+ * there to the end: the ghost rows' partial sums are one contiguous tail of `values`
+ * when ghosts are numbered last (zero-copy NCCL send buffer). */
+AFB_API int afb_values_tail(afb_ctx* ctx, int32_t first_block_row, int64_t* first_value, int64_t* nb_values);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+
+/* Milliseconds spent by the last call of each phase, measured with CUDA events on the
+ * context stream (Timer::Action scopes "BuildMatrix" / "AddAndCompute" of the reference:
+ * modules/testlab/CsrGpuBiliAssembly.cc:313-337).  Synchronises the stream. */
+AFB_API int afb_last_timings(afb_ctx* ctx, float* connectivity_ms, float* pattern_ms, float* assemble_ms);
+/* number of kernels launched by this context so far (bench.py "gpu_launches") */
+AFB_API int64_t afb_launch_count(afb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFB200_H */

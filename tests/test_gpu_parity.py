@@ -1,0 +1,486 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through
+the C ABI, against the CPU oracle on the same inputs.
+
+Bars: sparsity pattern, DoF numbering and every integer array
+bit-exact; fp64 values within 1e-12 relative, measured as
+    |a-b| <= 1e-12 * max(|a|, |b|, max|row|)
+because entries are sums of <= ~30 mixed-sign terms (exact cancellations exist on
+right-angled boxes) and the atomic variant's summation order is arbitrary.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from arcanefem_b200 import capi as A
+from arcanefem_b200 import mesh as M
+from oracle import oracle as O
+from tests import cases as CS
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.0e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = A.Context(0)
+    yield c
+    c.close()
+
+
+def _fixture_mesh(name):
+    return M.read_msh(os.path.join(CS.GOLDEN, name))
+
+
+MESHES = {
+    "L-shape_2D": lambda: _fixture_mesh("L-shape.msh"),
+    "circle_2D": lambda: _fixture_mesh("circle_cut.msh"),
+    "porous_2D": lambda: _fixture_mesh("porous-medium.msh"),
+    "L-shape_3D": lambda: _fixture_mesh("L-shape-3D.msh"),
+    "sphere_3D": lambda: _fixture_mesh("sphere_cut.msh"),
+    "bar_3D": lambda: _fixture_mesh("bar_dynamic_3D.msh"),
+    "box2d_n17": lambda: M.box_mesh(2, 17),
+    "box3d_n9": lambda: M.box_mesh(3, 9),
+    "box3d_n6_nojitter": lambda: M.box_mesh(3, 6, jitter=0.0),
+    "L-shape_2D_P2": lambda: M.to_p2(_fixture_mesh("L-shape.msh")),
+    "sphere_3D_P2": lambda: M.to_p2(_fixture_mesh("sphere_cut.msh")),
+    "box3d_n4_P2": lambda: M.to_p2(M.box_mesh(3, 4)),
+}
+_cache = {}
+
+
+def get_mesh(name):
+    if name not in _cache:
+        _cache[name] = MESHES[name]()
+    return _cache[name]
+
+
+def row_scaled_close(got, ref, rows, b=1, layout=O.LAYOUT_PER_BLOCK, tol=TOL):
+    """|a-b| <= tol*max(|a|,|b|,rowmax) with rowmax over the block row of the reference."""
+    nbr = rows.shape[0] - 1
+    bb = b * b
+    # every block row occupies the contiguous range [rows[r]*bb, rows[r+1]*bb) in both layouts
+    rowmax = np.zeros(nbr)
+    seg = np.repeat(np.arange(nbr), np.diff(rows) * bb)
+    np.maximum.at(rowmax, seg, np.abs(ref))
+    scale = np.maximum(np.maximum(np.abs(got), np.abs(ref)), rowmax[seg])
+    err = np.abs(got - ref)
+    bad = err > tol * scale
+    worst = float(np.max(err / np.where(scale > 0, scale, 1.0))) if err.size else 0.0
+    assert not bad.any(), f"{bad.sum()} entries beyond {tol}: worst scaled error {worst}"
+    return worst
+
+
+# ---------------------------------------------------------------------------------------------
+# connectivity + pattern: bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(MESHES))
+def test_pattern_bit_exact(ctx, name):
+    m = get_mesh(name)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    nbr, nnz = ctx.build_pattern(1)
+    rows_ref, cols_ref = O.build_pattern(m.npc, m.nb_node, m.cells)
+    assert nbr == m.nb_node and nnz == cols_ref.size
+    assert np.array_equal(ctx.to_host(A.ARRAY_ROWS), rows_ref)
+    assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+    assert np.array_equal(ctx.to_host(A.ARRAY_NZ_PER_ROW), np.diff(rows_ref))
+    # node -> cell lists ascending
+    ptr, lst = ctx.to_host(A.ARRAY_NODE_CELL_PTR), ctx.to_host(A.ARRAY_NODE_CELL_LIST)
+    order = np.argsort(m.cells.ravel(), kind="stable")
+    ref_list = (order // m.npc).astype(np.int32)
+    ref_ptr = np.concatenate([[0], np.cumsum(np.bincount(m.cells.ravel(), minlength=m.nb_node))]).astype(np.int32)
+    assert np.array_equal(ptr, ref_ptr) and np.array_equal(lst, ref_list)
+    # COO rows (_translateCSRToCOO)
+    assert np.array_equal(ctx.to_host(A.ARRAY_COO_ROWS), O.csr_to_coo_rows(rows_ref))
+
+
+def test_pattern_with_isolated_node_and_high_valence(ctx):
+    # a fan of 150 triangles around node 0 (valence > 128: slow path) + one isolated node
+    k = 150
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    coords = np.zeros((k + 2, 3))
+    coords[1:k + 1, 0], coords[1:k + 1, 1] = np.cos(ang), np.sin(ang)
+    coords[k + 1] = (5.0, 5.0, 0.0)
+    cells = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.int32)
+    ctx.set_mesh(2, coords, cells)
+    ctx.build_pattern(1)
+    rows_ref, cols_ref = O.build_pattern(3, k + 2, cells)
+    assert np.array_equal(ctx.to_host(A.ARRAY_ROWS), rows_ref)
+    assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+    ctx.assemble(A.OP_POISSON, variant=A.VARIANT_NODEWISE)
+    ref = O.assemble(2, coords, cells, rows_ref, cols_ref, form=O.FORM_BSR)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows_ref)
+
+
+def test_device_box_generator_bit_identical(ctx):
+    for dim, n in ((3, 7), (2, 13)):
+        ref = M.box_mesh(dim, n)
+        info = ctx.generate_box(dim, n)
+        assert (info["nb_node"], info["nb_cell"]) == (ref.nb_node, ref.nb_cell)
+        assert np.array_equal(ctx.to_host(A.ARRAY_COORDS).reshape(-1, 3), ref.coords)
+        assert np.array_equal(ctx.to_host(A.ARRAY_CELL_NODES).reshape(-1, dim + 1), ref.cells)
+        nbc, nbn, nbe, nnz = M.box_counts(dim, n)
+        assert ctx.build_pattern(1) == (nbn, nnz)
+
+
+# ---------------------------------------------------------------------------------------------
+# values: every format x variant x layout against the oracle
+# ---------------------------------------------------------------------------------------------
+P1_POISSON = ["L-shape_2D", "circle_2D", "porous_2D", "L-shape_3D", "sphere_3D", "box2d_n17", "box3d_n9", "box3d_n6_nojitter"]
+
+
+@pytest.mark.parametrize("name", P1_POISSON)
+@pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_COO, A.VARIANT_CELLWISE_ATOMIC),
+                                         (A.FORMAT_CSR, A.VARIANT_NODEWISE), (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
+                         ids=["csr-gpu", "coo-gpu", "nwcsr", "bsr", "af-bsr"])
+def test_poisson_values(ctx, name, fmt, variant):
+    m = get_mesh(name)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(1)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    # the reference formulation each back-end uses
+    form = {A.FORMAT_CSR: O.FORM_COMPACT, A.FORMAT_COO: O.FORM_COMPACT, A.FORMAT_BSR: O.FORM_BSR}[fmt]
+    nodewise = variant == A.VARIANT_NODEWISE
+    if nodewise and fmt == A.FORMAT_CSR:
+        form = O.FORM_NODEWISE
+    flags = A.FLAG_SIGNED_TRI_AREA if fmt != A.FORMAT_BSR else 0
+    ctx.assemble(A.OP_POISSON, fmt=fmt, variant=variant, flags=flags)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=form, nodewise=nodewise)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows)
+    # re-assembly after reset gives the same matrix; without reset it accumulates (adds)
+    v1 = ctx.to_host(A.ARRAY_VALUES)
+    ctx.assemble(A.OP_POISSON, fmt=fmt, variant=variant, flags=flags)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), 2.0 * v1, rows)
+    ctx.reset_values()
+    ctx.assemble(A.OP_POISSON, fmt=fmt, variant=variant, flags=flags)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), v1, rows)
+
+
+def test_signed_area_of_clockwise_triangles(ctx):
+    """the testlab compact path gives a negative-definite K_e for a
+    clockwise triangle, the BSR path does not."""
+    m = get_mesh("L-shape_2D")
+    cells = m.cells[:, [0, 2, 1]].copy()
+    ctx.set_mesh(2, m.coords, cells)
+    ctx.build_pattern(1)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    ctx.assemble(A.OP_POISSON, fmt=A.FORMAT_CSR, flags=A.FLAG_SIGNED_TRI_AREA)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), O.assemble(2, m.coords, cells, rows, cols, form=O.FORM_COMPACT), rows)
+    ctx.reset_values()
+    ctx.assemble(A.OP_POISSON, fmt=A.FORMAT_BSR)
+    ref = O.assemble(2, m.coords, cells, rows, cols, form=O.FORM_BSR)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows)
+    assert ref[rows[0]:rows[1]].max() > 0
+
+
+@pytest.mark.parametrize("name", ["bar_3D", "sphere_3D", "box3d_n9", "L-shape_2D", "box2d_n17"])
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_elasticity_values(ctx, name, variant, layout):
+    m = get_mesh(name)
+    b = m.dim
+    lam, mu = O.lame(21.0e5, 0.28)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(b)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=layout)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[lam, mu], layout=layout,
+                     nodewise=variant == A.VARIANT_NODEWISE)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows, b=b, layout=layout)
+    if layout == A.LAYOUT_PER_ROW:
+        # BSRMatrix::toCsr hand-off arrays, bit-exact
+        crow, ccol, nbc = O.bsr_to_csr(b, rows, cols)
+        assert np.array_equal(ctx.to_host(A.ARRAY_CSR_ROWS), crow)
+        assert np.array_equal(ctx.to_host(A.ARRAY_CSR_COLUMNS), ccol)
+        assert np.array_equal(ctx.to_host(A.ARRAY_CSR_NB_COLUMN), nbc)
+        v = ctx.csr_view()
+        assert v["nb_row"] == m.nb_node * b and v["nnz"] == cols.size * b * b
+    else:
+        with pytest.raises(A.AfbError):
+            ctx.csr_view()
+
+
+@pytest.mark.parametrize("name", ["L-shape_2D", "box2d_n17"])
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_bilaplacian_values(ctx, name, variant, layout):
+    m = get_mesh(name)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(2)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    ctx.assemble(A.OP_BILAPLACIAN, fmt=A.FORMAT_BSR, variant=variant, layout=layout)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_BILAPLACIAN, form=O.FORM_BSR, layout=layout, nodewise=variant == A.VARIANT_NODEWISE)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows, b=2, layout=layout)
+
+
+@pytest.mark.parametrize("name", ["L-shape_2D_P2", "sphere_3D_P2", "box3d_n4_P2"])
+@pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_COO, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
+                         ids=["csr", "coo", "af-bsr"])
+def test_p2_poisson_values(ctx, name, fmt, variant):
+    m = get_mesh(name)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(1)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    ctx.assemble(A.OP_POISSON, fmt=fmt, variant=variant)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, nodewise=variant == A.VARIANT_NODEWISE)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows, tol=1e-11)
+    # stiffness annihilates constants
+    Acsr = sp.csr_matrix((ctx.to_host(A.ARRAY_VALUES), cols, rows))
+    assert np.max(np.abs(Acsr @ np.ones(m.nb_node))) < 1e-10 * np.abs(Acsr).max()
+
+
+def test_is_own_gate(ctx):
+    """Rows of non-owned nodes stay zero (modules/testlab/CsrGpuBiliAssembly.cc:351)."""
+    m = get_mesh("sphere_3D")
+    own = np.ones(m.nb_node, dtype=np.uint8)
+    own[::3] = 0
+    ctx.set_mesh(m.dim, m.coords, m.cells, is_own=own)
+    ctx.build_pattern(1)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE):
+        ctx.reset_values()
+        ctx.assemble(A.OP_POISSON, variant=variant)
+        ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, form=O.FORM_COMPACT, is_own=own)
+        got = ctx.to_host(A.ARRAY_VALUES)
+        row_scaled_close(got, ref, rows)
+        for r in np.nonzero(own == 0)[0]:
+            assert not got[rows[r]:rows[r + 1]].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# end-to-end anchor: reference golden solutions through the GPU-assembled system
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CS.POISSON_CASES))
+@pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_COO, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_CSR, A.VARIANT_NODEWISE),
+                                         (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
+                         ids=["csr-gpu", "coo-gpu", "nwcsr", "bsr", "af-bsr"])
+def test_poisson_golden_solution(ctx, name, fmt, variant):
+    case = CS.POISSON_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(1)
+    ctx.assemble(A.OP_POISSON, fmt=fmt, variant=variant, flags=A.FLAG_SIGNED_TRI_AREA if fmt != A.FORMAT_BSR else 0)
+    ctx.set_dirichlet_nodes(ids)
+    ctx.rhs_reset()
+    ctx.rhs_source(case["f"], nodewise=False, signed_tri_area=True)
+    ctx.dirichlet_penalty(ids, g, case["penalty"])
+    rows, cols, vals, rhs = (ctx.to_host(w) for w in (A.ARRAY_ROWS, A.ARRAY_COLUMNS, A.ARRAY_VALUES, A.ARRAY_RHS))
+    # rhs parity with the oracle (atomic order differs)
+    isd = np.zeros(m.nb_node, dtype=np.uint8)
+    isd[ids] = 1
+    rhs_ref = O.rhs_source_cellwise(m.dim, m.coords, m.cells, case["f"], signed_area=True, is_dirichlet=isd)
+    rhs_ref[ids] = case["penalty"] * g
+    free = isd == 0
+    assert np.array_equal(rhs[ids], rhs_ref[ids])
+    assert np.all(np.abs(rhs[free] - rhs_ref[free]) <= 1e-12 * np.abs(rhs_ref[free]).max())
+    u = spla.spsolve(sp.csr_matrix((vals, cols, rows)).tocsc(), rhs)
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16)
+    assert worst < 1.0e-7
+
+
+@pytest.mark.parametrize("name", list(CS.ELASTICITY_CASES))
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+def test_elasticity_golden_solution(ctx, name, variant):
+    case = CS.ELASTICITY_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    b = m.dim
+    lam, mu = O.lame(case["E"], case["nu"])
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(b)
+    ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=A.LAYOUT_PER_ROW)
+    ctx.rhs_reset()
+    ctx.rhs_source(case["f"], nodewise=False)
+    ctx.dirichlet_penalty(ids, g, case["penalty"])
+    crow, ccol, vals, rhs = (ctx.to_host(w) for w in (A.ARRAY_CSR_ROWS, A.ARRAY_CSR_COLUMNS, A.ARRAY_VALUES, A.ARRAY_RHS))
+    u = spla.spsolve(sp.csr_matrix((vals, ccol, crow)).tocsc(), rhs)
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10)
+    assert worst < 1.0e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# Dirichlet: penalty / weak penalty / forced / row / row-column elimination, bit-exact
+# against the oracle applied to the SAME (GPU-assembled) values
+# ---------------------------------------------------------------------------------------------
+def _assembled_elasticity(ctx, layout):
+    case = CS.ELASTICITY_CASES["bar_2D"]
+    m = _fixture_mesh(case["mesh"])
+    b = m.dim
+    lam, mu = O.lame(case["E"], case["nu"])
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(b)
+    ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_NODEWISE, layout=layout)
+    ctx.rhs_reset()
+    ctx.rhs_source(case["f"], nodewise=True)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    return case, m, b, ids, g
+
+
+@pytest.mark.parametrize("weak", [False, True], ids=["penalty", "weak-penalty"])
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_penalty_bit_exact(ctx, weak, layout):
+    case, m, b, ids, g = _assembled_elasticity(ctx, layout)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    vals, rhs = ctx.to_host(A.ARRAY_VALUES).copy(), ctx.to_host(A.ARRAY_RHS).copy()
+    ctx.dirichlet_penalty(ids, g + 0.25, 1.0e30, weak=weak)
+    for k, d in enumerate(ids):
+        s = O.value_index(rows, cols, b, layout, int(d), int(d))
+        vals[s] = vals[s] + 1.0e30 if weak else 1.0e30
+        rhs[d] = 1.0e30 * (g[k] + 0.25)
+    assert np.array_equal(ctx.to_host(A.ARRAY_VALUES), vals)
+    assert np.array_equal(ctx.to_host(A.ARRAY_RHS), rhs)
+
+
+@pytest.mark.parametrize("kind", [A.ELIMINATE_ROW, A.ELIMINATE_ROW_COLUMN], ids=["row", "row-column"])
+@pytest.mark.parametrize("quirk", [True, False], ids=["col0-quirk", "no-quirk"])
+def test_elimination_bit_exact_and_golden(ctx, kind, quirk):
+    case, m, b, ids, g = _assembled_elasticity(ctx, A.LAYOUT_PER_ROW)
+    crow, ccol = ctx.to_host(A.ARRAY_CSR_ROWS), ctx.to_host(A.ARRAY_CSR_COLUMNS)
+    vals, rhs = ctx.to_host(A.ARRAY_VALUES).copy(), ctx.to_host(A.ARRAY_RHS).copy()
+    gg = g + 0.125  # non-zero values exercise the RHS correction
+    # forced value on one free DoF as well
+    free = int(np.setdiff1d(np.arange(m.nb_node * b), ids)[5])
+    ctx.set_elimination(kind, ids, gg)
+    ctx.set_forced_values([free], [7.5])
+    ctx.apply_matrix_transformation(replicate_column0_quirk=quirk)
+    ctx.apply_rhs_transformation()
+    info = np.zeros(m.nb_node * b, dtype=np.uint8)
+    val = np.zeros(m.nb_node * b)
+    info[ids], val[ids] = kind, gg
+    finfo = np.zeros(m.nb_node * b, dtype=np.uint8)
+    fval = np.zeros(m.nb_node * b)
+    finfo[free], fval[free] = 1, 7.5
+    O.apply_elimination(crow, ccol, vals, rhs, info, val, forced_info=finfo, forced_value=fval, quirk_skip_col0=quirk)
+    assert np.array_equal(ctx.to_host(A.ARRAY_VALUES), vals)
+    assert np.array_equal(ctx.to_host(A.ARRAY_RHS), rhs)
+    # and the reference's golden field with the case's own values
+    ctx.clear_dirichlet()
+    ctx.reset_values()
+    lam, mu = O.lame(case["E"], case["nu"])
+    ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_CELLWISE_ATOMIC, layout=A.LAYOUT_PER_ROW)
+    ctx.rhs_reset()
+    ctx.rhs_source(case["f"])
+    ctx.set_elimination(kind, ids, g)
+    ctx.apply_matrix_transformation(replicate_column0_quirk=quirk)
+    ctx.apply_rhs_transformation()
+    u = spla.spsolve(sp.csr_matrix((ctx.to_host(A.ARRAY_VALUES), ccol, crow)).tocsc(), ctx.to_host(A.ARRAY_RHS))
+    CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10)
+
+
+def test_rhs_source_variants(ctx):
+    for name in ("sphere_3D", "L-shape_2D"):
+        m = get_mesh(name)
+        for b, f in ((1, [5.5]), (m.dim, [0.5, -1.0, 2.0][:m.dim])):
+            ctx.set_mesh(m.dim, m.coords, m.cells)
+            ctx.build_pattern(b)
+            ctx.rhs_reset()
+            ctx.rhs_source(f, nodewise=False, signed_tri_area=(b == 1))
+            ref = O.rhs_source_cellwise(m.dim, m.coords, m.cells, f, signed_area=(b == 1))
+            got = ctx.to_host(A.ARRAY_RHS)
+            assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref).max())
+            ctx.rhs_source(f, nodewise=True)
+            ref = O.rhs_source_nodewise(m.dim, m.coords, m.cells, f)
+            got = ctx.to_host(A.ARRAY_RHS)
+            assert np.all(np.abs(got - ref) <= 1e-14 * np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour mirrors the reference's exceptions
+# ---------------------------------------------------------------------------------------------
+def test_errors(ctx):
+    m = get_mesh("sphere_3D")
+    c2 = A.Context(0)
+    with pytest.raises(A.AfbError):
+        c2.build_pattern(1)                      # no mesh
+    with pytest.raises(A.AfbError):
+        c2.set_mesh(3, m.coords, m.cells[:, :3])  # Tri3 cells in 3-D
+    c2.set_mesh(m.dim, m.coords, m.cells)
+    with pytest.raises(A.AfbError):
+        c2.assemble(A.OP_POISSON)                # no pattern
+    with pytest.raises(A.AfbError):
+        c2.build_pattern(4)                      # block size
+    c2.build_pattern(3)
+    with pytest.raises(A.AfbError):
+        c2.assemble(A.OP_POISSON, fmt=A.FORMAT_BSR)   # b mismatch
+    with pytest.raises(A.AfbError):
+        c2.assemble(A.OP_ELASTICITY, fmt=A.FORMAT_BSR)  # missing lambda, mu
+    with pytest.raises(A.AfbError):
+        c2.assemble(A.OP_BILAPLACIAN, fmt=A.FORMAT_BSR)  # Tri3 only
+    c2.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE configs C2 / C3-like)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_poisson_properties(ctx):
+    import torch
+    n = 120  # C2: 10 368 000 tets
+    info = ctx.generate_box(3, n)
+    nbc, nbn, nbe, nnz = M.box_counts(3, n)
+    assert (info["nb_cell"], info["nb_node"]) == (nbc, nbn)
+    assert ctx.build_pattern(1) == (nbn, nnz)
+    v = ctx.csr_view()
+    rows = A.as_torch(v["rows"], nbn + 1, np.int32, 0).long()
+    cols = A.as_torch(v["columns"], nnz, np.int32, 0).long()
+    vals = A.as_torch(v["values"], nnz, np.float64, 0)
+    assert bool((rows[1:] > rows[:-1]).all()) and int(rows[-1]) == nnz
+    rid = torch.repeat_interleave(torch.arange(nbn, device="cuda"), rows[1:] - rows[:-1])
+    # ascending columns inside rows, diagonal present
+    same_row = rid[1:] == rid[:-1]
+    assert bool((cols[1:][same_row] > cols[:-1][same_row]).all())
+    assert int((cols == rid).sum()) == nbn
+    results = {}
+    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE):
+        ctx.reset_values()
+        ctx.assemble(A.OP_POISSON, variant=variant)
+        ctx.synchronize()
+        x = vals.clone()
+        results[variant] = x
+        rowmax = torch.zeros(nbn, dtype=torch.float64, device="cuda").scatter_reduce(0, rid, x.abs(), "amax")
+        rowsum = torch.zeros(nbn, dtype=torch.float64, device="cuda").scatter_add(0, rid, x)
+        assert float((rowsum.abs() / rowmax).max()) < 1e-12      # constants are in the kernel
+        assert bool((x[cols == rid] > 0).all())                   # positive diagonal
+        # symmetry: entry (r,c) equals entry (c,r); key-sort both orientations
+        k1 = rid * nbn + cols
+        k2 = cols * nbn + rid
+        xt = x[torch.argsort(k2)]
+        assert bool(torch.equal(torch.sort(k1).values, torch.sort(k2).values))
+        assert float(((x - xt).abs() / rowmax[rid]).max()) < 1e-12
+    a, b_ = results[A.VARIANT_CELLWISE_ATOMIC], results[A.VARIANT_NODEWISE]
+    rowmax = torch.zeros(nbn, dtype=torch.float64, device="cuda").scatter_reduce(0, rid, a.abs(), "amax")
+    assert float(((a - b_).abs() / rowmax[rid]).max()) < 1e-12
+
+
+def test_full_size_elasticity_rigid_body_modes(ctx):
+    import torch
+    n = 48  # 663 552 tets, b=3
+    ctx.generate_box(3, n)
+    nbc, nbn, nbe, nnz = M.box_counts(3, n)
+    lam, mu = O.lame(21.0e5, 0.28)
+    ctx.build_pattern(3)
+    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE):
+        ctx.reset_values()
+        ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=A.LAYOUT_PER_ROW)
+        v = ctx.csr_view()
+        crow = A.as_torch(v["rows"], v["nb_row"] + 1, np.int32, 0)
+        ccol = A.as_torch(v["columns"], v["nnz"], np.int32, 0)
+        vals = A.as_torch(v["values"], v["nnz"], np.float64, 0)
+        Acsr = torch.sparse_csr_tensor(crow, ccol, vals, size=(v["nb_row"], v["nb_row"]))
+        xyz = A.as_torch(ctx.mesh_info()["xyz"], (nbn, 3), np.float64, 0)
+        scale = float(vals.abs().max())
+        # translations and infinitesimal rotations are in the kernel of the stiffness matrix
+        modes = []
+        for k in range(3):
+            t = torch.zeros(nbn, 3, dtype=torch.float64, device="cuda")
+            t[:, k] = 1.0
+            modes.append(t)
+        rx = torch.stack([torch.zeros_like(xyz[:, 0]), -xyz[:, 2], xyz[:, 1]], dim=1)
+        rz = torch.stack([-xyz[:, 1], xyz[:, 0], torch.zeros_like(xyz[:, 0])], dim=1)
+        modes += [rx, rz]
+        for mode in modes:
+            r = Acsr @ mode.reshape(-1)
+            assert float(r.abs().max()) < 1e-11 * scale
