@@ -948,3 +948,115 @@ ORC_API int64_t orc_build_pattern_host(int npc, int32_t nb_node, int64_t nb_cell
   free(list);
   return nnz;
 }
+
+/*
+ * One "MPI rank" of the reference's sequential CSR back-end on a sub-domain
+ * (bench.py --impl reference / cpu_baseline; run concurrently from N host threads,
+ * which is how `mpirun -n N Testlab` splits the work: Arcane partitions the mesh,
+ * every rank loops over its own + ghost cells and writes only the rows of the nodes
+ * it owns, modules/testlab/CsrBiliAssembly.cc:23-92 (BuildMatrix) and :97-182
+ * (AddAndCompute, isOwn gate :174); no communication during assembly).
+ * Sub-domain = cells [cell_lo, cell_hi) (own + ghost layer) and owned nodes
+ * [owner_lo, owner_hi).  The rank allocates its own row/column/value arrays like
+ * CsrFormat::initialize does on every assembly (femutils/CsrFormatMatrix.cc:35-58),
+ * fills them, and returns nnz of its owned rows; *checksum = sum of values so the
+ * work cannot be elided.  If out_rows/out_cols/out_vals are non-NULL they receive the
+ * rank's arrays (rows relative to the rank's first entry; tests compare them with the
+ * global oracle).  seconds[0] = BuildMatrix, seconds[1] = AddAndCompute.
+ */
+#include <time.h>
+static double now_s(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+ORC_API int64_t orc_reference_rank(int npc, int dim, int64_t cell_lo, int64_t cell_hi, int32_t owner_lo, int32_t owner_hi,
+                                   const double* coords, const int32_t* conn, double* checksum, double* seconds,
+                                   int32_t* out_rows, int32_t* out_cols, double* out_vals, int64_t out_capacity)
+{
+  const double t0 = now_s();
+  const int32_t nb_own = owner_hi - owner_lo;
+  /* BuildMatrix: node -> cells of the sub-domain restricted to owned nodes, then per owned
+   * node the diagonal + neighbours (ascending) */
+  int64_t* ptr = (int64_t*)calloc((size_t)nb_own + 1, sizeof(int64_t));
+  for (int64_t c = cell_lo; c < cell_hi; ++c)
+    for (int i = 0; i < npc; ++i) {
+      int32_t v = conn[c * npc + i];
+      if (v >= owner_lo && v < owner_hi) ptr[v - owner_lo + 1]++;
+    }
+  for (int32_t n = 0; n < nb_own; ++n) ptr[n + 1] += ptr[n];
+  int32_t* list = (int32_t*)malloc(sizeof(int32_t) * (size_t)(ptr[nb_own] > 0 ? ptr[nb_own] : 1));
+  int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nb_own + 1));
+  memcpy(fill, ptr, sizeof(int64_t) * (size_t)(nb_own + 1));
+  for (int64_t c = cell_lo; c < cell_hi; ++c)
+    for (int i = 0; i < npc; ++i) {
+      int32_t v = conn[c * npc + i];
+      if (v >= owner_lo && v < owner_hi) list[fill[v - owner_lo]++] = (int32_t)c;
+    }
+  free(fill);
+  int32_t* rows = (int32_t*)malloc(sizeof(int32_t) * ((size_t)nb_own + 1));
+  int64_t cap = 0;
+  for (int32_t n = 0; n < nb_own; ++n) cap += 1 + (ptr[n + 1] - ptr[n]) * (npc - 1); /* upper bound */
+  int32_t* cols = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cap > 0 ? cap : 1));
+  int64_t nnz = 0;
+  int32_t tmp[4096];
+  for (int32_t n = 0; n < nb_own; ++n) {
+    const int32_t r = owner_lo + n;
+    int cnt = 0;
+    tmp[cnt++] = r;
+    for (int64_t q = ptr[n]; q < ptr[n + 1]; ++q) {
+      const int32_t* cn = conn + (int64_t)list[q] * npc;
+      for (int i = 0; i < npc; ++i) {
+        int32_t v = cn[i];
+        int found = 0;
+        for (int t = 0; t < cnt; ++t) if (tmp[t] == v) { found = 1; break; }
+        if (!found && cnt < 4096) tmp[cnt++] = v;
+      }
+    }
+    qsort(tmp, (size_t)cnt, sizeof(int32_t), cmp_i32);
+    rows[n] = (int32_t)nnz;
+    memcpy(cols + nnz, tmp, sizeof(int32_t) * (size_t)cnt);
+    nnz += cnt;
+  }
+  rows[nb_own] = (int32_t)nnz;
+  free(ptr);
+  free(list);
+  double* vals = (double*)calloc((size_t)(nnz > 0 ? nnz : 1), sizeof(double));
+  const double t1 = now_s();
+  /* AddAndCompute */
+  double K[16];
+  int rc = 0;
+  for (int64_t c = cell_lo; c < cell_hi && !rc; ++c) {
+    const int32_t* cn = conn + c * npc;
+    if (element_matrix(npc, dim, ORC_OP_POISSON, ORC_FORM_HOST, NULL, coords, cn, K)) { rc = -1; break; }
+    for (int a1 = 0; a1 < npc; ++a1) {
+      int32_t r = cn[a1];
+      if (r < owner_lo || r >= owner_hi) continue;
+      const int32_t rb = rows[r - owner_lo], re = rows[r - owner_lo + 1];
+      for (int a2 = 0; a2 < npc; ++a2) {
+        double v = K[a1 * npc + a2];
+        if (v == 0.0) continue; /* femutils/CsrFormatMatrix.h:64 */
+        int32_t p = -1;
+        for (int32_t q = rb; q < re; ++q) if (cols[q] == cn[a2]) { p = q; break; }
+        if (p < 0) { rc = -2; break; }
+        vals[p] += v;
+      }
+    }
+  }
+  const double t2 = now_s();
+  double s = 0.0;
+  for (int64_t i = 0; i < nnz; ++i) s += vals[i];
+  if (checksum) *checksum = s;
+  if (seconds) { seconds[0] = t1 - t0; seconds[1] = t2 - t1; }
+  if (out_rows && out_cols && out_vals && nnz <= out_capacity) {
+    memcpy(out_rows, rows, sizeof(int32_t) * ((size_t)nb_own + 1));
+    memcpy(out_cols, cols, sizeof(int32_t) * (size_t)nnz);
+    memcpy(out_vals, vals, sizeof(double) * (size_t)nnz);
+  }
+  free(rows);
+  free(cols);
+  free(vals);
+  return rc ? rc : nnz;
+}

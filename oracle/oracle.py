@@ -181,3 +181,24 @@ def assemble_csr_host_range(mesh_dim, coords, cells, rows, cols, values, cell_lo
     rc = lib().orc_assemble_csr_host_range(cells.shape[1], mesh_dim, C.c_int64(cell_lo), C.c_int64(cell_hi), C.c_int32(owner_lo), C.c_int32(owner_hi),
                                            _p(coords), _p(cells), _p(rows), _p(cols), _p(values))
     assert rc == 0, rc
+
+
+def reference_rank(mesh_dim, coords, cells, cell_lo, cell_hi, owner_lo, owner_hi, want_arrays=False, capacity=0):
+    """One MPI-rank-equivalent of the reference's sequential CSR back-end (BuildMatrix + AddAndCompute)
+    on the sub-domain cells [cell_lo,cell_hi) / owned nodes [owner_lo,owner_hi).  ctypes releases the
+    GIL, so N python threads run N ranks concurrently.  Returns dict(nnz, checksum, seconds[, rows, cols, vals])."""
+    lib().orc_reference_rank.restype = C.c_int64
+    chk = C.c_double()
+    sec = (C.c_double * 2)()
+    rows = cols = vals = None
+    if want_arrays:
+        rows = np.empty(owner_hi - owner_lo + 1, dtype=np.int32)
+        cols = np.empty(capacity, dtype=np.int32)
+        vals = np.empty(capacity, dtype=np.float64)
+    nnz = lib().orc_reference_rank(cells.shape[1], mesh_dim, C.c_int64(cell_lo), C.c_int64(cell_hi), C.c_int32(owner_lo), C.c_int32(owner_hi),
+                                   _p(coords), _p(cells), C.byref(chk), sec, _p(rows), _p(cols), _p(vals), C.c_int64(capacity))
+    assert nnz >= 0, nnz
+    out = dict(nnz=int(nnz), checksum=chk.value, seconds=(sec[0], sec[1]))
+    if want_arrays:
+        out.update(rows=rows, cols=cols[:nnz], vals=vals[:nnz])
+    return out
