@@ -112,7 +112,7 @@ int afb_destroy(afb_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,
                      &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
-                     &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag,
+                     &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback,
                      &ctx->plan.tile_desc, &ctx->plan.tile_rows, &ctx->plan.tile_foot, &ctx->plan.tile_cells, &ctx->plan.pair_ptr, &ctx->plan.pairs, &ctx->plan.node_tile };
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 6; ++i)
@@ -158,6 +158,7 @@ int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cel
   if (node_is_own) AFB_TRY(upload(ctx, ctx->is_own, node_is_own, (size_t)nb_node, mem_space));
   ctx->has_dir_nodes = false;
   ctx->has_mesh = true;
+  ctx->mesh_gen++;
   AFB_TRY(time_begin(ctx, 0));
   AFB_TRY(build_node_cells(ctx));
   AFB_TRY(time_end(ctx, 0));
@@ -173,6 +174,7 @@ int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t 
   if (!ctx->conn.owned) ctx->conn.release();
   if (!ctx->is_own.owned) ctx->is_own.release();
   AFB_TRY(generate_box(ctx, dim, n, jitter, seed, k_lo, k_hi));
+  ctx->mesh_gen++;
   ctx->has_dir_nodes = false;
   AFB_TRY(time_begin(ctx, 0));
   AFB_TRY(build_node_cells(ctx));

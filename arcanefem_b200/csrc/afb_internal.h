@@ -132,7 +132,9 @@ struct afb_ctx {
   bool saved_valid = false;
 
   // scratch
-  afb::DevBuf tmp_i32a, tmp_i32b, tmp_scan, tmp_ids, tmp_vals, tmp_flag;
+  afb::DevBuf tmp_i32a, tmp_i32b, tmp_scan, tmp_ids, tmp_vals, tmp_flag, tmp_lookback;
+  uint64_t mesh_gen = 0;        // bumped by afb_set_mesh / afb_mesh_generate_box
+  uint64_t pattern_mesh_gen = ~0ull; // mesh generation the column buffer was last sized for
 
   afb::TilePlan plan;
 
@@ -151,6 +153,12 @@ int exclusive_scan_i32(afb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n)
 // ---- connectivity.cu -------------------------------------------------------------------------
 int build_node_cells(afb_ctx* ctx);
 int build_pattern(afb_ctx* ctx);
+
+// ---- pattern_rows.cu -------------------------------------------------------------------------
+bool pattern_rows_supported(const afb_ctx* ctx);
+int pattern_rows_count(afb_ctx* ctx, int32_t* deg);
+int pattern_rows_write(afb_ctx* ctx);
+int pattern_rows_fused(afb_ctx* ctx, int* exceeded, int32_t* nnz_out);
 
 // ---- assemble.cu -----------------------------------------------------------------------------
 int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, int variant, int layout, int flags);

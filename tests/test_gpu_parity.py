@@ -95,6 +95,13 @@ def test_pattern_bit_exact(ctx, name):
     assert np.array_equal(ptr, ref_ptr) and np.array_equal(lst, ref_list)
     # COO rows (_translateCSRToCOO)
     assert np.array_equal(ctx.to_host(A.ARRAY_COO_ROWS), O.csr_to_coo_rows(rows_ref))
+    # re-build on the same mesh (steady state: fused single-pass kernel with look-back offsets)
+    for b in (1, 2):
+        assert ctx.build_pattern(b) == (nbr, nnz)
+        assert np.array_equal(ctx.to_host(A.ARRAY_ROWS), rows_ref)
+        assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+        assert np.array_equal(ctx.to_host(A.ARRAY_NZ_PER_ROW), np.diff(rows_ref))
+        assert not ctx.to_host(A.ARRAY_VALUES).any()
 
 
 def test_pattern_with_isolated_node_and_high_valence(ctx):
@@ -113,6 +120,9 @@ def test_pattern_with_isolated_node_and_high_valence(ctx):
     ctx.assemble(A.OP_POISSON, variant=A.VARIANT_NODEWISE)
     ref = O.assemble(2, coords, cells, rows_ref, cols_ref, form=O.FORM_BSR)
     row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows_ref)
+    ctx.build_pattern(1)  # fused re-build: node 0 overflows the private table (warp-cooperative path)
+    assert np.array_equal(ctx.to_host(A.ARRAY_ROWS), rows_ref)
+    assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
 
 
 def test_device_box_generator_bit_identical(ctx):
