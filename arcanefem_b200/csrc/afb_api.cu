@@ -42,7 +42,6 @@ static void invalidate_pattern(afb_ctx* ctx)
   ctx->coo_rows_valid = false;
   ctx->csr_valid = false;
   ctx->saved_valid = false;
-  ctx->plan.valid = false;
   ctx->has_elim = ctx->has_forced = ctx->has_rc = false;
 }
 
@@ -113,7 +112,8 @@ int afb_destroy(afb_ctx* ctx)
   DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,
                      &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
                      &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback,
-                     &ctx->plan.tile_desc, &ctx->plan.tile_rows, &ctx->plan.tile_foot, &ctx->plan.tile_cells, &ctx->plan.pair_ptr, &ctx->plan.pairs, &ctx->plan.node_tile };
+                     &ctx->plan.tile_desc, &ctx->plan.tile_nodes, &ctx->plan.tile_cells, &ctx->plan.unit_base, &ctx->plan.unit_len, &ctx->plan.gpos, &ctx->plan.lists,
+                     &ctx->plan.node_tile, &ctx->plan.node_lrow, &ctx->plan.scratch_a, &ctx->plan.scratch_b, &ctx->plan.scratch_c, &ctx->plan.stats };
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -224,7 +224,7 @@ int afb_assemble_bilinear(afb_ctx* ctx, int op, const double* params, int nb_par
   ctx->layout = value_layout;
   AFB_TRY(time_begin(ctx, 2));
   if (variant == AFB_VARIANT_TILED_GATHER) {
-    if (!ctx->plan.valid) AFB_TRY(build_tile_plan(ctx));
+    if (!ctx->plan.valid || ctx->plan.mesh_gen != ctx->mesh_gen || ctx->plan.b != ctx->b) AFB_TRY(build_tile_plan(ctx));
     AFB_TRY(assemble_tiled(ctx, op, params, value_layout, flags));
   }
   else

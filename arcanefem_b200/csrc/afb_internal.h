@@ -75,18 +75,26 @@ struct DevBuf {
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
-// Plan of the tiled-gather variant (built by tiles.cu from the pattern + connectivity).
+// Plan of the tiled-gather variant (inspector output, built by tiles.cu from the mesh
+// connectivity and the pattern; a pure function of the mesh topology, so it is kept across
+// pattern re-builds on the same mesh).
 struct TilePlan {
   bool valid = false;
+  uint64_t mesh_gen = ~0ull;
+  int b = 0;
   int32_t nb_tile = 0;
-  int max_rows = 0, max_cells = 0, max_foot = 0, max_vals = 0;
-  DevBuf tile_desc;   // int32[nb_tile+1][8]
-  DevBuf tile_rows;   // int32 : owned rows of each tile (global node ids), concatenated
-  DevBuf tile_foot;   // int32 : footprint nodes (owned rows first, then halo), concatenated
-  DevBuf tile_cells;  // uint16[4] (or npc) local footprint indices per tile cell, concatenated
-  DevBuf pair_ptr;    // int32 : per owned row, start of its (cell,slots) pair list
-  DevBuf pairs;       // uint32 packed (local cell idx, a, slots...) -- see tiles.cu
-  DevBuf node_tile;   // scratch
+  int64_t nb_tile_cell = 0, nb_unit = 0, nb_list = 0;
+  float build_ms = 0.f;
+  DevBuf tile_desc;   // int32[nb_tile][8]: node_off, nb_row, cell_off, nb_cell, unit_off, nb_unit, list_off, nb_entry
+  DevBuf tile_nodes;  // int32: rows (node ids) of each tile, concatenated
+  DevBuf tile_cells;  // int32: global ids of the cells touching each tile (ascending inside a tile), concatenated
+  DevBuf unit_base;   // uint32 per unit: offset of the unit's index slab inside the tile's list region
+  DevBuf unit_len;    // uint16 per unit: contributions per entry of the unit (even)
+  DevBuf gpos;        // uint32 per (unit, lane): index into values, 0xFFFFFFFF = padding lane
+  DevBuf lists;       // uint16: K-cache indices, per unit [len/2][32 lanes][2]
+  DevBuf node_tile;   // int32[nb_node]: tile of each owned node (-1: none)
+  DevBuf node_lrow;   // int32[nb_node]: row index inside its tile
+  DevBuf scratch_a, scratch_b, scratch_c, stats; // builder scratch
 };
 
 } // namespace afb

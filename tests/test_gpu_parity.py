@@ -125,6 +125,29 @@ def test_pattern_with_isolated_node_and_high_valence(ctx):
     assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
 
 
+def test_tiled_gather_limits(ctx):
+    """Tiles shrink until they fit the shared-memory cache; a single row that cannot fit is an
+    explicit error (no silent fallback), the other variants still work."""
+    # fan of 600 triangles: node 0 has valence 600 -> the brick holding it must be split finely
+    for k, ok in ((600, True), (3000, False)):
+        ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+        coords = np.zeros((k + 1, 3))
+        coords[1:, 0], coords[1:, 1] = np.cos(ang), np.sin(ang)
+        cells = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.int32)
+        ctx.set_mesh(2, coords, cells)
+        ctx.build_pattern(1)
+        rows_ref, cols_ref = O.build_pattern(3, k + 1, cells)
+        ref = O.assemble(2, coords, cells, rows_ref, cols_ref, form=O.FORM_BSR)
+        if ok:
+            ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+            row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows_ref)
+        else:
+            with pytest.raises(A.AfbError):
+                ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+            ctx.assemble(A.OP_POISSON, variant=A.VARIANT_NODEWISE)
+            row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows_ref)
+
+
 def test_device_box_generator_bit_identical(ctx):
     for dim, n in ((3, 7), (2, 13)):
         ref = M.box_mesh(dim, n)
@@ -144,8 +167,9 @@ P1_POISSON = ["L-shape_2D", "circle_2D", "porous_2D", "L-shape_3D", "sphere_3D",
 
 @pytest.mark.parametrize("name", P1_POISSON)
 @pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_COO, A.VARIANT_CELLWISE_ATOMIC),
-                                         (A.FORMAT_CSR, A.VARIANT_NODEWISE), (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
-                         ids=["csr-gpu", "coo-gpu", "nwcsr", "bsr", "af-bsr"])
+                                         (A.FORMAT_CSR, A.VARIANT_NODEWISE), (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE),
+                                         (A.FORMAT_CSR, A.VARIANT_TILED_GATHER), (A.FORMAT_BSR, A.VARIANT_TILED_GATHER)],
+                         ids=["csr-gpu", "coo-gpu", "nwcsr", "bsr", "af-bsr", "tiled-csr", "tiled-bsr"])
 def test_poisson_values(ctx, name, fmt, variant):
     m = get_mesh(name)
     ctx.set_mesh(m.dim, m.coords, m.cells)
@@ -153,7 +177,7 @@ def test_poisson_values(ctx, name, fmt, variant):
     rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
     # the reference formulation each back-end uses
     form = {A.FORMAT_CSR: O.FORM_COMPACT, A.FORMAT_COO: O.FORM_COMPACT, A.FORMAT_BSR: O.FORM_BSR}[fmt]
-    nodewise = variant == A.VARIANT_NODEWISE
+    nodewise = variant in (A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER)
     if nodewise and fmt == A.FORMAT_CSR:
         form = O.FORM_NODEWISE
     flags = A.FLAG_SIGNED_TRI_AREA if fmt != A.FORMAT_BSR else 0
@@ -250,7 +274,7 @@ def test_is_own_gate(ctx):
     ctx.set_mesh(m.dim, m.coords, m.cells, is_own=own)
     ctx.build_pattern(1)
     rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
-    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE):
+    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER):
         ctx.reset_values()
         ctx.assemble(A.OP_POISSON, variant=variant)
         ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, form=O.FORM_COMPACT, is_own=own)
@@ -265,8 +289,8 @@ def test_is_own_gate(ctx):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", list(CS.POISSON_CASES))
 @pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_COO, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_CSR, A.VARIANT_NODEWISE),
-                                         (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
-                         ids=["csr-gpu", "coo-gpu", "nwcsr", "bsr", "af-bsr"])
+                                         (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE), (A.FORMAT_CSR, A.VARIANT_TILED_GATHER)],
+                         ids=["csr-gpu", "coo-gpu", "nwcsr", "bsr", "af-bsr", "tiled"])
 def test_poisson_golden_solution(ctx, name, fmt, variant):
     case = CS.POISSON_CASES[name]
     m = _fixture_mesh(case["mesh"])
@@ -444,11 +468,18 @@ def test_full_size_poisson_properties(ctx):
     assert bool((cols[1:][same_row] > cols[:-1][same_row]).all())
     assert int((cols == rid).sum()) == nbn
     results = {}
-    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE):
+    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER):
         ctx.reset_values()
         ctx.assemble(A.OP_POISSON, variant=variant)
         ctx.synchronize()
         x = vals.clone()
+        torch.cuda.synchronize()  # the context owns a non-blocking stream: finish the copy before it works again
+        if variant == A.VARIANT_TILED_GATHER:
+            # fixed summation order: a second assembly is bit-identical
+            ctx.reset_values()
+            ctx.assemble(A.OP_POISSON, variant=variant)
+            ctx.synchronize()
+            assert bool(torch.equal(x, vals))
         results[variant] = x
         rowmax = torch.zeros(nbn, dtype=torch.float64, device="cuda").scatter_reduce(0, rid, x.abs(), "amax")
         rowsum = torch.zeros(nbn, dtype=torch.float64, device="cuda").scatter_add(0, rid, x)
@@ -460,9 +491,10 @@ def test_full_size_poisson_properties(ctx):
         xt = x[torch.argsort(k2)]
         assert bool(torch.equal(torch.sort(k1).values, torch.sort(k2).values))
         assert float(((x - xt).abs() / rowmax[rid]).max()) < 1e-12
-    a, b_ = results[A.VARIANT_CELLWISE_ATOMIC], results[A.VARIANT_NODEWISE]
+    a = results[A.VARIANT_CELLWISE_ATOMIC]
     rowmax = torch.zeros(nbn, dtype=torch.float64, device="cuda").scatter_reduce(0, rid, a.abs(), "amax")
-    assert float(((a - b_).abs() / rowmax[rid]).max()) < 1e-12
+    for other in (A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER):
+        assert float(((a - results[other]).abs() / rowmax[rid]).max()) < 1e-12
 
 
 def test_full_size_elasticity_rigid_body_modes(ctx):
