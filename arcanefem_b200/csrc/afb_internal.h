@@ -88,10 +88,14 @@ struct TilePlan {
   DevBuf tile_desc;   // int32[nb_tile][8]: node_off, nb_row, cell_off, nb_cell, unit_off, nb_unit, list_off, nb_entry
   DevBuf tile_nodes;  // int32: rows (node ids) of each tile, concatenated
   DevBuf tile_cells;  // int32: global ids of the cells touching each tile (ascending inside a tile), concatenated
-  DevBuf unit_base;   // uint32 per unit: offset of the unit's index slab inside the tile's list region
+  DevBuf unit_base;   // uint32 per unit: offset (16-bit slots) of the unit's index slab inside the tile's list region
   DevBuf unit_len;    // uint16 per unit: contributions per entry of the unit (even)
   DevBuf gpos;        // uint32 per (unit, lane): index into values, 0xFFFFFFFF = padding lane
-  DevBuf lists;       // uint16: K-cache indices, per unit [len/2][32 lanes][2]
+  DevBuf gpos2;       // uint32 per (unit, lane): mirror index (symmetric twin inside the tile) or 0xFFFFFFFF
+  DevBuf foot;        // int32: footprint nodes of each tile (rows first, then halo), concatenated
+  DevBuf lconn;       // ushort4 per tile cell: footprint-local node indices
+  DevBuf lists;       // uint16: K-cache indices, per unit [len/2][32 lanes][2]; one contiguous region per tile (TMA bulk copy)
+  int64_t nb_foot = 0;
   DevBuf node_tile;   // int32[nb_node]: tile of each owned node (-1: none)
   DevBuf node_lrow;   // int32[nb_node]: row index inside its tile
   DevBuf scratch_a, scratch_b, scratch_c, stats; // builder scratch

@@ -90,6 +90,10 @@ struct Tri3Geom {
     load3(coords, nd[1], x1, y1, z1);
     load3(coords, nd[2], x2, y2, z2);
     (void)z0; (void)z1; (void)z2;
+    init_xy(x0, y0, x1, y1, x2, y2, signed_area);
+  }
+  __device__ __forceinline__ void init_xy(double x0, double y0, double x1, double y1, double x2, double y2, bool signed_area)
+  {
     c[0][0] = y1 - y2; c[0][1] = x2 - x1;
     c[1][0] = y2 - y0; c[1][1] = x0 - x2;
     c[2][0] = y0 - y1; c[2][1] = x1 - x0;
