@@ -22,7 +22,7 @@ FORMAT_CSR, FORMAT_COO, FORMAT_BSR = 0, 1, 2
 VARIANT_CELLWISE_ATOMIC, VARIANT_NODEWISE, VARIANT_TILED_GATHER = 0, 1, 2
 LAYOUT_PER_BLOCK, LAYOUT_PER_ROW = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-FLAG_SIGNED_TRI_AREA = 1
+FLAG_SIGNED_TRI_AREA, FLAG_OWN_CELLS_ONLY, FLAG_ALL_ROWS = 1, 2, 4
 ELIMINATE_ROW, ELIMINATE_ROW_COLUMN = 1, 2
 (ARRAY_ROWS, ARRAY_COLUMNS, ARRAY_VALUES, ARRAY_NZ_PER_ROW, ARRAY_RHS, ARRAY_COO_ROWS, ARRAY_CSR_ROWS, ARRAY_CSR_COLUMNS,
  ARRAY_CSR_NB_COLUMN, ARRAY_COORDS, ARRAY_CELL_NODES, ARRAY_NODE_CELL_PTR, ARRAY_NODE_CELL_LIST) = range(13)
@@ -32,7 +32,7 @@ _ARRAY_DTYPE = {ARRAY_ROWS: np.int32, ARRAY_COLUMNS: np.int32, ARRAY_VALUES: np.
                 ARRAY_COORDS: np.float64, ARRAY_CELL_NODES: np.int32, ARRAY_NODE_CELL_PTR: np.int32, ARRAY_NODE_CELL_LIST: np.int32}
 
 EXPORTS = [
-    "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_mesh_generate_box",
+    "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_set_own_cell_count", "afb_mesh_generate_box",
     "afb_build_pattern", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_set_dirichlet_nodes",
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
@@ -128,6 +128,9 @@ class Context:
         nb_node, npc = int(coords.shape[0]), int(cells.shape[1])
         _check(lib().afb_set_mesh(self._h, int(dim), npc, C.c_int32(nb_node), C.c_int64(int(cells.shape[0])), _ptr(coords), _ptr(cells), _ptr(is_own), mem_space))
         self.dim, self.npc, self.nb_node, self.nb_cell = dim, npc, nb_node, int(cells.shape[0])
+
+    def set_own_cell_count(self, nb_own_cell):
+        _check(lib().afb_set_own_cell_count(self._h, C.c_int64(int(nb_own_cell))))
 
     def generate_box(self, dim, n, jitter=0.2, seed=12345, k_lo=0, k_hi=None):
         k_hi = n if k_hi is None else k_hi

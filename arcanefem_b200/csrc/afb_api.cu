@@ -112,7 +112,8 @@ int afb_destroy(afb_ctx* ctx)
   DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,
                      &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
                      &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback,
-                     &ctx->plan.tile_desc, &ctx->plan.tile_nodes, &ctx->plan.tile_cells, &ctx->plan.unit_base, &ctx->plan.unit_len, &ctx->plan.gpos, &ctx->plan.gpos2, &ctx->plan.foot, &ctx->plan.lconn, &ctx->plan.lists,
+                     &ctx->plan.tile_desc, &ctx->plan.tile_nodes, &ctx->plan.tile_cells, &ctx->plan.unit_base, &ctx->plan.unit_len, &ctx->plan.emap, &ctx->plan.rowinfo, &ctx->plan.foot, &ctx->plan.lconn, &ctx->plan.lists,
+                     &ctx->plan.rowf, &ctx->plan.inc, &ctx->plan.inc_grp,
                      &ctx->plan.node_tile, &ctx->plan.node_lrow, &ctx->plan.scratch_a, &ctx->plan.scratch_b, &ctx->plan.scratch_c, &ctx->plan.stats };
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 6; ++i)
@@ -155,6 +156,7 @@ int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cel
   AFB_TRY(upload(ctx, ctx->conn, cell_nodes, sizeof(int32_t) * (size_t)npc * (size_t)nb_cell, mem_space));
   ctx->all_own = (node_is_own == nullptr);
   ctx->nb_own_node = nb_node;
+  ctx->nb_own_cell = nb_cell;
   if (node_is_own) AFB_TRY(upload(ctx, ctx->is_own, node_is_own, (size_t)nb_node, mem_space));
   ctx->has_dir_nodes = false;
   ctx->has_mesh = true;
@@ -162,6 +164,16 @@ int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cel
   AFB_TRY(time_begin(ctx, 0));
   AFB_TRY(build_node_cells(ctx));
   AFB_TRY(time_end(ctx, 0));
+  return AFB_OK;
+}
+
+int afb_set_own_cell_count(afb_ctx* ctx, int64_t nb_own_cell)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_mesh, AFB_ERR_INVALID, "afb_set_own_cell_count: no mesh");
+  AFB_REQUIRE(nb_own_cell >= 0 && nb_own_cell <= ctx->nb_cell, AFB_ERR_INVALID, "nb_own_cell %lld out of range [0,%lld]", (long long)nb_own_cell, (long long)ctx->nb_cell);
+  ctx->nb_own_cell = nb_own_cell;
+  ctx->plan.lists_valid = false;
   return AFB_OK;
 }
 
@@ -204,6 +216,7 @@ int afb_reset_values(afb_ctx* ctx)
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_reset_values: no pattern");
   AFB_CUDA(cudaMemsetAsync(ctx->values.p, 0, sizeof(double) * (size_t)ctx->nnz * ctx->b * ctx->b, ctx->stream));
+  ctx->values_dirty = false;
   ctx->assembled = false;
   ctx->saved_valid = false;
   return AFB_OK;
@@ -223,12 +236,11 @@ int afb_assemble_bilinear(afb_ctx* ctx, int op, const double* params, int nb_par
   AFB_REQUIRE(!(ctx->assembled && ctx->layout != value_layout), AFB_ERR_INVALID, "values already hold the other layout; afb_reset_values first");
   ctx->layout = value_layout;
   AFB_TRY(time_begin(ctx, 2));
-  if (variant == AFB_VARIANT_TILED_GATHER) {
-    if (!ctx->plan.valid || ctx->plan.mesh_gen != ctx->mesh_gen || ctx->plan.b != ctx->b) AFB_TRY(build_tile_plan(ctx));
-    AFB_TRY(assemble_tiled(ctx, op, params, value_layout, flags));
-  }
-  else
+  if (variant == AFB_VARIANT_TILED_GATHER) AFB_TRY(assemble_tiled(ctx, op, params, value_layout, flags));
+  else {
+    AFB_TRY(ensure_values_zeroed(ctx));
     AFB_TRY(assemble_bilinear(ctx, op, params, format, variant, value_layout, flags));
+  }
   AFB_TRY(time_end(ctx, 2));
   ctx->assembled = true;
   return AFB_OK;
@@ -269,6 +281,7 @@ int afb_dirichlet_penalty(afb_ctx* ctx, int weak, double penalty, int32_t n, con
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_dirichlet_penalty: no pattern");
   if (n <= 0) return AFB_OK;
+  AFB_TRY(ensure_values_zeroed(ctx));
   const void *ids = nullptr, *vals = nullptr;
   AFB_TRY(stage(ctx, ctx->tmp_ids, dof_ids, sizeof(int32_t) * (size_t)n, mem_space, &ids));
   AFB_TRY(stage(ctx, ctx->tmp_vals, g, sizeof(double) * (size_t)n, mem_space, &vals));
@@ -327,6 +340,7 @@ int afb_apply_matrix_transformation(afb_ctx* ctx, int replicate_column0_quirk)
 {
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_apply_matrix_transformation: no pattern");
+  AFB_TRY(ensure_values_zeroed(ctx));
   return apply_matrix_transformation(ctx, replicate_column0_quirk);
 }
 
@@ -334,6 +348,7 @@ int afb_apply_rhs_transformation(afb_ctx* ctx)
 {
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_apply_rhs_transformation: no pattern");
+  AFB_TRY(ensure_values_zeroed(ctx));
   return apply_rhs_transformation(ctx);
 }
 
@@ -341,6 +356,7 @@ int afb_get_csr_view(afb_ctx* ctx, const int32_t** rows, const int32_t** rows_nb
 {
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_get_csr_view: no pattern");
+  AFB_TRY(ensure_values_zeroed(ctx));
   if (ctx->b == 1) {
     if (rows) *rows = ctx->rows.as<int32_t>();
     if (rows_nb_column) *rows_nb_column = ctx->nz_per_row.as<int32_t>();
@@ -368,6 +384,7 @@ int afb_get_bsr(afb_ctx* ctx, const int32_t** rows_index, const int32_t** column
 {
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_get_bsr: no pattern");
+  AFB_TRY(ensure_values_zeroed(ctx));
   if (rows_index) *rows_index = ctx->rows.as<int32_t>();
   if (columns) *columns = ctx->cols.as<int32_t>();
   if (values) *values = ctx->values.as<double>();
@@ -384,6 +401,7 @@ int afb_get_coo(afb_ctx* ctx, const int32_t** coo_rows, const int32_t** coo_cols
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_get_coo: no pattern");
   AFB_REQUIRE(ctx->b == 1, AFB_ERR_UNSUPPORTED, "COO view is defined for one dof per node");
+  AFB_TRY(ensure_values_zeroed(ctx));
   AFB_TRY(ensure_coo_rows(ctx));
   if (coo_rows) *coo_rows = ctx->coo_rows.as<int32_t>();
   if (coo_cols) *coo_cols = ctx->cols.as<int32_t>();
@@ -429,7 +447,9 @@ int afb_copy_to_host(afb_ctx* ctx, int which, void* dst, size_t* bytes)
   switch (which) {
   case AFB_ARRAY_ROWS: src = ctx->rows.p; n = sizeof(int32_t) * ((size_t)ctx->nb_node + 1); break;
   case AFB_ARRAY_COLUMNS: src = ctx->cols.p; n = sizeof(int32_t) * (size_t)ctx->nnz; break;
-  case AFB_ARRAY_VALUES: src = ctx->values.p; n = sizeof(double) * (size_t)ctx->nnz * b * b; break;
+  case AFB_ARRAY_VALUES:
+    AFB_TRY(ensure_values_zeroed(ctx));
+    src = ctx->values.p; n = sizeof(double) * (size_t)ctx->nnz * b * b; break;
   case AFB_ARRAY_NZ_PER_ROW: src = ctx->nz_per_row.p; n = sizeof(int32_t) * (size_t)ctx->nb_node; break;
   case AFB_ARRAY_RHS: src = ctx->rhs.p; n = sizeof(double) * (size_t)ctx->nb_node * b; break;
   case AFB_ARRAY_COO_ROWS:
@@ -471,6 +491,7 @@ int afb_add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, const doubl
 {
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_add_values_at: no pattern");
+  AFB_TRY(ensure_values_zeroed(ctx));
   return add_values_at(ctx, n, slots, contrib);
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "afb200.h"
 
@@ -75,29 +76,39 @@ struct DevBuf {
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
-// Plan of the tiled-gather variant (inspector output, built by tiles.cu from the mesh
-// connectivity and the pattern; a pure function of the mesh topology, so it is kept across
-// pattern re-builds on the same mesh).
+// Plan of the tiled path (inspector output, tiles_plan.cu).  The mesh tiling is a pure function
+// of the mesh topology and coordinates; the value plan additionally depends on the pattern, the
+// block size and the ownership mode.  Both survive pattern re-builds on the same mesh.
 struct TilePlan {
-  bool valid = false;
+  // ---- mesh tiling ----
+  bool mesh_valid = false;
   uint64_t mesh_gen = ~0ull;
-  int b = 0;
+  int mesh_b_class = 0;        // 0: scalar limits (TG_CMAX), 1: vector limits (TV_CMAX)
   int32_t nb_tile = 0;
-  int64_t nb_tile_cell = 0, nb_unit = 0, nb_list = 0;
-  float build_ms = 0.f;
-  DevBuf tile_desc;   // int32[nb_tile][8]: node_off, nb_row, cell_off, nb_cell, unit_off, nb_unit, list_off, nb_entry
-  DevBuf tile_nodes;  // int32: rows (node ids) of each tile, concatenated
-  DevBuf tile_cells;  // int32: global ids of the cells touching each tile (ascending inside a tile), concatenated
+  int max_rows = 0;
+  int64_t nb_tile_cell = 0, nb_foot = 0, nb_inc = 0;
+  float mesh_ms = 0.f, lists_ms = 0.f;
+  DevBuf tile_desc;   // TileDesc[nb_tile]
+  DevBuf tile_nodes;  // int32: rows (node ids, ascending) of each tile, concatenated
+  DevBuf tile_cells;  // int32: global ids of the cells touching each tile (ascending), concatenated
+  DevBuf foot;        // int32: footprint nodes of each tile (ascending ids), concatenated
+  DevBuf lconn;       // ushort4 per tile cell: footprint-local node indices
+  DevBuf rowf;        // uint16 per tile row: footprint index of the row's node
+  DevBuf inc;         // uint32 per (row, incident cell): the cell's other nodes, 3 x 10-bit footprint indices
+  DevBuf inc_grp;     // uint2 per (tile, group of 32 rows): offset (words, inside the tile) and list length
+  DevBuf node_tile;   // int32[nb_node]: tile of each node
+  DevBuf node_lrow;   // int32[nb_node]: row index inside its tile
+  std::vector<int32_t> hdesc_host; // host copy of tile_desc (16 words per tile)
+  // ---- value plan ----
+  bool lists_valid = false;
+  uint64_t lists_mesh_gen = ~0ull;
+  int lists_b = 0, lists_mode = 0;
+  int64_t nb_unit = 0, nb_list = 0;
+  DevBuf rowinfo;     // uint32 per tile row: first entry | diagonal position << 16 | owned << 31
   DevBuf unit_base;   // uint32 per unit: offset (16-bit slots) of the unit's index slab inside the tile's list region
   DevBuf unit_len;    // uint16 per unit: contributions per entry of the unit (even)
-  DevBuf gpos;        // uint32 per (unit, lane): index into values, 0xFFFFFFFF = padding lane
-  DevBuf gpos2;       // uint32 per (unit, lane): mirror index (symmetric twin inside the tile) or 0xFFFFFFFF
-  DevBuf foot;        // int32: footprint nodes of each tile (rows first, then halo), concatenated
-  DevBuf lconn;       // ushort4 per tile cell: footprint-local node indices
-  DevBuf lists;       // uint16: K-cache indices, per unit [len/2][32 lanes][2]; one contiguous region per tile (TMA bulk copy)
-  int64_t nb_foot = 0;
-  DevBuf node_tile;   // int32[nb_node]: tile of each owned node (-1: none)
-  DevBuf node_lrow;   // int32[nb_node]: row index inside its tile
+  DevBuf emap;        // uint32 per (unit, lane): tile-local entry | mirror entry << 16; 0xFFFFFFFF = padding lane
+  DevBuf lists;       // uint16: cache indices, per unit [len/2][32 lanes][2]; one contiguous region per tile (TMA bulk copy)
   DevBuf scratch_a, scratch_b, scratch_c, stats; // builder scratch
 };
 
@@ -114,6 +125,7 @@ struct afb_ctx {
   int dim = 0, npc = 0;
   int32_t nb_node = 0, nb_own_node = 0;
   int64_t nb_cell = 0;
+  int64_t nb_own_cell = 0;      // cells [0, nb_own_cell) belong to this sub-domain, the rest are ghost cells
   bool has_mesh = false;
   afb::DevBuf coords, conn, is_own; // double[nb_node*3], int32[nb_cell*npc], uint8[nb_node] (may be null => all owned)
   bool all_own = true;
@@ -127,6 +139,7 @@ struct afb_ctx {
   afb::DevBuf rows, cols, nz_per_row, coo_rows; // int32
   bool coo_rows_valid = false;
   afb::DevBuf values; // double[nnz*b*b]
+  bool values_dirty = false; // allocated but not yet zeroed (a fresh tiled assembly overwrites every entry)
   afb::DevBuf rhs;    // double[nb_node*b]
   int layout = AFB_LAYOUT_PER_BLOCK;
   bool assembled = false;
@@ -175,9 +188,14 @@ int pattern_rows_fused(afb_ctx* ctx, int* exceeded, int32_t* nnz_out);
 // ---- assemble.cu -----------------------------------------------------------------------------
 int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, int variant, int layout, int flags);
 
-// ---- tiles.cu --------------------------------------------------------------------------------
-int build_tile_plan(afb_ctx* ctx);
+// ---- tiles_plan.cu / tiles_exec.cu / pattern_tiled.cu ----------------------------------------
+int build_tile_mesh(afb_ctx* ctx);
+int build_tile_lists(afb_ctx* ctx, int mode_flags);
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags);
+bool pattern_tiled_ready(const afb_ctx* ctx);
+int pattern_tiled_count(afb_ctx* ctx, int32_t* deg);
+int pattern_tiled_write(afb_ctx* ctx);
+int ensure_values_zeroed(afb_ctx* ctx);
 
 // ---- linear.cu (rhs, dirichlet, views) -------------------------------------------------------
 int rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed_area);

@@ -120,7 +120,7 @@ __device__ __forceinline__ void add_element_row_dyn(const E& e, int a, const int
 template <class E, int LAYOUT>
 __global__ void __launch_bounds__(128)
 k_assemble_nodewise(const double* __restrict__ coords, const int32_t* __restrict__ conn, const uint8_t* __restrict__ is_own, int32_t nb_node,
-                    const int32_t* __restrict__ nc_ptr, const int32_t* __restrict__ nc_list,
+                    const int32_t* __restrict__ nc_ptr, const int32_t* __restrict__ nc_list, int64_t nb_own_cell,
                     const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, double* __restrict__ values, ElemParams prm)
 {
   constexpr int NPC = E::NPC, B = E::B;
@@ -132,6 +132,7 @@ k_assemble_nodewise(const double* __restrict__ coords, const int32_t* __restrict
   const int qb = __ldg(nc_ptr + r), qe = __ldg(nc_ptr + r + 1);
   for (int q = qb; q < qe; ++q) {
     const int64_t cell = __ldg(nc_list + q);
+    if (cell >= nb_own_cell) continue; // ghost cells contribute nothing in AFB_FLAG_OWN_CELLS_ONLY mode
     int32_t nd[NPC];
     load_cell_nodes<NPC>(conn, cell, nd);
     int a = 0;
@@ -162,26 +163,28 @@ static int launch(afb_ctx* ctx, int format, int variant, int layout, const ElemP
 {
   const double* coords = ctx->coords.as<double>();
   const int32_t* conn = ctx->conn.as<int32_t>();
-  const uint8_t* own = ctx->all_own ? nullptr : ctx->is_own.as<uint8_t>();
+  // domain-decomposition modes (afb200.h): ALL_ROWS drops the isOwn gate, OWN_CELLS_ONLY the ghost cells
+  const uint8_t* own = (ctx->all_own || (prm.flags & AFB_FLAG_ALL_ROWS)) ? nullptr : ctx->is_own.as<uint8_t>();
+  const int64_t nb_cell = (prm.flags & AFB_FLAG_OWN_CELLS_ONLY) ? ctx->nb_own_cell : ctx->nb_cell;
   const int32_t* rows = ctx->rows.as<int32_t>();
   const int32_t* cols = ctx->cols.as<int32_t>();
   double* values = ctx->values.as<double>();
   if (variant == AFB_VARIANT_CELLWISE_ATOMIC) {
-    if (ctx->nb_cell == 0) return AFB_OK;
-    int grid = grid_for(ctx->nb_cell, 128);
+    if (nb_cell == 0) return AFB_OK;
+    int grid = grid_for(nb_cell, 128);
     if (format == AFB_FORMAT_COO) {
       AFB_TRY(ensure_coo_rows(ctx));
       const int32_t* coo = ctx->coo_rows.as<int32_t>();
       if (layout == AFB_LAYOUT_PER_BLOCK)
-        k_assemble_cellwise<E, AFB_LAYOUT_PER_BLOCK, true><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, ctx->nb_cell, rows, cols, coo, ctx->nnz, values, prm);
+        k_assemble_cellwise<E, AFB_LAYOUT_PER_BLOCK, true><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, nb_cell, rows, cols, coo, ctx->nnz, values, prm);
       else
-        k_assemble_cellwise<E, AFB_LAYOUT_PER_ROW, true><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, ctx->nb_cell, rows, cols, coo, ctx->nnz, values, prm);
+        k_assemble_cellwise<E, AFB_LAYOUT_PER_ROW, true><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, nb_cell, rows, cols, coo, ctx->nnz, values, prm);
     }
     else {
       if (layout == AFB_LAYOUT_PER_BLOCK)
-        k_assemble_cellwise<E, AFB_LAYOUT_PER_BLOCK, false><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, ctx->nb_cell, rows, cols, nullptr, ctx->nnz, values, prm);
+        k_assemble_cellwise<E, AFB_LAYOUT_PER_BLOCK, false><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, nb_cell, rows, cols, nullptr, ctx->nnz, values, prm);
       else
-        k_assemble_cellwise<E, AFB_LAYOUT_PER_ROW, false><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, ctx->nb_cell, rows, cols, nullptr, ctx->nnz, values, prm);
+        k_assemble_cellwise<E, AFB_LAYOUT_PER_ROW, false><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, nb_cell, rows, cols, nullptr, ctx->nnz, values, prm);
     }
     AFB_LAUNCH_CHECK(ctx);
     return AFB_OK;
@@ -192,9 +195,9 @@ static int launch(afb_ctx* ctx, int format, int variant, int layout, const ElemP
     const int32_t* ptr = ctx->nc_ptr.as<int32_t>();
     const int32_t* list = ctx->nc_list.as<int32_t>();
     if (layout == AFB_LAYOUT_PER_BLOCK)
-      k_assemble_nodewise<E, AFB_LAYOUT_PER_BLOCK><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, ctx->nb_node, ptr, list, rows, cols, values, prm);
+      k_assemble_nodewise<E, AFB_LAYOUT_PER_BLOCK><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, ctx->nb_node, ptr, list, nb_cell, rows, cols, values, prm);
     else
-      k_assemble_nodewise<E, AFB_LAYOUT_PER_ROW><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, ctx->nb_node, ptr, list, rows, cols, values, prm);
+      k_assemble_nodewise<E, AFB_LAYOUT_PER_ROW><<<grid, 128, 0, ctx->stream>>>(coords, conn, own, ctx->nb_node, ptr, list, nb_cell, rows, cols, values, prm);
     AFB_LAUNCH_CHECK(ctx);
     return AFB_OK;
   }

@@ -376,9 +376,24 @@ int build_pattern(afb_ctx* ctx)
   AFB_TRY(ctx->nz_per_row.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
   const bool fast = pattern_rows_supported(ctx);
   bool done = false;
-  if (fast && ctx->pattern_mesh_gen == ctx->mesh_gen && ctx->cols.p) {
-    // steady state (the reference re-builds the sparsity on every AssembleBilinearOperator,
-    // SURVEY.md App. C.6): one fused pass into the buffers sized by the first build
+  if (pattern_tiled_ready(ctx) && ctx->pattern_mesh_gen == ctx->mesh_gen && ctx->cols.p) {
+    // steady state with the mesh tiling available (the reference re-builds the sparsity on every
+    // AssembleBilinearOperator): per-tile bitmap kernel, degree -> scan -> columns
+    AFB_TRY(ctx->tmp_i32b.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
+    int32_t* deg = ctx->tmp_i32b.as<int32_t>();
+    AFB_TRY(pattern_tiled_count(ctx, deg));
+    AFB_TRY(exclusive_scan_i32(ctx, deg, ctx->rows.as<int32_t>(), nb_node));
+    int32_t nnz32 = 0;
+    AFB_CUDA(cudaMemcpyAsync(&nnz32, ctx->rows.as<int32_t>() + nb_node, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    AFB_REQUIRE(nnz32 >= 0, AFB_ERR_OVERFLOW, "block nnz exceeds Int32");
+    ctx->nnz = nnz32;
+    AFB_TRY(ctx->cols.reserve(sizeof(int32_t) * (size_t)ctx->nnz));
+    AFB_TRY(pattern_tiled_write(ctx));
+    done = true;
+  }
+  if (!done && fast && ctx->pattern_mesh_gen == ctx->mesh_gen && ctx->cols.p) {
+    // steady state without a tiling: one fused pass into the buffers sized by the first build
     int exceeded = 0;
     int32_t nnz32 = 0;
     AFB_TRY(pattern_rows_fused(ctx, &exceeded, &nnz32));
@@ -408,7 +423,10 @@ int build_pattern(afb_ctx* ctx)
               "scalar nnz %lld exceeds the Int32 index space of the reference containers (femutils/BSRFormat.cc:362-364)", (long long)(ctx->nnz * b * b));
   AFB_TRY(ctx->values.reserve(sizeof(double) * (size_t)ctx->nnz * b * b));
   AFB_TRY(ctx->rhs.reserve(sizeof(double) * (size_t)nb_node * b));
-  AFB_CUDA(cudaMemsetAsync(ctx->values.p, 0, sizeof(double) * (size_t)ctx->nnz * b * b, ctx->stream));
+  // CsrFormat::initialize fills the values with 0 (femutils/CsrFormatMatrix.cc:35-58).  Here the fill is
+  // deferred to the first reader/accumulator (ensure_values_zeroed): a fresh tiled assembly writes
+  // every entry exactly once and never needs it.
+  ctx->values_dirty = true;
   AFB_CUDA(cudaMemsetAsync(ctx->rhs.p, 0, sizeof(double) * (size_t)nb_node * b, ctx->stream));
   return AFB_OK;
 }

@@ -122,6 +122,7 @@ int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int
   ctx->nb_node = (int32_t)nb_node;
   ctx->nb_own_node = d.nb_own;
   ctx->nb_cell = nb_cell;
+  ctx->nb_own_cell = nb_cell;
   ctx->all_own = (k_lo == 0);
   ctx->has_mesh = true;
   return AFB_OK;

@@ -1,0 +1,168 @@
+// Sparsity pattern from the mesh tiling (steady-state BuildMatrix).
+//
+// Replaces the reference's BuildMatrix kernels: the sort-based sparsity
+// of modules/testlab/CsrGpuBiliAssembly.cc:42-207 / femutils/BSRFormat.cc:799-1006 (pack edges,
+// cub radix sort of 6*nbCell u64 keys, atomic degree count, scan, atomic column slot claim) and the
+// connectivity-based one (femutils/BSRFormat.cc:445-790), which walks a node-node connectivity that
+// Arcane builds on the host at init (MeshUtils::computeNodeNodeViaEdgeConnectivity).
+//
+// Here the init-time structure is the mesh tiling of tiles_plan.cu: per tile the footprint nodes in
+// ascending id order and, per row, the incident cells' other nodes as packed 10-bit footprint
+// indices.  One CTA per tile, one thread per row: the thread ORs its neighbours into a private
+// bitmap over the footprint (shared memory, layout [word][row]: conflict-free), so duplicates vanish
+// without hashing or sorting, the degree is a popcount, and walking the set bits emits the columns
+// already in ascending order.  Two passes (degree -> scan -> columns), streaming 4 bytes per
+// (row, incident cell) each; no atomics, no global sort, deterministic.
+#include <algorithm>
+
+#include "tiles.cuh"
+
+namespace afb {
+
+constexpr int PT_UNROLL = 4;
+
+template <bool WRITE>
+__global__ void __launch_bounds__(TG_RMAX)
+k_pattern_tiled(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const uint16_t* __restrict__ rowf, const uint32_t* __restrict__ inc,
+                const uint2* __restrict__ inc_grp, const int32_t* __restrict__ foot, int32_t* __restrict__ deg_out, const int32_t* __restrict__ rows,
+                int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row)
+{
+  extern __shared__ uint32_t pt_smem[];
+  const int32_t t = blockIdx.x;
+  const TileDesc d = desc[t];
+  const int R = d.nb_row;
+  if (R == 0) return;
+  const int RP = (R + 31) & ~31;             // bitmap row stride
+  const int W = (d.nb_foot + 31) >> 5;       // bitmap words per row
+  uint32_t* bm = pt_smem;                    // [W][RP]
+  uint32_t* s_foot = pt_smem + W * RP;       // [nb_foot] (WRITE)
+  const int i = threadIdx.x;
+  if constexpr (WRITE) {
+    for (int f = threadIdx.x; f < d.nb_foot; f += blockDim.x) s_foot[f] = (uint32_t)__ldg(foot + d.foot_off + f);
+  }
+  if (i < RP) {
+    for (int w = 0; w < W; ++w) bm[w * RP + i] = 0u;
+  }
+  int32_t node = -1;
+  if (i < R) {
+    node = __ldg(tile_nodes + d.node_off + i);
+    const unsigned self = __ldg(rowf + d.node_off + i);
+    uint32_t* my = bm + i;
+    my[(self >> 5) * RP] = 1u << (self & 31);
+    const uint2 g = __ldg(inc_grp + (size_t)t * TG_GMAX + (i >> 5));
+    const uint32_t* src = inc + d.inc_off + g.x + (i & 31);
+    const int len = (int)g.y;
+    int k = 0;
+    for (; k + PT_UNROLL <= len; k += PT_UNROLL) {
+      uint32_t w[PT_UNROLL];
+#pragma unroll
+      for (int q = 0; q < PT_UNROLL; ++q) w[q] = __ldg(src + (k + q) * 32);
+#pragma unroll
+      for (int q = 0; q < PT_UNROLL; ++q) {
+        const unsigned f0 = w[q] & 1023u, f1 = (w[q] >> 10) & 1023u, f2 = (w[q] >> 20) & 1023u;
+        my[(f0 >> 5) * RP] |= 1u << (f0 & 31);
+        my[(f1 >> 5) * RP] |= 1u << (f1 & 31);
+        my[(f2 >> 5) * RP] |= 1u << (f2 & 31);
+      }
+    }
+    for (; k < len; ++k) {
+      const uint32_t w = __ldg(src + k * 32);
+      const unsigned f0 = w & 1023u, f1 = (w >> 10) & 1023u, f2 = (w >> 20) & 1023u;
+      my[(f0 >> 5) * RP] |= 1u << (f0 & 31);
+      my[(f1 >> 5) * RP] |= 1u << (f1 & 31);
+      my[(f2 >> 5) * RP] |= 1u << (f2 & 31);
+    }
+  }
+  if constexpr (!WRITE) {
+    if (i < R) {
+      const uint32_t* my = bm + i;
+      int deg = 0;
+      for (int w = 0; w < W; ++w) deg += __popc(my[w * RP]);
+      deg_out[node] = deg;
+    }
+  }
+  else {
+    // columns are staged in shared memory in row order (tile-local offsets from a block scan of the
+    // degrees) and leave as contiguous runs: rows with consecutive node ids are adjacent in `cols`
+    uint32_t* s_cols = s_foot + d.nb_foot;                  // [nb_entry]
+    int32_t* s_erow = reinterpret_cast<int32_t*>(s_cols + d.nb_entry); // [RP + 1]
+    int32_t* s_shift = s_erow + RP + 1;                     // [RP]: rows[node] - erow
+    uint16_t* s_etab = reinterpret_cast<uint16_t*>(s_shift + RP); // [nb_entry / 8 + 1]
+    __shared__ int s_wsum[TG_RMAX / 32];
+    int deg = 0;
+    if (i < R) {
+      const uint32_t* my = bm + i;
+      for (int w = 0; w < W; ++w) deg += __popc(my[w * RP]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc_ = deg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc_, o);
+      if (lane >= o) inc_ += v;
+    }
+    if (lane == 31) s_wsum[warp] = inc_;
+    __syncthreads(); // also: s_foot complete
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+    const int e0 = woff + inc_ - deg;
+    if (i < R) {
+      s_erow[i] = e0;
+      s_shift[i] = __ldg(rows + node) - e0;
+      nz_per_row[node] = deg;
+      for (int q = (e0 + 7) >> 3; (q << 3) < e0 + deg; ++q) s_etab[q] = (uint16_t)i;
+      const uint32_t* my = bm + i;
+      int k = e0;
+      for (int w = 0; w < W; ++w) {
+        uint32_t bits = my[w * RP];
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          s_cols[k++] = s_foot[w * 32 + b];
+        }
+      }
+      if (i == R - 1) s_erow[R] = e0 + deg;
+    }
+    __syncthreads();
+    const int E = s_erow[R];
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      int r = s_etab[e >> 3];
+      while (e >= s_erow[r + 1]) ++r;
+      cols[s_shift[r] + e] = (int32_t)s_cols[e];
+    }
+  }
+}
+
+bool pattern_tiled_ready(const afb_ctx* ctx)
+{
+  const TilePlan& P = ctx->plan;
+  return P.mesh_valid && P.mesh_gen == ctx->mesh_gen && (ctx->npc == 3 || ctx->npc == 4);
+}
+
+static int launch_pattern_tiled(afb_ctx* ctx, bool write, int32_t* deg)
+{
+  const TilePlan& P = ctx->plan;
+  if (P.nb_tile == 0) return AFB_OK;
+  const int threads = std::max(32, (P.max_rows + 31) & ~31);
+  // bitmap [W][RP] + footprint ids (+ staged columns, row offsets, entry->row table): bounded by the tile limits
+  const size_t smem = sizeof(uint32_t) * ((size_t)((TG_FMAX + 31) / 32) * (size_t)threads + TG_FMAX) +
+                      (write ? sizeof(uint32_t) * ((size_t)TG_EMAX + 2 * (size_t)threads + 2) + sizeof(uint16_t) * (TG_EMAX / 8 + 2) : 0);
+  if (!write) {
+    AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pattern_tiled<false><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(), P.inc.as<uint32_t>(),
+                                                                      P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), deg, nullptr, nullptr, nullptr);
+  }
+  else {
+    AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pattern_tiled<true><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(), P.inc.as<uint32_t>(),
+                                                                     P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), nullptr, ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(),
+                                                                     ctx->nz_per_row.as<int32_t>());
+  }
+  AFB_LAUNCH_CHECK(ctx);
+  return AFB_OK;
+}
+
+int pattern_tiled_count(afb_ctx* ctx, int32_t* deg) { return launch_pattern_tiled(ctx, false, deg); }
+int pattern_tiled_write(afb_ctx* ctx) { return launch_pattern_tiled(ctx, true, nullptr); }
+
+} // namespace afb

@@ -1,0 +1,66 @@
+// Shared declarations of the tiled path (inspector: tiles_plan.cu; executors: tiles_exec.cu;
+// sparsity pattern from tiles: pattern_tiled.cu).
+//
+// A *tile* is a spatial brick of matrix rows (nodes) small enough that everything one CTA needs
+// to finish those rows lives in shared memory: the coordinates of the tile's footprint (rows +
+// halo nodes), the element matrices of every cell touching the tile, and the tile's matrix
+// entries.  Two CTAs are resident per SM (113 KB each), so one tile's element phase (fp64 pipe)
+// overlaps the other's gather phase (shared-memory pipe) and its HBM traffic.
+#pragma once
+
+#include "afb_internal.h"
+
+namespace afb {
+
+// ---- executor geometry (2 CTAs per SM) ---------------------------------------------------------
+constexpr int TG_THREADS = 512;            // executor CTA
+constexpr int TG_MINB = 2;                 // CTAs per SM
+constexpr int TG_CMAX = 1408;              // cells per tile
+constexpr int TG_CS = TG_CMAX + 1;         // cache plane stride (odd)
+constexpr int TG_KP = 6;                   // cached values per cell: the off-diagonal pairs of a 4-node cell
+constexpr int TG_ZERO = TG_KP * TG_CS;     // cache slot that holds 0.0 (list padding)
+constexpr int TG_EMAX = 2304;              // matrix entries per tile
+constexpr int TG_RMAX = 384;               // rows per tile
+constexpr int TG_FMAX = 384;               // footprint nodes per tile
+constexpr int TG_LMAX = 7680;              // 16-bit list slots per tile (TMA-staged)
+constexpr int TG_UMAX = TG_EMAX / 32;      // units (32 entries with equally long lists) per tile
+constexpr int TG_ROUNDS = (TG_CMAX + TG_THREADS - 1) / TG_THREADS;
+constexpr int TG_GMAX = TG_RMAX / 32;      // row groups per tile (incidence lists)
+constexpr unsigned TG_NONE16 = 0xFFFFu;
+
+// vector (b = 2, 3) executor: cache of sqrt(s)*grad(phi_a) per cell, blocks accumulated in registers
+constexpr int TV_PLANES = 12;              // 4 nodes x 3 components
+constexpr int TV_CMAX = 1024;
+constexpr int TV_CS = TV_CMAX + 1;
+
+struct TileDesc {
+  int32_t node_off, nb_row;    // rows (node ids ascending) in tile_nodes / rowinfo
+  int32_t cell_off, nb_cell;   // tile_cells / lconn
+  int32_t foot_off, nb_foot;   // foot (ascending node ids)
+  uint32_t inc_off;            // first word of the tile in `inc`
+  int32_t nb_group;            // row groups of 32
+  int32_t unit_off, nb_unit;   // unit tables / emap (value plan)
+  uint32_t list_off;           // first 16-bit slot of the tile in `lists` (multiple of 8)
+  int32_t list_len;            // used slots (multiple of 8)
+  int32_t nb_entry;            // matrix entries of the tile's rows
+  int32_t max_val;             // largest node valence in the tile
+  int32_t pad0, pad1;
+};
+static_assert(sizeof(TileDesc) == 64, "TileDesc is copied as 16 words");
+
+// off-diagonal pair (a<b) of an NPC-node cell -> cache plane
+__host__ __device__ __forceinline__ constexpr int off_pair(int npc, int a, int b)
+{
+  const int lo = a < b ? a : b, hi = a < b ? b : a;
+  return lo * (2 * npc - lo - 1) / 2 + (hi - lo - 1);
+}
+
+// rowinfo word of a tile row: first entry (tile-local), position of the diagonal, ownership
+__host__ __device__ __forceinline__ uint32_t pack_rowinfo(int erow, int pdiag, bool own) { return (uint32_t)erow | ((uint32_t)pdiag << 16) | (own ? 0x80000000u : 0u); }
+__host__ __device__ __forceinline__ int rowinfo_erow(uint32_t w) { return (int)(w & 0xFFFFu); }
+__host__ __device__ __forceinline__ int rowinfo_pdiag(uint32_t w) { return (int)((w >> 16) & 0x7FFFu); }
+__host__ __device__ __forceinline__ bool rowinfo_own(uint32_t w) { return (w >> 31) != 0; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+} // namespace afb

@@ -1,0 +1,510 @@
+// Tiled gather assembly: the B200 path of the atomic-free ("node-wise") back-ends.
+//
+// Reference behaviour replaced: _assembleNodeWiseCsrBilinearOperator{Tria3,Tetra4}
+// (modules/testlab/NodeWiseCsrBiliAssembly.cc:157-297) and BSRFormat::assembleBilinearAtomicFree
+// (femutils/BSRFormat.h:406-577): every matrix row is written by exactly one owner, without
+// atomics.  The reference does it with one thread per node that recomputes the geometry of
+// every incident cell (4x redundant fp64 work on tetrahedra, valence-divergent).  Here one CTA
+// finishes one tile of rows (inspector: tiles_plan.cu), two CTAs resident per SM:
+//
+//   stage    footprint coordinates, row offsets and unit tables go to shared memory; the tile's
+//            contribution lists arrive asynchronously through the TMA engine (cp.async.bulk)
+//   phase A  one thread per tile cell: geometry once (one determinant, one reciprocal); scalar
+//            operators cache the 6 (Tet4) / 3 (Tri3) off-diagonal K_e values, vector operators
+//            cache sqrt(s)*grad(phi_a) (the blocks are rank-one sums of those)
+//   phase B  one lane per matrix entry: sum the cached contributions in a fixed order (ascending
+//            cell id => bit-reproducible); symmetric twins inside the tile are summed once
+//   phase C  scalar: the diagonal is minus the sum of the row's off-diagonals (zero row sums of
+//            the stiffness matrix), rows leave shared memory as contiguous, coalesced stores;
+//            vector: blocks are written from registers in either BSR value layout
+//   Rows are written exactly once, so a fresh assembly needs no zero fill of `values`.
+#include "element.cuh"
+#include "tiles.cuh"
+
+namespace afb {
+
+// ---------------------------------------------------------------------------------------------
+// element caches
+// ---------------------------------------------------------------------------------------------
+template <int NPC> struct OffDiagK;
+template <> struct OffDiagK<4> {
+  static constexpr int N = 6;
+  __device__ static __forceinline__ void compute(const double* __restrict__ cx, ushort4 ln, const ElemParams&, double (&K)[6])
+  {
+    const double* p0 = cx + 3 * ln.x;
+    const double* p1 = cx + 3 * ln.y;
+    const double* p2 = cx + 3 * ln.z;
+    const double* p3 = cx + 3 * ln.w;
+    Tet4Geom g;
+    g.init_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+    K[0] = g.dot(0, 1) * g.s; K[1] = g.dot(0, 2) * g.s; K[2] = g.dot(0, 3) * g.s;
+    K[3] = g.dot(1, 2) * g.s; K[4] = g.dot(1, 3) * g.s; K[5] = g.dot(2, 3) * g.s;
+  }
+};
+template <> struct OffDiagK<3> {
+  static constexpr int N = 3;
+  __device__ static __forceinline__ void compute(const double* __restrict__ cx, ushort4 ln, const ElemParams& prm, double (&K)[6])
+  {
+    const double* p0 = cx + 3 * ln.x;
+    const double* p1 = cx + 3 * ln.y;
+    const double* p2 = cx + 3 * ln.z;
+    Tri3Geom g;
+    g.init_xy(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], (prm.flags & AFB_FLAG_SIGNED_TRI_AREA) != 0);
+    K[0] = g.dot(0, 1) * g.s; K[1] = g.dot(0, 2) * g.s; K[2] = g.dot(1, 2) * g.s;
+    K[3] = K[4] = K[5] = 0.0;
+  }
+};
+
+struct ExecSmem {
+  double Kc[TG_ZERO + 1];
+  double cx[3 * TG_FMAX];
+  double vout[TG_EMAX];
+  __align__(16) uint16_t lists[TG_LMAX];
+  int32_t rowbeg[TG_RMAX];        // first value of the row minus its first tile-local entry: dest(e) = e + rowbeg[row(e)]
+  uint32_t rowinfo[TG_RMAX + 1];  // + sentinel (first entry = nb_entry)
+  uint32_t ubase[TG_UMAX];
+  uint16_t ulen[TG_UMAX];
+  uint16_t etab[TG_EMAX / 8];     // row holding entry 8*q
+  __align__(16) TileDesc desc[3]; // ring: current, next, next-next tile of this CTA
+  __align__(8) unsigned long long mbar;
+};
+static_assert(sizeof(ExecSmem) <= 115712, "two executor CTAs must fit one SM (227 KB, 1 KB reserved per CTA)");
+
+// inputs of the next tile a thread carries in registers across phases B and C
+struct TilePrefetch {
+  double c0, c1, c2;      // coordinates of footprint node `threadIdx.x`
+  ushort4 ln[TG_ROUNDS];  // local connectivity of this thread's cells
+  uint32_t ubase;         // unit table entry `threadIdx.x`
+  uint16_t ulen;
+  int32_t rowbeg;         // row `threadIdx.x`: first value of the row, plan word
+  uint32_t rowinfo;
+};
+
+struct ExecArgs {
+  const TileDesc* desc;
+  int32_t nb_tile;
+  const double* coords;
+  const int32_t* foot;
+  const ushort4* lconn;
+  const int32_t* tile_nodes;
+  const uint32_t* rowinfo;
+  const int32_t* rows;
+  const uint32_t* unit_base;
+  const uint16_t* unit_len;
+  const uint32_t* emap;
+  const uint16_t* lists;
+  double* values;
+  int accumulate;
+};
+
+template <int ROUNDS, int THREADS>
+__device__ __forceinline__ void prefetch_tile(const TileDesc& d, const ExecArgs& A, TilePrefetch& pf)
+{
+  if ((int)threadIdx.x < d.nb_foot) {
+    const double* p = A.coords + 3 * (int64_t)__ldg(A.foot + d.foot_off + threadIdx.x);
+    pf.c0 = __ldg(p);
+    pf.c1 = __ldg(p + 1);
+    pf.c2 = __ldg(p + 2);
+  }
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int lc = r * THREADS + threadIdx.x;
+    if (lc < d.nb_cell) pf.ln[r] = __ldg(A.lconn + d.cell_off + lc);
+  }
+  if ((int)threadIdx.x < d.nb_unit) {
+    pf.ubase = __ldg(A.unit_base + d.unit_off + threadIdx.x);
+    pf.ulen = __ldg(A.unit_len + d.unit_off + threadIdx.x);
+  }
+  if ((int)threadIdx.x < d.nb_row) {
+    pf.rowbeg = __ldg(A.rows + __ldg(A.tile_nodes + d.node_off + threadIdx.x));
+    pf.rowinfo = __ldg(A.rowinfo + d.node_off + threadIdx.x);
+  }
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, unsigned parity)
+{
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar executor (b = 1, zero-row-sum operators: Poisson)
+// ---------------------------------------------------------------------------------------------
+template <int NPC>
+__global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs A, ElemParams prm)
+{
+  extern __shared__ __align__(16) unsigned char ex_raw[];
+  ExecSmem& S = *reinterpret_cast<ExecSmem*>(ex_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = TG_THREADS / 32;
+  constexpr int DW = sizeof(TileDesc) / 4;
+  const uint32_t mbar = smem_u32(&S.mbar);
+  int32_t t = blockIdx.x;
+  if (threadIdx.x == 0) {
+    S.Kc[TG_ZERO] = 0.0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 2 * DW) { // descriptors of the first two tiles
+    const int k = threadIdx.x / DW, w = threadIdx.x % DW;
+    const int64_t tt = (int64_t)t + (int64_t)k * gridDim.x;
+    if (tt < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[k])[w] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tt) + w);
+  }
+  __syncthreads();
+  unsigned parity = 0;
+  int slot = 0;
+  TilePrefetch pf;
+  if (t < A.nb_tile) prefetch_tile<TG_ROUNDS, TG_THREADS>(S.desc[0], A, pf);
+  while (t < A.nb_tile) {
+    const TileDesc d = S.desc[slot];
+    const bool staged = d.list_len <= TG_LMAX; // lists of an oversized tile are read from global memory
+    // ---- stage ----
+    if ((int)threadIdx.x < d.nb_foot) {
+      S.cx[3 * threadIdx.x] = pf.c0;
+      S.cx[3 * threadIdx.x + 1] = pf.c1;
+      S.cx[3 * threadIdx.x + 2] = pf.c2;
+    }
+    if ((int)threadIdx.x < d.nb_unit) {
+      S.ubase[threadIdx.x] = pf.ubase;
+      S.ulen[threadIdx.x] = pf.ulen;
+    }
+    if ((int)threadIdx.x < d.nb_row) {
+      S.rowbeg[threadIdx.x] = pf.rowbeg - rowinfo_erow(pf.rowinfo);
+      S.rowinfo[threadIdx.x] = pf.rowinfo;
+    }
+    else if ((int)threadIdx.x == d.nb_row) S.rowinfo[threadIdx.x] = pack_rowinfo(d.nb_entry, 0, false);
+    if (threadIdx.x == 0 && staged && d.list_len > 0) {
+      const uint32_t bytes = (uint32_t)d.list_len * 2u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(S.lists)), "l"(A.lists + d.list_off),
+                   "r"(bytes), "r"(mbar)
+                   : "memory");
+    }
+    __syncthreads();
+    // entry -> row table for the write-out (row holding every 8th entry)
+    if ((int)threadIdx.x < d.nb_row) {
+      const int e0 = rowinfo_erow(S.rowinfo[threadIdx.x]), e1 = rowinfo_erow(S.rowinfo[threadIdx.x + 1]);
+      for (int q = (e0 + 7) >> 3; (q << 3) < e1; ++q) S.etab[q] = (uint16_t)threadIdx.x;
+    }
+    // ---- phase A: off-diagonal element-matrix values of the tile's cells, once each ----
+#pragma unroll
+    for (int r = 0; r < TG_ROUNDS; ++r) {
+      const int lc = r * TG_THREADS + threadIdx.x;
+      if (lc < d.nb_cell) {
+        double K[6];
+        OffDiagK<NPC>::compute(S.cx, pf.ln[r], prm, K);
+#pragma unroll
+        for (int p = 0; p < OffDiagK<NPC>::N; ++p) S.Kc[p * TG_CS + lc] = K[p];
+      }
+    }
+    // the next tile's inputs and the descriptor after it travel while phases B and C run
+    const int64_t tn = (int64_t)t + gridDim.x, tnn = tn + gridDim.x;
+    const int nslot = slot == 2 ? 0 : slot + 1, nnslot = nslot == 2 ? 0 : nslot + 1;
+    if (tn < A.nb_tile) prefetch_tile<TG_ROUNDS, TG_THREADS>(S.desc[nslot], A, pf);
+    if (threadIdx.x < DW && tnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnslot])[threadIdx.x] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnn) + threadIdx.x);
+    int u = warp;
+    uint32_t em = 0xFFFFFFFFu;
+    if (u < d.nb_unit) em = __ldg(A.emap + (size_t)(d.unit_off + u) * 32 + lane);
+    __syncthreads();
+    if (staged && d.list_len > 0) {
+      mbar_wait(mbar, parity);
+      parity ^= 1u;
+    }
+    // ---- phase B: one warp per unit of 32 entries with equally long contribution lists ----
+    {
+      const uint32_t* l32 = staged ? reinterpret_cast<const uint32_t*>(S.lists) : reinterpret_cast<const uint32_t*>(A.lists + d.list_off);
+      while (u < d.nb_unit) {
+        const int un = u + NW;
+        uint32_t emn = 0xFFFFFFFFu;
+        if (un < d.nb_unit) emn = __ldg(A.emap + (size_t)(d.unit_off + un) * 32 + lane);
+        const uint32_t* l = l32 + (S.ubase[u] >> 1) + lane;
+        const int len2 = S.ulen[u] >> 1;
+        double acc0 = 0.0, acc1 = 0.0;
+        constexpr uint32_t ZPAIR = (uint32_t)TG_ZERO | ((uint32_t)TG_ZERO << 16);
+#pragma unroll 1
+        for (int k = 0; k < len2; k += 2) {
+          const uint32_t i0 = l[k * 32];
+          const uint32_t i1 = (k + 1 < len2) ? l[(k + 1) * 32] : ZPAIR;
+          acc0 += S.Kc[i0 & 0xFFFFu]; acc1 += S.Kc[i0 >> 16];
+          acc0 += S.Kc[i1 & 0xFFFFu]; acc1 += S.Kc[i1 >> 16];
+        }
+        if (em != 0xFFFFFFFFu) {
+          const double v = acc0 + acc1;
+          S.vout[em & 0xFFFFu] = v;
+          if ((em >> 16) != TG_NONE16) S.vout[em >> 16] = v;
+        }
+        u = un;
+        em = emn;
+      }
+    }
+    __syncthreads();
+    // ---- phase C: diagonal = -(sum of the row's off-diagonals) ... ----
+    if ((int)threadIdx.x < d.nb_row) {
+      const uint32_t ri = S.rowinfo[threadIdx.x];
+      if (rowinfo_own(ri)) {
+        const int e0 = rowinfo_erow(ri), e1 = rowinfo_erow(S.rowinfo[threadIdx.x + 1]), ed = e0 + rowinfo_pdiag(ri);
+        double s0 = 0.0, s1 = 0.0;
+        int e = e0;
+        for (; e + 1 < ed; e += 2) { s0 += S.vout[e]; s1 += S.vout[e + 1]; }
+        if (e < ed) s0 += S.vout[e];
+        e = ed + 1;
+        for (; e + 1 < e1; e += 2) { s0 += S.vout[e]; s1 += S.vout[e + 1]; }
+        if (e < e1) s0 += S.vout[e];
+        S.vout[ed] = -(s0 + s1);
+      }
+    }
+    __syncthreads();
+    // ---- ... and the tile's entries leave shared memory in row order: contiguous, coalesced stores ----
+    for (int e = threadIdx.x; e < d.nb_entry; e += TG_THREADS) {
+      int r = S.etab[e >> 3];
+      uint32_t ri = S.rowinfo[r + 1];
+      while (e >= rowinfo_erow(ri)) {
+        ++r;
+        ri = S.rowinfo[r + 1];
+      }
+      const double v = rowinfo_own(S.rowinfo[r]) ? S.vout[e] : 0.0;
+      double* dst = A.values + ((int64_t)S.rowbeg[r] + e);
+      if (A.accumulate) *dst += v; else *dst = v;
+    }
+    __syncthreads();
+    t = (int32_t)tn;
+    slot = nslot;
+    if (tn >= A.nb_tile) break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector executor (b = DIM dofs per node: isotropic elasticity)
+//   K_ab = s [ lambda c_a c_b^T + mu c_b c_a^T + mu (c_a.c_b) I ]  with g_a = sqrt(s) c_a:
+//   sum over cells of K_ab = lambda M + mu M^T + mu tr(M) I,  M = sum g_a (x) g_b
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+struct VecSmem {
+  double G[TV_PLANES * TV_CS];
+  double cx[3 * TG_FMAX];
+  int32_t rowbeg[TG_RMAX];
+  uint32_t rowinfo[TG_RMAX];
+  uint32_t ubase[TG_UMAX];
+  uint16_t ulen[TG_UMAX];
+  __align__(16) TileDesc desc[3];
+};
+static_assert(sizeof(VecSmem<3>) <= 115712, "two vector-executor CTAs must fit one SM");
+
+constexpr int TV_ROUNDS = (TV_CMAX + TG_THREADS - 1) / TG_THREADS;
+
+template <int NPC, int LAYOUT>
+__global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(ExecArgs A, ElemParams prm)
+{
+  constexpr int DIM = NPC - 1, B = DIM;
+  extern __shared__ __align__(16) unsigned char ex_raw[];
+  VecSmem<DIM>& S = *reinterpret_cast<VecSmem<DIM>*>(ex_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = TG_THREADS / 32;
+  constexpr int DW = sizeof(TileDesc) / 4;
+  int32_t t = blockIdx.x;
+  // zero slot of every plane (list padding)
+  if (threadIdx.x < TV_PLANES) S.G[threadIdx.x * TV_CS + TV_CS - 1] = 0.0;
+  if (threadIdx.x < 2 * DW) {
+    const int k = threadIdx.x / DW, w = threadIdx.x % DW;
+    const int64_t tt = (int64_t)t + (int64_t)k * gridDim.x;
+    if (tt < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[k])[w] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tt) + w);
+  }
+  __syncthreads();
+  int slot = 0;
+  TilePrefetch pf;
+  if (t < A.nb_tile) prefetch_tile<TV_ROUNDS, TG_THREADS>(S.desc[0], A, pf);
+  const double lam = prm.p0, mu = prm.p1;
+  while (t < A.nb_tile) {
+    const TileDesc d = S.desc[slot];
+    if ((int)threadIdx.x < d.nb_foot) {
+      S.cx[3 * threadIdx.x] = pf.c0;
+      S.cx[3 * threadIdx.x + 1] = pf.c1;
+      S.cx[3 * threadIdx.x + 2] = pf.c2;
+    }
+    if ((int)threadIdx.x < d.nb_unit) {
+      S.ubase[threadIdx.x] = pf.ubase;
+      S.ulen[threadIdx.x] = pf.ulen;
+    }
+    if ((int)threadIdx.x < d.nb_row) {
+      S.rowbeg[threadIdx.x] = pf.rowbeg;
+      S.rowinfo[threadIdx.x] = pf.rowinfo;
+    }
+    __syncthreads();
+    // ---- phase A: g_a = sqrt(s) * cofactor gradients ----
+#pragma unroll
+    for (int r = 0; r < TV_ROUNDS; ++r) {
+      const int lc = r * TG_THREADS + threadIdx.x;
+      if (lc < d.nb_cell) {
+        const ushort4 ln = pf.ln[r];
+        if constexpr (NPC == 4) {
+          const double* p0 = S.cx + 3 * ln.x;
+          const double* p1 = S.cx + 3 * ln.y;
+          const double* p2 = S.cx + 3 * ln.z;
+          const double* p3 = S.cx + 3 * ln.w;
+          Tet4Geom g;
+          g.init_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+          const double q = sqrt(g.s);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) S.G[(a * 3 + k) * TV_CS + lc] = g.c[a][k] * q;
+        }
+        else {
+          const double* p0 = S.cx + 3 * ln.x;
+          const double* p1 = S.cx + 3 * ln.y;
+          const double* p2 = S.cx + 3 * ln.z;
+          Tri3Geom g;
+          g.init_xy(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], false);
+          const double q = sqrt(g.s);
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) S.G[(a * 2 + k) * TV_CS + lc] = g.c[a][k] * q;
+        }
+      }
+    }
+    const int64_t tn = (int64_t)t + gridDim.x, tnn = tn + gridDim.x;
+    const int nslot = slot == 2 ? 0 : slot + 1, nnslot = nslot == 2 ? 0 : nslot + 1;
+    if (tn < A.nb_tile) prefetch_tile<TV_ROUNDS, TG_THREADS>(S.desc[nslot], A, pf);
+    if (threadIdx.x < DW && tnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnslot])[threadIdx.x] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnn) + threadIdx.x);
+    __syncthreads();
+    // ---- phase B: one lane per block entry; M accumulated in registers, lists streamed from global ----
+    const uint32_t* l32 = reinterpret_cast<const uint32_t*>(A.lists + d.list_off);
+    for (int u = warp; u < d.nb_unit; u += NW) {
+      const uint32_t em = __ldg(A.emap + (size_t)(d.unit_off + u) * 32 + lane);
+      const uint32_t* l = l32 + (S.ubase[u] >> 1) + lane;
+      const int len2 = S.ulen[u] >> 1;
+      double M[DIM][DIM];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) M[i][j] = 0.0;
+      uint32_t w = len2 > 0 ? __ldg(l) : 0u;
+      for (int k = 0; k < len2; ++k) {
+        const uint32_t wn = (k + 1 < len2) ? __ldg(l + (k + 1) * 32) : 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t code = h ? (w >> 16) : (w & 0xFFFFu);
+          const uint32_t plane = code / TV_CS, lc = code - plane * TV_CS;
+          const uint32_t a = plane / NPC, b = plane - a * NPC;
+          double ga[DIM], gb[DIM];
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) {
+            ga[i] = S.G[(a * DIM + i) * TV_CS + lc];
+            gb[i] = S.G[(b * DIM + i) * TV_CS + lc];
+          }
+#pragma unroll
+          for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) M[i][j] = fma(ga[i], gb[j], M[i][j]);
+        }
+        w = wn;
+      }
+      if (em != 0xFFFFFFFFu) {
+        double tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) tr += M[i][i];
+        double blk[B * B];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+          for (int j = 0; j < DIM; ++j) blk[i * B + j] = lam * M[i][j] + mu * M[j][i] + (i == j ? mu * tr : 0.0);
+        // locate (row, position) of the entry and of its mirror from the tile-local entry index
+        auto emit = [&](int e, bool transpose) {
+          int lo = 0, hi = d.nb_row;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (rowinfo_erow(S.rowinfo[mid]) <= e) lo = mid; else hi = mid;
+          }
+          const int e0 = rowinfo_erow(S.rowinfo[lo]);
+          const int nz = (lo + 1 < d.nb_row ? rowinfo_erow(S.rowinfo[lo + 1]) : d.nb_entry) - e0;
+          const int rb = S.rowbeg[lo], p = rb + (e - e0);
+#pragma unroll
+          for (int i = 0; i < B; ++i)
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              double* dst = A.values + value_index<B, LAYOUT>(rb, nz, p, i, j);
+              const double v = transpose ? blk[j * B + i] : blk[i * B + j];
+              if (A.accumulate) *dst += v; else *dst = v;
+            }
+        };
+        emit((int)(em & 0xFFFFu), false);
+        if ((em >> 16) != TG_NONE16) emit((int)(em >> 16), true);
+      }
+    }
+    __syncthreads();
+    t = (int32_t)tn;
+    slot = nslot;
+    if (tn >= A.nb_tile) break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int ensure_values_zeroed(afb_ctx* ctx)
+{
+  if (!ctx->values_dirty) return AFB_OK;
+  AFB_CUDA(cudaMemsetAsync(ctx->values.p, 0, sizeof(double) * (size_t)ctx->nnz * ctx->b * ctx->b, ctx->stream));
+  ctx->values_dirty = false;
+  return AFB_OK;
+}
+
+int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags)
+{
+  const bool vec = ctx->b > 1;
+  AFB_REQUIRE((ctx->npc == 3 || ctx->npc == 4) && ((op == AFB_OP_POISSON && !vec) || (op == AFB_OP_ELASTICITY && vec)), AFB_ERR_UNSUPPORTED,
+              "AFB_VARIANT_TILED_GATHER is not available for operator %d on %d-node cells (P1 Poisson and P1 elasticity only); use AFB_VARIANT_NODEWISE", op, ctx->npc);
+  TilePlan& P = ctx->plan;
+  const int mode = flags & (AFB_FLAG_ALL_ROWS | AFB_FLAG_OWN_CELLS_ONLY);
+  if (!P.mesh_valid || P.mesh_gen != ctx->mesh_gen || P.mesh_b_class != (vec ? 1 : 0)) AFB_TRY(build_tile_mesh(ctx));
+  if (!P.lists_valid || P.lists_mesh_gen != ctx->mesh_gen || P.lists_b != ctx->b || P.lists_mode != mode) AFB_TRY(build_tile_lists(ctx, mode));
+  ElemParams prm;
+  prm.p0 = params ? params[0] : 0.0;
+  prm.p1 = params ? params[1] : 0.0;
+  prm.flags = flags;
+  if (P.nb_tile == 0) return AFB_OK;
+  // values already holding contributions (a second operator added on top) are accumulated into;
+  // a fresh matrix is simply overwritten (every entry of every row is written exactly once; the
+  // vector executor does not write the rows of non-owned nodes: those need the zero fill)
+  const int accumulate = ctx->assembled ? 1 : 0;
+  const bool all_rows = ctx->all_own || (flags & AFB_FLAG_ALL_ROWS);
+  if (accumulate || (vec && !all_rows)) AFB_TRY(ensure_values_zeroed(ctx));
+  else ctx->values_dirty = false;
+  ExecArgs A;
+  A.desc = P.tile_desc.as<TileDesc>();
+  A.nb_tile = P.nb_tile;
+  A.coords = ctx->coords.as<double>();
+  A.foot = P.foot.as<int32_t>();
+  A.lconn = P.lconn.as<ushort4>();
+  A.tile_nodes = P.tile_nodes.as<int32_t>();
+  A.rowinfo = P.rowinfo.as<uint32_t>();
+  A.rows = ctx->rows.as<int32_t>();
+  A.unit_base = P.unit_base.as<uint32_t>();
+  A.unit_len = P.unit_len.as<uint16_t>();
+  A.emap = P.emap.as<uint32_t>();
+  A.lists = P.lists.as<uint16_t>();
+  A.values = ctx->values.as<double>();
+  A.accumulate = accumulate;
+  const int grid = std::min<int>(P.nb_tile, TG_MINB * ctx->sm_count);
+  auto go = [&](auto kernel, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, TG_THREADS, smem, ctx->stream>>>(A, prm);
+    return cudaGetLastError();
+  };
+  cudaError_t e;
+  if (!vec) e = ctx->npc == 4 ? go(k_assemble_tiled<4>, sizeof(ExecSmem)) : go(k_assemble_tiled<3>, sizeof(ExecSmem));
+  else if (ctx->npc == 4)
+    e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_tiled_vec<4, AFB_LAYOUT_PER_BLOCK>, sizeof(VecSmem<3>)) : go(k_assemble_tiled_vec<4, AFB_LAYOUT_PER_ROW>, sizeof(VecSmem<3>));
+  else
+    e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_tiled_vec<3, AFB_LAYOUT_PER_BLOCK>, sizeof(VecSmem<2>)) : go(k_assemble_tiled_vec<3, AFB_LAYOUT_PER_ROW>, sizeof(VecSmem<2>));
+  AFB_CUDA(e);
+  ctx->launches++;
+  return AFB_OK;
+}
+
+} // namespace afb

@@ -86,7 +86,13 @@ enum { AFB_MEM_HOST = 0, AFB_MEM_DEVICE = 1 };
 enum {
   /* Tri3: use the SIGNED area like the testlab CSR/COO back-ends (modules/testlab/FemModule.h:359);
    * default is the unsigned area of the BSR lambdas (femutils/ArcaneFemFunctionsGpu.h:76-86). */
-  AFB_FLAG_SIGNED_TRI_AREA = 1
+  AFB_FLAG_SIGNED_TRI_AREA = 1,
+  /* Domain decomposition with ghost-row exchange (design B): only the sub-domain's
+   * own cells [0, nb_own_cell) contribute (afb_set_own_cell_count) ... */
+  AFB_FLAG_OWN_CELLS_ONLY = 2,
+  /* ... into the rows of ALL local nodes, ghost nodes included (no isOwn gate): the ghost rows then
+   * hold the partial sums that the owner adds (afb_add_values_at). */
+  AFB_FLAG_ALL_ROWS = 4
 };
 
 /* matrix elimination type: femutils/FemUtilsGlobal.h:51-62 */
@@ -135,6 +141,10 @@ AFB_API int afb_synchronize(afb_ctx* ctx);
  */
 AFB_API int afb_set_mesh(afb_ctx* ctx, int dim, int nodes_per_cell, int32_t nb_node, int64_t nb_cell,
                          const double* xyz, const int32_t* cell_nodes, const uint8_t* node_is_own, int mem_space);
+
+/* Cells [0, nb_own_cell) belong to this sub-domain, cells [nb_own_cell, nb_cell) are ghost cells
+ * (Arcane's one-layer ghost cells; Cell::isOwn()).  Default after afb_set_mesh: all cells own. */
+AFB_API int afb_set_own_cell_count(afb_ctx* ctx, int64_t nb_own_cell);
 
 /*
  * Synthetic structured box of SURVEY.md §8(d), generated on the device (bench + tests):

@@ -5,7 +5,7 @@ ctx = A.Context(0)
 ctx.generate_box(3, int(sys.argv[1]) if len(sys.argv) > 1 else 120)
 ctx.build_pattern(1)
 for _ in range(3):
-    ctx.reset_values()
+    ctx.build_pattern(1)
     ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
 ctx.synchronize()
 print("ok", ctx.last_timings())

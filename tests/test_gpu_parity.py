@@ -125,11 +125,58 @@ def test_pattern_with_isolated_node_and_high_valence(ctx):
     assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
 
 
+@pytest.mark.parametrize("name", ["L-shape_2D", "porous_2D", "sphere_3D", "box3d_n9", "box2d_n17"])
+def test_tiled_pattern_rebuild_bit_exact(ctx, name):
+    """Steady-state BuildMatrix: once the tile inspector has run (first tiled assembly), the pattern is
+    re-built by the per-tile bitmap kernel (pattern_tiled.cu); rows/columns stay bit-exact, the values
+    of a fresh pattern read as zero, and a tiled assembly right after needs no zero fill."""
+    m = get_mesh(name)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    nbr, nnz = ctx.build_pattern(1)
+    rows_ref, cols_ref = O.build_pattern(m.npc, m.nb_node, m.cells)
+    ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+    v1 = ctx.to_host(A.ARRAY_VALUES)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows_ref, cols_ref, form=O.FORM_BSR)
+    row_scaled_close(v1, ref, rows_ref)
+    for rep in range(2):
+        assert ctx.build_pattern(1) == (nbr, nnz)
+        assert np.array_equal(ctx.to_host(A.ARRAY_ROWS), rows_ref)
+        assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+        assert np.array_equal(ctx.to_host(A.ARRAY_NZ_PER_ROW), np.diff(rows_ref))
+        if rep == 0:
+            assert not ctx.to_host(A.ARRAY_VALUES).any()
+        ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+        assert np.array_equal(ctx.to_host(A.ARRAY_VALUES), v1), "tiled gather must be bit-reproducible"
+    # another block size on the same mesh re-uses the tiling for the pattern
+    assert ctx.build_pattern(m.dim) == (nbr, nnz)
+    assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+
+
+def test_ownership_modes(ctx):
+    """Domain-decomposition flags: OWN_CELLS_ONLY drops the ghost cells, ALL_ROWS the isOwn gate.
+    Every variant must agree with the atomic cell-wise one (itself checked against the oracle)."""
+    m = get_mesh("box3d_n9")
+    nb_own_cell = (m.nb_cell * 2) // 3
+    own = np.ones(m.nb_node, dtype=np.uint8)
+    own[::5] = 0
+    ctx.set_mesh(3, m.coords, m.cells, own)
+    ctx.set_own_cell_count(nb_own_cell)
+    ctx.build_pattern(1)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    full = O.assemble(3, m.coords, m.cells[:nb_own_cell], rows, cols, form=O.FORM_BSR)
+    seg = np.repeat(np.arange(m.nb_node), np.diff(rows))
+    for flags, ref in ((A.FLAG_OWN_CELLS_ONLY | A.FLAG_ALL_ROWS, full), (A.FLAG_OWN_CELLS_ONLY, np.where(own[seg] != 0, full, 0.0))):
+        for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER):
+            ctx.reset_values()
+            ctx.assemble(A.OP_POISSON, variant=variant, flags=flags)
+            row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows)
+
+
 def test_tiled_gather_limits(ctx):
     """Tiles shrink until they fit the shared-memory cache; a single row that cannot fit is an
     explicit error (no silent fallback), the other variants still work."""
-    # fan of 600 triangles: node 0 has valence 600 -> the brick holding it must be split finely
-    for k, ok in ((600, True), (3000, False)):
+    # fan of 300 triangles: node 0 has valence 300 (fits a tile: 384 footprint nodes); 3000 cannot fit
+    for k, ok in ((300, True), (3000, False)):
         ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
         coords = np.zeros((k + 1, 3))
         coords[1:, 0], coords[1:, 1] = np.cos(ang), np.sin(ang)
@@ -211,7 +258,7 @@ def test_signed_area_of_clockwise_triangles(ctx):
 
 
 @pytest.mark.parametrize("name", ["bar_3D", "sphere_3D", "box3d_n9", "L-shape_2D", "box2d_n17"])
-@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER], ids=["bsr", "af-bsr", "tiled-bsr"])
 @pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
 def test_elasticity_values(ctx, name, variant, layout):
     m = get_mesh(name)
@@ -222,8 +269,16 @@ def test_elasticity_values(ctx, name, variant, layout):
     rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
     ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=layout)
     ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[lam, mu], layout=layout,
-                     nodewise=variant == A.VARIANT_NODEWISE)
+                     nodewise=variant != A.VARIANT_CELLWISE_ATOMIC)
     row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows, b=b, layout=layout)
+    if variant == A.VARIANT_TILED_GATHER:
+        # accumulate on top, then a fresh matrix again
+        v1 = ctx.to_host(A.ARRAY_VALUES)
+        ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=layout)
+        row_scaled_close(ctx.to_host(A.ARRAY_VALUES), 2.0 * v1, rows, b=b, layout=layout)
+        ctx.reset_values()
+        ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=layout)
+        assert np.array_equal(ctx.to_host(A.ARRAY_VALUES), v1), "tiled gather must be bit-reproducible"
     if layout == A.LAYOUT_PER_ROW:
         # BSRMatrix::toCsr hand-off arrays, bit-exact
         crow, ccol, nbc = O.bsr_to_csr(b, rows, cols)
