@@ -32,7 +32,7 @@ _ARRAY_DTYPE = {ARRAY_ROWS: np.int32, ARRAY_COLUMNS: np.int32, ARRAY_VALUES: np.
                 ARRAY_COORDS: np.float64, ARRAY_CELL_NODES: np.int32, ARRAY_NODE_CELL_PTR: np.int32, ARRAY_NODE_CELL_LIST: np.int32}
 
 EXPORTS = [
-    "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_set_own_cell_count", "afb_mesh_generate_box",
+    "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_set_own_cell_count", "afb_get_own_cell_count", "afb_renumber_columns", "afb_mesh_generate_box",
     "afb_build_pattern", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_set_dirichlet_nodes",
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
@@ -132,9 +132,9 @@ class Context:
     def set_own_cell_count(self, nb_own_cell):
         _check(lib().afb_set_own_cell_count(self._h, C.c_int64(int(nb_own_cell))))
 
-    def generate_box(self, dim, n, jitter=0.2, seed=12345, k_lo=0, k_hi=None):
+    def generate_box(self, dim, n, jitter=0.2, seed=12345, k_lo=0, k_hi=None, ghost_cell_layer=False):
         k_hi = n if k_hi is None else k_hi
-        _check(lib().afb_mesh_generate_box(self._h, dim, n, C.c_double(jitter), C.c_uint32(seed), k_lo, k_hi))
+        _check(lib().afb_mesh_generate_box(self._h, dim, n, C.c_double(jitter), C.c_uint32(seed), k_lo, k_hi, int(ghost_cell_layer)))
         info = self.mesh_info()
         self.dim, self.npc, self.nb_node, self.nb_cell = info["dim"], info["npc"], info["nb_node"], info["nb_cell"]
         return info
@@ -144,7 +144,10 @@ class Context:
         nbc = C.c_int64()
         xyz, cn, own = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(lib().afb_get_mesh(self._h, C.byref(dim), C.byref(npc), C.byref(nbn), C.byref(nbc), C.byref(nbo), C.byref(xyz), C.byref(cn), C.byref(own)))
-        return dict(dim=dim.value, npc=npc.value, nb_node=nbn.value, nb_cell=nbc.value, nb_own_node=nbo.value, xyz=xyz.value, cell_nodes=cn.value, is_own=own.value)
+        noc = C.c_int64()
+        _check(lib().afb_get_own_cell_count(self._h, C.byref(noc)))
+        return dict(dim=dim.value, npc=npc.value, nb_node=nbn.value, nb_cell=nbc.value, nb_own_node=nbo.value, nb_own_cell=noc.value,
+                    xyz=xyz.value, cell_nodes=cn.value, is_own=own.value)
 
     # -- pattern / assembly ------------------------------------------------------------------
     def build_pattern(self, nb_dof_per_node=1):

@@ -177,7 +177,15 @@ int afb_set_own_cell_count(afb_ctx* ctx, int64_t nb_own_cell)
   return AFB_OK;
 }
 
-int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi)
+int afb_get_own_cell_count(afb_ctx* ctx, int64_t* nb_own_cell)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_mesh && nb_own_cell, AFB_ERR_INVALID, "afb_get_own_cell_count: no mesh / null output");
+  *nb_own_cell = ctx->nb_own_cell;
+  return AFB_OK;
+}
+
+int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi, int ghost_cell_layer)
 {
   AFB_TRY(check_ctx(ctx));
   invalidate_pattern(ctx);
@@ -185,7 +193,7 @@ int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t 
   if (!ctx->coords.owned) ctx->coords.release();
   if (!ctx->conn.owned) ctx->conn.release();
   if (!ctx->is_own.owned) ctx->is_own.release();
-  AFB_TRY(generate_box(ctx, dim, n, jitter, seed, k_lo, k_hi));
+  AFB_TRY(generate_box(ctx, dim, n, jitter, seed, k_lo, k_hi, ghost_cell_layer));
   ctx->mesh_gen++;
   ctx->has_dir_nodes = false;
   AFB_TRY(time_begin(ctx, 0));
@@ -507,6 +515,13 @@ int afb_values_tail(afb_ctx* ctx, int32_t first_block_row, int64_t* first_value,
   if (first_value) *first_value = (int64_t)rb * bb;
   if (nb_values) *nb_values = (ctx->nnz - rb) * bb;
   return AFB_OK;
+}
+
+int afb_renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_global, int32_t* out)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern && dof_local_to_global && out, AFB_ERR_INVALID, "afb_renumber_columns: no pattern / null arrays");
+  return renumber_columns(ctx, dof_local_to_global, out);
 }
 
 int afb_last_timings(afb_ctx* ctx, float* connectivity_ms, float* pattern_ms, float* assemble_ms)

@@ -206,10 +206,11 @@ int ensure_coo_rows(afb_ctx* ctx);
 int ensure_scalar_csr(afb_ctx* ctx);
 int lookup_value_slots(afb_ctx* ctx, int64_t n, const int32_t* dof_rows, const int32_t* dof_cols, int64_t* slots);
 int add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, const double* contrib);
+int renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_global, int32_t* out);
 int scatter_flags(afb_ctx* ctx, uint8_t* flags, double* vals, uint8_t flag, int32_t n, const int32_t* ids, const double* v);
 
 // ---- mesh_gen.cu -----------------------------------------------------------------------------
-int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi);
+int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi, int ghost_cell_layer);
 
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 

@@ -127,6 +127,30 @@ __global__ void k_add_values_at(int64_t n, const int64_t* __restrict__ slots, co
   if (i < n && slots[i] >= 0) values[slots[i]] += contrib[i];
 }
 
+__global__ void k_renumber(int64_t n, const int32_t* __restrict__ cols, const int32_t* __restrict__ l2g, int32_t* __restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int32_t c = cols[i];
+    out[i] = c >= 0 ? __ldg(l2g + c) : c;
+  }
+}
+
+int renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_global, int32_t* out)
+{
+  const int32_t* cols = ctx->cols.as<int32_t>();
+  int64_t n = ctx->nnz;
+  if (ctx->b > 1) {
+    AFB_TRY(ensure_scalar_csr(ctx));
+    cols = ctx->csr_cols.as<int32_t>();
+    n = ctx->nnz * ctx->b * ctx->b;
+  }
+  if (n <= 0) return AFB_OK;
+  k_renumber<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, cols, dof_local_to_global, out);
+  AFB_LAUNCH_CHECK(ctx);
+  return AFB_OK;
+}
+
 int lookup_value_slots(afb_ctx* ctx, int64_t n, const int32_t* dof_rows, const int32_t* dof_cols, int64_t* slots)
 {
   if (n <= 0) return AFB_OK;

@@ -19,16 +19,20 @@ __device__ __forceinline__ double jitter_unit(uint32_t id, uint32_t comp, uint32
 
 struct BoxDesc {
   int dim, n, m;       // m = n+1
-  int k_lo, k_hi;      // cube layers of the last axis
+  int k_lo, k_hi;      // own cube layers of the last axis
+  int k_top;           // node planes k_lo..k_top are local (k_top = k_hi, or k_hi+1 with a ghost cell layer)
   int32_t plane;       // nodes per layer of the last axis: m^(dim-1)
   int32_t nb_own, nb_node;
   double jitter;
   uint32_t seed;
 };
 
-// local id of the node in layer `k` (last axis) with in-layer offset `inl`
+// local id of the node in plane `k` (last axis) with in-plane offset `inl`: owned planes first
+// (ascending), then the bottom ghost plane (owner: lower neighbour), then the top ghost plane
+// (owner: upper neighbour)
 __device__ __forceinline__ int32_t local_node(const BoxDesc& d, int k, int32_t inl)
 {
+  if (k > d.k_hi) return d.nb_own + (d.k_lo > 0 ? d.plane : 0) + inl;
   if (d.k_lo > 0) return (k == d.k_lo) ? d.nb_own + inl : (int32_t)(k - d.k_lo - 1) * d.plane + inl;
   return (int32_t)k * d.plane + inl;
 }
@@ -37,8 +41,6 @@ __global__ void __launch_bounds__(256) k_gen_nodes(BoxDesc d, double* __restrict
 {
   int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= d.nb_node) return;
-  const int layers = d.k_hi - d.k_lo + 1;
-  (void)layers;
   int k = d.k_lo + t / d.plane;
   int32_t inl = t % d.plane;
   int i = inl % d.m, j = (d.dim == 3) ? inl / d.m : k;
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(256) k_gen_nodes(BoxDesc d, double* __restrict
   xyz[3 * (int64_t)lid] = c[0];
   xyz[3 * (int64_t)lid + 1] = c[1];
   xyz[3 * (int64_t)lid + 2] = c[2];
-  if (is_own) is_own[lid] = (d.k_lo > 0 && k == d.k_lo) ? 0 : 1;
+  if (is_own) is_own[lid] = ((d.k_lo > 0 && k == d.k_lo) || k > d.k_hi) ? 0 : 1;
 }
 
 // 3-D: one thread per cube -> 6 Kuhn tets {v0, v0+e_p1, v0+e_p1+e_p2, v0+e_p1+e_p2+e_p3}
@@ -93,21 +95,24 @@ __global__ void __launch_bounds__(256) k_gen_tris(BoxDesc d, int64_t nb_sq, int3
   o[3] = v00; o[4] = v11; o[5] = v01;
 }
 
-int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi)
+int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi, int ghost_cell_layer)
 {
   AFB_REQUIRE(dim == 2 || dim == 3, AFB_ERR_INVALID, "box dimension must be 2 or 3");
   AFB_REQUIRE(n >= 1 && k_lo >= 0 && k_hi <= n && k_lo < k_hi, AFB_ERR_INVALID, "bad box slab n=%d layers [%d,%d)", n, k_lo, k_hi);
+  const bool ghost = ghost_cell_layer && k_hi < n;
   BoxDesc d;
-  d.dim = dim; d.n = n; d.m = n + 1; d.k_lo = k_lo; d.k_hi = k_hi;
+  d.dim = dim; d.n = n; d.m = n + 1; d.k_lo = k_lo; d.k_hi = k_hi; d.k_top = ghost ? k_hi + 1 : k_hi;
   d.jitter = jitter; d.seed = seed;
   int64_t plane = dim == 3 ? (int64_t)d.m * d.m : d.m;
-  int64_t nb_node = plane * (k_hi - k_lo + 1);
-  int64_t nb_cube = (dim == 3 ? (int64_t)n * n : n) * (int64_t)(k_hi - k_lo);
+  int64_t nb_node = plane * (d.k_top - k_lo + 1);
+  // the ghost layer's cubes directly follow the own ones: same kernel, cube layers [k_lo, k_hi + ghost)
+  int64_t nb_cube_own = (dim == 3 ? (int64_t)n * n : n) * (int64_t)(k_hi - k_lo);
+  int64_t nb_cube = (dim == 3 ? (int64_t)n * n : n) * (int64_t)(k_hi - k_lo + (ghost ? 1 : 0));
   int64_t nb_cell = nb_cube * (dim == 3 ? 6 : 2);
   AFB_REQUIRE(nb_node < 2147483647LL && (int64_t)(dim + 1) * nb_cell < 2147483647LL, AFB_ERR_OVERFLOW, "box too large for Int32 ids");
   d.plane = (int32_t)plane;
   d.nb_node = (int32_t)nb_node;
-  d.nb_own = (int32_t)(k_lo > 0 ? nb_node - plane : nb_node);
+  d.nb_own = (int32_t)(nb_node - (k_lo > 0 ? plane : 0) - (ghost ? plane : 0));
   const int npc = dim + 1;
   AFB_TRY(ctx->coords.reserve(sizeof(double) * 3 * (size_t)nb_node));
   AFB_TRY(ctx->conn.reserve(sizeof(int32_t) * (size_t)npc * (size_t)nb_cell));
@@ -122,8 +127,8 @@ int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int
   ctx->nb_node = (int32_t)nb_node;
   ctx->nb_own_node = d.nb_own;
   ctx->nb_cell = nb_cell;
-  ctx->nb_own_cell = nb_cell;
-  ctx->all_own = (k_lo == 0);
+  ctx->nb_own_cell = nb_cube_own * (dim == 3 ? 6 : 2);
+  ctx->all_own = (k_lo == 0 && !ghost);
   ctx->has_mesh = true;
   return AFB_OK;
 }

@@ -87,12 +87,16 @@ k_pattern_tiled(const TileDesc* __restrict__ desc, const int32_t* __restrict__ t
     uint32_t* s_cols = s_foot + d.nb_foot;                  // [nb_entry]
     int32_t* s_erow = reinterpret_cast<int32_t*>(s_cols + d.nb_entry); // [RP + 1]
     int32_t* s_shift = s_erow + RP + 1;                     // [RP]: rows[node] - erow
-    uint16_t* s_etab = reinterpret_cast<uint16_t*>(s_shift + RP); // [nb_entry / 8 + 1]
+    uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_shift + RP);    // [W][RP]: set bits of the row in the words before w
+    uint16_t* s_etab = s_pre + W * RP;                      // [nb_entry / 8 + 1]
     __shared__ int s_wsum[TG_RMAX / 32];
     int deg = 0;
-    if (i < R) {
+    if (i < RP) {
       const uint32_t* my = bm + i;
-      for (int w = 0; w < W; ++w) deg += __popc(my[w * RP]);
+      for (int w = 0; w < W; ++w) {
+        s_pre[w * RP + i] = (uint16_t)deg;
+        deg += __popc(my[w * RP]);
+      }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int inc_ = deg;
@@ -111,17 +115,20 @@ k_pattern_tiled(const TileDesc* __restrict__ desc, const int32_t* __restrict__ t
       s_shift[i] = __ldg(rows + node) - e0;
       nz_per_row[node] = deg;
       for (int q = (e0 + 7) >> 3; (q << 3) < e0 + deg; ++q) s_etab[q] = (uint16_t)i;
-      const uint32_t* my = bm + i;
-      int k = e0;
-      for (int w = 0; w < W; ++w) {
-        uint32_t bits = my[w * RP];
-        while (bits) {
-          const int b = __ffs(bits) - 1;
-          bits &= bits - 1;
-          s_cols[k++] = s_foot[w * 32 + b];
-        }
-      }
       if (i == R - 1) s_erow[R] = e0 + deg;
+    }
+    __syncthreads();
+    // one thread per bitmap word: balanced extraction, columns land in row order
+    for (int idx = threadIdx.x; idx < W * RP; idx += blockDim.x) {
+      uint32_t bits = bm[idx];
+      if (!bits) continue;
+      const int w = idx / RP, r = idx - w * RP;
+      int k = s_erow[r] + s_pre[idx];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        s_cols[k++] = s_foot[w * 32 + b];
+      }
     }
     __syncthreads();
     const int E = s_erow[R];
@@ -146,7 +153,9 @@ static int launch_pattern_tiled(afb_ctx* ctx, bool write, int32_t* deg)
   const int threads = std::max(32, (P.max_rows + 31) & ~31);
   // bitmap [W][RP] + footprint ids (+ staged columns, row offsets, entry->row table): bounded by the tile limits
   const size_t smem = sizeof(uint32_t) * ((size_t)((TG_FMAX + 31) / 32) * (size_t)threads + TG_FMAX) +
-                      (write ? sizeof(uint32_t) * ((size_t)TG_EMAX + 2 * (size_t)threads + 2) + sizeof(uint16_t) * (TG_EMAX / 8 + 2) : 0);
+                      (write ? sizeof(uint32_t) * ((size_t)TG_EMAX + 2 * (size_t)threads + 2) +
+                                   sizeof(uint16_t) * ((size_t)((TG_FMAX + 31) / 32) * (size_t)threads + TG_EMAX / 8 + 2)
+                             : 0);
   if (!write) {
     AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_pattern_tiled<false><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(), P.inc.as<uint32_t>(),

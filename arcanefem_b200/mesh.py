@@ -271,3 +271,112 @@ def box_counts(dim: int, n: int):
     nb_node = (n + 1) ** 2
     nb_edge = 2 * n * (n + 1) + n * n
     return 2 * n * n, nb_node, nb_edge, nb_node + 2 * nb_edge
+
+
+# ---------------------------------------------------------------------------
+# Domain decomposition.  The reference gets its sub-domains from
+# Arcane's partitioner at mesh-read time: every rank holds its own cells plus one
+# layer of ghost cells, each node has exactly one owner, and only rows of owned
+# nodes are assembled (modules/testlab/CsrGpuBiliAssembly.cc:273,351).  These
+# helpers produce sub-domains with the same semantics as plain arrays.
+# ---------------------------------------------------------------------------
+@dataclass
+class Subdomain:
+    rank: int
+    world: int
+    dim: int
+    coords: np.ndarray            # float64 [nb_node,3]   local nodes: owned first, then ghosts ordered by (owner, global id)
+    cells: np.ndarray             # int32 [nb_cell,npc]   own cells first, then ghost cells (local node ids)
+    nb_own_cell: int
+    nb_own_node: int
+    is_own: np.ndarray            # uint8 [nb_node]
+    node_gid: np.ndarray          # int64 [nb_node]  global node id
+    node_owner: np.ndarray        # int32 [nb_node]  owning rank
+    cell_gid: np.ndarray          # int64 [nb_cell]
+
+    @property
+    def nb_node(self):
+        return int(self.coords.shape[0])
+
+    @property
+    def nb_cell(self):
+        return int(self.cells.shape[0])
+
+    @property
+    def npc(self):
+        return int(self.cells.shape[1])
+
+
+def slab_layers(n: int, world: int, rank: int):
+    """cube layers [k_lo,k_hi) of rank's slab along the last axis (balanced)."""
+    base, rem = divmod(n, world)
+    k_lo = rank * base + min(rank, rem)
+    return k_lo, k_lo + base + (1 if rank < rem else 0)
+
+
+def box_slab_numbering(dim: int, n: int, k_lo: int, k_hi: int, ghost_cell_layer: bool):
+    """Global node ids / owners (relative: -1 lower neighbour, 0 self, +1 upper neighbour) of the local
+    nodes of `afb_mesh_generate_box(dim, n, ..., k_lo, k_hi, ghost_cell_layer)`, in local order."""
+    m = n + 1
+    plane = m * m if dim == 3 else m
+    ghost = bool(ghost_cell_layer) and k_hi < n
+    own_planes = list(range(k_lo + 1 if k_lo > 0 else 0, k_hi + 1))
+    planes = own_planes + ([k_lo] if k_lo > 0 else []) + ([k_hi + 1] if ghost else [])
+    rel = [0] * len(own_planes) + ([-1] if k_lo > 0 else []) + ([1] if ghost else [])
+    inl = np.arange(plane, dtype=np.int64)
+    gid = np.concatenate([k * plane + inl for k in planes])
+    owner_rel = np.concatenate([np.full(plane, r, dtype=np.int32) for r in rel])
+    nb_own = len(own_planes) * plane
+    cubes_per_layer = n * n if dim == 3 else n
+    cells_per_cube = 6 if dim == 3 else 2
+    nb_own_cell = (k_hi - k_lo) * cubes_per_layer * cells_per_cube
+    nb_cell = nb_own_cell + (cubes_per_layer * cells_per_cube if ghost else 0)
+    cell_gid = k_lo * cubes_per_layer * cells_per_cube + np.arange(nb_cell, dtype=np.int64)
+    return gid, owner_rel, nb_own, nb_own_cell, cell_gid
+
+
+def box_slab(dim: int, n: int, world: int, rank: int, ghost_cell_layer: bool = True, jitter: float = 0.2, seed: int = 12345) -> Subdomain:
+    """Host mirror of the device slab generator (bit-identical arrays): rank's z-slab of the box."""
+    full = box_mesh(dim, n, jitter, seed)
+    k_lo, k_hi = slab_layers(n, world, rank)
+    gid, owner_rel, nb_own, nb_own_cell, cell_gid = box_slab_numbering(dim, n, k_lo, k_hi, ghost_cell_layer)
+    g2l = np.full(full.nb_node, -1, dtype=np.int64)
+    g2l[gid] = np.arange(gid.size)
+    cells = g2l[full.cells[cell_gid]].astype(np.int32)
+    assert (cells >= 0).all()
+    return Subdomain(rank=rank, world=world, dim=dim, coords=np.ascontiguousarray(full.coords[gid]), cells=np.ascontiguousarray(cells), nb_own_cell=int(nb_own_cell),
+                     nb_own_node=int(nb_own), is_own=(owner_rel == 0).astype(np.uint8), node_gid=gid, node_owner=(rank + owner_rel).astype(np.int32), cell_gid=cell_gid)
+
+
+def partition_mesh(mesh: Mesh, world: int, axis: int | None = None) -> list:
+    """Generic slab-like partition of any mesh into `world` sub-domains: cells are sorted by centroid along
+    `axis` (default: the last one) and cut in equal parts; a node belongs to the lowest rank among its
+    cells; every rank also gets the ghost cells touching its owned nodes (one ghost layer)."""
+    axis = mesh.dim - 1 if axis is None else axis
+    cent = mesh.coords[mesh.cells][:, :, axis].mean(axis=1)
+    order = np.argsort(cent, kind="stable")
+    cell_rank = np.empty(mesh.nb_cell, dtype=np.int32)
+    bounds = [(mesh.nb_cell * r) // world for r in range(world + 1)]
+    for r in range(world):
+        cell_rank[order[bounds[r]:bounds[r + 1]]] = r
+    node_owner = np.full(mesh.nb_node, world, dtype=np.int32)
+    np.minimum.at(node_owner, mesh.cells.ravel(), np.repeat(cell_rank, mesh.npc))
+    node_owner[node_owner == world] = 0  # isolated nodes
+    subs = []
+    for r in range(world):
+        own_cells = np.nonzero(cell_rank == r)[0]
+        touches_owned = (node_owner[mesh.cells] == r).any(axis=1)
+        ghost_cells = np.nonzero(touches_owned & (cell_rank != r))[0]
+        cell_gid = np.concatenate([own_cells, ghost_cells]).astype(np.int64)
+        used = np.unique(mesh.cells[cell_gid].ravel()) if cell_gid.size else np.empty(0, dtype=np.int64)
+        owned = np.nonzero(node_owner == r)[0]
+        ghosts = np.setdiff1d(used, owned)
+        ghosts = ghosts[np.lexsort((ghosts, node_owner[ghosts]))]
+        gid = np.concatenate([owned, ghosts]).astype(np.int64)
+        g2l = np.full(mesh.nb_node, -1, dtype=np.int64)
+        g2l[gid] = np.arange(gid.size)
+        cells = g2l[mesh.cells[cell_gid]].astype(np.int32).reshape(-1, mesh.npc)
+        subs.append(Subdomain(rank=r, world=world, dim=mesh.dim, coords=np.ascontiguousarray(mesh.coords[gid]), cells=np.ascontiguousarray(cells),
+                              nb_own_cell=int(own_cells.size), nb_own_node=int(owned.size), is_own=(node_owner[gid] == r).astype(np.uint8),
+                              node_gid=gid, node_owner=node_owner[gid].astype(np.int32), cell_gid=cell_gid))
+    return subs

@@ -145,16 +145,23 @@ AFB_API int afb_set_mesh(afb_ctx* ctx, int dim, int nodes_per_cell, int32_t nb_n
 /* Cells [0, nb_own_cell) belong to this sub-domain, cells [nb_own_cell, nb_cell) are ghost cells
  * (Arcane's one-layer ghost cells; Cell::isOwn()).  Default after afb_set_mesh: all cells own. */
 AFB_API int afb_set_own_cell_count(afb_ctx* ctx, int64_t nb_own_cell);
+AFB_API int afb_get_own_cell_count(afb_ctx* ctx, int64_t* nb_own_cell);
 
 /*
  * Synthetic structured box of SURVEY.md §8(d), generated on the device (bench + tests):
  * [0,1]^dim, n^dim cubes, Kuhn 6-tet / 2-triangle split, node id = i+(n+1)(j+(n+1)k),
  * deterministic interior jitter (bit-identical to arcanefem_b200/mesh.py::box_mesh).
- * Cube layers [k_lo,k_hi) of the last axis only (domain-decomposition slab); local node
- * numbering is owned-first: when k_lo > 0 the bottom node layer is a ghost layer owned by
- * the lower neighbour and numbered last (node_is_own = 0).  k_lo=0,k_hi=n = whole box.
+ * Domain-decomposition slab = cube layers [k_lo,k_hi) of the last axis (k_lo=0,k_hi=n = whole box).
+ * Node ownership follows the reference's rule "one owner per node": the planes k_lo+1..k_hi are
+ * owned (plane 0 too when k_lo = 0); plane k_lo > 0 belongs to the lower neighbour.  Local node
+ * numbering is owned-first: owned planes ascending, then the bottom ghost plane, then -- with
+ * ghost_cell_layer != 0 and k_hi < n -- the top ghost plane k_hi+1, whose cube layer k_hi is appended
+ * after the own cells as Arcane's one-layer ghost cells (afb_get_mesh reports nb_own_node; the own
+ * cell count is set as by afb_set_own_cell_count).  With the ghost layer every owned row sees all its
+ * cells (reference scheme, no exchange); without it -- or with AFB_FLAG_OWN_CELLS_ONLY -- the rows of
+ * the interface planes hold partial sums to be exchanged.
  */
-AFB_API int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi);
+AFB_API int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi, int ghost_cell_layer);
 
 /* ---- sparsity --------------------------------------------------------------------------- */
 
@@ -273,6 +280,14 @@ AFB_API int afb_add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, con
  * there to the end: the ghost rows' partial sums are one contiguous tail of `values`
  * when ghosts are numbered last (zero-copy NCCL send buffer). */
 AFB_API int afb_values_tail(afb_ctx* ctx, int32_t first_block_row, int64_t* first_value, int64_t* nb_values);
+
+/*
+ * Columns of the scalar CSR view in the solver's global numbering: out[j] = dof_local_to_global[col[j]]
+ * (device arrays; dof_local_to_global has nb_row entries, out has nnz entries of the CSR view).
+ * Replaces the host loop of HypreDoFLinearSystemImpl::solve that renumbers the columns through
+ * m_dof_matrix_numbering when running in parallel (femutils/HypreDoFLinearSystem.cc:390-406).
+ */
+AFB_API int afb_renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_global, int32_t* out);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 
