@@ -360,6 +360,51 @@ int afb_apply_rhs_transformation(afb_ctx* ctx)
   return apply_rhs_transformation(ctx);
 }
 
+static int single_slot(afb_ctx* ctx, int32_t dof_row, int32_t dof_col, int64_t* slot)
+{
+  const int32_t nb_dof = ctx->nb_node * ctx->b;
+  AFB_REQUIRE(dof_row >= 0 && dof_row < nb_dof && dof_col >= 0 && dof_col < nb_dof, AFB_ERR_INVALID, "DoF (%d,%d) out of range [0,%d)", dof_row, dof_col, nb_dof);
+  AFB_TRY(ensure_values_zeroed(ctx));
+  AFB_TRY(ctx->tmp_ids.reserve(2 * sizeof(int32_t) + sizeof(int64_t) + 8));
+  int32_t rc[2] = { dof_row, dof_col };
+  char* base = ctx->tmp_ids.as<char>();
+  int64_t* dslot = reinterpret_cast<int64_t*>(base + 8);
+  AFB_CUDA(cudaMemcpyAsync(base, rc, sizeof(rc), cudaMemcpyHostToDevice, ctx->stream));
+  AFB_TRY(lookup_value_slots(ctx, 1, reinterpret_cast<int32_t*>(base), reinterpret_cast<int32_t*>(base) + 1, dslot));
+  AFB_CUDA(cudaMemcpyAsync(slot, dslot, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  AFB_REQUIRE(*slot >= 0, AFB_ERR_INVALID, "entry (%d,%d) is not in the sparsity pattern", dof_row, dof_col);
+  return AFB_OK;
+}
+
+int afb_matrix_get_value(afb_ctx* ctx, int32_t dof_row, int32_t dof_col, double* value)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern && value, AFB_ERR_INVALID, "afb_matrix_get_value: no pattern / null output");
+  int64_t slot = -1;
+  AFB_TRY(single_slot(ctx, dof_row, dof_col, &slot));
+  AFB_CUDA(cudaMemcpyAsync(value, ctx->values.as<double>() + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AFB_OK;
+}
+
+int afb_matrix_set_value(afb_ctx* ctx, int32_t dof_row, int32_t dof_col, double value, int mode)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_matrix_set_value: no pattern");
+  int64_t slot = -1;
+  AFB_TRY(single_slot(ctx, dof_row, dof_col, &slot));
+  if (mode == 1) {
+    double old = 0.0;
+    AFB_CUDA(cudaMemcpyAsync(&old, ctx->values.as<double>() + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    value += old;
+  }
+  AFB_CUDA(cudaMemcpyAsync(ctx->values.as<double>() + slot, &value, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AFB_OK;
+}
+
 int afb_get_csr_view(afb_ctx* ctx, const int32_t** rows, const int32_t** rows_nb_column, const int32_t** columns, double** values, int32_t* nb_row, int64_t* nnz)
 {
   AFB_TRY(check_ctx(ctx));

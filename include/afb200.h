@@ -238,6 +238,16 @@ AFB_API int afb_apply_matrix_transformation(afb_ctx* ctx, int replicate_column0_
  * RC-eliminated rows (DoFLinearSystemImplBase.cc:55-88), then rhs[row] = g_row. */
 AFB_API int afb_apply_rhs_transformation(afb_ctx* ctx);
 
+/*
+ * Single-entry host access of the reference containers (UVM dereference in the reference):
+ * BSRMatrix::getValue / setValue / addValue (femutils/BSRFormat.h:89-104, index by
+ * BSRMatrix::findValueIndex femutils/BSRFormat.cc:79-106) and CsrFormat::matrixSetValue /
+ * matrixAddValue (femutils/CsrFormatMatrix.h:58-70,107-110).  Scalar DoF ids; synchronous.
+ * mode: 0 = set, 1 = add.  AFB_ERR_INVALID when (dof_row, dof_col) is not in the pattern.
+ */
+AFB_API int afb_matrix_get_value(afb_ctx* ctx, int32_t dof_row, int32_t dof_col, double* value);
+AFB_API int afb_matrix_set_value(afb_ctx* ctx, int32_t dof_row, int32_t dof_col, double value, int mode);
+
 /* ---- views out (device pointers) ---------------------------------------------------------- */
 
 /*
