@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libafb200.so")
+LIB_PATH = os.environ.get("AFB200_LIB") or os.path.join(_HERE, "libafb200.so")  # AFB200_LIB: tuning builds (scratch/build_variants.sh)
 
 # enums of afb200.h
 OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN = 0, 1, 2

@@ -86,7 +86,7 @@ struct TilePlan {
   int mesh_b_class = 0;        // 0: scalar limits (TG_CMAX), 1: vector limits (TV_CMAX)
   int32_t nb_tile = 0;
   int max_rows = 0;
-  int64_t nb_tile_cell = 0, nb_foot = 0, nb_inc = 0;
+  int64_t nb_tile_cell = 0, nb_foot = 0, nb_inc = 0, nb_entry = 0;
   float mesh_ms = 0.f, lists_ms = 0.f;
   DevBuf tile_desc;   // TileDesc[nb_tile]
   DevBuf tile_nodes;  // int32: rows (node ids, ascending) of each tile, concatenated
@@ -109,6 +109,7 @@ struct TilePlan {
   DevBuf unit_len;    // uint16 per unit: contributions per entry of the unit (even)
   DevBuf emap;        // uint32 per (unit, lane): tile-local entry | mirror entry << 16; 0xFFFFFFFF = padding lane
   DevBuf lists;       // uint16: cache indices, per unit [len/2][32 lanes][2]; one contiguous region per tile (TMA bulk copy)
+  DevBuf col_scratch; // int32[nb_entry]: columns in tile order between the two BuildMatrix passes (pattern_tiled.cu)
   DevBuf scratch_a, scratch_b, scratch_c, stats; // builder scratch
 };
 
@@ -193,8 +194,8 @@ int build_tile_mesh(afb_ctx* ctx);
 int build_tile_lists(afb_ctx* ctx, int mode_flags);
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags);
 bool pattern_tiled_ready(const afb_ctx* ctx);
-int pattern_tiled_count(afb_ctx* ctx, int32_t* deg);
-int pattern_tiled_write(afb_ctx* ctx);
+int pattern_tiled_extract(afb_ctx* ctx, int32_t* deg, int* stale);
+int pattern_tiled_place(afb_ctx* ctx);
 int ensure_values_zeroed(afb_ctx* ctx);
 
 // ---- linear.cu (rhs, dirichlet, views) -------------------------------------------------------

@@ -381,15 +381,18 @@ int build_pattern(afb_ctx* ctx)
     // AssembleBilinearOperator): per-tile bitmap kernel, degree -> scan -> columns
     AFB_TRY(ctx->tmp_i32b.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
     int32_t* deg = ctx->tmp_i32b.as<int32_t>();
-    AFB_TRY(pattern_tiled_count(ctx, deg));
+    int stale = 0;
+    AFB_TRY(pattern_tiled_extract(ctx, deg, &stale));
     AFB_TRY(exclusive_scan_i32(ctx, deg, ctx->rows.as<int32_t>(), nb_node));
     int32_t nnz32 = 0;
     AFB_CUDA(cudaMemcpyAsync(&nnz32, ctx->rows.as<int32_t>() + nb_node, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AFB_CUDA(cudaMemcpyAsync(&stale, ctx->tmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    AFB_REQUIRE(stale == 0, AFB_ERR_CUDA, "tiled BuildMatrix: a tile produced more entries than its scratch capacity (stale tiling)");
     AFB_REQUIRE(nnz32 >= 0, AFB_ERR_OVERFLOW, "block nnz exceeds Int32");
     ctx->nnz = nnz32;
     AFB_TRY(ctx->cols.reserve(sizeof(int32_t) * (size_t)ctx->nnz));
-    AFB_TRY(pattern_tiled_write(ctx));
+    AFB_TRY(pattern_tiled_place(ctx));
     done = true;
   }
   if (!done && fast && ctx->pattern_mesh_gen == ctx->mesh_gen && ctx->cols.p) {

@@ -11,23 +11,43 @@
 // indices.  One CTA per tile, one thread per row: the thread ORs its neighbours into a private
 // bitmap over the footprint (shared memory, layout [word][row]: conflict-free), so duplicates vanish
 // without hashing or sorting, the degree is a popcount, and walking the set bits emits the columns
-// already in ascending order.  Two passes (degree -> scan -> columns), streaming 4 bytes per
-// (row, incident cell) each; no atomics, no global sort, deterministic.
+// already in ascending order.  Pass 1 writes the degrees and parks the tile's columns in a tile-ordered
+// scratch (coalesced); after the scan of the degrees pass 2 moves them to their rows (contiguous runs).
+// 4 bytes per (row, incident cell) are streamed once; no atomics, no global sort, deterministic.
 #include <algorithm>
 
 #include "tiles.cuh"
 
 namespace afb {
 
-constexpr int PT_UNROLL = 4;
+constexpr int PT_UNROLL = 8;
 
-template <bool WRITE>
+// block exclusive scan of one int per thread (blockDim <= TG_RMAX); s_wsum: one int per warp
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_wsum)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+  return woff + inc - v;
+}
+
+// pass 1: bitmaps -> degrees (to `deg_out`, node order) and the tile's columns, row by row, into the
+// tile-ordered scratch (coalesced).  `stale` is raised when a tile holds more entries than its slot.
 __global__ void __launch_bounds__(TG_RMAX)
-k_pattern_tiled(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const uint16_t* __restrict__ rowf, const uint32_t* __restrict__ inc,
-                const uint2* __restrict__ inc_grp, const int32_t* __restrict__ foot, int32_t* __restrict__ deg_out, const int32_t* __restrict__ rows,
-                int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row)
+k_pattern_tiled_extract(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const uint16_t* __restrict__ rowf, const uint32_t* __restrict__ inc,
+                        const uint2* __restrict__ inc_grp, const int32_t* __restrict__ foot, int32_t* __restrict__ deg_out, int32_t* __restrict__ scratch,
+                        int* __restrict__ stale)
 {
   extern __shared__ uint32_t pt_smem[];
+  __shared__ int s_wsum[TG_RMAX / 32];
   const int32_t t = blockIdx.x;
   const TileDesc d = desc[t];
   const int R = d.nb_row;
@@ -35,11 +55,12 @@ k_pattern_tiled(const TileDesc* __restrict__ desc, const int32_t* __restrict__ t
   const int RP = (R + 31) & ~31;             // bitmap row stride
   const int W = (d.nb_foot + 31) >> 5;       // bitmap words per row
   uint32_t* bm = pt_smem;                    // [W][RP]
-  uint32_t* s_foot = pt_smem + W * RP;       // [nb_foot] (WRITE)
+  uint32_t* s_foot = bm + W * RP;            // [nb_foot]
+  uint32_t* s_cols = s_foot + d.nb_foot;     // [nb_entry]
+  int32_t* s_erow = reinterpret_cast<int32_t*>(s_cols + d.nb_entry);  // [RP + 1]
+  uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_erow + RP + 1);     // [W][RP]: set bits of the row in the words before w
   const int i = threadIdx.x;
-  if constexpr (WRITE) {
-    for (int f = threadIdx.x; f < d.nb_foot; f += blockDim.x) s_foot[f] = (uint32_t)__ldg(foot + d.foot_off + f);
-  }
+  for (int f = threadIdx.x; f < d.nb_foot; f += blockDim.x) s_foot[f] = (uint32_t)__ldg(foot + d.foot_off + f);
   if (i < RP) {
     for (int w = 0; w < W; ++w) bm[w * RP + i] = 0u;
   }
@@ -73,69 +94,92 @@ k_pattern_tiled(const TileDesc* __restrict__ desc, const int32_t* __restrict__ t
       my[(f2 >> 5) * RP] |= 1u << (f2 & 31);
     }
   }
-  if constexpr (!WRITE) {
-    if (i < R) {
-      const uint32_t* my = bm + i;
-      int deg = 0;
-      for (int w = 0; w < W; ++w) deg += __popc(my[w * RP]);
-      deg_out[node] = deg;
+  int deg = 0;
+  if (i < RP) {
+    const uint32_t* my = bm + i;
+    for (int w = 0; w < W; ++w) {
+      s_pre[w * RP + i] = (uint16_t)deg;
+      deg += __popc(my[w * RP]);
     }
   }
-  else {
-    // columns are staged in shared memory in row order (tile-local offsets from a block scan of the
-    // degrees) and leave as contiguous runs: rows with consecutive node ids are adjacent in `cols`
-    uint32_t* s_cols = s_foot + d.nb_foot;                  // [nb_entry]
-    int32_t* s_erow = reinterpret_cast<int32_t*>(s_cols + d.nb_entry); // [RP + 1]
-    int32_t* s_shift = s_erow + RP + 1;                     // [RP]: rows[node] - erow
-    uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_shift + RP);    // [W][RP]: set bits of the row in the words before w
-    uint16_t* s_etab = s_pre + W * RP;                      // [nb_entry / 8 + 1]
-    __shared__ int s_wsum[TG_RMAX / 32];
-    int deg = 0;
-    if (i < RP) {
-      const uint32_t* my = bm + i;
-      for (int w = 0; w < W; ++w) {
-        s_pre[w * RP + i] = (uint16_t)deg;
-        deg += __popc(my[w * RP]);
-      }
+  const int e0 = block_exclusive_scan(deg, s_wsum); // barrier inside: s_foot complete
+  if (i < R) {
+    deg_out[node] = deg;
+    s_erow[i] = e0;
+    if (i == R - 1) s_erow[R] = e0 + deg;
+  }
+  __syncthreads();
+  const int E = s_erow[R];
+  if (E > d.nb_entry) { // the tiling was built for another pattern: never write past the tile's slot
+    if (threadIdx.x == 0) atomicExch(stale, 1);
+    return;
+  }
+  // one thread per bitmap word: balanced extraction, columns land in row order
+  for (int idx = threadIdx.x; idx < W * RP; idx += blockDim.x) {
+    uint32_t bits = bm[idx];
+    if (!bits) continue;
+    const int w = idx / RP, r = idx - w * RP;
+    int k = s_erow[r] + s_pre[idx];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      s_cols[k++] = s_foot[w * 32 + b];
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc_ = deg;
+  }
+  __syncthreads();
+  int32_t* out = scratch + d.ent_off;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) out[e] = (int32_t)s_cols[e];
+}
+
+// pass 2 (after the scan of the degrees): the tile's columns move from the scratch to their rows;
+// rows with consecutive node ids are adjacent in `cols`, so the stores are contiguous runs
+__global__ void __launch_bounds__(TG_RMAX)
+k_pattern_tiled_place(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ rows, const int32_t* __restrict__ scratch,
+                      int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row)
+{
+  __shared__ int s_wsum[TG_RMAX / 32];
+  __shared__ int32_t s_erow[TG_RMAX + 1];
+  __shared__ int32_t s_shift[TG_RMAX];
+  __shared__ uint16_t s_etab[TG_EMAX / 8 + 1];
+  const int32_t t = blockIdx.x;
+  const TileDesc d = desc[t];
+  const int R = d.nb_row;
+  if (R == 0) return;
+  const int i = threadIdx.x;
+  int deg = 0, rb = 0;
+  int32_t node = -1;
+  if (i < R) {
+    node = __ldg(tile_nodes + d.node_off + i);
+    rb = __ldg(rows + node);
+    deg = __ldg(rows + node + 1) - rb;
+  }
+  const int e0 = block_exclusive_scan(deg, s_wsum);
+  if (i < R) {
+    s_erow[i] = e0;
+    s_shift[i] = rb - e0;
+    nz_per_row[node] = deg;
+    for (int q = (e0 + 7) >> 3; (q << 3) < e0 + deg; ++q) s_etab[q] = (uint16_t)i;
+    if (i == R - 1) s_erow[R] = e0 + deg;
+  }
+  __syncthreads();
+  const int E = min(s_erow[R], d.nb_entry);
+  const int32_t* src = scratch + d.ent_off;
+  // four independent loads in flight per thread
+  for (int e = threadIdx.x; e < E; e += 4 * blockDim.x) {
+    int32_t c[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, inc_, o);
-      if (lane >= o) inc_ += v;
+    for (int q = 0; q < 4; ++q) {
+      const int eq = e + q * blockDim.x;
+      c[q] = eq < E ? __ldg(src + eq) : 0;
     }
-    if (lane == 31) s_wsum[warp] = inc_;
-    __syncthreads(); // also: s_foot complete
-    int woff = 0;
-    for (int w = 0; w < warp; ++w) woff += s_wsum[w];
-    const int e0 = woff + inc_ - deg;
-    if (i < R) {
-      s_erow[i] = e0;
-      s_shift[i] = __ldg(rows + node) - e0;
-      nz_per_row[node] = deg;
-      for (int q = (e0 + 7) >> 3; (q << 3) < e0 + deg; ++q) s_etab[q] = (uint16_t)i;
-      if (i == R - 1) s_erow[R] = e0 + deg;
-    }
-    __syncthreads();
-    // one thread per bitmap word: balanced extraction, columns land in row order
-    for (int idx = threadIdx.x; idx < W * RP; idx += blockDim.x) {
-      uint32_t bits = bm[idx];
-      if (!bits) continue;
-      const int w = idx / RP, r = idx - w * RP;
-      int k = s_erow[r] + s_pre[idx];
-      while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        s_cols[k++] = s_foot[w * 32 + b];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int eq = e + q * blockDim.x;
+      if (eq < E) {
+        int r = s_etab[eq >> 3];
+        while (eq >= s_erow[r + 1]) ++r;
+        cols[s_shift[r] + eq] = c[q];
       }
-    }
-    __syncthreads();
-    const int E = s_erow[R];
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-      int r = s_etab[e >> 3];
-      while (e >= s_erow[r + 1]) ++r;
-      cols[s_shift[r] + e] = (int32_t)s_cols[e];
     }
   }
 }
@@ -146,32 +190,35 @@ bool pattern_tiled_ready(const afb_ctx* ctx)
   return P.mesh_valid && P.mesh_gen == ctx->mesh_gen && (ctx->npc == 3 || ctx->npc == 4);
 }
 
-static int launch_pattern_tiled(afb_ctx* ctx, bool write, int32_t* deg)
+static int pattern_threads(const TilePlan& P) { return std::max(32, (P.max_rows + 31) & ~31); }
+
+int pattern_tiled_extract(afb_ctx* ctx, int32_t* deg, int* stale)
 {
-  const TilePlan& P = ctx->plan;
+  (void)stale;
+  TilePlan& P = ctx->plan;
+  AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
+  AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), ctx->stream));
   if (P.nb_tile == 0) return AFB_OK;
-  const int threads = std::max(32, (P.max_rows + 31) & ~31);
-  // bitmap [W][RP] + footprint ids (+ staged columns, row offsets, entry->row table): bounded by the tile limits
-  const size_t smem = sizeof(uint32_t) * ((size_t)((TG_FMAX + 31) / 32) * (size_t)threads + TG_FMAX) +
-                      (write ? sizeof(uint32_t) * ((size_t)TG_EMAX + 2 * (size_t)threads + 2) +
-                                   sizeof(uint16_t) * ((size_t)((TG_FMAX + 31) / 32) * (size_t)threads + TG_EMAX / 8 + 2)
-                             : 0);
-  if (!write) {
-    AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pattern_tiled<false><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(), P.inc.as<uint32_t>(),
-                                                                      P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), deg, nullptr, nullptr, nullptr);
-  }
-  else {
-    AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pattern_tiled<true><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(), P.inc.as<uint32_t>(),
-                                                                     P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), nullptr, ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(),
-                                                                     ctx->nz_per_row.as<int32_t>());
-  }
+  AFB_TRY(P.col_scratch.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(P.nb_entry, 1)));
+  const int threads = pattern_threads(P);
+  constexpr size_t WMAX = (TG_FMAX + 31) / 32;
+  // bitmap [W][RP] + footprint ids + staged columns + row offsets + per-word prefix counts: bounded by the tile limits
+  const size_t smem = sizeof(uint32_t) * (WMAX * (size_t)threads + TG_FMAX + TG_EMAX + (size_t)threads + 1) + sizeof(uint16_t) * WMAX * (size_t)threads;
+  AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pattern_tiled_extract<<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(), P.inc.as<uint32_t>(),
+                                                                      P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), deg, P.col_scratch.as<int32_t>(), ctx->tmp_flag.as<int>());
   AFB_LAUNCH_CHECK(ctx);
   return AFB_OK;
 }
 
-int pattern_tiled_count(afb_ctx* ctx, int32_t* deg) { return launch_pattern_tiled(ctx, false, deg); }
-int pattern_tiled_write(afb_ctx* ctx) { return launch_pattern_tiled(ctx, true, nullptr); }
+int pattern_tiled_place(afb_ctx* ctx)
+{
+  const TilePlan& P = ctx->plan;
+  if (P.nb_tile == 0) return AFB_OK;
+  k_pattern_tiled_place<<<P.nb_tile, pattern_threads(P), 0, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), ctx->rows.as<int32_t>(),
+                                                                           P.col_scratch.as<int32_t>(), ctx->cols.as<int32_t>(), ctx->nz_per_row.as<int32_t>());
+  AFB_LAUNCH_CHECK(ctx);
+  return AFB_OK;
+}
 
 } // namespace afb

@@ -12,17 +12,31 @@
 
 namespace afb {
 
-// ---- executor geometry (2 CTAs per SM) ---------------------------------------------------------
-constexpr int TG_THREADS = 512;            // executor CTA
-constexpr int TG_MINB = 2;                 // CTAs per SM
-constexpr int TG_CMAX = 1408;              // cells per tile
+// ---- executor geometry (TG_MINB CTAs per SM; overridable for tuning builds) --------------------
+#ifndef AFB_TG_THREADS
+#define AFB_TG_THREADS 384
+#define AFB_TG_MINB 2
+#define AFB_TG_CMAX 1408
+#define AFB_TG_EMAX 2304
+#define AFB_TG_FMAX 384
+#define AFB_TG_LMAX 7680
+#define AFB_TG_RT3 125
+#define AFB_TG_RT2 288
+#endif
+constexpr int TG_THREADS = AFB_TG_THREADS; // executor CTA
+constexpr int TG_MINB = AFB_TG_MINB;       // CTAs per SM
+constexpr int TG_CMAX = AFB_TG_CMAX;       // cells per tile
 constexpr int TG_CS = TG_CMAX + 1;         // cache plane stride (odd)
 constexpr int TG_KP = 6;                   // cached values per cell: the off-diagonal pairs of a 4-node cell
 constexpr int TG_ZERO = TG_KP * TG_CS;     // cache slot that holds 0.0 (list padding)
-constexpr int TG_EMAX = 2304;              // matrix entries per tile
-constexpr int TG_RMAX = 384;               // rows per tile
-constexpr int TG_FMAX = 384;               // footprint nodes per tile
-constexpr int TG_LMAX = 7680;              // 16-bit list slots per tile (TMA-staged)
+constexpr int TG_EMAX = AFB_TG_EMAX;       // matrix entries per tile
+constexpr int TG_FMAX = AFB_TG_FMAX;       // footprint nodes per tile
+constexpr int TG_RMAX = TG_FMAX;           // rows per tile
+constexpr int TG_LMAX = AFB_TG_LMAX;       // 16-bit list slots per tile (TMA-staged)
+constexpr int TG_RT3 = AFB_TG_RT3;         // target rows per tile, 3-D / 2-D
+constexpr int TG_RT2 = AFB_TG_RT2;
+constexpr int TG_SMEM_LIMIT = (233472 / TG_MINB) - 1024; // 228 KB per SM, 1 KB reserved per CTA
+static_assert(TG_THREADS >= TG_FMAX && TG_THREADS >= TG_EMAX / 32, "one thread per footprint node / row / unit");
 constexpr int TG_UMAX = TG_EMAX / 32;      // units (32 entries with equally long lists) per tile
 constexpr int TG_ROUNDS = (TG_CMAX + TG_THREADS - 1) / TG_THREADS;
 constexpr int TG_GMAX = TG_RMAX / 32;      // row groups per tile (incidence lists)
@@ -30,7 +44,7 @@ constexpr unsigned TG_NONE16 = 0xFFFFu;
 
 // vector (b = 2, 3) executor: cache of sqrt(s)*grad(phi_a) per cell, blocks accumulated in registers
 constexpr int TV_PLANES = 12;              // 4 nodes x 3 components
-constexpr int TV_CMAX = 1024;
+constexpr int TV_CMAX = (TG_SMEM_LIMIT - 3 * 8 * TG_FMAX - 8 * TG_RMAX - 1024) / (8 * TV_PLANES) - 1 < 1024 ? (TG_SMEM_LIMIT - 3 * 8 * TG_FMAX - 8 * TG_RMAX - 1024) / (8 * TV_PLANES) - 1 : 1024;
 constexpr int TV_CS = TV_CMAX + 1;
 
 struct TileDesc {
@@ -44,7 +58,8 @@ struct TileDesc {
   int32_t list_len;            // used slots (multiple of 8)
   int32_t nb_entry;            // matrix entries of the tile's rows
   int32_t max_val;             // largest node valence in the tile
-  int32_t pad0, pad1;
+  uint32_t ent_off;            // first entry of the tile in the tile-ordered column scratch (capacity nb_entry)
+  int32_t pad1;
 };
 static_assert(sizeof(TileDesc) == 64, "TileDesc is copied as 16 words");
 

@@ -65,19 +65,25 @@ struct ExecSmem {
   uint32_t ubase[TG_UMAX];
   uint16_t ulen[TG_UMAX];
   uint16_t etab[TG_EMAX / 8];     // row holding entry 8*q
-  __align__(16) TileDesc desc[3]; // ring: current, next, next-next tile of this CTA
+  __align__(16) TileDesc desc[4]; // ring: current tile of this CTA and the three after it
   __align__(8) unsigned long long mbar;
 };
-static_assert(sizeof(ExecSmem) <= 115712, "two executor CTAs must fit one SM (227 KB, 1 KB reserved per CTA)");
+static_assert(sizeof(ExecSmem) <= TG_SMEM_LIMIT, "TG_MINB executor CTAs must fit one SM (228 KB, 1 KB reserved per CTA)");
+
+constexpr int TV_ROUNDS = (TV_CMAX + TG_THREADS - 1) / TG_THREADS;
+constexpr int TG_PF_ROUNDS = TG_ROUNDS > TV_ROUNDS ? TG_ROUNDS : TV_ROUNDS;
+constexpr int TG_UPW = (TG_UMAX + TG_THREADS / 32 - 1) / (TG_THREADS / 32); // units per warp
 
 // inputs of the next tile a thread carries in registers across phases B and C
 struct TilePrefetch {
   double c0, c1, c2;      // coordinates of footprint node `threadIdx.x`
-  ushort4 ln[TG_ROUNDS];  // local connectivity of this thread's cells
+  ushort4 ln[TG_PF_ROUNDS]; // local connectivity of this thread's cells
   uint32_t ubase;         // unit table entry `threadIdx.x`
   uint16_t ulen;
   int32_t rowbeg;         // row `threadIdx.x`: first value of the row, plan word
   uint32_t rowinfo;
+  int32_t fidx, node;     // level-1 indices (footprint node, row node) of the tile after that
+  uint32_t em[TG_UPW];    // entry map words of this warp's units (scalar executor)
 };
 
 struct ExecArgs {
@@ -97,11 +103,29 @@ struct ExecArgs {
   int accumulate;
 };
 
-template <int ROUNDS, int THREADS>
-__device__ __forceinline__ void prefetch_tile(const TileDesc& d, const ExecArgs& A, TilePrefetch& pf)
+// The next tiles' inputs travel in two waves so that no warp ever waits on a dependent load:
+// level 1 (indices: footprint node ids, row node ids) is requested TWO tiles ahead, level 2 (the data
+// those indices address, plus everything addressed directly) one tile ahead, by which time its
+// addresses sit in registers.
+__device__ __forceinline__ void prefetch_level1(const TileDesc& d, const ExecArgs& A, TilePrefetch& pf)
 {
+  if ((int)threadIdx.x < d.nb_foot) pf.fidx = __ldg(A.foot + d.foot_off + threadIdx.x);
+  if ((int)threadIdx.x < d.nb_row) pf.node = __ldg(A.tile_nodes + d.node_off + threadIdx.x);
+}
+
+template <int ROUNDS, int THREADS, bool EMAP = false>
+__device__ __forceinline__ void prefetch_level2(const TileDesc& d, const ExecArgs& A, TilePrefetch& pf)
+{
+  if constexpr (EMAP) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < TG_UPW; ++q) {
+      const int u = warp + q * (THREADS / 32);
+      if (u < d.nb_unit) pf.em[q] = __ldg(A.emap + (size_t)(d.unit_off + u) * 32 + lane);
+    }
+  }
   if ((int)threadIdx.x < d.nb_foot) {
-    const double* p = A.coords + 3 * (int64_t)__ldg(A.foot + d.foot_off + threadIdx.x);
+    const double* p = A.coords + 3 * (int64_t)pf.fidx;
     pf.c0 = __ldg(p);
     pf.c1 = __ldg(p + 1);
     pf.c2 = __ldg(p + 2);
@@ -116,7 +140,7 @@ __device__ __forceinline__ void prefetch_tile(const TileDesc& d, const ExecArgs&
     pf.ulen = __ldg(A.unit_len + d.unit_off + threadIdx.x);
   }
   if ((int)threadIdx.x < d.nb_row) {
-    pf.rowbeg = __ldg(A.rows + __ldg(A.tile_nodes + d.node_off + threadIdx.x));
+    pf.rowbeg = __ldg(A.rows + pf.node);
     pf.rowinfo = __ldg(A.rowinfo + d.node_off + threadIdx.x);
   }
 }
@@ -147,7 +171,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 2 * DW) { // descriptors of the first two tiles
+  if (threadIdx.x < 3 * DW) { // descriptors of the first three tiles
     const int k = threadIdx.x / DW, w = threadIdx.x % DW;
     const int64_t tt = (int64_t)t + (int64_t)k * gridDim.x;
     if (tt < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[k])[w] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tt) + w);
@@ -156,7 +180,11 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
   unsigned parity = 0;
   int slot = 0;
   TilePrefetch pf;
-  if (t < A.nb_tile) prefetch_tile<TG_ROUNDS, TG_THREADS>(S.desc[0], A, pf);
+  if (t < A.nb_tile) {
+    prefetch_level1(S.desc[0], A, pf);
+    prefetch_level2<TG_ROUNDS, TG_THREADS, true>(S.desc[0], A, pf); // the only exposed dependent load of the kernel
+    if ((int64_t)t + gridDim.x < A.nb_tile) prefetch_level1(S.desc[1], A, pf);
+  }
   while (t < A.nb_tile) {
     const TileDesc d = S.desc[slot];
     const bool staged = d.list_len <= TG_LMAX; // lists of an oversized tile are read from global memory
@@ -200,14 +228,18 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
         for (int p = 0; p < OffDiagK<NPC>::N; ++p) S.Kc[p * TG_CS + lc] = K[p];
       }
     }
-    // the next tile's inputs and the descriptor after it travel while phases B and C run
-    const int64_t tn = (int64_t)t + gridDim.x, tnn = tn + gridDim.x;
-    const int nslot = slot == 2 ? 0 : slot + 1, nnslot = nslot == 2 ? 0 : nslot + 1;
-    if (tn < A.nb_tile) prefetch_tile<TG_ROUNDS, TG_THREADS>(S.desc[nslot], A, pf);
-    if (threadIdx.x < DW && tnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnslot])[threadIdx.x] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnn) + threadIdx.x);
-    int u = warp;
-    uint32_t em = 0xFFFFFFFFu;
-    if (u < d.nb_unit) em = __ldg(A.emap + (size_t)(d.unit_off + u) * 32 + lane);
+    // software pipeline: level-2 inputs of the next tile (addresses already in registers), level-1
+    // indices of the tile after it, descriptor of the tile after that -- all in flight during B and C
+    const int64_t tn = (int64_t)t + gridDim.x, tnn = tn + gridDim.x, tnnn = tnn + gridDim.x;
+    const int nslot = (slot + 1) & 3, nnslot = (slot + 2) & 3, nnnslot = (slot + 3) & 3;
+    // (the entry-map words of the current tile move to their own registers first)
+    uint32_t em[TG_UPW];
+#pragma unroll
+    for (int q = 0; q < TG_UPW; ++q) em[q] = pf.em[q];
+    if (tn < A.nb_tile) prefetch_level2<TG_ROUNDS, TG_THREADS, true>(S.desc[nslot], A, pf);
+    if (tnn < A.nb_tile) prefetch_level1(S.desc[nnslot], A, pf);
+    int32_t desc_word = 0;
+    if (threadIdx.x < DW && tnnn < A.nb_tile) desc_word = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnnn) + threadIdx.x);
     __syncthreads();
     if (staged && d.list_len > 0) {
       mbar_wait(mbar, parity);
@@ -216,28 +248,28 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
     // ---- phase B: one warp per unit of 32 entries with equally long contribution lists ----
     {
       const uint32_t* l32 = staged ? reinterpret_cast<const uint32_t*>(S.lists) : reinterpret_cast<const uint32_t*>(A.lists + d.list_off);
-      while (u < d.nb_unit) {
-        const int un = u + NW;
-        uint32_t emn = 0xFFFFFFFFu;
-        if (un < d.nb_unit) emn = __ldg(A.emap + (size_t)(d.unit_off + un) * 32 + lane);
-        const uint32_t* l = l32 + (S.ubase[u] >> 1) + lane;
-        const int len2 = S.ulen[u] >> 1;
-        double acc0 = 0.0, acc1 = 0.0;
-        constexpr uint32_t ZPAIR = (uint32_t)TG_ZERO | ((uint32_t)TG_ZERO << 16);
+      constexpr uint32_t ZPAIR = (uint32_t)TG_ZERO | ((uint32_t)TG_ZERO << 16);
+#pragma unroll
+      for (int q = 0; q < TG_UPW; ++q) {
+        const int u = warp + q * NW;
+        if (u < d.nb_unit) {
+          const uint32_t* l = l32 + (S.ubase[u] >> 1) + lane;
+          const int len2 = S.ulen[u] >> 1;
+          double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 1
-        for (int k = 0; k < len2; k += 2) {
-          const uint32_t i0 = l[k * 32];
-          const uint32_t i1 = (k + 1 < len2) ? l[(k + 1) * 32] : ZPAIR;
-          acc0 += S.Kc[i0 & 0xFFFFu]; acc1 += S.Kc[i0 >> 16];
-          acc0 += S.Kc[i1 & 0xFFFFu]; acc1 += S.Kc[i1 >> 16];
+          for (int k = 0; k < len2; k += 2) {
+            const uint32_t i0 = l[k * 32];
+            const uint32_t i1 = (k + 1 < len2) ? l[(k + 1) * 32] : ZPAIR;
+            acc0 += S.Kc[i0 & 0xFFFFu]; acc1 += S.Kc[i0 >> 16];
+            acc0 += S.Kc[i1 & 0xFFFFu]; acc1 += S.Kc[i1 >> 16];
+          }
+          const uint32_t w = em[q];
+          if (w != 0xFFFFFFFFu) {
+            const double v = acc0 + acc1;
+            S.vout[w & 0xFFFFu] = v;
+            if ((w >> 16) != TG_NONE16) S.vout[w >> 16] = v;
+          }
         }
-        if (em != 0xFFFFFFFFu) {
-          const double v = acc0 + acc1;
-          S.vout[em & 0xFFFFu] = v;
-          if ((em >> 16) != TG_NONE16) S.vout[em >> 16] = v;
-        }
-        u = un;
-        em = emn;
       }
     }
     __syncthreads();
@@ -269,6 +301,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
       double* dst = A.values + ((int64_t)S.rowbeg[r] + e);
       if (A.accumulate) *dst += v; else *dst = v;
     }
+    if (threadIdx.x < DW && tnnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnnslot])[threadIdx.x] = desc_word;
     __syncthreads();
     t = (int32_t)tn;
     slot = nslot;
@@ -289,11 +322,11 @@ struct VecSmem {
   uint32_t rowinfo[TG_RMAX];
   uint32_t ubase[TG_UMAX];
   uint16_t ulen[TG_UMAX];
-  __align__(16) TileDesc desc[3];
+  __align__(16) TileDesc desc[4];
 };
-static_assert(sizeof(VecSmem<3>) <= 115712, "two vector-executor CTAs must fit one SM");
+static_assert(sizeof(VecSmem<3>) <= TG_SMEM_LIMIT, "TG_MINB vector-executor CTAs must fit one SM");
 
-constexpr int TV_ROUNDS = (TV_CMAX + TG_THREADS - 1) / TG_THREADS;
+
 
 template <int NPC, int LAYOUT>
 __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(ExecArgs A, ElemParams prm)
@@ -307,7 +340,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
   int32_t t = blockIdx.x;
   // zero slot of every plane (list padding)
   if (threadIdx.x < TV_PLANES) S.G[threadIdx.x * TV_CS + TV_CS - 1] = 0.0;
-  if (threadIdx.x < 2 * DW) {
+  if (threadIdx.x < 3 * DW) {
     const int k = threadIdx.x / DW, w = threadIdx.x % DW;
     const int64_t tt = (int64_t)t + (int64_t)k * gridDim.x;
     if (tt < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[k])[w] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tt) + w);
@@ -315,7 +348,11 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
   __syncthreads();
   int slot = 0;
   TilePrefetch pf;
-  if (t < A.nb_tile) prefetch_tile<TV_ROUNDS, TG_THREADS>(S.desc[0], A, pf);
+  if (t < A.nb_tile) {
+    prefetch_level1(S.desc[0], A, pf);
+    prefetch_level2<TV_ROUNDS, TG_THREADS>(S.desc[0], A, pf);
+    if ((int64_t)t + gridDim.x < A.nb_tile) prefetch_level1(S.desc[1], A, pf);
+  }
   const double lam = prm.p0, mu = prm.p1;
   while (t < A.nb_tile) {
     const TileDesc d = S.desc[slot];
@@ -366,10 +403,12 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
         }
       }
     }
-    const int64_t tn = (int64_t)t + gridDim.x, tnn = tn + gridDim.x;
-    const int nslot = slot == 2 ? 0 : slot + 1, nnslot = nslot == 2 ? 0 : nslot + 1;
-    if (tn < A.nb_tile) prefetch_tile<TV_ROUNDS, TG_THREADS>(S.desc[nslot], A, pf);
-    if (threadIdx.x < DW && tnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnslot])[threadIdx.x] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnn) + threadIdx.x);
+    const int64_t tn = (int64_t)t + gridDim.x, tnn = tn + gridDim.x, tnnn = tnn + gridDim.x;
+    const int nslot = (slot + 1) & 3, nnslot = (slot + 2) & 3, nnnslot = (slot + 3) & 3;
+    if (tn < A.nb_tile) prefetch_level2<TV_ROUNDS, TG_THREADS>(S.desc[nslot], A, pf);
+    if (tnn < A.nb_tile) prefetch_level1(S.desc[nnslot], A, pf);
+    int32_t desc_word = 0;
+    if (threadIdx.x < DW && tnnn < A.nb_tile) desc_word = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnnn) + threadIdx.x);
     __syncthreads();
     // ---- phase B: one lane per block entry; M accumulated in registers, lists streamed from global ----
     const uint32_t* l32 = reinterpret_cast<const uint32_t*>(A.lists + d.list_off);
@@ -435,6 +474,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
         if ((em >> 16) != TG_NONE16) emit((int)(em >> 16), true);
       }
     }
+    if (threadIdx.x < DW && tnnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnnslot])[threadIdx.x] = desc_word;
     __syncthreads();
     t = (int32_t)tn;
     slot = nslot;

@@ -596,7 +596,7 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
         __syncthreads();
       }
     }
-    // ---- fixed summation order: ascending local cell index (= ascending global cell id) ----
+    // ---- canonical order first: ascending local cell index (= ascending global cell id) ----
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       uint16_t* l = S.clist + S.eoff[e];
       const int n = S.cnt[e];
@@ -652,14 +652,48 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
     constexpr uint16_t PAD = (uint16_t)(VEC ? (CS - 1) : TG_ZERO);
     for (int x = S.ubase[nunit] + threadIdx.x; x < list_total; x += blockDim.x) lists[d.list_off + x] = PAD;
     for (int x = threadIdx.x; x < nunit * 32; x += blockDim.x) {
-      const int u = x >> 5, l = x & 31;
       const bool valid = x < EC;
       const int e = valid ? (int)(S.keys[x] & 0xFFFFu) : 0;
-      emap[(size_t)(d.unit_off + u) * 32 + l] = valid ? ((uint32_t)e | ((uint32_t)S.e2[e] << 16)) : 0xFFFFFFFFu;
-      const int len = S.ulen[u], n = valid ? S.cnt[e] : 0;
-      uint16_t* out = lists + d.list_off + S.ubase[u] + l * 2; // [len/2][32 lanes][2]
-      const uint16_t* src = S.clist + (valid ? S.eoff[e] : 0);
-      for (int k = 0; k < len; ++k) out[(k >> 1) * 64 + (k & 1)] = k < n ? src[k] : PAD;
+      emap[(size_t)(d.unit_off + (x >> 5)) * 32 + (x & 31)] = valid ? ((uint32_t)e | ((uint32_t)S.e2[e] << 16)) : 0xFFFFFFFFu;
+    }
+    // Lists of a unit, one thread per half-warp of lanes.  The executor reads contribution k of its 16
+    // lanes with one shared-memory instruction: the k-th slots of the 16 lists are chosen greedily so that
+    // they fall into different banks (8-byte bank = cache index mod 16) whenever an entry still has such a
+    // contribution left.  The order inside an entry's list is therefore plan-defined (not ascending cell
+    // id), but fixed: the sums stay bit-reproducible.
+    for (int hx = threadIdx.x; hx < nunit * 2; hx += blockDim.x) {
+      const int u = hx >> 1, l0 = (hx & 1) * 16;
+      const int len = S.ulen[u];
+      unsigned short used[64];
+      for (int k = 0; k < 64; ++k) used[k] = 0;
+      for (int l = l0; l < l0 + 16; ++l) {
+        const int x = u * 32 + l;
+        const bool valid = x < EC;
+        const int e = valid ? (int)(S.keys[x] & 0xFFFFu) : 0;
+        const int n = valid ? S.cnt[e] : 0;
+        const uint16_t* src = S.clist + (valid ? S.eoff[e] : 0);
+        uint16_t* out = lists + d.list_off + S.ubase[u] + l * 2; // [len/2][32 lanes][2]
+        unsigned long long taken = 0ull;
+        for (int k = 0; k < len; ++k) {
+          uint16_t code = PAD;
+          if (k < n) {
+            if (n <= 64 && k < 64) {
+              int pick = -1, first = -1;
+              for (int q = 0; q < n; ++q) {
+                if ((taken >> q) & 1ull) continue;
+                if (first < 0) first = q;
+                if (!((used[k] >> (src[q] & 15)) & 1)) { pick = q; break; }
+              }
+              if (pick < 0) pick = first;
+              taken |= 1ull << pick;
+              code = src[pick];
+              used[k] |= (unsigned short)(1u << (code & 15));
+            }
+            else code = src[k];
+          }
+          out[(k >> 1) * 64 + (k & 1)] = code;
+        }
+      }
     }
     __syncthreads();
   }
@@ -714,7 +748,7 @@ int build_tile_mesh(afb_ctx* ctx)
   int32_t* brick_of = P.scratch_c.as<int32_t>();
 
   // bricks holding ~rtarget nodes on a uniform mesh
-  const int rtarget = dim == 3 ? (vec ? 100 : 125) : 288;
+  const int rtarget = dim == 3 ? (vec ? std::max(8, TG_RT3 * TV_CMAX / TG_CMAX) : TG_RT3) : TG_RT2;
   double vol = 1.0;
   int nd_ext = 0;
   for (int a = 0; a < 3; ++a)
@@ -806,7 +840,7 @@ int build_tile_mesh(afb_ctx* ctx)
   }
   P.nb_tile = nb_tile;
   // sizes -> offsets
-  int64_t cell_off = 0, foot_off = 0, inc_off = 0;
+  int64_t cell_off = 0, foot_off = 0, inc_off = 0, ent_off = 0;
   int max_rows = 0;
   for (int32_t t = 0; t < nb_tile; ++t) {
     TileDesc& d = hdesc[t];
@@ -818,6 +852,8 @@ int build_tile_mesh(afb_ctx* ctx)
     d.inc_off = (uint32_t)inc_off;
     d.nb_group = (d.nb_row + 31) / 32;
     d.nb_entry = E;
+    d.ent_off = (uint32_t)ent_off;
+    ent_off += E;
     d.max_val = V;
     d.unit_off = d.nb_unit = 0;
     d.list_off = 0;
@@ -832,6 +868,7 @@ int build_tile_mesh(afb_ctx* ctx)
   P.nb_tile_cell = cell_off;
   P.nb_foot = foot_off;
   P.nb_inc = inc_off;
+  P.nb_entry = ent_off;
   AFB_TRY(P.tile_cells.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(cell_off, 1)));
   AFB_TRY(P.lconn.reserve(sizeof(ushort4) * (size_t)std::max<int64_t>(cell_off, 1)));
   AFB_TRY(P.foot.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(foot_off, 1)));
