@@ -100,6 +100,8 @@ int afb_create(int device, afb_ctx** out)
   AFB_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   for (int i = 0; i < 6; ++i) AFB_CUDA(cudaEventCreate(&ctx->ev[i]));
+  AFB_CUDA(cudaEventCreateWithFlags(&ctx->check_event, cudaEventDisableTiming));
+  AFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin_check), 2 * sizeof(int32_t), cudaHostAllocDefault));
   *out = ctx;
   return AFB_OK;
 }
@@ -118,6 +120,8 @@ int afb_destroy(afb_ctx* ctx)
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->check_event) cudaEventDestroy(ctx->check_event);
+  if (ctx->pin_check) cudaFreeHost(ctx->pin_check);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return AFB_OK;
@@ -127,6 +131,7 @@ int afb_set_stream(afb_ctx* ctx, void* cuda_stream)
 {
   AFB_TRY(check_ctx(ctx));
   AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  AFB_TRY(verify_pending(ctx));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return AFB_OK;
 }
@@ -135,6 +140,7 @@ int afb_synchronize(afb_ctx* ctx)
 {
   AFB_TRY(check_ctx(ctx));
   AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  AFB_TRY(verify_pending(ctx));
   return AFB_OK;
 }
 
@@ -491,6 +497,7 @@ int afb_get_mesh(afb_ctx* ctx, int* dim, int* npc, int32_t* nb_node, int64_t* nb
 int afb_copy_to_host(afb_ctx* ctx, int which, void* dst, size_t* bytes)
 {
   AFB_TRY(check_ctx(ctx));
+  AFB_TRY(verify_pending(ctx));
   const void* src = nullptr;
   size_t n = 0;
   const int b = ctx->b;
@@ -573,6 +580,7 @@ int afb_last_timings(afb_ctx* ctx, float* connectivity_ms, float* pattern_ms, fl
 {
   AFB_TRY(check_ctx(ctx));
   AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  AFB_TRY(verify_pending(ctx));
   float* out[3] = { connectivity_ms, pattern_ms, assemble_ms };
   for (int p = 0; p < 3; ++p) {
     if (!out[p]) continue;

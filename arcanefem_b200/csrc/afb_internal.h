@@ -164,6 +164,12 @@ struct afb_ctx {
 
   afb::TilePlan plan;
 
+  // deferred host-side check of a steady-state pattern re-build (connectivity.cu: verify_pending)
+  int32_t* pin_check = nullptr;     // pinned int32[2]: rows[nb_node] and the stale flag of the last re-build
+  cudaEvent_t check_event = nullptr;
+  bool check_pending = false;
+  uint64_t nnz_mesh_gen = ~0ull;    // mesh generation ctx->nnz was last read back for
+
   // timings
   cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   bool timed[3] = { false, false, false };
@@ -179,6 +185,7 @@ int exclusive_scan_i32(afb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n)
 // ---- connectivity.cu -------------------------------------------------------------------------
 int build_node_cells(afb_ctx* ctx);
 int build_pattern(afb_ctx* ctx);
+int verify_pending(afb_ctx* ctx);
 
 // ---- pattern_rows.cu -------------------------------------------------------------------------
 bool pattern_rows_supported(const afb_ctx* ctx);

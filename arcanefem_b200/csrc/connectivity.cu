@@ -368,8 +368,21 @@ static int dispatch_row_unique(afb_ctx* ctx, bool write, int32_t* deg)
   return AFB_ERR_UNSUPPORTED;
 }
 
+// completes the deferred check of the last steady-state re-build (see build_pattern)
+int verify_pending(afb_ctx* ctx)
+{
+  if (!ctx->check_pending) return AFB_OK;
+  ctx->check_pending = false;
+  AFB_CUDA(cudaEventSynchronize(ctx->check_event));
+  AFB_REQUIRE(ctx->pin_check[1] == 0, AFB_ERR_CUDA, "tiled BuildMatrix: a tile produced more entries than its scratch capacity (stale tiling)");
+  AFB_REQUIRE((int64_t)ctx->pin_check[0] == ctx->nnz, AFB_ERR_CUDA, "BuildMatrix re-build: the device computed nnz=%d, the host assumed %lld (same mesh)", ctx->pin_check[0],
+              (long long)ctx->nnz);
+  return AFB_OK;
+}
+
 int build_pattern(afb_ctx* ctx)
 {
+  AFB_TRY(verify_pending(ctx));
   const int32_t nb_node = ctx->nb_node;
   const int b = ctx->b;
   AFB_TRY(ctx->rows.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
@@ -384,13 +397,26 @@ int build_pattern(afb_ctx* ctx)
     int stale = 0;
     AFB_TRY(pattern_tiled_extract(ctx, deg, &stale));
     AFB_TRY(exclusive_scan_i32(ctx, deg, ctx->rows.as<int32_t>(), nb_node));
-    int32_t nnz32 = 0;
-    AFB_CUDA(cudaMemcpyAsync(&nnz32, ctx->rows.as<int32_t>() + nb_node, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    AFB_CUDA(cudaMemcpyAsync(&stale, ctx->tmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    AFB_CUDA(cudaStreamSynchronize(ctx->stream));
-    AFB_REQUIRE(stale == 0, AFB_ERR_CUDA, "tiled BuildMatrix: a tile produced more entries than its scratch capacity (stale tiling)");
-    AFB_REQUIRE(nnz32 >= 0, AFB_ERR_OVERFLOW, "block nnz exceeds Int32");
-    ctx->nnz = nnz32;
+    if (ctx->nnz_mesh_gen == ctx->mesh_gen && ctx->pin_check) {
+      // Same mesh as the previous complete build: nnz (a function of the mesh alone) is already known on
+      // the host, so the host does not wait for the device here.  The device still recomputes everything;
+      // its rows[nb_node] and stale flag are copied back asynchronously and compared at the next host
+      // synchronisation point or re-build (verify_pending).
+      AFB_CUDA(cudaMemcpyAsync(ctx->pin_check, ctx->rows.as<int32_t>() + nb_node, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      AFB_CUDA(cudaMemcpyAsync(ctx->pin_check + 1, ctx->tmp_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      AFB_CUDA(cudaEventRecord(ctx->check_event, ctx->stream));
+      ctx->check_pending = true;
+    }
+    else {
+      int32_t nnz32 = 0;
+      AFB_CUDA(cudaMemcpyAsync(&nnz32, ctx->rows.as<int32_t>() + nb_node, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      AFB_CUDA(cudaMemcpyAsync(&stale, ctx->tmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+      AFB_REQUIRE(stale == 0, AFB_ERR_CUDA, "tiled BuildMatrix: a tile produced more entries than its scratch capacity (stale tiling)");
+      AFB_REQUIRE(nnz32 >= 0, AFB_ERR_OVERFLOW, "block nnz exceeds Int32");
+      ctx->nnz = nnz32;
+      ctx->nnz_mesh_gen = ctx->mesh_gen;
+    }
     AFB_TRY(ctx->cols.reserve(sizeof(int32_t) * (size_t)ctx->nnz));
     AFB_TRY(pattern_tiled_place(ctx));
     done = true;
@@ -422,6 +448,7 @@ int build_pattern(afb_ctx* ctx)
     else AFB_TRY(dispatch_row_unique(ctx, true, nullptr));
     ctx->pattern_mesh_gen = ctx->mesh_gen;
   }
+  if (!ctx->check_pending) ctx->nnz_mesh_gen = ctx->mesh_gen; // nnz was read back synchronously above
   AFB_REQUIRE((int64_t)ctx->nnz * b * b < 2147483647LL, AFB_ERR_OVERFLOW,
               "scalar nnz %lld exceeds the Int32 index space of the reference containers (femutils/BSRFormat.cc:362-364)", (long long)(ctx->nnz * b * b));
   AFB_TRY(ctx->values.reserve(sizeof(double) * (size_t)ctx->nnz * b * b));
