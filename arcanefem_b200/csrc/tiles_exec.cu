@@ -33,12 +33,12 @@ namespace afb {
 template <int NPC> struct OffDiagK;
 template <> struct OffDiagK<4> {
   static constexpr int N = 6;
-  __device__ static __forceinline__ void compute(const double* __restrict__ cx, ushort4 ln, const ElemParams&, double (&K)[6])
+  __device__ static __forceinline__ void compute(const double* __restrict__ cx, uint2 ln, const ElemParams&, double (&K)[6])
   {
-    const double* p0 = cx + 3 * ln.x;
-    const double* p1 = cx + 3 * ln.y;
-    const double* p2 = cx + 3 * ln.z;
-    const double* p3 = cx + 3 * ln.w;
+    const double* p0 = cx + 3 * (ln.x & 0xFFFFu);
+    const double* p1 = cx + 3 * (ln.x >> 16);
+    const double* p2 = cx + 3 * (ln.y & 0xFFFFu);
+    const double* p3 = cx + 3 * (ln.y >> 16);
     Tet4Geom g;
     g.init_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
     K[0] = g.dot(0, 1) * g.s; K[1] = g.dot(0, 2) * g.s; K[2] = g.dot(0, 3) * g.s;
@@ -47,11 +47,11 @@ template <> struct OffDiagK<4> {
 };
 template <> struct OffDiagK<3> {
   static constexpr int N = 3;
-  __device__ static __forceinline__ void compute(const double* __restrict__ cx, ushort4 ln, const ElemParams& prm, double (&K)[6])
+  __device__ static __forceinline__ void compute(const double* __restrict__ cx, uint2 ln, const ElemParams& prm, double (&K)[6])
   {
-    const double* p0 = cx + 3 * ln.x;
-    const double* p1 = cx + 3 * ln.y;
-    const double* p2 = cx + 3 * ln.z;
+    const double* p0 = cx + 3 * (ln.x & 0xFFFFu);
+    const double* p1 = cx + 3 * (ln.x >> 16);
+    const double* p2 = cx + 3 * (ln.y & 0xFFFFu);
     Tri3Geom g;
     g.init_xy(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], (prm.flags & AFB_FLAG_SIGNED_TRI_AREA) != 0);
     K[0] = g.dot(0, 1) * g.s; K[1] = g.dot(0, 2) * g.s; K[2] = g.dot(1, 2) * g.s;
@@ -63,15 +63,20 @@ struct ExecSmem {
   double Kc[TG_ZERO + 1];
   double cx[3 * TG_FMAX];
   double vout[TG_EMAX];
-  __align__(16) uint16_t lists[TG_LMAX];
+  __align__(16) uint16_t lists[TG_LMAX]; // phase B input; afterwards (phase C, write-out) reused as OutTables
   int32_t rowbeg[TG_RMAX];        // first value of the row minus its first tile-local entry: dest(e) = e + rowbeg[row(e)]
   uint32_t rowinfo[TG_RMAX + 1];  // + sentinel (first entry = nb_entry)
   uint32_t ubase[TG_UMAX];
   uint16_t ulen[TG_UMAX];
-  uint16_t etab[TG_EMAX / 8];     // row holding entry 8*q
   __align__(16) TileDesc desc[4]; // ring: current tile of this CTA and the three after it
   __align__(8) unsigned long long mbar;
 };
+// write-out table, built by phase C over the (by then consumed) contribution lists; the tables staged per
+// tile (rowbeg, rowinfo, ...) are not read by the write-out, so staging the next tile does not wait for it
+struct OutTables {
+  int32_t dbase[TG_EMAX]; // value offset of the entry's row minus the row's first tile-local entry: dest(e) = e + dbase[e]
+};
+static_assert(sizeof(OutTables) <= sizeof(uint16_t) * TG_LMAX, "write-out tables alias the list region");
 static_assert(sizeof(ExecSmem) <= TG_SMEM_LIMIT, "TG_MINB executor CTAs must fit one SM (228 KB, 1 KB reserved per CTA)");
 
 constexpr int TV_ROUNDS = (TV_CMAX + TG_THREADS - 1) / TG_THREADS;
@@ -81,7 +86,8 @@ constexpr int TG_UPW = (TG_UMAX + TG_THREADS / 32 - 1) / (TG_THREADS / 32); // u
 // inputs of the next tile a thread carries in registers across phases B and C
 struct TilePrefetch {
   double c0, c1, c2;      // coordinates of footprint node `threadIdx.x`
-  ushort4 ln[TG_PF_ROUNDS]; // local connectivity of this thread's cells
+  uint2 ln[TG_PF_ROUNDS];   // local connectivity of this thread's cells (4 x 16 bit, unpacked at use: a
+                            // predicated ushort4 load makes ptxas merge halves right after the load = a stall)
   uint32_t ubase;         // unit table entry `threadIdx.x`
   uint16_t ulen;
   int32_t rowbeg;         // row `threadIdx.x`: first value of the row, plan word
@@ -136,8 +142,8 @@ __device__ __forceinline__ void prefetch_level2(const TileDesc& d, const ExecArg
   }
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
-    const int lc = r * THREADS + threadIdx.x;
-    if (lc < d.nb_cell) pf.ln[r] = __ldg(A.lconn + d.cell_off + lc);
+    const int lc = min(r * THREADS + (int)threadIdx.x, d.nb_cell - 1);
+    if (d.nb_cell > 0) pf.ln[r] = __ldg(reinterpret_cast<const uint2*>(A.lconn) + d.cell_off + lc);
   }
   if ((int)threadIdx.x < d.nb_unit) {
     pf.ubase = __ldg(A.unit_base + d.unit_off + threadIdx.x);
@@ -160,11 +166,38 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, unsigned parity)
 // ---------------------------------------------------------------------------------------------
 // scalar executor (b = 1, zero-row-sum operators: Poisson)
 // ---------------------------------------------------------------------------------------------
+// registers -> shared memory.  stage_early: what phases C/write-out of the previous tile do not read (coordinates:
+// phase A only; unit tables: phase B only) -- done in the tail of the previous iteration, while other warps may
+// still be writing out.  stage_rows: the row tables phase C reads -- done after the top barrier.
+template <class SM>
+__device__ __forceinline__ void stage_early(SM& S, const TileDesc& d, const TilePrefetch& pf)
+{
+  if ((int)threadIdx.x < d.nb_foot) {
+    S.cx[3 * threadIdx.x] = pf.c0;
+    S.cx[3 * threadIdx.x + 1] = pf.c1;
+    S.cx[3 * threadIdx.x + 2] = pf.c2;
+  }
+  if ((int)threadIdx.x < d.nb_unit) {
+    S.ubase[threadIdx.x] = pf.ubase;
+    S.ulen[threadIdx.x] = pf.ulen;
+  }
+}
+template <class SM>
+__device__ __forceinline__ void stage_rows(SM& S, const TileDesc& d, const TilePrefetch& pf)
+{
+  if ((int)threadIdx.x < d.nb_row) {
+    S.rowbeg[threadIdx.x] = pf.rowbeg - rowinfo_erow(pf.rowinfo);
+    S.rowinfo[threadIdx.x] = pf.rowinfo;
+  }
+  else if ((int)threadIdx.x == d.nb_row) S.rowinfo[threadIdx.x] = pack_rowinfo(d.nb_entry, 0, false);
+}
+
 template <int NPC>
 __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs A, ElemParams prm)
 {
   extern __shared__ __align__(16) unsigned char ex_raw[];
   ExecSmem& S = *reinterpret_cast<ExecSmem*>(ex_raw);
+  OutTables& O = *reinterpret_cast<OutTables*>(S.lists);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = TG_THREADS / 32;
   constexpr int DW = sizeof(TileDesc) / 4;
@@ -188,25 +221,15 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
     prefetch_level1(S.desc[0], A, pf);
     prefetch_level2<TG_ROUNDS, TG_THREADS, true>(S.desc[0], A, pf); // the only exposed dependent load of the kernel
     if ((int64_t)t + gridDim.x < A.nb_tile) prefetch_level1(S.desc[1], A, pf);
+    stage_early(S, S.desc[0], pf);
   }
   while (t < A.nb_tile) {
+    // ---- barrier 1: coordinates and unit tables are staged (tail of the previous iteration); every warp is done
+    //      with the previous tile's phase C and write-out, so the row tables and the list region may be overwritten ----
+    __syncthreads();
     const TileDesc d = S.desc[slot];
     const bool staged = d.list_len <= TG_LMAX; // lists of an oversized tile are read from global memory
-    // ---- stage ----
-    if ((int)threadIdx.x < d.nb_foot) {
-      S.cx[3 * threadIdx.x] = pf.c0;
-      S.cx[3 * threadIdx.x + 1] = pf.c1;
-      S.cx[3 * threadIdx.x + 2] = pf.c2;
-    }
-    if ((int)threadIdx.x < d.nb_unit) {
-      S.ubase[threadIdx.x] = pf.ubase;
-      S.ulen[threadIdx.x] = pf.ulen;
-    }
-    if ((int)threadIdx.x < d.nb_row) {
-      S.rowbeg[threadIdx.x] = pf.rowbeg - rowinfo_erow(pf.rowinfo);
-      S.rowinfo[threadIdx.x] = pf.rowinfo;
-    }
-    else if ((int)threadIdx.x == d.nb_row) S.rowinfo[threadIdx.x] = pack_rowinfo(d.nb_entry, 0, false);
+    stage_rows(S, d, pf);
     if (threadIdx.x == 0 && staged && d.list_len > 0) {
       const uint32_t bytes = (uint32_t)d.list_len * 2u;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -215,17 +238,15 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
                    "r"(bytes), "r"(mbar)
                    : "memory");
     }
-    __syncthreads();
-    // entry -> row table for the write-out (row holding every 8th entry)
-    if ((int)threadIdx.x < d.nb_row) {
-      const int e0 = rowinfo_erow(S.rowinfo[threadIdx.x]), e1 = rowinfo_erow(S.rowinfo[threadIdx.x + 1]);
-      for (int q = (e0 + 7) >> 3; (q << 3) < e1; ++q) S.etab[q] = (uint16_t)threadIdx.x;
-    }
     // ---- phase A: off-diagonal element-matrix values of the tile's cells, once each ----
 #pragma unroll
     for (int r = 0; r < TG_ROUNDS; ++r) {
       const int lc = r * TG_THREADS + threadIdx.x;
+#ifdef AFB_EXP_A_PCT
+      if (lc < d.nb_cell * AFB_EXP_A_PCT / 100) {
+#else
       if (lc < d.nb_cell) {
+#endif
         double K[6];
         OffDiagK<NPC>::compute(S.cx, pf.ln[r], prm, K);
 #pragma unroll
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
     if (tnn < A.nb_tile) prefetch_level1(S.desc[nnslot], A, pf);
     int32_t desc_word = 0;
     if (threadIdx.x < DW && tnnn < A.nb_tile) desc_word = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnnn) + threadIdx.x);
-    __syncthreads();
+    __syncthreads(); // ---- barrier 2: the element cache is complete ----
     if (staged && d.list_len > 0) {
       mbar_wait(mbar, parity);
       parity ^= 1u;
@@ -256,7 +277,11 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
 #pragma unroll
       for (int q = 0; q < TG_UPW; ++q) {
         const int u = warp + q * NW;
+#ifdef AFB_EXP_B_PCT
+        if (u < d.nb_unit * AFB_EXP_B_PCT / 100) {
+#else
         if (u < d.nb_unit) {
+#endif
           const uint32_t* l = l32 + (S.ubase[u] >> 1) + lane;
           const int len2 = S.ulen[u] >> 1;
           double acc0 = 0.0, acc1 = 0.0;
@@ -276,40 +301,57 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
         }
       }
     }
-    __syncthreads();
-    // ---- phase C: diagonal = -(sum of the row's off-diagonals) ... ----
-    if ((int)threadIdx.x < d.nb_row) {
-      const uint32_t ri = S.rowinfo[threadIdx.x];
-      if (rowinfo_own(ri)) {
-        const int e0 = rowinfo_erow(ri), e1 = rowinfo_erow(S.rowinfo[threadIdx.x + 1]), ed = e0 + rowinfo_pdiag(ri);
-        double s0 = 0.0, s1 = 0.0;
-        int e = e0;
-        for (; e + 1 < ed; e += 2) { s0 += S.vout[e]; s1 += S.vout[e + 1]; }
-        if (e < ed) s0 += S.vout[e];
-        e = ed + 1;
-        for (; e + 1 < e1; e += 2) { s0 += S.vout[e]; s1 += S.vout[e + 1]; }
-        if (e < e1) s0 += S.vout[e];
-        S.vout[ed] = -(s0 + s1);
+    __syncthreads(); // ---- barrier 3: off-diagonals are in vout; the list region is free ----
+    // ---- phase C + write-out, one contiguous range of rows per warp (no block barrier in between):
+    //      G lanes per row derive the diagonal = -(sum of the row's off-diagonals) and note the row's value
+    //      offset for each of its entries; then the warp's entries leave shared memory in row order
+    //      (contiguous, coalesced stores) ----
+    {
+      const int rw = (d.nb_row + NW - 1) / NW;             // rows per warp (<= 32)
+      const int r0 = min(warp * rw, d.nb_row), r1 = min(r0 + rw, d.nb_row);
+      const int gs = rw <= 8 ? 2 : (rw <= 16 ? 1 : 0);     // log2(lanes per row)
+      const int i = r0 + (lane >> gs), q = lane & ((1 << gs) - 1), G = 1 << gs;
+      double sum = 0.0;
+      int ed = -1;
+      if (i < r1) {
+        const uint32_t ri = S.rowinfo[i];
+        const int e0 = rowinfo_erow(ri), e1 = rowinfo_erow(S.rowinfo[i + 1]);
+        const int32_t rb = S.rowbeg[i];
+        if (rowinfo_own(ri)) {
+          ed = e0 + rowinfo_pdiag(ri);
+          for (int e = e0 + q; e < e1; e += G) {
+            O.dbase[e] = rb;
+            if (e != ed) sum += S.vout[e];
+          }
+        }
+        else { // rows of non-owned nodes stay zero (the isOwn gate of the reference)
+          for (int e = e0 + q; e < e1; e += G) {
+            O.dbase[e] = rb;
+            S.vout[e] = 0.0;
+          }
+        }
+      }
+      if (gs >= 1) sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (gs >= 2) sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      if (q == 0 && ed >= 0) S.vout[ed] = -sum;
+      __syncwarp();
+      const int eb = rowinfo_erow(S.rowinfo[r0]), ee = rowinfo_erow(S.rowinfo[r1]);
+#ifdef AFB_EXP_OUT_PCT
+      for (int e = eb + lane; e < eb + (ee - eb) * AFB_EXP_OUT_PCT / 100; e += 32) {
+#else
+      for (int e = eb + lane; e < ee; e += 32) {
+#endif
+        double* dst = A.values + ((int64_t)O.dbase[e] + e);
+        const double v = S.vout[e];
+        if (A.accumulate) *dst += v; else *dst = v;
       }
     }
-    __syncthreads();
-    // ---- ... and the tile's entries leave shared memory in row order: contiguous, coalesced stores ----
-    for (int e = threadIdx.x; e < d.nb_entry; e += TG_THREADS) {
-      int r = S.etab[e >> 3];
-      uint32_t ri = S.rowinfo[r + 1];
-      while (e >= rowinfo_erow(ri)) {
-        ++r;
-        ri = S.rowinfo[r + 1];
-      }
-      const double v = rowinfo_own(S.rowinfo[r]) ? S.vout[e] : 0.0;
-      double* dst = A.values + ((int64_t)S.rowbeg[r] + e);
-      if (A.accumulate) *dst += v; else *dst = v;
-    }
+    // ---- tail: stage what the next tile's phases A and B read (other warps may still be in phase C / write-out) ----
     if (threadIdx.x < DW && tnnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnnslot])[threadIdx.x] = desc_word;
-    __syncthreads();
+    if (tn >= A.nb_tile) break;
+    stage_early(S, S.desc[nslot], pf);
     t = (int32_t)tn;
     slot = nslot;
-    if (tn >= A.nb_tile) break;
   }
 }
 
@@ -379,12 +421,12 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
     for (int r = 0; r < TV_ROUNDS; ++r) {
       const int lc = r * TG_THREADS + threadIdx.x;
       if (lc < d.nb_cell) {
-        const ushort4 ln = pf.ln[r];
+        const uint2 ln = pf.ln[r];
         if constexpr (NPC == 4) {
-          const double* p0 = S.cx + 3 * ln.x;
-          const double* p1 = S.cx + 3 * ln.y;
-          const double* p2 = S.cx + 3 * ln.z;
-          const double* p3 = S.cx + 3 * ln.w;
+          const double* p0 = S.cx + 3 * (ln.x & 0xFFFFu);
+          const double* p1 = S.cx + 3 * (ln.x >> 16);
+          const double* p2 = S.cx + 3 * (ln.y & 0xFFFFu);
+          const double* p3 = S.cx + 3 * (ln.y >> 16);
           Tet4Geom g;
           g.init_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
           const double q = sqrt(g.s);
@@ -394,9 +436,9 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
             for (int k = 0; k < 3; ++k) S.G[(a * 3 + k) * TV_CS + lc] = g.c[a][k] * q;
         }
         else {
-          const double* p0 = S.cx + 3 * ln.x;
-          const double* p1 = S.cx + 3 * ln.y;
-          const double* p2 = S.cx + 3 * ln.z;
+          const double* p0 = S.cx + 3 * (ln.x & 0xFFFFu);
+          const double* p1 = S.cx + 3 * (ln.x >> 16);
+          const double* p2 = S.cx + 3 * (ln.y & 0xFFFFu);
           Tri3Geom g;
           g.init_xy(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], false);
           const double q = sqrt(g.s);

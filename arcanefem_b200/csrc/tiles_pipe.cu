@@ -34,12 +34,12 @@ static_assert(PG_THREADS >= TG_FMAX && PG_THREADS >= TG_RMAX && PG_THREADS >= TG
 template <int NPC> struct PipeK;
 template <> struct PipeK<4> {
   static constexpr int N = 6;
-  __device__ static __forceinline__ void compute(const double* __restrict__ cx, ushort4 ln, const ElemParams&, double (&K)[6])
+  __device__ static __forceinline__ void compute(const double* __restrict__ cx, uint2 ln, const ElemParams&, double (&K)[6])
   {
-    const double* p0 = cx + 3 * ln.x;
-    const double* p1 = cx + 3 * ln.y;
-    const double* p2 = cx + 3 * ln.z;
-    const double* p3 = cx + 3 * ln.w;
+    const double* p0 = cx + 3 * (ln.x & 0xFFFFu);
+    const double* p1 = cx + 3 * (ln.x >> 16);
+    const double* p2 = cx + 3 * (ln.y & 0xFFFFu);
+    const double* p3 = cx + 3 * (ln.y >> 16);
     Tet4Geom g;
     g.init_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
     K[0] = g.dot(0, 1) * g.s; K[1] = g.dot(0, 2) * g.s; K[2] = g.dot(0, 3) * g.s;
@@ -48,11 +48,11 @@ template <> struct PipeK<4> {
 };
 template <> struct PipeK<3> {
   static constexpr int N = 3;
-  __device__ static __forceinline__ void compute(const double* __restrict__ cx, ushort4 ln, const ElemParams& prm, double (&K)[6])
+  __device__ static __forceinline__ void compute(const double* __restrict__ cx, uint2 ln, const ElemParams& prm, double (&K)[6])
   {
-    const double* p0 = cx + 3 * ln.x;
-    const double* p1 = cx + 3 * ln.y;
-    const double* p2 = cx + 3 * ln.z;
+    const double* p0 = cx + 3 * (ln.x & 0xFFFFu);
+    const double* p1 = cx + 3 * (ln.x >> 16);
+    const double* p2 = cx + 3 * (ln.y & 0xFFFFu);
     Tri3Geom g;
     g.init_xy(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], (prm.flags & AFB_FLAG_SIGNED_TRI_AREA) != 0);
     K[0] = g.dot(0, 1) * g.s; K[1] = g.dot(0, 2) * g.s; K[2] = g.dot(1, 2) * g.s;
@@ -121,7 +121,7 @@ __device__ __forceinline__ void pipe_tma_tile(const TileDesc& d, const PipeArgs&
 }
 
 template <int NPC>
-__device__ __forceinline__ void pipe_phase_a(const TileDesc& d, const double* __restrict__ cx, double* __restrict__ Kc, const ushort4 (&ln)[PG_ROUNDS], const ElemParams& prm)
+__device__ __forceinline__ void pipe_phase_a(const TileDesc& d, const double* __restrict__ cx, double* __restrict__ Kc, const uint2 (&ln)[PG_ROUNDS], const ElemParams& prm)
 {
 #pragma unroll
   for (int r = 0; r < PG_ROUNDS; ++r) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_assemble_tiled_pipe(PipeArgs 
   if (tile_of(0) >= A.nb_tile) return;
 
   // ---- registers carried across phases ----
-  ushort4 ln[PG_ROUNDS];            // lconn of the tile whose phase A comes next
+  uint2 ln[PG_ROUNDS];              // lconn of the tile whose phase A comes next
   double c0 = 0, c1 = 0, c2 = 0;    // coordinates on their way to cx
   int32_t fidx = 0, node = 0;       // level-1 indices
   int32_t r_rowbeg = 0;             // rows of the tile whose phase C comes next
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_assemble_tiled_pipe(PipeArgs 
   auto load_lconn = [&](const TileDesc& d) {
 #pragma unroll
     for (int r = 0; r < PG_ROUNDS; ++r) {
-      const int lc = r * PG_THREADS + tid;
-      if (lc < d.nb_cell) ln[r] = __ldg(A.lconn + d.cell_off + lc);
+      const int lc = min(r * PG_THREADS + tid, d.nb_cell - 1); // never predicated per lane: see TilePrefetch::ln
+      if (d.nb_cell > 0) ln[r] = __ldg(reinterpret_cast<const uint2*>(A.lconn) + d.cell_off + lc);
     }
   };
   auto load_fidx = [&](const TileDesc& d) { if (tid < d.nb_foot) fidx = __ldg(A.foot + d.foot_off + tid); };
