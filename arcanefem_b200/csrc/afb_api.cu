@@ -136,6 +136,14 @@ int afb_set_stream(afb_ctx* ctx, void* cuda_stream)
   return AFB_OK;
 }
 
+int afb_set_sparsity_algorithm(afb_ctx* ctx, int algorithm)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(algorithm >= AFB_SPARSITY_AUTO && algorithm <= AFB_SPARSITY_FROM_CONNECTIVITY, AFB_ERR_INVALID, "afb_set_sparsity_algorithm: unknown algorithm %d", algorithm);
+  ctx->sparsity_algo = algorithm;
+  return AFB_OK;
+}
+
 int afb_synchronize(afb_ctx* ctx)
 {
   AFB_TRY(check_ctx(ctx));
@@ -220,6 +228,9 @@ int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_block_row, 
   AFB_TRY(build_pattern(ctx));
   AFB_TRY(time_end(ctx, 1));
   ctx->has_pattern = true;
+  // explicit connectivity-based sparsity: the init-time connectivity is created right after the first build
+  // of a mesh (AUTO creates it with the first tiled assembly)
+  if (ctx->sparsity_algo == AFB_SPARSITY_FROM_CONNECTIVITY && !pattern_nn_ready(ctx) && (ctx->npc == 3 || ctx->npc == 4)) AFB_TRY(build_tile_mesh(ctx));
   if (nb_block_row) *nb_block_row = ctx->nb_node;
   if (nb_block_nnz) *nb_block_nnz = ctx->nnz;
   return AFB_OK;

@@ -98,6 +98,11 @@ struct TilePlan {
   DevBuf inc_grp;     // uint2 per (tile, group of 32 rows): offset (words, inside the tile) and list length
   DevBuf node_tile;   // int32[nb_node]: tile of each node
   DevBuf node_lrow;   // int32[nb_node]: row index inside its tile
+  // ---- tile-local node-node connectivity (connectivity-based BuildMatrix, pattern_tiled.cu) ----
+  bool nn_valid = false;
+  uint64_t nn_mesh_gen = ~0ull;
+  DevBuf nn_deg;      // int32[nb_node]: neighbours + 1 of each node
+  DevBuf nn_local;    // uint16[nb_entry]: per tile row its neighbours (self included) as ascending footprint indices
   std::vector<int32_t> hdesc_host; // host copy of tile_desc (16 words per tile)
   // ---- value plan ----
   bool lists_valid = false;
@@ -168,6 +173,7 @@ struct afb_ctx {
   int32_t* pin_check = nullptr;     // pinned int32[2]: rows[nb_node] and the stale flag of the last re-build
   cudaEvent_t check_event = nullptr;
   bool check_pending = false;
+  int sparsity_algo = 0;            // AFB_SPARSITY_*
   uint64_t nnz_mesh_gen = ~0ull;    // mesh generation ctx->nnz was last read back for
 
   // timings
@@ -201,6 +207,9 @@ int build_tile_mesh(afb_ctx* ctx);
 int build_tile_lists(afb_ctx* ctx, int mode_flags);
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags);
 bool pattern_tiled_ready(const afb_ctx* ctx);
+bool pattern_nn_ready(const afb_ctx* ctx);
+int pattern_nn_build(afb_ctx* ctx);
+int pattern_nn_place(afb_ctx* ctx);
 int pattern_tiled_extract(afb_ctx* ctx, int32_t* deg, int* stale);
 int pattern_tiled_place(afb_ctx* ctx);
 int ensure_values_zeroed(afb_ctx* ctx);

@@ -389,8 +389,25 @@ int build_pattern(afb_ctx* ctx)
   AFB_TRY(ctx->nz_per_row.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
   const bool fast = pattern_rows_supported(ctx);
   bool done = false;
-  if (pattern_tiled_ready(ctx) && ctx->pattern_mesh_gen == ctx->mesh_gen && ctx->cols.p) {
-    // steady state with the mesh tiling available (the reference re-builds the sparsity on every
+  const bool steady = ctx->pattern_mesh_gen == ctx->mesh_gen && ctx->cols.p;
+  if (steady && ctx->sparsity_algo != AFB_SPARSITY_FROM_CELLS && pattern_nn_ready(ctx) && ctx->nnz_mesh_gen == ctx->mesh_gen && ctx->pin_check) {
+    // steady state, connectivity-based (the reference's computeSparsityAtomicFree walks Arcane's init-time
+    // node-node connectivity: femutils/BSRFormat.cc:445-790): scan of the init-time degrees -> row_index,
+    // columns from the tile-local node-node connectivity.  nnz is a function of the mesh alone and already
+    // known on the host: no host synchronisation; rows[nb_node] and the stale flag are compared later
+    // (verify_pending).
+    AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
+    AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), ctx->stream));
+    AFB_TRY(exclusive_scan_i32(ctx, ctx->plan.nn_deg.as<int32_t>(), ctx->rows.as<int32_t>(), nb_node));
+    AFB_TRY(pattern_nn_place(ctx));
+    AFB_CUDA(cudaMemcpyAsync(ctx->pin_check, ctx->rows.as<int32_t>() + nb_node, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AFB_CUDA(cudaMemcpyAsync(ctx->pin_check + 1, ctx->tmp_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AFB_CUDA(cudaEventRecord(ctx->check_event, ctx->stream));
+    ctx->check_pending = true;
+    done = true;
+  }
+  if (!done && steady && pattern_tiled_ready(ctx)) {
+    // steady state from the cells, with the mesh tiling available (the reference re-builds the sparsity on every
     // AssembleBilinearOperator): per-tile bitmap kernel, degree -> scan -> columns
     AFB_TRY(ctx->tmp_i32b.reserve(sizeof(int32_t) * ((size_t)nb_node + 1)));
     int32_t* deg = ctx->tmp_i32b.as<int32_t>();

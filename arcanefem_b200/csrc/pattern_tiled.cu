@@ -14,6 +14,16 @@
 // already in ascending order.  Pass 1 writes the degrees and parks the tile's columns in a tile-ordered
 // scratch (coalesced); after the scan of the degrees pass 2 moves them to their rows (contiguous runs).
 // 4 bytes per (row, incident cell) are streamed once; no atomics, no global sort, deterministic.
+//
+// Connectivity-based variant (AFB_SPARSITY_FROM_CONNECTIVITY, the twin of the reference's
+// BSRFormat::computeSparsityAtomicFree, femutils/BSRFormat.cc:445-790, and of _buildMatrixNodeWiseCsr,
+// modules/testlab/NodeWiseCsrBiliAssembly.cc:90-152): those walk a node-node connectivity that exists
+// since init (MeshUtils::computeNodeNodeViaEdgeConnectivity, modules/testlab/FemModule.cc:124,136) --
+// degree = neighbours + 1, scan, columns = the neighbours.  The init-time structure here is the
+// tile-local node-node connectivity written once by the inspector (the bitmap kernel above in LOCAL
+// mode): per node its degree, per tile row its neighbours (self included) as ascending 16-bit
+// footprint indices.  A re-build is then: scan of the degrees -> row_index; k_pattern_nn_place
+// translates the footprint indices to node ids and stores them to their rows (coalesced runs).
 #include <algorithm>
 
 #include "tiles.cuh"
@@ -41,10 +51,13 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_wsum)
 
 // pass 1: bitmaps -> degrees (to `deg_out`, node order) and the tile's columns, row by row, into the
 // tile-ordered scratch (coalesced).  `stale` is raised when a tile holds more entries than its slot.
+// LOCAL (inspector, once per tiling): the footprint indices themselves go to `scratch16` = the tile-local
+// node-node connectivity of the connectivity-based re-build.
+template <bool LOCAL>
 __global__ void __launch_bounds__(TG_RMAX)
 k_pattern_tiled_extract(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const uint16_t* __restrict__ rowf, const uint32_t* __restrict__ inc,
                         const uint2* __restrict__ inc_grp, const int32_t* __restrict__ foot, int32_t* __restrict__ deg_out, int32_t* __restrict__ scratch,
-                        int* __restrict__ stale)
+                        uint16_t* __restrict__ scratch16, int* __restrict__ stale)
 {
   extern __shared__ uint32_t pt_smem[];
   __shared__ int s_wsum[TG_RMAX / 32];
@@ -123,12 +136,72 @@ k_pattern_tiled_extract(const TileDesc* __restrict__ desc, const int32_t* __rest
     while (bits) {
       const int b = __ffs(bits) - 1;
       bits &= bits - 1;
-      s_cols[k++] = s_foot[w * 32 + b];
+      s_cols[k++] = LOCAL ? (uint32_t)(w * 32 + b) : s_foot[w * 32 + b];
     }
   }
   __syncthreads();
-  int32_t* out = scratch + d.ent_off;
-  for (int e = threadIdx.x; e < E; e += blockDim.x) out[e] = (int32_t)s_cols[e];
+  if constexpr (LOCAL) {
+    uint16_t* out = scratch16 + d.ent_off;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) out[e] = (uint16_t)s_cols[e];
+  }
+  else {
+    int32_t* out = scratch + d.ent_off;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) out[e] = (int32_t)s_cols[e];
+  }
+}
+
+// connectivity-based re-build, after the scan of the init-time degrees: one CTA per tile, one thread per row
+// notes its row's value offset for each of its entries, then one thread per entry translates the 16-bit
+// footprint index to the node id and stores it (rows with consecutive node ids are adjacent: contiguous runs)
+__global__ void __launch_bounds__(TG_RMAX)
+k_pattern_nn_place(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ rows, const uint16_t* __restrict__ nn_local,
+                   const int32_t* __restrict__ foot, int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row, int* __restrict__ stale)
+{
+  __shared__ int s_wsum[TG_RMAX / 32];
+  __shared__ int32_t s_foot[TG_FMAX];
+  __shared__ int32_t s_dbase[TG_EMAX];
+  __shared__ int s_E;
+  const int32_t t = blockIdx.x;
+  const TileDesc d = desc[t];
+  const int R = d.nb_row;
+  if (R == 0) return;
+  const int i = threadIdx.x;
+  // the tile's neighbour indices do not depend on the scan: requested first
+  constexpr int PER = 12;
+  const uint16_t* src = nn_local + d.ent_off;
+  uint16_t loc[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int e = i + q * blockDim.x;
+    loc[q] = e < d.nb_entry ? __ldg(src + e) : (uint16_t)0;
+  }
+  for (int f = i; f < d.nb_foot; f += blockDim.x) s_foot[f] = __ldg(foot + d.foot_off + f);
+  int deg = 0, rb = 0;
+  int32_t node = -1;
+  if (i < R) {
+    node = __ldg(tile_nodes + d.node_off + i);
+    rb = __ldg(rows + node);
+    deg = __ldg(rows + node + 1) - rb;
+  }
+  const int e0 = block_exclusive_scan(deg, s_wsum);
+  if (i < R) {
+    nz_per_row[node] = deg;
+    if (e0 + deg <= TG_EMAX)
+      for (int k = 0; k < deg; ++k) s_dbase[e0 + k] = rb - e0;
+    if (i == R - 1) s_E = e0 + deg;
+  }
+  __syncthreads();
+  const int E = s_E;
+  if (E != d.nb_entry) { // the connectivity was built for another pattern
+    if (threadIdx.x == 0) atomicExch(stale, 1);
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int e = i + q * blockDim.x;
+    if (e < E) cols[s_dbase[e] + e] = s_foot[loc[q]];
+  }
+  for (int e = i + PER * blockDim.x; e < E; e += blockDim.x) cols[s_dbase[e] + e] = s_foot[__ldg(src + e)];
 }
 
 // pass 2 (after the scan of the degrees): the tile's columns move from the scratch to their rows;
@@ -184,6 +257,12 @@ k_pattern_tiled_place(const TileDesc* __restrict__ desc, const int32_t* __restri
   }
 }
 
+bool pattern_nn_ready(const afb_ctx* ctx)
+{
+  const TilePlan& P = ctx->plan;
+  return pattern_tiled_ready(ctx) && P.nn_valid && P.nn_mesh_gen == ctx->mesh_gen;
+}
+
 bool pattern_tiled_ready(const afb_ctx* ctx)
 {
   const TilePlan& P = ctx->plan;
@@ -204,9 +283,50 @@ int pattern_tiled_extract(afb_ctx* ctx, int32_t* deg, int* stale)
   constexpr size_t WMAX = (TG_FMAX + 31) / 32;
   // bitmap [W][RP] + footprint ids + staged columns + row offsets + per-word prefix counts: bounded by the tile limits
   const size_t smem = sizeof(uint32_t) * (WMAX * (size_t)threads + TG_FMAX + TG_EMAX + (size_t)threads + 1) + sizeof(uint16_t) * WMAX * (size_t)threads;
-  AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pattern_tiled_extract<<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(), P.inc.as<uint32_t>(),
-                                                                      P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), deg, P.col_scratch.as<int32_t>(), ctx->tmp_flag.as<int>());
+  AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pattern_tiled_extract<false><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(),
+                                                                             P.inc.as<uint32_t>(), P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), deg,
+                                                                             P.col_scratch.as<int32_t>(), nullptr, ctx->tmp_flag.as<int>());
+  AFB_LAUNCH_CHECK(ctx);
+  return AFB_OK;
+}
+
+// inspector: the tile-local node-node connectivity (once per mesh tiling)
+int pattern_nn_build(afb_ctx* ctx)
+{
+  TilePlan& P = ctx->plan;
+  P.nn_valid = false;
+  AFB_TRY(P.nn_deg.reserve(sizeof(int32_t) * ((size_t)ctx->nb_node + 1)));
+  AFB_TRY(P.nn_local.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(P.nb_entry, 1)));
+  AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
+  AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), ctx->stream));
+  AFB_CUDA(cudaMemsetAsync(P.nn_deg.p, 0, sizeof(int32_t) * ((size_t)ctx->nb_node + 1), ctx->stream));
+  if (P.nb_tile > 0) {
+    const int threads = pattern_threads(P);
+    constexpr size_t WMAX = (TG_FMAX + 31) / 32;
+    const size_t smem = sizeof(uint32_t) * (WMAX * (size_t)threads + TG_FMAX + TG_EMAX + (size_t)threads + 1) + sizeof(uint16_t) * WMAX * (size_t)threads;
+    AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled_extract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pattern_tiled_extract<true><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(),
+                                                                              P.inc.as<uint32_t>(), P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), P.nn_deg.as<int32_t>(),
+                                                                              nullptr, P.nn_local.as<uint16_t>(), ctx->tmp_flag.as<int>());
+    AFB_LAUNCH_CHECK(ctx);
+  }
+  int stale = 0;
+  AFB_CUDA(cudaMemcpyAsync(&stale, ctx->tmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  AFB_REQUIRE(stale == 0, AFB_ERR_CUDA, "tile inspector: node-node connectivity does not fit the tiling");
+  P.nn_mesh_gen = ctx->mesh_gen;
+  P.nn_valid = true;
+  return AFB_OK;
+}
+
+int pattern_nn_place(afb_ctx* ctx)
+{
+  const TilePlan& P = ctx->plan;
+  if (P.nb_tile == 0) return AFB_OK;
+  k_pattern_nn_place<<<P.nb_tile, pattern_threads(P), 0, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), ctx->rows.as<int32_t>(),
+                                                                        P.nn_local.as<uint16_t>(), P.foot.as<int32_t>(), ctx->cols.as<int32_t>(),
+                                                                        ctx->nz_per_row.as<int32_t>(), ctx->tmp_flag.as<int>());
   AFB_LAUNCH_CHECK(ctx);
   return AFB_OK;
 }

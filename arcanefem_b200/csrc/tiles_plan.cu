@@ -901,6 +901,7 @@ int build_tile_mesh(afb_ctx* ctx)
   P.mesh_gen = ctx->mesh_gen;
   P.mesh_b_class = vec ? 1 : 0;
   P.mesh_valid = true;
+  AFB_TRY(pattern_nn_build(ctx)); // tile-local node-node connectivity of the connectivity-based BuildMatrix
   return AFB_OK;
 }
 

@@ -74,6 +74,16 @@ enum {
   AFB_VARIANT_TILED_GATHER = 2     /* B200 path: row tiles staged in shared memory, every row written exactly once   */
 };
 
+/* sparsity algorithm of a re-build on an unchanged mesh (the first build of a mesh always starts from the cells) */
+enum {
+  AFB_SPARSITY_AUTO = 0,             /* FROM_CONNECTIVITY once the init-time connectivity exists (first tiled assembly), else FROM_CELLS */
+  AFB_SPARSITY_FROM_CELLS = 1,       /* from the cells' nodes, as computeSparsityAtomic / _computeSparsity
+                                        (femutils/BSRFormat.cc:799-1006, modules/testlab/CsrGpuBiliAssembly.cc:42-207)            */
+  AFB_SPARSITY_FROM_CONNECTIVITY = 2 /* from the init-time node-node connectivity, as computeSparsityAtomicFree /
+                                        _buildMatrixNodeWiseCsr (femutils/BSRFormat.cc:445-790,
+                                        modules/testlab/NodeWiseCsrBiliAssembly.cc:90-152); P1 cells, else FROM_CELLS              */
+};
+
 /* BSR value layout (femutils/BSRFormat.cc:367: per-block unless the solver consumes CSR) */
 enum {
   AFB_LAYOUT_PER_BLOCK = 0, /* begin*b*b + i*b + j                   (femutils/BSRFormat.h:292-296) */
@@ -176,6 +186,14 @@ AFB_API int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, u
  * femutils/BSRFormat.cc:400-440) and zeroes values/rhs.
  */
 AFB_API int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_block_row, int64_t* nb_block_nnz);
+
+/*
+ * Which of the reference's two sparsity algorithms a re-build on an unchanged mesh follows (AFB_SPARSITY_*):
+ * BSRFormat::computeSparsityAtomic (from the cells) or BSRFormat::computeSparsityAtomicFree (from the node-node
+ * connectivity Arcane holds since init; here: the tile-local node-node connectivity of the mesh tiling).
+ * Both produce the same row_index / columns (ascending); the setting persists until changed.
+ */
+AFB_API int afb_set_sparsity_algorithm(afb_ctx* ctx, int algorithm);
 
 /* ---- bilinear form ------------------------------------------------------------------------ */
 

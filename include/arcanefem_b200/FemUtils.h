@@ -361,8 +361,18 @@ class BSRFormat {
     check(afb_build_pattern(m_ctx.handle(), m_nb_dof, &nb_row, &nnz));
     m_bsr_matrix._refresh();
   }
-  void computeSparsityAtomic() { computeSparsity(); }     // one deterministic builder replaces both reference algorithms
-  void computeSparsityAtomicFree() { computeSparsity(); }
+  //! from the cells (femutils/BSRFormat.cc:799-1006) / from the init-time node-node connectivity (:445-790);
+  //! both emit the same deterministic pattern (columns ascending)
+  void computeSparsityAtomic()
+  {
+    check(afb_set_sparsity_algorithm(m_ctx.handle(), AFB_SPARSITY_FROM_CELLS));
+    computeSparsity();
+  }
+  void computeSparsityAtomicFree()
+  {
+    check(afb_set_sparsity_algorithm(m_ctx.handle(), AFB_SPARSITY_FROM_CONNECTIVITY));
+    computeSparsity();
+  }
   //! assembleBilinearAtomic(lambda cell -> RealMatrix): cell-wise, fp64 atomics
   void assembleBilinearAtomic(Operator op, const Real* params = nullptr, int nb_params = 0) { _assemble(op, params, nb_params, AFB_VARIANT_CELLWISE_ATOMIC); }
   //! assembleBilinearAtomicFree(lambda (cell, i) -> RealMatrix<1,n>): every row written once; B200: tiled gather

@@ -6,7 +6,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 ctx = A.Context(0)
 ctx.generate_box(3, n)
 ctx.build_pattern(1)
-for name, v in (("atomic", A.VARIANT_CELLWISE_ATOMIC), ("tiled", A.VARIANT_TILED_GATHER)):
+for name, v, algo in (("atomic", A.VARIANT_CELLWISE_ATOMIC, A.SPARSITY_FROM_CELLS), ("tiled/cells", A.VARIANT_TILED_GATHER, A.SPARSITY_FROM_CELLS),
+                      ("tiled/conn", A.VARIANT_TILED_GATHER, A.SPARSITY_AUTO)):
+    ctx.set_sparsity_algorithm(algo)
     tp, ta = [], []
     for _ in range(6):
         ctx.build_pattern(1)

@@ -125,13 +125,24 @@ def test_pattern_with_isolated_node_and_high_valence(ctx):
     assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
 
 
-@pytest.mark.parametrize("name", ["L-shape_2D", "porous_2D", "sphere_3D", "box3d_n9", "box2d_n17"])
-def test_tiled_pattern_rebuild_bit_exact(ctx, name):
-    """Steady-state BuildMatrix: once the tile inspector has run (first tiled assembly), the pattern is
-    re-built by the per-tile bitmap kernel (pattern_tiled.cu); rows/columns stay bit-exact, the values
-    of a fresh pattern read as zero, and a tiled assembly right after needs no zero fill."""
+@pytest.mark.parametrize("algo", [A.SPARSITY_AUTO, A.SPARSITY_FROM_CELLS, A.SPARSITY_FROM_CONNECTIVITY])
+@pytest.mark.parametrize("name", ["L-shape_2D", "porous_2D", "sphere_3D", "bar_3D", "box3d_n9", "box2d_n17"])
+def test_tiled_pattern_rebuild_bit_exact(ctx, name, algo):
+    """Steady-state BuildMatrix: once the tile inspector has run (first tiled assembly, or the first build
+    with SPARSITY_FROM_CONNECTIVITY), the pattern is re-built from the cells by the per-tile bitmap kernel
+    (computeSparsityAtomic) or from the tile-local node-node connectivity (computeSparsityAtomicFree; AUTO
+    picks it); rows/columns stay bit-exact, the values of a fresh pattern read as zero, and a tiled
+    assembly right after needs no zero fill."""
     m = get_mesh(name)
     ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.set_sparsity_algorithm(algo)
+    try:
+        _tiled_pattern_rebuild(ctx, m)
+    finally:
+        ctx.set_sparsity_algorithm(A.SPARSITY_AUTO)
+
+
+def _tiled_pattern_rebuild(ctx, m):
     nbr, nnz = ctx.build_pattern(1)
     rows_ref, cols_ref = O.build_pattern(m.npc, m.nb_node, m.cells)
     ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
@@ -149,7 +160,16 @@ def test_tiled_pattern_rebuild_bit_exact(ctx, name):
         assert np.array_equal(ctx.to_host(A.ARRAY_VALUES), v1), "tiled gather must be bit-reproducible"
     # another block size on the same mesh re-uses the tiling for the pattern
     assert ctx.build_pattern(m.dim) == (nbr, nnz)
+    assert np.array_equal(ctx.to_host(A.ARRAY_ROWS), rows_ref)
     assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+    # ... and a vector operator on it (the tiling is re-cut for b > 1, the connectivity with it)
+    if m.npc in (3, 4):
+        lam, mu = 1.0e6, 8.0e5
+        ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER)
+        assert ctx.build_pattern(m.dim) == (nbr, nnz)
+        assert np.array_equal(ctx.to_host(A.ARRAY_ROWS), rows_ref)
+        assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+        assert np.array_equal(ctx.to_host(A.ARRAY_NZ_PER_ROW), np.diff(rows_ref))
 
 
 def test_ownership_modes(ctx):
