@@ -113,6 +113,7 @@ struct TilePlan {
   DevBuf unit_base;   // uint32 per unit: offset (16-bit slots) of the unit's index slab inside the tile's list region
   DevBuf unit_len;    // uint16 per unit: contributions per entry of the unit (even)
   DevBuf emap;        // uint32 per (unit, lane): tile-local entry | mirror entry << 16; 0xFFFFFFFF = padding lane
+  DevBuf emap_rows;   // uint32 per (unit, lane), vector plans only: tile row of the entry | tile row of the mirror << 16
   DevBuf lists;       // uint16: cache indices, per unit [len/2][32 lanes][2]; one contiguous region per tile (TMA bulk copy)
   DevBuf col_scratch; // int32[nb_entry]: columns in tile order between the two BuildMatrix passes (pattern_tiled.cu)
   DevBuf scratch_a, scratch_b, scratch_c, stats; // builder scratch

@@ -108,6 +108,7 @@ struct ExecArgs {
   const uint32_t* unit_base;
   const uint16_t* unit_len;
   const uint32_t* emap;
+  const uint32_t* emap_rows; // vector plans only
   const uint16_t* lists;
   double* values;
   int accumulate;
@@ -217,6 +218,12 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
   unsigned parity = 0;
   int slot = 0;
   TilePrefetch pf;
+#ifdef AFB_EXP_STAGGER
+  if (blockIdx.x >= gridDim.x / 2) { // experiment: start the second CTA of every SM half a tile later
+    const long long t0 = clock64();
+    while (clock64() - t0 < AFB_EXP_STAGGER) {}
+  }
+#endif
   if (t < A.nb_tile) {
     prefetch_level1(S.desc[0], A, pf);
     prefetch_level2<TG_ROUNDS, TG_THREADS, true>(S.desc[0], A, pf); // the only exposed dependent load of the kernel
@@ -284,14 +291,22 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
 #endif
           const uint32_t* l = l32 + (S.ubase[u] >> 1) + lane;
           const int len2 = S.ulen[u] >> 1;
-          double acc0 = 0.0, acc1 = 0.0;
+          // four list words (8 contributions) per step: the list loads, then the cache gathers, are all in
+          // flight together (the lane's sum is latency-bound otherwise); fixed association => reproducible
+          double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll 1
-          for (int k = 0; k < len2; k += 2) {
+          for (int k = 0; k < len2; k += 4) {
             const uint32_t i0 = l[k * 32];
             const uint32_t i1 = (k + 1 < len2) ? l[(k + 1) * 32] : ZPAIR;
-            acc0 += S.Kc[i0 & 0xFFFFu]; acc1 += S.Kc[i0 >> 16];
-            acc0 += S.Kc[i1 & 0xFFFFu]; acc1 += S.Kc[i1 >> 16];
+            const uint32_t i2 = (k + 2 < len2) ? l[(k + 2) * 32] : ZPAIR;
+            const uint32_t i3 = (k + 3 < len2) ? l[(k + 3) * 32] : ZPAIR;
+            const double a0 = S.Kc[i0 & 0xFFFFu], a1 = S.Kc[i0 >> 16], a2 = S.Kc[i1 & 0xFFFFu], a3 = S.Kc[i1 >> 16];
+            const double a4 = S.Kc[i2 & 0xFFFFu], a5 = S.Kc[i2 >> 16], a6 = S.Kc[i3 & 0xFFFFu], a7 = S.Kc[i3 >> 16];
+            acc0 += a0; acc1 += a1; acc2 += a2; acc3 += a3;
+            acc0 += a4; acc1 += a5; acc2 += a6; acc3 += a7;
           }
+          acc0 += acc2;
+          acc1 += acc3;
           const uint32_t w = em[q];
           if (w != 0xFFFFFFFFu) {
             const double v = acc0 + acc1;
@@ -319,10 +334,21 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
         const int32_t rb = S.rowbeg[i];
         if (rowinfo_own(ri)) {
           ed = e0 + rowinfo_pdiag(ri);
-          for (int e = e0 + q; e < e1; e += G) {
+          double s1 = 0.0;
+          int e = e0 + q;
+          for (; e + G < e1; e += 2 * G) { // two independent loads and sums per step (the diagonal slot holds stale data: select, never add)
+            const double v0 = S.vout[e], v1 = S.vout[e + G];
             O.dbase[e] = rb;
-            if (e != ed) sum += S.vout[e];
+            O.dbase[e + G] = rb;
+            sum += e != ed ? v0 : 0.0;
+            s1 += e + G != ed ? v1 : 0.0;
           }
+          if (e < e1) {
+            const double v0 = S.vout[e];
+            O.dbase[e] = rb;
+            sum += e != ed ? v0 : 0.0;
+          }
+          sum += s1;
         }
         else { // rows of non-owned nodes stay zero (the isOwn gate of the reference)
           for (int e = e0 + q; e < e1; e += G) {
@@ -456,10 +482,12 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
     int32_t desc_word = 0;
     if (threadIdx.x < DW && tnnn < A.nb_tile) desc_word = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnnn) + threadIdx.x);
     __syncthreads();
-    // ---- phase B: one lane per block entry; M accumulated in registers, lists streamed from global ----
+    // ---- phase B: one lane per block entry; M accumulated in registers, lists streamed from global
+    //      (dynamic unit hand-out and deeper list prefetch were measured slower) ----
     const uint32_t* l32 = reinterpret_cast<const uint32_t*>(A.lists + d.list_off);
     for (int u = warp; u < d.nb_unit; u += NW) {
       const uint32_t em = __ldg(A.emap + (size_t)(d.unit_off + u) * 32 + lane);
+      const uint32_t er = __ldg(A.emap_rows + (size_t)(d.unit_off + u) * 32 + lane);
       const uint32_t* l = l32 + (S.ubase[u] >> 1) + lane;
       const int len2 = S.ulen[u] >> 1;
       double M[DIM][DIM];
@@ -497,13 +525,8 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
         for (int i = 0; i < DIM; ++i)
 #pragma unroll
           for (int j = 0; j < DIM; ++j) blk[i * B + j] = lam * M[i][j] + mu * M[j][i] + (i == j ? mu * tr : 0.0);
-        // locate (row, position) of the entry and of its mirror from the tile-local entry index
-        auto emit = [&](int e, bool transpose) {
-          int lo = 0, hi = d.nb_row;
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (rowinfo_erow(S.rowinfo[mid]) <= e) lo = mid; else hi = mid;
-          }
+        // (row, position) of the entry and of its mirror: rows from the plan, positions from the tile-local entry index
+        auto emit = [&](int e, int lo, bool transpose) {
           const int e0 = rowinfo_erow(S.rowinfo[lo]);
           const int nz = (lo + 1 < d.nb_row ? rowinfo_erow(S.rowinfo[lo + 1]) : d.nb_entry) - e0;
           const int rb = S.rowbeg[lo], p = rb + (e - e0);
@@ -516,8 +539,8 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
               if (A.accumulate) *dst += v; else *dst = v;
             }
         };
-        emit((int)(em & 0xFFFFu), false);
-        if ((em >> 16) != TG_NONE16) emit((int)(em >> 16), true);
+        emit((int)(em & 0xFFFFu), (int)(er & 0xFFFFu), false);
+        if ((em >> 16) != TG_NONE16) emit((int)(em >> 16), (int)(er >> 16), true);
       }
     }
     if (threadIdx.x < DW && tnnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnnslot])[threadIdx.x] = desc_word;
@@ -587,6 +610,7 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   A.unit_base = P.unit_base.as<uint32_t>();
   A.unit_len = P.unit_len.as<uint16_t>();
   A.emap = P.emap.as<uint32_t>();
+  A.emap_rows = vec ? P.emap_rows.as<uint32_t>() : nullptr;
   A.lists = P.lists.as<uint16_t>();
   A.values = ctx->values.as<double>();
   A.accumulate = accumulate;

@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1)
 k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __restrict__ tnodes, const int32_t* __restrict__ tile_cells, const int32_t* __restrict__ conn,
              const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, const int32_t* __restrict__ node_tile, const int32_t* __restrict__ node_lrow,
              const uint8_t* __restrict__ is_own, int64_t nb_own_cell, uint32_t* __restrict__ rowinfo, uint32_t* __restrict__ unit_base, uint16_t* __restrict__ unit_len,
-             uint32_t* __restrict__ emap, uint16_t* __restrict__ lists, int list_max, int* __restrict__ error)
+             uint32_t* __restrict__ emap, uint32_t* __restrict__ emap_rows, uint16_t* __restrict__ lists, int list_max, int* __restrict__ error)
 {
   extern __shared__ unsigned char tl_raw[];
   ListBuilderSmem& S = *reinterpret_cast<ListBuilderSmem*>(tl_raw);
@@ -655,6 +655,19 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
       const bool valid = x < EC;
       const int e = valid ? (int)(S.keys[x] & 0xFFFFu) : 0;
       emap[(size_t)(d.unit_off + (x >> 5)) * 32 + (x & 31)] = valid ? ((uint32_t)e | ((uint32_t)S.e2[e] << 16)) : 0xFFFFFFFFu;
+      if (VEC) { // tile rows holding the entry and its mirror (the vector executor writes blocks straight to their rows)
+        auto row_of = [&](int ee) {
+          int lo = 0, hi = R;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (S.erow[mid] <= ee) lo = mid; else hi = mid;
+          }
+          return (uint32_t)lo;
+        };
+        uint32_t w = 0xFFFFFFFFu;
+        if (valid) w = row_of(e) | ((S.e2[e] != TG_NONE16 ? row_of((int)S.e2[e]) : (uint32_t)TG_NONE16) << 16);
+        emap_rows[(size_t)(d.unit_off + (x >> 5)) * 32 + (x & 31)] = w;
+      }
     }
     // Lists of a unit, one thread per half-warp of lanes.  The executor reads contribution k of its 16
     // lanes with one shared-memory instruction: the k-th slots of the 16 lists are chosen greedily so that
@@ -939,6 +952,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
   AFB_TRY(P.unit_base.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(unit_off, 1)));
   AFB_TRY(P.unit_len.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(unit_off, 1)));
   AFB_TRY(P.emap.reserve(sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(unit_off, 1)));
+  if (vec) AFB_TRY(P.emap_rows.reserve(sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(unit_off, 1)));
   AFB_TRY(P.lists.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
   AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
   AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
@@ -953,7 +967,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
       if (e != cudaSuccess) return e;
       kernel<<<grid, TB_THREADS, smem, st>>>(P.tile_desc.as<TileDesc>(), nb_tile, P.tile_nodes.as<int32_t>(), P.tile_cells.as<int32_t>(), ctx->conn.as<int32_t>(),
                                              ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(), P.node_tile.as<int32_t>(), P.node_lrow.as<int32_t>(), own, nb_own_cell,
-                                             P.rowinfo.as<uint32_t>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), P.emap.as<uint32_t>(), P.lists.as<uint16_t>(),
+                                             P.rowinfo.as<uint32_t>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), P.emap.as<uint32_t>(), P.emap_rows.as<uint32_t>(), P.lists.as<uint16_t>(),
                                              list_max, ctx->tmp_flag.as<int>());
       return cudaGetLastError();
     };

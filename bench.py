@@ -223,6 +223,24 @@ def cpu_baseline_leg(args, n_job):
 VARIANT_NAMES = {0: "cellwise-atomic (csr-gpu)", 1: "nodewise (nwcsr / AF-CSR)", 2: "tiled-gather (atomic-free, B200)"}
 
 
+VARIANT_KERNEL = {0: "k_assemble_cellwise", 1: "k_assemble_nodewise", 2: "k_assemble_tiled"}
+
+
+def committed_traffic(kernel, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the value kernel, from the committed
+    `ncu --set full` capture of the same kernel on the same box size (profiles/traffic.json); None otherwise
+    (a bench run is never taken under the profiler)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if kernel is None or n is None or not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        t = json.load(f)
+    e = t.get(f"{kernel}:n={n}")
+    if not e:
+        return None, None
+    return float(e["dram_bytes_read"] + e["dram_bytes_write"]), e["source"]
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -302,6 +320,24 @@ def run_b200(args):
         dist.broadcast(t, 0)
         variant = int(t.item())
     mode = args.mode if world > 1 else "single"
+    # BuildMatrix algorithm of the steady-state step: the reference pairs the atomic assembly with the sparsity
+    # computed from the cells (computeSparsityAtomic) and the atomic-free assembly with the one walking the
+    # init-time node-node connectivity (computeSparsityAtomicFree); --sparsity overrides.
+    SPARSITY = {"cells": A.SPARSITY_FROM_CELLS, "connectivity": A.SPARSITY_FROM_CONNECTIVITY}
+    sparsity = args.sparsity if args.sparsity != "auto" else ("cells" if variant == A.VARIANT_CELLWISE_ATOMIC else "connectivity")
+    per_sparsity = {}
+    for name, algo in SPARSITY.items():
+        ctx.set_sparsity_algorithm(algo)
+        ts = []
+        for _ in range(4):
+            e0, e1 = ev(), ev()
+            e0.record(stream)
+            ctx.build_pattern(1)
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        per_sparsity[name] = min(ts[1:])
+    ctx.set_sparsity_algorithm(SPARSITY[sparsity])
 
     def step(events=None):
         if events is not None:
@@ -431,19 +467,23 @@ def run_b200(args):
         value = cells_all * args.steps / (total_ms * 1e-3)
         ach_values = float(mx[8]) / (values_ms * 1e-3) / 1e9      # slowest rank's kernel on its own slab
         ach_pattern = float(mx[9]) / (pattern_ms * 1e-3) / 1e9
+        traffic, traffic_src = committed_traffic(VARIANT_KERNEL.get(variant), n if world == 1 else None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C2 3-D Poisson P1 Tet4 CSR, structured box n={n} jitter 0.2 ({int(cells_all)} Tet4), z-slab per GPU",
-                       "format": "csr", "variant": VARIANT_NAMES[variant], "l2": "inputs larger than L2 (connectivity+values > 126 MB per GPU), no flush",
+                       "format": "csr", "variant": VARIANT_NAMES[variant],
+                       "sparsity": {"cells": "from the cells (computeSparsityAtomic)",
+                                    "connectivity": "from the init-time node-node connectivity (computeSparsityAtomicFree)"}[sparsity], "l2": "inputs larger than L2 (connectivity+values > 126 MB per GPU), no flush",
                        "parallelism": f"slab{world}" + ("" if world == 1 else f" ({mode}: " + ("own cells + NCCL ghost-row exchange" if mode == "exchange" else "ghost cells recomputed, no exchange") + ")")},
             "phases": {"build_matrix_ms": pattern_ms, "add_and_compute_ms": values_ms,
                        "values_only_elements_per_s": cells_all / (values_ms * 1e-3),
                        "variants_ms": {VARIANT_NAMES[k]: v for k, v in per_variant.items()},
+                       "build_matrix_ms_by_sparsity": per_sparsity,
                        "decomposition": mode, "exchange_bytes_sent_recv_rank0": list(exch_bytes),
                        "other_scheme_ms_per_step": None if other_ms is None else {other_ms[0]: other_ms[1]}},
             "roofline": {"bound": "hbm", "kernel": "value assembly (AddAndCompute)", "achieved": ach_values, "peak": peak, "unit": "GB/s", "frac": ach_values / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": float(mx[8])},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": float(mx[8])},
             "roofline_pattern": {"bound": "hbm", "kernel": "BuildMatrix phase (degree, scan, columns)", "achieved": ach_pattern, "peak": peak, "unit": "GB/s",
                                  "frac": ach_pattern / peak, "algorithmic_bytes": float(mx[9])},
             "e2e": {"value": cells_all * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sm[6]), "d2h_bytes_per_step": int(sm[7]),
@@ -471,6 +511,7 @@ def main():
     ap.add_argument("--n", type=int, default=120, help="box size at N=1 (C2: 120)")
     ap.add_argument("--cpu-n", type=int, default=120, help="largest box the CPU legs run (bounded sample)")
     ap.add_argument("--variant", default="auto", choices=["auto", "atomic", "nodewise", "tiled"])
+    ap.add_argument("--sparsity", default="auto", choices=["auto", "cells", "connectivity"], help="steady-state BuildMatrix algorithm (auto: by variant, as the reference pairs them)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="exchange", choices=["exchange", "replicate"], help="N>1: ghost-row exchange over NCCL (north star) or the reference's ghost-cell replication")
     args = ap.parse_args()
