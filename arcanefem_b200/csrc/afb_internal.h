@@ -102,6 +102,7 @@ struct TilePlan {
   bool nn_valid = false;
   uint64_t nn_mesh_gen = ~0ull;
   DevBuf nn_deg;      // int32[nb_node]: neighbours + 1 of each node
+  DevBuf nn_e0;       // uint16[nb_node] (tile-row order): first tile-local entry of each tile row
   DevBuf nn_local;    // uint16[nb_entry]: per tile row its neighbours (self included) as ascending footprint indices
   std::vector<int32_t> hdesc_host; // host copy of tile_desc (16 words per tile)
   // ---- value plan ----
@@ -164,7 +165,7 @@ struct afb_ctx {
   bool saved_valid = false;
 
   // scratch
-  afb::DevBuf tmp_i32a, tmp_i32b, tmp_scan, tmp_ids, tmp_vals, tmp_flag, tmp_lookback;
+  afb::DevBuf tmp_i32a, tmp_i32b, tmp_scan, tmp_ids, tmp_vals, tmp_flag, tmp_lookback, scan_state;
   uint64_t mesh_gen = 0;        // bumped by afb_set_mesh / afb_mesh_generate_box
   uint64_t pattern_mesh_gen = ~0ull; // mesh generation the column buffer was last sized for
 
@@ -175,6 +176,7 @@ struct afb_ctx {
   cudaEvent_t check_event = nullptr;
   bool check_pending = false;
   int sparsity_algo = 0;            // AFB_SPARSITY_*
+  unsigned scan_tickets = 0, scan_epoch = 0; // chained scan (scan.cu): tiles handed out so far, epoch of the last call
   uint64_t nnz_mesh_gen = ~0ull;    // mesh generation ctx->nnz was last read back for
 
   // timings

@@ -57,7 +57,7 @@ template <bool LOCAL>
 __global__ void __launch_bounds__(TG_RMAX)
 k_pattern_tiled_extract(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const uint16_t* __restrict__ rowf, const uint32_t* __restrict__ inc,
                         const uint2* __restrict__ inc_grp, const int32_t* __restrict__ foot, int32_t* __restrict__ deg_out, int32_t* __restrict__ scratch,
-                        uint16_t* __restrict__ scratch16, int* __restrict__ stale)
+                        uint16_t* __restrict__ scratch16, uint16_t* __restrict__ row_e0, int* __restrict__ stale)
 {
   extern __shared__ uint32_t pt_smem[];
   __shared__ int s_wsum[TG_RMAX / 32];
@@ -120,6 +120,7 @@ k_pattern_tiled_extract(const TileDesc* __restrict__ desc, const int32_t* __rest
     deg_out[node] = deg;
     s_erow[i] = e0;
     if (i == R - 1) s_erow[R] = e0 + deg;
+    if constexpr (LOCAL) row_e0[d.node_off + i] = (uint16_t)e0;
   }
   __syncthreads();
   const int E = s_erow[R];
@@ -155,45 +156,45 @@ k_pattern_tiled_extract(const TileDesc* __restrict__ desc, const int32_t* __rest
 // footprint index to the node id and stores it (rows with consecutive node ids are adjacent: contiguous runs)
 __global__ void __launch_bounds__(TG_RMAX)
 k_pattern_nn_place(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ rows, const uint16_t* __restrict__ nn_local,
-                   const int32_t* __restrict__ foot, int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row, int* __restrict__ stale)
+                   const uint16_t* __restrict__ nn_e0, const int32_t* __restrict__ foot, int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row, int* __restrict__ stale)
 {
-  __shared__ int s_wsum[TG_RMAX / 32];
   __shared__ int32_t s_foot[TG_FMAX];
   __shared__ int32_t s_dbase[TG_EMAX];
-  __shared__ int s_E;
+  __shared__ int s_bad;
   const int32_t t = blockIdx.x;
   const TileDesc d = desc[t];
-  const int R = d.nb_row;
+  const int R = d.nb_row, E = d.nb_entry;
   if (R == 0) return;
   const int i = threadIdx.x;
-  // the tile's neighbour indices do not depend on the scan: requested first
+  if (i == 0) s_bad = 0;
+  // everything addressed by the descriptor alone is requested at once; rows[node] is the only dependent load
   constexpr int PER = 12;
   const uint16_t* src = nn_local + d.ent_off;
   uint16_t loc[PER];
 #pragma unroll
   for (int q = 0; q < PER; ++q) {
-    const int e = i + q * blockDim.x;
-    loc[q] = e < d.nb_entry ? __ldg(src + e) : (uint16_t)0;
+    const int e = min(i + q * (int)blockDim.x, E - 1);
+    loc[q] = __ldg(src + e);
   }
-  for (int f = i; f < d.nb_foot; f += blockDim.x) s_foot[f] = __ldg(foot + d.foot_off + f);
-  int deg = 0, rb = 0;
-  int32_t node = -1;
+  int32_t node = 0;
+  int e0 = 0, e1 = 0;
   if (i < R) {
     node = __ldg(tile_nodes + d.node_off + i);
-    rb = __ldg(rows + node);
-    deg = __ldg(rows + node + 1) - rb;
+    e0 = __ldg(nn_e0 + d.node_off + i);
+    e1 = i + 1 < R ? (int)__ldg(nn_e0 + d.node_off + i + 1) : E;
   }
-  const int e0 = block_exclusive_scan(deg, s_wsum);
+  for (int f = i; f < d.nb_foot; f += blockDim.x) s_foot[f] = __ldg(foot + d.foot_off + f);
+  __syncthreads();
   if (i < R) {
+    const int rb = __ldg(rows + node), deg = __ldg(rows + node + 1) - rb;
     nz_per_row[node] = deg;
-    if (e0 + deg <= TG_EMAX)
-      for (int k = 0; k < deg; ++k) s_dbase[e0 + k] = rb - e0;
-    if (i == R - 1) s_E = e0 + deg;
+    if (deg != e1 - e0) s_bad = 1; // the connectivity was built for another pattern
+    else
+      for (int e = e0; e < e1; ++e) s_dbase[e] = rb - e0;
   }
   __syncthreads();
-  const int E = s_E;
-  if (E != d.nb_entry) { // the connectivity was built for another pattern
-    if (threadIdx.x == 0) atomicExch(stale, 1);
+  if (s_bad) {
+    if (i == 0) atomicExch(stale, 1);
     return;
   }
 #pragma unroll
@@ -286,7 +287,7 @@ int pattern_tiled_extract(afb_ctx* ctx, int32_t* deg, int* stale)
   AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_pattern_tiled_extract<false><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(),
                                                                              P.inc.as<uint32_t>(), P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), deg,
-                                                                             P.col_scratch.as<int32_t>(), nullptr, ctx->tmp_flag.as<int>());
+                                                                             P.col_scratch.as<int32_t>(), nullptr, nullptr, ctx->tmp_flag.as<int>());
   AFB_LAUNCH_CHECK(ctx);
   return AFB_OK;
 }
@@ -298,6 +299,7 @@ int pattern_nn_build(afb_ctx* ctx)
   P.nn_valid = false;
   AFB_TRY(P.nn_deg.reserve(sizeof(int32_t) * ((size_t)ctx->nb_node + 1)));
   AFB_TRY(P.nn_local.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(P.nb_entry, 1)));
+  AFB_TRY(P.nn_e0.reserve(sizeof(uint16_t) * ((size_t)ctx->nb_node + 1)));
   AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
   AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), ctx->stream));
   AFB_CUDA(cudaMemsetAsync(P.nn_deg.p, 0, sizeof(int32_t) * ((size_t)ctx->nb_node + 1), ctx->stream));
@@ -308,7 +310,7 @@ int pattern_nn_build(afb_ctx* ctx)
     AFB_CUDA(cudaFuncSetAttribute(k_pattern_tiled_extract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_pattern_tiled_extract<true><<<P.nb_tile, threads, smem, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), P.rowf.as<uint16_t>(),
                                                                               P.inc.as<uint32_t>(), P.inc_grp.as<uint2>(), P.foot.as<int32_t>(), P.nn_deg.as<int32_t>(),
-                                                                              nullptr, P.nn_local.as<uint16_t>(), ctx->tmp_flag.as<int>());
+                                                                              nullptr, P.nn_local.as<uint16_t>(), P.nn_e0.as<uint16_t>(), ctx->tmp_flag.as<int>());
     AFB_LAUNCH_CHECK(ctx);
   }
   int stale = 0;
@@ -325,7 +327,7 @@ int pattern_nn_place(afb_ctx* ctx)
   const TilePlan& P = ctx->plan;
   if (P.nb_tile == 0) return AFB_OK;
   k_pattern_nn_place<<<P.nb_tile, pattern_threads(P), 0, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), ctx->rows.as<int32_t>(),
-                                                                        P.nn_local.as<uint16_t>(), P.foot.as<int32_t>(), ctx->cols.as<int32_t>(),
+                                                                        P.nn_local.as<uint16_t>(), P.nn_e0.as<uint16_t>(), P.foot.as<int32_t>(), ctx->cols.as<int32_t>(),
                                                                         ctx->nz_per_row.as<int32_t>(), ctx->tmp_flag.as<int>());
   AFB_LAUNCH_CHECK(ctx);
   return AFB_OK;
