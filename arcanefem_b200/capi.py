@@ -37,7 +37,8 @@ EXPORTS = [
     "afb_build_pattern", "afb_set_sparsity_algorithm", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_set_dirichlet_nodes",
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
-    "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail", "afb_last_timings", "afb_launch_count",
+    "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail",
+    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_status", "afb_p2p_disconnect", "afb_last_timings", "afb_launch_count",
 ]
 
 
@@ -248,6 +249,34 @@ class Context:
 
     def add_values_at(self, n, slots_ptr, contrib_ptr):
         _check(lib().afb_add_values_at(self._h, C.c_int64(n), _ptr(slots_ptr), _ptr(contrib_ptr)))
+
+    # ghost-row exchange over NVLink peer memory (p2p.cu)
+    def p2p_export(self):
+        vh, fh = C.create_string_buffer(64), C.create_string_buffer(64)
+        _check(lib().afb_p2p_export(self._h, vh, fh))
+        return vh.raw, fh.raw
+
+    def p2p_connect(self, my_rank, peer_rank, values_handles, flags_handles, pull_first, pull_count, slots, send_first, send_count):
+        """peer_rank: list of ranks; *_handles: list of 64-byte strings; slots: list of device int64 tensors (or None)."""
+        n = len(peer_rank)
+        pr = (C.c_int32 * max(n, 1))(*peer_rank)
+        vh = C.create_string_buffer(b"".join(values_handles), max(64 * n, 1))
+        fh = C.create_string_buffer(b"".join(flags_handles), max(64 * n, 1))
+        i64 = lambda a: (C.c_int64 * max(n, 1))(*[int(x) for x in a])
+        sl = (C.c_void_p * max(n, 1))(*[None if (t is None or t.numel() == 0) else t.data_ptr() for t in slots])
+        self._p2p_keep = list(slots)
+        _check(lib().afb_p2p_connect(self._h, int(my_rank), n, pr, vh, fh, i64(pull_first), i64(pull_count), sl, i64(send_first), i64(send_count)))
+
+    def p2p_exchange(self):
+        _check(lib().afb_p2p_exchange(self._h))
+
+    def p2p_status(self):
+        st = C.c_int()
+        _check(lib().afb_p2p_status(self._h, C.byref(st)))
+        return st.value
+
+    def p2p_disconnect(self):
+        _check(lib().afb_p2p_disconnect(self._h))
 
     def values_tail(self, first_block_row):
         first, nb = C.c_int64(), C.c_int64()

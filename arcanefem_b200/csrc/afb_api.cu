@@ -111,6 +111,7 @@ int afb_destroy(afb_ctx* ctx)
   if (!ctx) return AFB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  p2p_destroy(ctx);
   DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,
                      &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
                      &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback, &ctx->scan_state,
@@ -142,6 +143,41 @@ int afb_set_sparsity_algorithm(afb_ctx* ctx, int algorithm)
   AFB_REQUIRE(algorithm >= AFB_SPARSITY_AUTO && algorithm <= AFB_SPARSITY_FROM_CONNECTIVITY, AFB_ERR_INVALID, "afb_set_sparsity_algorithm: unknown algorithm %d", algorithm);
   ctx->sparsity_algo = algorithm;
   return AFB_OK;
+}
+
+// ---- ghost-row exchange over NVLink peer memory (p2p.cu) ----
+int afb_p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern && values_handle && flags_handle, AFB_ERR_INVALID, "afb_p2p_export: no pattern / null handle buffer");
+  return p2p_export(ctx, values_handle, flags_handle);
+}
+
+int afb_p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const int64_t* pull_first,
+                    const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_p2p_connect: no pattern");
+  return p2p_connect(ctx, my_rank, nb_peer, peer_rank, values_handles, flags_handles, pull_first, pull_count, slots, send_first, send_count);
+}
+
+int afb_p2p_exchange(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  return p2p_exchange(ctx);
+}
+
+int afb_p2p_status(afb_ctx* ctx, int* status)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(status, AFB_ERR_INVALID, "afb_p2p_status: null");
+  return p2p_status(ctx, status);
+}
+
+int afb_p2p_disconnect(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  return p2p_disconnect(ctx);
 }
 
 int afb_synchronize(afb_ctx* ctx)

@@ -176,6 +176,7 @@ struct afb_ctx {
   cudaEvent_t check_event = nullptr;
   bool check_pending = false;
   int sparsity_algo = 0;            // AFB_SPARSITY_*
+  void* p2p = nullptr;              // afb::P2PState (p2p.cu): ghost-row exchange over NVLink peer memory
   unsigned scan_tickets = 0, scan_epoch = 0; // chained scan (scan.cu): tiles handed out so far, epoch of the last call
   uint64_t nnz_mesh_gen = ~0ull;    // mesh generation ctx->nnz was last read back for
 
@@ -210,6 +211,13 @@ int build_tile_mesh(afb_ctx* ctx);
 int build_tile_lists(afb_ctx* ctx, int mode_flags);
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags);
 bool pattern_tiled_ready(const afb_ctx* ctx);
+void p2p_destroy(afb_ctx* ctx);
+int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle);
+int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const int64_t* pull_first,
+                const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count);
+int p2p_exchange(afb_ctx* ctx);
+int p2p_status(afb_ctx* ctx, int* status);
+int p2p_disconnect(afb_ctx* ctx);
 bool pattern_nn_ready(const afb_ctx* ctx);
 int pattern_nn_build(afb_ctx* ctx);
 int pattern_nn_place(afb_ctx* ctx);

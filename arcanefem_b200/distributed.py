@@ -85,10 +85,13 @@ class ExchangePlan:
       make_buffer(n)            -> float64 tensor for receiving
     comm_device: where the tensors handed to torch.distributed live ("cpu" for gloo, "cuda:i" for nccl).
     After the sends the ghost rows are zeroed (the reference's ghost rows are all-zero: isOwn gate).
+    p2p: optional object with export() / connect(...) / exchange() (capi.Context: afb_p2p_*): the per-assembly
+    exchange then is ONE kernel pulling the neighbours' partial rows over NVLink peer memory (csrc/p2p.cu);
+    torch.distributed only carries the set-up (IPC handles, slice offsets).
     """
 
     def __init__(self, rank, world, node_gid, node_owner, nb_own_node, b, layout_per_row, tail_pattern, lookup, values_slice, add_at, make_buffer,
-                 group=None, comm_device="cpu"):
+                 group=None, comm_device="cpu", p2p=None):
         import torch.distributed as dist
         self.dist, self.group, self.comm_device = dist, group, comm_device
         self.rank, self.world, self.b = rank, world, b
@@ -98,7 +101,10 @@ class ExchangePlan:
         self.values_slice, self.add_at, self.make_buffer = values_slice, add_at, make_buffer
         self.send = []   # (peer, first_value, nb_values)
         self.recv = []   # (peer, slots tensor, buffer)
+        self.p2p = None
         self._setup(layout_per_row, tail_pattern, lookup)
+        if p2p is not None:
+            self._setup_p2p(p2p)
 
     # -- helpers ---------------------------------------------------------------------------------
     def _exchange_arrays(self, out_by_peer, dtype):
@@ -166,9 +172,39 @@ class ExchangePlan:
             assert bool((slots >= 0).all()), "a neighbour's partial row has an entry outside this rank's pattern"
             self.recv.append((q, slots, self.make_buffer(int(dr.size))))
 
+    def _setup_p2p(self, p2p):
+        """Collective: IPC handles of every rank's values array, and for every neighbour pair the slice one pulls
+        from the other."""
+        import torch
+        dist = self.dist
+        send = {q: (first, n) for q, first, n in self.send}
+        recv = {q: slots for q, slots, _ in self.recv}
+        peers = sorted(set(send) | set(recv))
+        told = self._exchange_arrays({q: np.array(send.get(q, (0, 0)), dtype=np.int64) for q in peers}, np.int64)
+        vh, fh = p2p.export()
+        mine = torch.tensor(list(vh + fh), dtype=torch.uint8).to(self.comm_device)
+        allh = [torch.zeros(128, dtype=torch.uint8, device=self.comm_device) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self.group)
+        allh = [bytes(t.cpu().numpy().tobytes()) for t in allh]
+        pull_first, pull_count, slots = [], [], []
+        for q in peers:
+            first, n = (int(x) for x in told[q])
+            sl = recv.get(q)
+            assert n == (0 if sl is None else int(sl.numel())), "neighbour's slice and the local slot list differ in length"
+            pull_first.append(first)
+            pull_count.append(n)
+            slots.append(sl)
+        p2p.connect(self.rank, peers, [allh[q][:64] for q in peers], [allh[q][64:] for q in peers], pull_first, pull_count, slots,
+                    [send.get(q, (0, 0))[0] for q in peers], [send.get(q, (0, 0))[1] for q in peers])
+        dist.barrier(group=self.group)
+        self.p2p = p2p
+
     # -- every assembly ------------------------------------------------------------------------------
     def exchange(self):
         """Send the partial ghost rows to their owners and add the received ones (stream-ordered for NCCL)."""
+        if self.p2p is not None:
+            self.p2p.exchange()
+            return
         dist = self.dist
         ops = []
         for q, first, n in self.send:
@@ -220,11 +256,31 @@ class ExchangePlan:
 # ---------------------------------------------------------------------------------------------------
 # GPU binding
 # ---------------------------------------------------------------------------------------------------
+class _P2P:
+    """afb_p2p_* of one context behind the three calls ExchangePlan needs."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def export(self):
+        return self.ctx.p2p_export()
+
+    def connect(self, *a):
+        self.ctx.p2p_connect(*a)
+
+    def exchange(self):
+        self.ctx.p2p_exchange()
+
+
 class DistributedAssembly:
     """One rank's share of a domain-decomposed assembly on its GPU (context `ctx`)."""
 
-    def __init__(self, ctx, rank, world, node_gid, node_owner, nb_own_node, device_index, group=None):
+    def __init__(self, ctx, rank, world, node_gid, node_owner, nb_own_node, device_index, group=None, transport="p2p", comm_device=None):
+        """transport "p2p": ghost rows travel in one kernel over NVLink peer memory (CUDA IPC, csrc/p2p.cu);
+        "nccl": torch.distributed send/recv of the rows + accumulate kernels.  comm_device: where set-up tensors live
+        (default the GPU, for the nccl backend; "cpu" with a gloo group)."""
         self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.transport, self.comm_device = transport, comm_device
         self.node_gid, self.node_owner, self.nb_own_node = node_gid, node_owner, int(nb_own_node)
         self.device_index = device_index
         self.plan = None
@@ -261,7 +317,7 @@ class DistributedAssembly:
                                  values_slice=lambda first, n: vals_t[first:first + n],
                                  add_at=lambda slots, buf: ctx.add_values_at(int(slots.numel()), slots, buf),
                                  make_buffer=lambda n: torch.empty(n, dtype=torch.float64, device=f"cuda:{dev}"), group=self.group,
-                                 comm_device=f"cuda:{dev}")
+                                 comm_device=self.comm_device or f"cuda:{dev}", p2p=_P2P(ctx) if self.transport == "p2p" else None)
 
     def assemble(self, op, params=None, fmt=None, variant=None, layout=None, mode="exchange", flags=0):
         """Fresh assembly of this rank's rows (call after ctx.build_pattern).  mode "exchange": own cells
@@ -280,7 +336,13 @@ class DistributedAssembly:
             # the value layout is stored by the assembly: build the plan after the first one
             self._build_plan(layout)
             self._plan_key = key
-        self.plan.exchange()
+        try:
+            self.plan.exchange()
+        except A.AfbError as e:
+            if "values array moved" not in str(e):
+                raise
+            self._build_plan(layout)  # collective: a re-allocation follows the pattern size, identical on the ranks' schedule
+            self.plan.exchange()
 
     def numbering(self):
         if self.plan is None:

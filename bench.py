@@ -275,7 +275,7 @@ def run_b200(args):
     da = None
     if world > 1:
         gid, owner_rel, nb_own, _, _ = M.box_slab_numbering(3, n, k_lo, k_hi, True)
-        da = DistributedAssembly(ctx, rank, world, gid, (rank + owner_rel).astype(np.int32), nb_own, local_rank)
+        da = DistributedAssembly(ctx, rank, world, gid, (rank + owner_rel).astype(np.int32), nb_own, local_rank, transport=args.transport)
 
     def barrier():
         if world > 1:
@@ -386,6 +386,10 @@ def run_b200(args):
         time.sleep(0.15)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0
+    if world > 1 and mode == "exchange" and args.transport == "p2p":
+        st = ctx.p2p_status()
+        if st != 0:
+            raise SystemExit(f"bench.py: ghost-row exchange timed out on rank {rank} (status {st})")
     total_ms = t_start.elapsed_time(t_end)
     pattern_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     values_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
@@ -407,7 +411,7 @@ def run_b200(args):
     ctx2 = A.Context(local_rank, stream=stream.cuda_stream)
     da2 = None
     if world > 1:
-        da2 = DistributedAssembly(ctx2, rank, world, da.node_gid, da.node_owner, da.nb_own_node, local_rank)
+        da2 = DistributedAssembly(ctx2, rank, world, da.node_gid, da.node_owner, da.nb_own_node, local_rank, transport=args.transport)
 
     def e2e_step(v):
         ctx2.set_mesh(3, coords_h.numpy(), cells_h.numpy(), own_h.numpy() if info["is_own"] else None)
@@ -514,7 +518,7 @@ def run_b200(args):
                        "format": "csr", "variant": VARIANT_NAMES[variant],
                        "sparsity": {"cells": "from the cells (computeSparsityAtomic)",
                                     "connectivity": "from the init-time node-node connectivity (computeSparsityAtomicFree)"}[sparsity], "l2": "inputs larger than L2 (connectivity+values > 126 MB per GPU), no flush",
-                       "parallelism": f"slab{world}" + ("" if world == 1 else f" ({mode}: " + ("own cells + NCCL ghost-row exchange" if mode == "exchange" else "ghost cells recomputed, no exchange") + ")")},
+                       "parallelism": f"slab{world}" + ("" if world == 1 else f" ({mode}: " + (("own cells + ghost rows pulled over NVLink peer memory in one kernel" if args.transport == "p2p" else "own cells + NCCL ghost-row exchange") if mode == "exchange" else "ghost cells recomputed, no exchange") + ")")},
             "phases": {"build_matrix_ms": pattern_ms, "add_and_compute_ms": values_ms,
                        "values_only_elements_per_s": cells_all / (values_ms * 1e-3),
                        "variants_ms": {VARIANT_NAMES[k]: v for k, v in per_variant.items()},
@@ -555,6 +559,7 @@ def main():
     ap.add_argument("--sparsity", default="auto", choices=["auto", "cells", "connectivity"], help="steady-state BuildMatrix algorithm (auto: by variant, as the reference pairs them)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e: one step at a time only")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1, exchange mode: one pull kernel over NVLink peer memory (CUDA IPC) or NCCL send/recv + accumulate kernels")
     ap.add_argument("--mode", default="exchange", choices=["exchange", "replicate"], help="N>1: ghost-row exchange over NCCL (north star) or the reference's ghost-cell replication")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -310,6 +310,33 @@ AFB_API int afb_add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, con
 AFB_API int afb_values_tail(afb_ctx* ctx, int32_t first_block_row, int64_t* first_value, int64_t* nb_values);
 
 /*
+ * Ghost-row exchange over NVLink peer memory (one process per GPU, CUDA IPC): the owner of a node pulls the
+ * partial rows its neighbours computed straight out of their `values` arrays and adds them, in ONE kernel per
+ * assembly (signal -> pull + add -> acknowledge -> the sender zeroes its ghost rows), instead of an NCCL
+ * send/recv group plus zero-fill and accumulate launches.  The reference leaves this step to the solver's
+ * parallel matrix (HYPRE IJ off-processor entries, femutils/HypreDoFLinearSystem.cc:461-520).
+ *   afb_p2p_export     IPC handles (AFB_P2P_HANDLE_BYTES each) of this context's values array and flag block;
+ *                      the host exchanges them with the neighbours (any transport: torch.distributed, MPI)
+ *   afb_p2p_connect    per neighbour k: its rank, its two handles, the slice [pull_first, +pull_count) of ITS
+ *                      values holding partial rows of nodes this rank owns, the device array slots[k] (this
+ *                      rank's value slot of every double of that slice, afb_lookup_value_slots), and the slice
+ *                      [send_first, +send_count) of THIS rank's values the neighbour pulls (zeroed afterwards).
+ *                      Neighbour relations must be symmetric (counts may be 0).  Ranks < 64.
+ *   afb_p2p_exchange   stream-ordered after afb_assemble_bilinear(AFB_FLAG_OWN_CELLS_ONLY | AFB_FLAG_ALL_ROWS);
+ *                      every rank of the decomposition must call it once per assembly
+ *   afb_p2p_status     synchronises; 0 = fine, 1/2 = a neighbour did not show up within the kernel's time-out
+ *   afb_p2p_disconnect closes the mappings (also done by afb_destroy); collective by convention
+ * Re-export and re-connect after afb_build_pattern moved the values array (afb_p2p_exchange reports it).
+ */
+#define AFB_P2P_HANDLE_BYTES 64
+AFB_API int afb_p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle);
+AFB_API int afb_p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles,
+                            const int64_t* pull_first, const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count);
+AFB_API int afb_p2p_exchange(afb_ctx* ctx);
+AFB_API int afb_p2p_status(afb_ctx* ctx, int* status);
+AFB_API int afb_p2p_disconnect(afb_ctx* ctx);
+
+/*
  * Columns of the scalar CSR view in the solver's global numbering: out[j] = dof_local_to_global[col[j]]
  * (device arrays; dof_local_to_global has nb_row entries, out has nnz entries of the CSR view).
  * Replaces the host loop of HypreDoFLinearSystemImpl::solve that renumbers the columns through

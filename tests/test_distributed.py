@@ -281,3 +281,73 @@ def test_device_slab_generator_with_ghost_layer():
                 assert (info["nb_node"], info["nb_cell"], info["nb_own_node"], info["nb_own_cell"]) == (ref.nb_node, ref.nb_cell, ref.nb_own_node, ref.nb_own_cell)
                 assert np.array_equal(ctx.to_host(A.ARRAY_COORDS).reshape(-1, 3), ref.coords)
                 assert np.array_equal(ctx.to_host(A.ARRAY_CELL_NODES).reshape(-1, dim + 1), ref.cells)
+
+
+# -------------------------------------------------------------------------------------------------
+# GPU: ghost rows pulled over peer memory (csrc/p2p.cu).  Two or three processes share the one GPU of
+# the test box (CUDA IPC works between processes on the same device; the kernels of the processes are
+# time-sliced, the waits inside the kernel see the other process' progress); gloo carries the set-up.
+# -------------------------------------------------------------------------------------------------
+def run_rank_p2p(rank, world, port, case, transport, errq):
+    try:
+        import torch
+        import torch.distributed as dist
+        from arcanefem_b200 import capi as A
+        from arcanefem_b200.distributed import DistributedAssembly
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        name, op, layout = case
+        mesh = M.box_mesh(3, 7) if name == "box3d" else M.read_msh(os.path.join(ROOT, "tests", "golden", name))
+        b = O.block_size(op, mesh.dim)
+        params = list(O.lame(21.0e5, 0.28)) if op == O.OP_ELASTICITY else None
+        fmt = A.FORMAT_BSR if b > 1 else A.FORMAT_CSR
+        s = M.partition_mesh(mesh, world)[rank]
+        grows, gcols, gvals = global_reference(mesh, op, params, layout)
+        ctx = A.Context(0)
+        ctx.set_mesh(s.dim, s.coords, s.cells, s.is_own)
+        ctx.set_own_cell_count(s.nb_own_cell)
+        da = DistributedAssembly(ctx, rank, world, s.node_gid, s.node_owner, s.nb_own_node, 0, transport=transport, comm_device="cpu")
+        for rep in range(3):  # steady state: pattern re-build + assembly + exchange, epochs advance
+            ctx.build_pattern(b)
+            da.assemble(op, params=params, fmt=fmt, variant=A.VARIANT_TILED_GATHER, layout=layout, mode="exchange")
+            if transport == "p2p":
+                assert ctx.p2p_status() == 0, "ghost-row exchange timed out"
+            else:
+                ctx.synchronize()
+            lrows, lcols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+            check_owned_rows(s, b, layout, lrows, lcols, ctx.to_host(A.ARRAY_VALUES), grows, gcols, gvals)
+            dist.barrier()
+        if transport == "p2p":
+            ctx.p2p_disconnect()
+        dist.barrier()
+        ctx.close()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put((rank, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", [("box3d", O.OP_POISSON, O.LAYOUT_PER_BLOCK), ("box3d", O.OP_ELASTICITY, O.LAYOUT_PER_ROW), ("sphere_cut.msh", O.OP_POISSON, O.LAYOUT_PER_BLOCK)],
+                         ids=["box-poisson", "box-elasticity-per-row", "sphere-poisson"])
+def test_ghost_rows_pulled_over_peer_memory(world, case):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    errq = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=run_rank_p2p, args=(r, world, port, case, "p2p", errq)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    errs = []
+    while not errq.empty():
+        errs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            errs.append((-1, "rank timed out"))
+    assert not errs, "\n".join(f"rank {r}:\n{t}" for r, t in errs)
+    assert all(p.exitcode == 0 for p in procs)
