@@ -322,6 +322,22 @@ int afb_assemble_rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewis
   return rhs_source(ctx, f, nb_f, nodewise, signed_tri_area);
 }
 
+int afb_assemble_rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* face_nodes, int kind, int nb_value, const double* values, int skip_dirichlet, int mem_space)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern && (nb_face == 0 || face_nodes) && values, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: no pattern / null argument");
+  AFB_REQUIRE(ctx->npc == ctx->dim + 1, AFB_ERR_UNSUPPORTED, "afb_assemble_rhs_neumann: P1 simplex meshes only (edges of Tri3, triangles of Tet4)");
+  AFB_REQUIRE(kind == AFB_NEUMANN_FLUX || kind == AFB_NEUMANN_TRACTION, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: unknown kind %d", kind);
+  if (kind == AFB_NEUMANN_FLUX)
+    AFB_REQUIRE(nb_value == 1 || nb_value == ctx->dim, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: a flux takes 1 value or one per space dimension (got %d)", nb_value);
+  else
+    AFB_REQUIRE(nb_value == ctx->b, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: a traction takes one value per DoF of a node (%d, got %d)", ctx->b, nb_value);
+  if (nb_face <= 0) return AFB_OK;
+  const void* faces = nullptr;
+  AFB_TRY(stage(ctx, ctx->tmp_ids, face_nodes, sizeof(int32_t) * (size_t)nb_face * (size_t)ctx->dim, mem_space, &faces));
+  return rhs_neumann(ctx, nb_face, static_cast<const int32_t*>(faces), kind, nb_value, values, skip_dirichlet);
+}
+
 int afb_set_dirichlet_nodes(afb_ctx* ctx, int32_t n, const int32_t* node_ids, int mem_space)
 {
   AFB_TRY(check_ctx(ctx));

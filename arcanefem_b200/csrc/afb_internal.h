@@ -211,6 +211,7 @@ int build_tile_mesh(afb_ctx* ctx);
 int build_tile_lists(afb_ctx* ctx, int mode_flags);
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags);
 bool pattern_tiled_ready(const afb_ctx* ctx);
+int rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* faces_dev, int kind, int nb_value, const double* values, int skip_dirichlet);
 void p2p_destroy(afb_ctx* ctx);
 int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle);
 int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const int64_t* pull_first,

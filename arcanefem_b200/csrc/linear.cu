@@ -98,6 +98,65 @@ int rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed
   return AFB_OK;
 }
 
+// boundary integrals on P1 faces (edges / triangles): constant flux, q.n flux, traction.  One thread per face, fp64
+// atomics like the reference (modules/testlab/FemModule.cc:1574-1693, femutils/ArcaneFemFunctionsGpu.cc:679-738,1082-1141;
+// traction: femutils/ArcaneFemFunctions.h:2188-2220,2854-2885 -- a host loop upstream).  Arithmetic as the helpers
+// computeLengthFace / computeAreaTria / computeNormalFace / computeNormalTriangle (ArcaneFemFunctionsGpu.h:92-102,139-214).
+template <int DIM>
+__global__ void __launch_bounds__(256) k_rhs_neumann(const double* __restrict__ coords, const int32_t* __restrict__ faces, int64_t nb_face, const uint8_t* __restrict__ is_own,
+                                                      const uint8_t* __restrict__ dir_node, int b, int kind, int nb_value, double v0, double v1, double v2,
+                                                      double* __restrict__ rhs)
+{
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nb_face) return;
+  const int32_t* fn = faces + f * DIM;
+  double x0, y0, z0, x1, y1, z1;
+  load3(coords, __ldg(fn), x0, y0, z0);
+  load3(coords, __ldg(fn + 1), x1, y1, z1);
+  double meas, w = v0;
+  if (DIM == 2) {
+    meas = sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0));
+    if (kind == AFB_NEUMANN_FLUX && nb_value > 1) {
+      const double norm_n = sqrt((y1 - y0) * (y1 - y0) + (x1 - x0) * (x1 - x0));
+      w = ((y1 - y0) / norm_n) * v0 + ((x0 - x1) / norm_n) * v1;
+    }
+  }
+  else {
+    double x2, y2, z2;
+    load3(coords, __ldg(fn + 2), x2, y2, z2);
+    const double ax = x1 - x0, ay = y1 - y0, az = z1 - z0, bx = x2 - x0, by = y2 - y0, bz = z2 - z0;
+    const double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    const double norm = sqrt(nx * nx + ny * ny + nz * nz);
+    meas = norm / 2.0;
+    if (kind == AFB_NEUMANN_FLUX && nb_value > 1) w = (nx / norm) * v0 + (ny / norm) * v1 + (nz / norm) * v2;
+  }
+  const double t[3] = { v0, v1, v2 };
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    const int32_t nd = __ldg(fn + i);
+    if ((dir_node && dir_node[nd]) || (is_own && !is_own[nd])) continue;
+    if (kind == AFB_NEUMANN_FLUX) atomicAdd(rhs + (int64_t)nd * b, w * meas / DIM);
+    else
+      for (int k = 0; k < b; ++k) atomicAdd(rhs + (int64_t)nd * b + k, t[k] * meas / DIM);
+  }
+}
+
+int rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* faces_dev, int kind, int nb_value, const double* values, int skip_dirichlet)
+{
+  if (nb_face <= 0) return AFB_OK;
+  double v[3] = { 0.0, 0.0, 0.0 };
+  for (int k = 0; k < nb_value && k < 3; ++k) v[k] = values[k];
+  const uint8_t* own = ctx->all_own ? nullptr : ctx->is_own.as<uint8_t>();
+  const uint8_t* dir = (skip_dirichlet && ctx->has_dir_nodes) ? ctx->dir_node.as<uint8_t>() : nullptr;
+  const int grid = grid_for(nb_face, 256);
+  if (ctx->dim == 2)
+    k_rhs_neumann<2><<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), faces_dev, nb_face, own, dir, ctx->b, kind, nb_value, v[0], v[1], v[2], ctx->rhs.as<double>());
+  else
+    k_rhs_neumann<3><<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), faces_dev, nb_face, own, dir, ctx->b, kind, nb_value, v[0], v[1], v[2], ctx->rhs.as<double>());
+  AFB_LAUNCH_CHECK(ctx);
+  return AFB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // scalar (dof_row, dof_col) -> index into values for the stored layout, or -1
 // (BSRMatrix::findValueIndex, femutils/BSRFormat.cc:79-106)

@@ -101,7 +101,7 @@ class ExchangePlan:
         self.values_slice, self.add_at, self.make_buffer = values_slice, add_at, make_buffer
         self.send = []   # (peer, first_value, nb_values)
         self.recv = []   # (peer, slots tensor, buffer)
-        self.p2p = None
+        self.p2p, self.p2p_error = None, None
         self._setup(layout_per_row, tail_pattern, lookup)
         if p2p is not None:
             self._setup_p2p(p2p)
@@ -181,7 +181,13 @@ class ExchangePlan:
         recv = {q: slots for q, slots, _ in self.recv}
         peers = sorted(set(send) | set(recv))
         told = self._exchange_arrays({q: np.array(send.get(q, (0, 0)), dtype=np.int64) for q in peers}, np.int64)
-        vh, fh = p2p.export()
+        # every step below is attempted on every rank and the outcome agreed on collectively: if peer memory cannot be
+        # mapped somewhere (no IPC in the container, no peer access), ALL ranks keep the torch.distributed transport
+        err = None
+        try:
+            vh, fh = p2p.export()
+        except Exception as e:  # noqa: BLE001
+            err, vh, fh = e, bytes(64), bytes(64)
         mine = torch.tensor(list(vh + fh), dtype=torch.uint8).to(self.comm_device)
         allh = [torch.zeros(128, dtype=torch.uint8, device=self.comm_device) for _ in range(self.world)]
         dist.all_gather(allh, mine, group=self.group)
@@ -194,9 +200,21 @@ class ExchangePlan:
             pull_first.append(first)
             pull_count.append(n)
             slots.append(sl)
-        p2p.connect(self.rank, peers, [allh[q][:64] for q in peers], [allh[q][64:] for q in peers], pull_first, pull_count, slots,
-                    [send.get(q, (0, 0))[0] for q in peers], [send.get(q, (0, 0))[1] for q in peers])
-        dist.barrier(group=self.group)
+        if err is None:
+            try:
+                p2p.connect(self.rank, peers, [allh[q][:64] for q in peers], [allh[q][64:] for q in peers], pull_first, pull_count, slots,
+                            [send.get(q, (0, 0))[0] for q in peers], [send.get(q, (0, 0))[1] for q in peers])
+            except Exception as e:  # noqa: BLE001
+                err = e
+        ok = torch.tensor([0 if err is None else 1], dtype=torch.int32).to(self.comm_device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=self.group)
+        if int(ok.item()) != 0:
+            self.p2p_error = str(err) if err is not None else "peer-memory mapping failed on another rank"
+            try:
+                p2p.disconnect()
+            except Exception:  # noqa: BLE001
+                pass
+            return
         self.p2p = p2p
 
     # -- every assembly ------------------------------------------------------------------------------
@@ -270,6 +288,9 @@ class _P2P:
 
     def exchange(self):
         self.ctx.p2p_exchange()
+
+    def disconnect(self):
+        self.ctx.p2p_disconnect()
 
 
 class DistributedAssembly:

@@ -171,6 +171,32 @@ def read_msh(path: str) -> Mesh:
     return Mesh(dim=dim, coords=coords, cells=np.ascontiguousarray(cells), node_uid=uid.astype(np.int64), groups=groups, faces=faces)
 
 
+def orient_boundary_faces(mesh: Mesh, faces: np.ndarray) -> np.ndarray:
+    """Boundary faces (edges of a Tri3 mesh, triangles of a Tet4 mesh) with their first two nodes ordered so that the
+    reference's normal formulas point OUT of the domain: N = (y1-y0, x0-x1) in 2-D, (n1-n0) x (n2-n0) in 3-D
+    (femutils/ArcaneFemFunctionsGpu.h:159-214).  This is the swap those helpers apply when Arcane reports the face as
+    not "subdomain boundary outside"; here the side is found from the cell the face belongs to."""
+    faces = np.array(faces, dtype=np.int32, copy=True)
+    nn = faces.shape[1]
+    corner = mesh.cells[:, :mesh.dim + 1]
+    key = lambda a: tuple(sorted(int(x) for x in a))
+    owner = {}
+    for c, cn in enumerate(corner):
+        for k in range(mesh.dim + 1):
+            owner.setdefault(key(np.delete(cn, k)), (c, int(cn[k])))
+    for f in range(faces.shape[0]):
+        c, opp = owner[key(faces[f, :mesh.dim])]
+        p0, p1 = mesh.coords[faces[f, 0]], mesh.coords[faces[f, 1]]
+        if mesh.dim == 2:
+            n = np.array([p1[1] - p0[1], p0[0] - p1[0], 0.0])
+        else:
+            n = np.cross(p1 - p0, mesh.coords[faces[f, 2]] - p0)
+        if np.dot(n, mesh.coords[opp] - p0) > 0.0:
+            faces[f, [0, 1]] = faces[f, [1, 0]]
+    assert nn == mesh.dim
+    return faces
+
+
 # ---------------------------------------------------------------------------
 # Synthetic structured boxes (SURVEY.md §8d).  The device generator
 # (`afb_mesh_generate_box`, csrc/mesh_gen.cu) produces bit-identical arrays.

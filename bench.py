@@ -386,7 +386,12 @@ def run_b200(args):
         time.sleep(0.15)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0
-    if world > 1 and mode == "exchange" and args.transport == "p2p":
+    transport = "none"
+    if da is not None and da.plan is not None:
+        transport = "p2p" if da.plan.p2p is not None else "nccl"
+        if args.transport == "p2p" and transport != "p2p" and rank == 0:
+            print(f"bench.py: peer-memory exchange unavailable ({da.plan.p2p_error}); NCCL send/recv used instead", file=sys.stderr)
+    if world > 1 and mode == "exchange" and transport == "p2p":
         st = ctx.p2p_status()
         if st != 0:
             raise SystemExit(f"bench.py: ghost-row exchange timed out on rank {rank} (status {st})")
@@ -518,7 +523,7 @@ def run_b200(args):
                        "format": "csr", "variant": VARIANT_NAMES[variant],
                        "sparsity": {"cells": "from the cells (computeSparsityAtomic)",
                                     "connectivity": "from the init-time node-node connectivity (computeSparsityAtomicFree)"}[sparsity], "l2": "inputs larger than L2 (connectivity+values > 126 MB per GPU), no flush",
-                       "parallelism": f"slab{world}" + ("" if world == 1 else f" ({mode}: " + (("own cells + ghost rows pulled over NVLink peer memory in one kernel" if args.transport == "p2p" else "own cells + NCCL ghost-row exchange") if mode == "exchange" else "ghost cells recomputed, no exchange") + ")")},
+                       "parallelism": f"slab{world}" + ("" if world == 1 else f" ({mode}: " + (("own cells + ghost rows pulled over NVLink peer memory in one kernel" if transport == "p2p" else "own cells + NCCL ghost-row exchange") if mode == "exchange" else "ghost cells recomputed, no exchange") + ")")},
             "phases": {"build_matrix_ms": pattern_ms, "add_and_compute_ms": values_ms,
                        "values_only_elements_per_s": cells_all / (values_ms * 1e-3),
                        "variants_ms": {VARIANT_NAMES[k]: v for k, v in per_variant.items()},

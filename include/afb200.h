@@ -226,6 +226,24 @@ AFB_API int afb_rhs_reset(afb_ctx* ctx);
  */
 AFB_API int afb_assemble_rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed_tri_area);
 
+/*
+ * Boundary integrals of the RHS over P1 faces (edges of a Tri3 mesh, triangles of a Tet4 mesh), added to rhs:
+ *   AFB_NEUMANN_FLUX, 1 value       rhs[dof(n,0)] += value * measure / nn                    constant flux
+ *   AFB_NEUMANN_FLUX, dim values    rhs[dof(n,0)] += (N . q) * measure / nn                  flux vector q, unit normal N
+ *   AFB_NEUMANN_TRACTION, b values  rhs[dof(n,k)] += t[k] * measure / nn                     traction (NULL components = 0)
+ * for the owned nodes n of every face (nn = nodes per face).  Replaces the flux part of _assembleCsrGpuLinearOperator
+ * (modules/testlab/FemModule.cc:1534-1706), BoundaryConditions{2D,3D}::applyNeumannToRhs{Tria3,Tetra4}
+ * (femutils/ArcaneFemFunctionsGpu.cc:679-738,1082-1141) and applyTractionToRhs{Tria3,Tetra4}
+ * (femutils/ArcaneFemFunctions.h:2854-2885,2188-2220; a host loop upstream).
+ * face_nodes[nb_face][dim]: Arcane's faceNode order of the group's faces, with the first two nodes swapped for faces that
+ * are not "subdomain boundary outside" -- the swap computeNormalFace / computeNormalTriangle apply
+ * (femutils/ArcaneFemFunctionsGpu.h:159-214), so that N = (y1-y0, x0-x1)/|.| resp. (n1-n0)x(n2-n0)/|.| points outward.
+ * skip_dirichlet != 0: nodes marked by afb_set_dirichlet_nodes receive nothing (testlab: FemModule.cc:1577).
+ */
+enum { AFB_NEUMANN_FLUX = 0, AFB_NEUMANN_TRACTION = 1 };
+AFB_API int afb_assemble_rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* face_nodes, int kind, int nb_value, const double* values, int skip_dirichlet,
+                                     int mem_space);
+
 /* Node flags m_u_dirichlet (modules/testlab/FemModule.cc:647-677); NULL / n=0 clears. */
 AFB_API int afb_set_dirichlet_nodes(afb_ctx* ctx, int32_t n, const int32_t* node_ids, int mem_space);
 

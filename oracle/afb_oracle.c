@@ -776,6 +776,56 @@ ORC_API void orc_rhs_source_nodewise(int npc, int dim, int b, int32_t nb_node, i
   free(list);
 }
 
+/* Boundary integrals of the RHS on P1 faces (edges of a Tri3 mesh, triangles of a Tet4 mesh).
+ * faces[nb_face][dim]: the face's nodes in Arcane's order with the swap of the reference's normal helpers
+ * already applied when the face is not "subdomain boundary outside" (computeNormalFace / computeNormalTriangle,
+ * femutils/ArcaneFemFunctionsGpu.h:159-214; _computeEdgeNormal2Gpu, modules/testlab/FemModule.cc:1825-1841).
+ * measure: edge length in the x-y plane (FemModule.cc:1782-1787, ArcaneFemFunctionsGpu.h:139-147) / triangle area
+ *          |(n1-n0) x (n2-n0)| / 2 (ArcaneFemFunctionsGpu.h:92-102).
+ * kind 0 (Neumann flux on DoF 0): nb_value == 1: rhs += value*measure/nn
+ *          (FemModule.cc:1574-1581, ArcaneFemFunctionsGpu.cc:701-717, 1105-1120);
+ *          nb_value == dim: rhs += (N.q)*measure/nn with the unit normal N of the helpers above
+ *          (FemModule.cc:1611-1621, ArcaneFemFunctionsGpu.cc:718-737, 1121-1141).
+ * kind 1 (traction, b DoFs per node): rhs[dof(node,k)] += t[k]*measure/nn
+ *          (femutils/ArcaneFemFunctions.h:2188-2220, 2854-2885).
+ * Gates: owned nodes only; testlab additionally skips Dirichlet nodes (FemModule.cc:1577). */
+ORC_API void orc_rhs_neumann(int dim, int b, int kind, int nb_value, int64_t nb_face, const double* coords, const int32_t* faces, const double* values,
+                             const uint8_t* is_own, const uint8_t* is_dirichlet, double* rhs)
+{
+  const int nn = dim; /* 2 nodes per edge, 3 per triangle */
+  for (int64_t f = 0; f < nb_face; ++f) {
+    const int32_t* fn = faces + f * nn;
+    double meas, w = 0.0;
+    r3 n0 = r3_load(coords, fn[0]), n1 = r3_load(coords, fn[1]);
+    if (dim == 2) {
+      meas = sqrt((n1.x - n0.x) * (n1.x - n0.x) + (n1.y - n0.y) * (n1.y - n0.y));
+      if (kind == 0 && nb_value > 1) {
+        double norm_N = sqrt((n1.y - n0.y) * (n1.y - n0.y) + (n1.x - n0.x) * (n1.x - n0.x));
+        double Nx = (n1.y - n0.y) / norm_N, Ny = (n0.x - n1.x) / norm_N;
+        w = (Nx * values[0] + Ny * values[1]);
+      }
+    }
+    else {
+      r3 n2 = r3_load(coords, fn[2]);
+      meas = area_tri3_unsigned(n0, n1, n2);
+      if (kind == 0 && nb_value > 1) {
+        r3 e1 = r3_sub(n1, n0), e2 = r3_sub(n2, n0);
+        r3 nr = r3_cross(e1, e2);
+        double norm = sqrt(nr.x * nr.x + nr.y * nr.y + nr.z * nr.z);
+        w = ((nr.x / norm) * values[0] + (nr.y / norm) * values[1] + (nr.z / norm) * values[2]);
+      }
+    }
+    for (int i = 0; i < nn; ++i) {
+      int32_t nd = fn[i];
+      if ((is_dirichlet && is_dirichlet[nd]) || (is_own && !is_own[nd])) continue;
+      if (kind == 0)
+        rhs[(int64_t)nd * b] += (nb_value > 1 ? w : values[0]) * meas / nn;
+      else
+        for (int k = 0; k < b; ++k) rhs[(int64_t)nd * b + k] += values[k] * meas / nn;
+    }
+  }
+}
+
 /* ========================================================================= */
 /* Dirichlet                                                                  */
 /* All operate on a scalar CSR view (rows[nb_dof+1], cols, values): for b>1    */

@@ -157,6 +157,20 @@ def rhs_source_nodewise(mesh_dim, coords, cells, f, is_own=None):
     return rhs
 
 
+NEUMANN_FLUX, NEUMANN_TRACTION = 0, 1
+
+
+def rhs_neumann(mesh_dim, b, coords, faces, values, rhs, kind=NEUMANN_FLUX, is_own=None, is_dirichlet=None):
+    """rhs += boundary integral over P1 faces (oriented: see orc_rhs_neumann); in place."""
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    values = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64)
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    assert faces.shape[1] == mesh_dim and rhs.dtype == np.float64
+    lib().orc_rhs_neumann(int(mesh_dim), int(b), int(kind), int(values.size), C.c_int64(faces.shape[0]), _p(coords), _p(faces), _p(values),
+                          _p(_u8(is_own)), _p(_u8(is_dirichlet)), _p(rhs))
+    return rhs
+
+
 def dirichlet_penalty(rows, cols, values, rhs, dof_ids, g, penalty, weak=False):
     dof_ids, g = _i32(dof_ids), _f64(g)
     rc = lib().orc_dirichlet_penalty(int(weak), C.c_double(penalty), C.c_int32(dof_ids.shape[0]), _p(dof_ids), _p(g), _p(_i32(rows)), _p(_i32(cols)), _p(values), _p(rhs))

@@ -23,6 +23,23 @@ POISSON_CASES = {
                       golden="poisson_test_ref_sphere_3D.txt"),
 }
 
+# Neumann flux cases of testlab (circle_cut.msh; modules/testlab/inputs/Test.circle.2D.trac*.arc): value = scalar flux,
+# valueX/valueY = flux vector q (q.n with the outward normal)
+NEUMANN_CASES = {
+    "trac": dict(mesh="circle_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("vertical", [1.0e4])], penalty=1.0e30,
+                 golden="poisson_test_ref_circle_trac_2D.txt"),
+    "x-trac": dict(mesh="circle_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("curved", [2.9e4, 0.0])], penalty=1.0e30,
+                   golden="poisson_test_ref_circle_x-trac_2D.txt"),
+    "y-trac": dict(mesh="circle_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("curved", [0.0, 2.9e4])], penalty=1.0e30,
+                   golden="poisson_test_ref_circle_y-trac_2D.txt"),
+    "vect-trac": dict(mesh="circle_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("curved", [2.9e4, -1.8e4])], penalty=1.0e30,
+                      golden="poisson_test_ref_circle_vect-trac_2D.txt"),
+}
+
+# modules/elasticity/inputs/bar.2D.Dirichlet.traction.arc (traction "1.0 NULL" on `right`, no body force)
+TRACTION_CASE = dict(mesh="bar.msh", E=21.0e5, nu=0.28, f=[0.0, 0.0], dirichlet=[("left", [0.0, 0.0])], traction=[("right", [1.0, 0.0])],
+                     penalty=1.0e30, golden="elasticity_bar.2D.Dirichlet.traction.txt")
+
 ELASTICITY_CASES = {
     # modules/elasticity/inputs/bar.2D.Dirichlet.bodyForce.arc
     "bar_2D": dict(mesh="bar.msh", E=21.0e5, nu=0.28, f=[0.0, -1.0], dirichlet=[("left", [0.0, 0.0])], penalty=1.0e30,

@@ -24,6 +24,11 @@ FILES = {
     "modules/testlab/tests/poisson_test_ref_L-shape_3D.txt": "poisson_test_ref_L-shape_3D.txt",
     "modules/testlab/tests/poisson_test_ref_circle_2D.txt": "poisson_test_ref_circle_2D.txt",
     "modules/testlab/tests/poisson_test_ref_sphere_3D.txt": "poisson_test_ref_sphere_3D.txt",
+    "modules/testlab/tests/poisson_test_ref_circle_trac_2D.txt": "poisson_test_ref_circle_trac_2D.txt",
+    "modules/testlab/tests/poisson_test_ref_circle_x-trac_2D.txt": "poisson_test_ref_circle_x-trac_2D.txt",
+    "modules/testlab/tests/poisson_test_ref_circle_y-trac_2D.txt": "poisson_test_ref_circle_y-trac_2D.txt",
+    "modules/testlab/tests/poisson_test_ref_circle_vect-trac_2D.txt": "poisson_test_ref_circle_vect-trac_2D.txt",
+    "modules/elasticity/check/bar.2D.Dirichlet.traction.txt": "elasticity_bar.2D.Dirichlet.traction.txt",
     "modules/elasticity/check/bar.2D.Dirichlet.bodyForce.txt": "elasticity_bar.2D.Dirichlet.bodyForce.txt",
     "modules/elasticity/check/bar.3D.Dirichlet.bodyForce.txt": "elasticity_bar.3D.Dirichlet.bodyForce.txt",
     "modules/bilaplacian/check/2d_test.txt": "bilaplacian_2d_test.txt",

@@ -480,6 +480,81 @@ def test_elimination_bit_exact_and_golden(ctx, kind, quirk):
     CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10)
 
 
+def test_rhs_neumann_and_traction(ctx):
+    """Boundary integrals of the RHS (afb_assemble_rhs_neumann) against the oracle: constant flux, q.n, traction; 2-D and
+    3-D; Dirichlet-node skip (testlab) and the isOwn gate.  Sums of <= ~8 fp64 atomics per node: 1e-12 of the largest entry."""
+    for name, group in (("circle_2D", "curved"), ("sphere_3D", "curved"), ("bar_3D", "sidesurfaces")):
+        m = get_mesh(name)
+        faces = M.orient_boundary_faces(m, m.faces[group])
+        own = (np.arange(m.nb_node) % 5 != 0).astype(np.uint8)
+        isd = np.zeros(m.nb_node, dtype=np.uint8)
+        isd[m.groups[group][::3]] = 1
+        for b, kind, vals in ((1, A.NEUMANN_FLUX, [1.0e4]), (1, A.NEUMANN_FLUX, [2.9e4, -1.8e4, 0.7e4][:m.dim]),
+                              (m.dim, A.NEUMANN_TRACTION, [1.0, -2.5, 0.25][:m.dim]), (m.dim, A.NEUMANN_FLUX, [3.0])):
+            for gate in (None, own):
+                ctx.set_mesh(m.dim, m.coords, m.cells, gate)
+                ctx.build_pattern(b)
+                ctx.set_dirichlet_nodes(np.nonzero(isd)[0].astype(np.int32))
+                for skip in (False, True):
+                    ctx.rhs_reset()
+                    ctx.rhs_neumann(faces, vals, kind=kind, skip_dirichlet=skip)
+                    ref = np.zeros(m.nb_node * b)
+                    O.rhs_neumann(m.dim, b, m.coords, faces, vals, ref, kind=kind, is_own=gate, is_dirichlet=isd if skip else None)
+                    got = ctx.to_host(A.ARRAY_RHS)
+                    assert np.abs(ref).max() > 0
+                    assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref).max()), (name, b, kind, skip)
+                ctx.clear_dirichlet()
+    # argument checks
+    m = get_mesh("circle_2D")
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(1)
+    with pytest.raises(A.AfbError):
+        ctx.rhs_neumann(m.faces["curved"], [1.0, 2.0, 3.0])          # a 2-D flux has 1 or 2 values
+    with pytest.raises(A.AfbError):
+        ctx.rhs_neumann(m.faces["curved"], [1.0, 2.0], kind=A.NEUMANN_TRACTION)  # b = 1: one traction component
+
+
+@pytest.mark.parametrize("name", list(CS.NEUMANN_CASES))
+def test_poisson_neumann_golden_solution(ctx, name):
+    """testlab's flux cases end to end on the GPU-assembled system (modules/testlab/inputs/Test.circle.2D.trac*.arc)."""
+    case = CS.NEUMANN_CASES[name]
+    m = M.read_msh(os.path.join(CS.GOLDEN, case["mesh"]))
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(1)
+    ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER, flags=A.FLAG_SIGNED_TRI_AREA)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    ctx.set_dirichlet_nodes(ids)
+    ctx.rhs_reset()
+    ctx.rhs_source([case["f"]], nodewise=False, signed_tri_area=True)
+    for group, q in case["neumann"]:
+        ctx.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), q, kind=A.NEUMANN_FLUX, skip_dirichlet=True)
+    ctx.dirichlet_penalty(ids, g, case["penalty"])
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    u = spla.spsolve(sp.csr_matrix((ctx.to_host(A.ARRAY_VALUES), cols, rows)).tocsc(), ctx.to_host(A.ARRAY_RHS))
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16)
+    assert worst < 1.0e-6
+    ctx.clear_dirichlet()
+
+
+def test_elasticity_traction_golden_solution(ctx):
+    case = CS.TRACTION_CASE
+    m = M.read_msh(os.path.join(CS.GOLDEN, case["mesh"]))
+    b = m.dim
+    lam, mu = O.lame(case["E"], case["nu"])
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(b)
+    ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER, layout=A.LAYOUT_PER_ROW)
+    ctx.rhs_reset()
+    for group, t in case["traction"]:
+        ctx.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), t, kind=A.NEUMANN_TRACTION)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    ctx.dirichlet_penalty(ids, g, case["penalty"])
+    crow, ccol, _ = O.bsr_to_csr(b, ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS))
+    u = spla.spsolve(sp.csr_matrix((ctx.to_host(A.ARRAY_VALUES), ccol, crow)).tocsc(), ctx.to_host(A.ARRAY_RHS))
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10)
+    assert worst < 1.0e-4
+
+
 def test_rhs_source_variants(ctx):
     for name in ("sphere_3D", "L-shape_2D"):
         m = get_mesh(name)

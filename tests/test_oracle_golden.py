@@ -79,6 +79,38 @@ def test_poisson_golden(name, variant):
     assert worst < 1.0e-7
 
 
+@pytest.mark.parametrize("name", list(CS.NEUMANN_CASES))
+def test_poisson_neumann_golden(name):
+    """Constant flux term (modules/testlab/FemModule.cc:1534-1706): scalar value and q.n with the outward normal."""
+    case = CS.NEUMANN_CASES[name]
+    m = _load(case)
+    rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=O.FORM_COMPACT)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    isd = np.zeros(m.nb_node, dtype=np.uint8)
+    isd[ids] = 1
+    rhs = O.rhs_source_cellwise(m.dim, m.coords, m.cells, case["f"], signed_area=True, is_dirichlet=isd)
+    for group, q in case["neumann"]:
+        O.rhs_neumann(m.dim, 1, m.coords, M.orient_boundary_faces(m, m.faces[group]), q, rhs, kind=O.NEUMANN_FLUX, is_dirichlet=isd)
+    O.dirichlet_penalty(rows, cols, vals, rhs, ids, g, case["penalty"])
+    u = spla.spsolve(_csr(rows, cols, vals).tocsc(), rhs)
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16)
+    assert worst < 1.0e-6
+
+
+def test_elasticity_traction_golden():
+    """Traction term (femutils/ArcaneFemFunctions.h:2854-2885) against modules/elasticity/check/bar.2D.Dirichlet.traction.txt."""
+    case = CS.TRACTION_CASE
+    m, b, rows, cols, vals, rhs, ids, g = _elasticity_system(case, O.LAYOUT_PER_ROW, False)
+    for group, t in case["traction"]:
+        O.rhs_neumann(m.dim, b, m.coords, M.orient_boundary_faces(m, m.faces[group]), t, rhs, kind=O.NEUMANN_TRACTION)
+    crow, ccol, _ = O.bsr_to_csr(b, rows, cols)
+    O.dirichlet_penalty(crow, ccol, vals, rhs, ids, g, case["penalty"])
+    u = spla.spsolve(_csr(crow, ccol, vals).tocsc(), rhs)
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10)
+    assert worst < 1.0e-4
+
+
 def test_formulations_agree_to_rounding():
     m = _load(CS.POISSON_CASES["sphere_3D"])
     rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
