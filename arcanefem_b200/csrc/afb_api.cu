@@ -101,7 +101,8 @@ int afb_create(int device, afb_ctx** out)
   ctx->stream = ctx->own_stream;
   for (int i = 0; i < 6; ++i) AFB_CUDA(cudaEventCreate(&ctx->ev[i]));
   AFB_CUDA(cudaEventCreateWithFlags(&ctx->check_event, cudaEventDisableTiming));
-  AFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin_check), 2 * sizeof(int32_t), cudaHostAllocDefault));
+  AFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin_check), 2 * sizeof(int32_t), cudaHostAllocMapped));
+  AFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->pin_check_dev), ctx->pin_check, 0));
   *out = ctx;
   return AFB_OK;
 }

@@ -172,7 +172,8 @@ struct afb_ctx {
   afb::TilePlan plan;
 
   // deferred host-side check of a steady-state pattern re-build (connectivity.cu: verify_pending)
-  int32_t* pin_check = nullptr;     // pinned int32[2]: rows[nb_node] and the stale flag of the last re-build
+  int32_t* pin_check = nullptr;     // pinned, device-mapped int32[2]: rows[nb_node] and the stale flag of the last re-build
+  int32_t* pin_check_dev = nullptr; // its device address (the connectivity-based re-build writes the two words from its kernel: no copy in the stream)
   cudaEvent_t check_event = nullptr;
   bool check_pending = false;
   int sparsity_algo = 0;            // AFB_SPARSITY_*
@@ -221,7 +222,7 @@ int p2p_status(afb_ctx* ctx, int* status);
 int p2p_disconnect(afb_ctx* ctx);
 bool pattern_nn_ready(const afb_ctx* ctx);
 int pattern_nn_build(afb_ctx* ctx);
-int pattern_nn_place(afb_ctx* ctx);
+int pattern_nn_place(afb_ctx* ctx, int32_t* check);
 int pattern_tiled_extract(afb_ctx* ctx, int32_t* deg, int* stale);
 int pattern_tiled_place(afb_ctx* ctx);
 int ensure_values_zeroed(afb_ctx* ctx);

@@ -396,12 +396,13 @@ int build_pattern(afb_ctx* ctx)
     // columns from the tile-local node-node connectivity.  nnz is a function of the mesh alone and already
     // known on the host: no host synchronisation; rows[nb_node] and the stale flag are compared later
     // (verify_pending).
-    AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
-    AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), ctx->stream));
+    // the two check words live in device-mapped pinned memory and are written by the place kernel itself:
+    // no memset and no copy between the BuildMatrix kernels and the assembly that follows
+    ctx->pin_check[0] = -1; // (the previous check was completed by verify_pending above: nothing is in flight)
+    ctx->pin_check[1] = 0;
     AFB_TRY(exclusive_scan_i32(ctx, ctx->plan.nn_deg.as<int32_t>(), ctx->rows.as<int32_t>(), nb_node));
-    AFB_TRY(pattern_nn_place(ctx));
-    AFB_CUDA(cudaMemcpyAsync(ctx->pin_check, ctx->rows.as<int32_t>() + nb_node, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    AFB_CUDA(cudaMemcpyAsync(ctx->pin_check + 1, ctx->tmp_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AFB_TRY(pattern_nn_place(ctx, ctx->pin_check_dev));
+    if (ctx->plan.nb_tile == 0) ctx->pin_check[0] = (int32_t)ctx->nnz; // no tile, no kernel: nothing to check
     AFB_CUDA(cudaEventRecord(ctx->check_event, ctx->stream));
     ctx->check_pending = true;
     done = true;

@@ -156,7 +156,8 @@ k_pattern_tiled_extract(const TileDesc* __restrict__ desc, const int32_t* __rest
 // footprint index to the node id and stores it (rows with consecutive node ids are adjacent: contiguous runs)
 __global__ void __launch_bounds__(TG_RMAX)
 k_pattern_nn_place(const TileDesc* __restrict__ desc, const int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ rows, const uint16_t* __restrict__ nn_local,
-                   const uint16_t* __restrict__ nn_e0, const int32_t* __restrict__ foot, int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row, int* __restrict__ stale)
+                   const uint16_t* __restrict__ nn_e0, const int32_t* __restrict__ foot, int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row,
+                   int32_t nb_node, int32_t* __restrict__ check /* device-mapped host words: rows[nb_node], stale flag */)
 {
   __shared__ int32_t s_foot[TG_FMAX];
   __shared__ int32_t s_dbase[TG_EMAX];
@@ -164,6 +165,7 @@ k_pattern_nn_place(const TileDesc* __restrict__ desc, const int32_t* __restrict_
   const int32_t t = blockIdx.x;
   const TileDesc d = desc[t];
   const int R = d.nb_row, E = d.nb_entry;
+  if (t == 0 && threadIdx.x == 0) check[0] = __ldg(rows + nb_node);
   if (R == 0) return;
   const int i = threadIdx.x;
   if (i == 0) s_bad = 0;
@@ -194,7 +196,7 @@ k_pattern_nn_place(const TileDesc* __restrict__ desc, const int32_t* __restrict_
   }
   __syncthreads();
   if (s_bad) {
-    if (i == 0) atomicExch(stale, 1);
+    if (i == 0) check[1] = 1;
     return;
   }
 #pragma unroll
@@ -322,13 +324,13 @@ int pattern_nn_build(afb_ctx* ctx)
   return AFB_OK;
 }
 
-int pattern_nn_place(afb_ctx* ctx)
+int pattern_nn_place(afb_ctx* ctx, int32_t* check)
 {
   const TilePlan& P = ctx->plan;
   if (P.nb_tile == 0) return AFB_OK;
   k_pattern_nn_place<<<P.nb_tile, pattern_threads(P), 0, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), ctx->rows.as<int32_t>(),
                                                                         P.nn_local.as<uint16_t>(), P.nn_e0.as<uint16_t>(), P.foot.as<int32_t>(), ctx->cols.as<int32_t>(),
-                                                                        ctx->nz_per_row.as<int32_t>(), ctx->tmp_flag.as<int>());
+                                                                        ctx->nz_per_row.as<int32_t>(), ctx->nb_node, check);
   AFB_LAUNCH_CHECK(ctx);
   return AFB_OK;
 }
