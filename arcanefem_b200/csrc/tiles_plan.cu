@@ -670,41 +670,76 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
       }
     }
     // Lists of a unit, one thread per half-warp of lanes.  The executor reads contribution k of its 16
-    // lanes with one shared-memory instruction: the k-th slots of the 16 lists are chosen greedily so that
-    // they fall into different banks (8-byte bank = cache index mod 16) whenever an entry still has such a
-    // contribution left.  The order inside an entry's list is therefore plan-defined (not ascending cell
-    // id), but fixed: the sums stay bit-reproducible.
+    // lanes with one shared-memory instruction: the k-th slots of the 16 lists are chosen so that they fall
+    // into different banks (8-byte bank = cache index mod 16) whenever possible -- greedy choice with
+    // one-step augmentation (a lane that finds all its banks taken may move an earlier lane to another
+    // free bank of that lane's remaining contributions).  The order inside an entry's list is therefore
+    // plan-defined (not ascending cell id), but fixed: the sums stay bit-reproducible.
     for (int hx = threadIdx.x; hx < nunit * 2; hx += blockDim.x) {
       const int u = hx >> 1, l0 = (hx & 1) * 16;
       const int len = S.ulen[u];
-      unsigned short used[64];
-      for (int k = 0; k < 64; ++k) used[k] = 0;
-      for (int l = l0; l < l0 + 16; ++l) {
-        const int x = u * 32 + l;
+      int cnt_l[16];
+      const uint16_t* src_l[16];
+      unsigned long long taken[16];
+      bool simple = false;
+      for (int j = 0; j < 16; ++j) {
+        const int x = u * 32 + l0 + j;
         const bool valid = x < EC;
         const int e = valid ? (int)(S.keys[x] & 0xFFFFu) : 0;
-        const int n = valid ? S.cnt[e] : 0;
-        const uint16_t* src = S.clist + (valid ? S.eoff[e] : 0);
-        uint16_t* out = lists + d.list_off + S.ubase[u] + l * 2; // [len/2][32 lanes][2]
-        unsigned long long taken = 0ull;
-        for (int k = 0; k < len; ++k) {
-          uint16_t code = PAD;
-          if (k < n) {
-            if (n <= 64 && k < 64) {
-              int pick = -1, first = -1;
-              for (int q = 0; q < n; ++q) {
-                if ((taken >> q) & 1ull) continue;
-                if (first < 0) first = q;
-                if (!((used[k] >> (src[q] & 15)) & 1)) { pick = q; break; }
-              }
-              if (pick < 0) pick = first;
-              taken |= 1ull << pick;
-              code = src[pick];
-              used[k] |= (unsigned short)(1u << (code & 15));
+        cnt_l[j] = valid ? S.cnt[e] : 0;
+        src_l[j] = S.clist + (valid ? S.eoff[e] : 0);
+        taken[j] = 0ull;
+        if (cnt_l[j] > 64) simple = true;
+      }
+      uint16_t* out0 = lists + d.list_off + S.ubase[u] + l0 * 2; // [len/2][32 lanes][2]
+      for (int k = 0; k < len; ++k) {
+        signed char owner[16];  // bank -> lane
+        signed char choice[16]; // lane -> index into its list
+        for (int j = 0; j < 16; ++j) { owner[j] = -1; choice[j] = -1; }
+        if (!simple) {
+          for (int j = 0; j < 16; ++j) {
+            if (k >= cnt_l[j]) continue;
+            const int n = cnt_l[j];
+            int first = -1;
+            for (int q = 0; q < n && choice[j] < 0; ++q) {
+              if ((taken[j] >> q) & 1ull) continue;
+              if (first < 0) first = q;
+              const int bk = src_l[j][q] & 15;
+              if (owner[bk] < 0) { owner[bk] = (signed char)j; choice[j] = (signed char)q; }
             }
-            else code = src[k];
+            if (choice[j] >= 0) continue;
+            // all banks of this lane's remaining contributions are taken: try to move one of their owners
+            for (int q = 0; q < n && choice[j] < 0; ++q) {
+              if ((taken[j] >> q) & 1ull) continue;
+              const int bk = src_l[j][q] & 15;
+              const int j2 = owner[bk];
+              if (j2 < 0 || j2 == j) continue;
+              const int n2 = cnt_l[j2];
+              for (int q2 = 0; q2 < n2; ++q2) {
+                if (((taken[j2] >> q2) & 1ull) || q2 == choice[j2]) continue;
+                const int b2 = src_l[j2][q2] & 15;
+                if (owner[b2] < 0) {
+                  owner[b2] = (signed char)j2;
+                  choice[j2] = (signed char)q2;
+                  owner[bk] = (signed char)j;
+                  choice[j] = (signed char)q;
+                  break;
+                }
+              }
+            }
+            if (choice[j] < 0) choice[j] = (signed char)first; // a bank conflict remains
           }
-          out[(k >> 1) * 64 + (k & 1)] = code;
+        }
+        for (int j = 0; j < 16; ++j) {
+          uint16_t code = PAD;
+          if (k < cnt_l[j]) {
+            if (simple) code = src_l[j][k];
+            else {
+              code = src_l[j][choice[j]];
+              taken[j] |= 1ull << choice[j];
+            }
+          }
+          out0[j * 2 + (k >> 1) * 64 + (k & 1)] = code;
         }
       }
     }
