@@ -460,9 +460,12 @@ def run_b200(args):
         # the GIL), so one step's H2D overlaps the other's D2H (PCIe is full duplex) and the kernels of either.
         # Every step still copies its own inputs in and its own CSR arrays out.
         import concurrent.futures
-        stream_b = torch.cuda.Stream(device=dev)
-        ctx3 = A.Context(local_rank, stream=stream_b.cuda_stream)
-        out_b = (torch.empty_like(rows_h).pin_memory(), torch.empty_like(cols_h).pin_memory(), torch.empty_like(vals_h).pin_memory())
+        nl = max(2, args.e2e_lanes)
+        extra = []
+        for _ in range(nl - 1):
+            st_k = torch.cuda.Stream(device=dev)
+            extra.append((st_k, A.Context(local_rank, stream=st_k.cuda_stream),
+                          (torch.empty_like(rows_h).pin_memory(), torch.empty_like(cols_h).pin_memory(), torch.empty_like(vals_h).pin_memory())))
 
         def lane_step(c, outs):
             c.set_mesh(3, coords_h.numpy(), cells_h.numpy(), None)
@@ -473,24 +476,26 @@ def run_b200(args):
             c.to_host(A.ARRAY_COLUMNS, outs[1].numpy())
             c.to_host(A.ARRAY_VALUES, outs[2].numpy())
 
-        lanes = [(ctx2, (rows_h, cols_h, vals_h)), (ctx3, out_b)]
-        pipe_steps = 4 * e2e_steps
-        half_step_s = 0.5e-3 * e2e_serial_ms / e2e_steps
-        with concurrent.futures.ThreadPoolExecutor(max_workers=2) as pool:
+        lanes = [(ctx2, (rows_h, cols_h, vals_h))] + [(c, o) for _, c, o in extra]
+        per_lane = 2 * e2e_steps
+        pipe_steps = nl * per_lane
+        step_s = 1e-3 * e2e_serial_ms / e2e_steps
+        with concurrent.futures.ThreadPoolExecutor(max_workers=nl) as pool:
             def run_lane(k, count):
-                if k == 1 and count > 1:
-                    time.sleep(half_step_s)  # half a step out of phase (inside the timed region): one lane uploads while the other downloads
+                if count > 1:
+                    time.sleep(k * step_s / nl)  # lanes start out of phase (inside the timed region): uploads meet downloads
                 for _ in range(count):
                     lane_step(*lanes[k])
-            list(pool.map(lambda k: run_lane(k, 1), range(2)))  # warm-up of both lanes
+            list(pool.map(lambda k: run_lane(k, 1), range(nl)))  # warm-up of every lane
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            list(pool.map(lambda k: run_lane(k, pipe_steps // 2), range(2)))
+            list(pool.map(lambda k: run_lane(k, per_lane), range(nl)))
             torch.cuda.synchronize(dev)
             pipe_ms = 1e3 * (time.perf_counter() - t0)
-        assert torch.equal(out_b[2], vals_h) or e2e_variant == A.VARIANT_CELLWISE_ATOMIC, "pipelined lanes disagree"
-        assert torch.equal(out_b[1], cols_h) and torch.equal(out_b[0], rows_h), "pipelined lanes disagree (pattern)"
-        ctx3.close()
+        for _, c, o in extra:
+            assert torch.equal(o[2], vals_h) or e2e_variant == A.VARIANT_CELLWISE_ATOMIC, "pipelined lanes disagree"
+            assert torch.equal(o[1], cols_h) and torch.equal(o[0], rows_h), "pipelined lanes disagree (pattern)"
+            c.close()
         if pipe_ms / pipe_steps < e2e_serial_ms / e2e_steps:
             e2e_ms, e2e_pipelined = pipe_ms * e2e_steps / pipe_steps, True
     h2d = coords_h.numel() * 8 + cells_h.numel() * 4 + (own_h.numel() if info["is_own"] else 0)
@@ -536,7 +541,7 @@ def run_b200(args):
                                  "frac": ach_pattern / peak, "algorithmic_bytes": float(mx[9])},
             "e2e": {"value": cells_all * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sm[6]), "d2h_bytes_per_step": int(sm[7]),
                     "steps": e2e_steps, "variant": VARIANT_NAMES[e2e_variant],
-                    "pipelined": "two contexts / streams / host threads: a step's H2D overlaps the other lane's D2H" if e2e_pipelined else "no (one step at a time)",
+                    "pipelined": f"{max(2, args.e2e_lanes)} lanes (contexts / streams / host threads) out of phase: one lane's H2D overlaps another's D2H and kernels" if e2e_pipelined else "no (one step at a time)",
                     "one_step_at_a_time_value": cells_all * e2e_steps / (float(mx[10]) * 1e-3),
                     "what": "afb_set_mesh(host) + afb_build_pattern + afb_assemble_bilinear (+ ghost-row exchange) + afb_copy_to_host(rows, columns, values)",
                     "values_checksum": checksum},
@@ -564,6 +569,7 @@ def main():
     ap.add_argument("--sparsity", default="auto", choices=["auto", "cells", "connectivity"], help="steady-state BuildMatrix algorithm (auto: by variant, as the reference pairs them)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e: one step at a time only")
+    ap.add_argument("--e2e-lanes", type=int, default=4, help="e2e: pipelined lanes (independent problems in flight)")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1, exchange mode: one pull kernel over NVLink peer memory (CUDA IPC) or NCCL send/recv + accumulate kernels")
     ap.add_argument("--mode", default="exchange", choices=["exchange", "replicate"], help="N>1: ghost-row exchange over NCCL (north star) or the reference's ghost-cell replication")
     args = ap.parse_args()
