@@ -35,7 +35,7 @@ _ARRAY_DTYPE = {ARRAY_ROWS: np.int32, ARRAY_COLUMNS: np.int32, ARRAY_VALUES: np.
 
 EXPORTS = [
     "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_set_own_cell_count", "afb_get_own_cell_count", "afb_renumber_columns", "afb_mesh_generate_box",
-    "afb_build_pattern", "afb_set_sparsity_algorithm", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_assemble_rhs_neumann", "afb_set_dirichlet_nodes",
+    "afb_build_pattern", "afb_set_sparsity_algorithm", "afb_options_from_name", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_assemble_rhs_neumann", "afb_set_dirichlet_nodes",
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
     "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail",
@@ -84,6 +84,13 @@ def _ptr(a):
         return a.ctypes.data_as(C.c_void_p)
     # torch tensor
     return C.c_void_p(a.data_ptr())
+
+
+def options_from_name(name: str):
+    """(format, variant, sparsity) of a reference matrix-format option name (Fem.axl): 'csr-gpu', 'nwcsr', 'bsr', 'AF-BSR', ..."""
+    f, v, sp = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().afb_options_from_name(name.encode(), C.byref(f), C.byref(v), C.byref(sp)))
+    return f.value, v.value, sp.value
 
 
 class Context:

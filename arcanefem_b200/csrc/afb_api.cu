@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cstring>
+
 #include "afb_internal.h"
 
 namespace afb {
@@ -136,6 +138,42 @@ int afb_set_stream(afb_ctx* ctx, void* cuda_stream)
   AFB_TRY(verify_pending(ctx));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return AFB_OK;
+}
+
+int afb_options_from_name(const char* name, int* format, int* variant, int* sparsity)
+{
+  AFB_REQUIRE(name && format && variant && sparsity, AFB_ERR_INVALID, "afb_options_from_name: null argument");
+  char low[32];
+  size_t n = 0;
+  for (; name[n] && n + 1 < sizeof(low); ++n) low[n] = (char)((name[n] >= 'A' && name[n] <= 'Z') ? name[n] - 'A' + 'a' : name[n]);
+  low[n] = 0;
+  struct Row { const char* name; int format, variant, sparsity; };
+  static const Row table[] = {
+    // host back-ends of testlab (same matrices as their device twins)
+    { "legacy", AFB_FORMAT_CSR, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    { "dok", AFB_FORMAT_CSR, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    { "coo", AFB_FORMAT_COO, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    { "coo-sorting", AFB_FORMAT_COO, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    { "csr", AFB_FORMAT_CSR, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    // device back-ends
+    { "coo-gpu", AFB_FORMAT_COO, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    { "coo-sorting-gpu", AFB_FORMAT_COO, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    { "csr-gpu", AFB_FORMAT_CSR, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    { "nwcsr", AFB_FORMAT_CSR, AFB_VARIANT_TILED_GATHER, AFB_SPARSITY_FROM_CONNECTIVITY },
+    { "blcsr", AFB_FORMAT_CSR, AFB_VARIANT_NODEWISE, AFB_SPARSITY_FROM_CONNECTIVITY },
+    { "bsr", AFB_FORMAT_BSR, AFB_VARIANT_CELLWISE_ATOMIC, AFB_SPARSITY_FROM_CELLS },
+    { "bsr-atomic-free", AFB_FORMAT_BSR, AFB_VARIANT_TILED_GATHER, AFB_SPARSITY_FROM_CONNECTIVITY },
+    { "af-bsr", AFB_FORMAT_BSR, AFB_VARIANT_TILED_GATHER, AFB_SPARSITY_FROM_CONNECTIVITY },
+  };
+  for (const Row& r : table)
+    if (!strcmp(low, r.name)) {
+      *format = r.format;
+      *variant = r.variant;
+      *sparsity = r.sparsity;
+      return AFB_OK;
+    }
+  set_error("afb_options_from_name: unknown matrix format option '%s'", name);
+  return AFB_ERR_INVALID;
 }
 
 int afb_set_sparsity_algorithm(afb_ctx* ctx, int algorithm)

@@ -195,6 +195,16 @@ AFB_API int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_blo
  */
 AFB_API int afb_set_sparsity_algorithm(afb_ctx* ctx, int algorithm);
 
+/*
+ * The reference's matrix-format options, kept as names: testlab's boolean options of modules/testlab/Fem.axl:42-95
+ * ("legacy", "coo", "coo-sorting", "coo-gpu", "coo-sorting-gpu", "csr", "csr-gpu", "nwcsr", "blcsr", "bsr", "bsr-atomic-free")
+ * and the production modules' <matrix-format> strings ("DOK", "BSR", "AF-BSR": modules/poisson/Fem.axl:31,
+ * modules/elasticity/Fem.axl:37).  Writes the AFB_FORMAT_*, AFB_VARIANT_* and AFB_SPARSITY_* values that back-end maps
+ * to here (host-only back-ends map to the device variant producing the same matrix).  Case-insensitive;
+ * AFB_ERR_INVALID for an unknown name.
+ */
+AFB_API int afb_options_from_name(const char* matrix_format_option, int* format, int* variant, int* sparsity);
+
 /* ---- bilinear form ------------------------------------------------------------------------ */
 
 /* BSRFormat::resetMatrixValues / DoFLinearSystem::clearValues (values only) */

@@ -56,3 +56,18 @@ def test_product_package_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
         for f in files:
             assert "oracle" not in open(os.path.join(dirpath, f)).read().lower(), f
+
+
+def test_reference_option_names_map_to_variants():
+    """The reference's matrix-format option names (modules/testlab/Fem.axl:42-95, modules/poisson/Fem.axl:31) stay valid
+    (host logic only: no device needed)."""
+    A = capi
+    assert A.options_from_name("csr-gpu") == (A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC, A.SPARSITY_FROM_CELLS)
+    assert A.options_from_name("nwcsr") == (A.FORMAT_CSR, A.VARIANT_TILED_GATHER, A.SPARSITY_FROM_CONNECTIVITY)
+    assert A.options_from_name("coo-sorting-gpu")[0] == A.FORMAT_COO
+    assert A.options_from_name("bsr") == (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC, A.SPARSITY_FROM_CELLS)
+    assert A.options_from_name("AF-BSR") == A.options_from_name("bsr-atomic-free") == (A.FORMAT_BSR, A.VARIANT_TILED_GATHER, A.SPARSITY_FROM_CONNECTIVITY)
+    for name in ("legacy", "DOK", "coo", "coo-sorting", "csr", "coo-gpu", "blcsr"):
+        A.options_from_name(name)
+    with pytest.raises(A.AfbError):
+        A.options_from_name("ellpack")
