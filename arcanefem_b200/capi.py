@@ -39,7 +39,7 @@ EXPORTS = [
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
     "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail",
-    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_status", "afb_p2p_disconnect", "afb_last_timings", "afb_launch_count",
+    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_status", "afb_p2p_disconnect", "afb_last_timings", "afb_inspector_timings", "afb_launch_count",
 ]
 
 
@@ -302,6 +302,11 @@ class Context:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         _check(lib().afb_last_timings(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(connectivity_ms=a.value, pattern_ms=b.value, assemble_ms=c.value)
+
+    def inspector_timings(self):
+        a, b = C.c_float(), C.c_float()
+        _check(lib().afb_inspector_timings(self._h, C.byref(a), C.byref(b)))
+        return dict(mesh_tiling_ms=a.value, value_plan_ms=b.value)
 
     def launch_count(self):
         return int(lib().afb_launch_count(self._h))

@@ -692,6 +692,15 @@ int afb_last_timings(afb_ctx* ctx, float* connectivity_ms, float* pattern_ms, fl
   return AFB_OK;
 }
 
+int afb_inspector_timings(afb_ctx* ctx, float* mesh_tiling_ms, float* value_plan_ms)
+{
+  AFB_TRY(check_ctx(ctx));
+  const TilePlan& P = ctx->plan;
+  if (mesh_tiling_ms) *mesh_tiling_ms = (P.mesh_valid && P.mesh_gen == ctx->mesh_gen) ? P.mesh_ms : -1.0f;
+  if (value_plan_ms) *value_plan_ms = (P.lists_valid && P.lists_mesh_gen == ctx->mesh_gen) ? P.lists_ms : -1.0f;
+  return AFB_OK;
+}
+
 int64_t afb_launch_count(afb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 } // extern "C"

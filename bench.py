@@ -386,6 +386,7 @@ def run_b200(args):
         time.sleep(0.15)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0
+    inspector = ctx.inspector_timings()
     transport = "none"
     if da is not None and da.plan is not None:
         transport = "p2p" if da.plan.p2p is not None else "nccl"
@@ -533,6 +534,7 @@ def run_b200(args):
                        "values_only_elements_per_s": cells_all / (values_ms * 1e-3),
                        "variants_ms": {VARIANT_NAMES[k]: v for k, v in per_variant.items()},
                        "build_matrix_ms_by_sparsity": per_sparsity,
+                       "inspector_ms_once_per_mesh": inspector,
                        "decomposition": mode, "exchange_bytes_sent_recv_rank0": list(exch_bytes),
                        "other_scheme_ms_per_step": None if other_ms is None else {other_ms[0]: other_ms[1]}},
             "roofline": {"bound": "hbm", "kernel": "value assembly (AddAndCompute)", "achieved": ach_values, "peak": peak, "unit": "GB/s", "frac": ach_values / peak,

@@ -378,6 +378,10 @@ AFB_API int afb_renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_globa
  * context stream (Timer::Action scopes "BuildMatrix" / "AddAndCompute" of the reference:
  * modules/testlab/CsrGpuBiliAssembly.cc:313-337).  Synchronises the stream. */
 AFB_API int afb_last_timings(afb_ctx* ctx, float* connectivity_ms, float* pattern_ms, float* assemble_ms);
+/* One-time cost of the tiled path's inspector for the current mesh (milliseconds, CUDA events): mesh tiling incl. the
+ * tile-local node-node connectivity, and the value plan (contribution lists); -1 when not built.  The analogue of
+ * the init-time connectivity the reference builds on the host (MeshUtils::computeNodeNodeViaEdgeConnectivity). */
+AFB_API int afb_inspector_timings(afb_ctx* ctx, float* mesh_tiling_ms, float* value_plan_ms);
 /* number of kernels launched by this context so far (bench.py "gpu_launches") */
 AFB_API int64_t afb_launch_count(afb_ctx* ctx);
 
