@@ -555,6 +555,33 @@ def test_elasticity_traction_golden_solution(ctx):
     assert worst < 1.0e-4
 
 
+def test_degenerate_meshes(ctx):
+    """Ragged / empty inputs: a mesh without cells (every row is its diagonal), a single cell, and a re-used context
+    going back to a regular mesh afterwards; every variant, pattern re-builds included."""
+    coords = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.3, 0.2, 0.9], [5.0, 5.0, 5.0]])
+    for dim, cells in ((2, np.zeros((0, 3), np.int32)), (3, np.zeros((0, 4), np.int32)), (2, np.array([[0, 1, 2]], np.int32)), (3, np.array([[0, 1, 2, 3]], np.int32))):
+        ctx.set_mesh(dim, coords, cells)
+        rows_ref, cols_ref = O.build_pattern(cells.shape[1], coords.shape[0], cells)
+        for rep in range(2):
+            nbr, nnz = ctx.build_pattern(1)
+            assert (nbr, nnz) == (coords.shape[0], cols_ref.size)
+            assert np.array_equal(ctx.to_host(A.ARRAY_ROWS), rows_ref) and np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+            ref = O.assemble(dim, coords, cells, rows_ref, cols_ref, form=O.FORM_BSR)
+            for v in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER):
+                ctx.reset_values()
+                ctx.assemble(A.OP_POISSON, variant=v)
+                got = ctx.to_host(A.ARRAY_VALUES)
+                assert np.all(np.abs(got - ref) <= 1e-12 * max(np.abs(ref).max(), 1.0)), (dim, cells.shape, v)
+        ctx.rhs_reset()
+        ctx.rhs_source([2.0])
+        assert np.all(np.isfinite(ctx.to_host(A.ARRAY_RHS)))
+    m = get_mesh("box3d_n6_nojitter")
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(1)
+    rows_ref, cols_ref = O.build_pattern(m.npc, m.nb_node, m.cells)
+    assert np.array_equal(ctx.to_host(A.ARRAY_COLUMNS), cols_ref)
+
+
 def test_rhs_source_variants(ctx):
     for name in ("sphere_3D", "L-shape_2D"):
         m = get_mesh(name)
