@@ -39,7 +39,7 @@ EXPORTS = [
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
     "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail",
-    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_status", "afb_p2p_disconnect", "afb_last_timings", "afb_inspector_timings", "afb_launch_count",
+    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_status", "afb_p2p_disconnect", "afb_solve_pcg", "afb_last_timings", "afb_inspector_timings", "afb_launch_count",
 ]
 
 
@@ -302,6 +302,13 @@ class Context:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         _check(lib().afb_last_timings(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(connectivity_ms=a.value, pattern_ms=b.value, assemble_ms=c.value)
+
+    def solve_pcg(self, rtol=1e-12, atol=0.0, max_iter=10000):
+        """Jacobi-PCG on the assembled system; returns (x, iterations, preconditioned residual)."""
+        x = np.empty(self.nb_block_row * self.b, dtype=np.float64)
+        it, res = C.c_int(), C.c_double()
+        _check(lib().afb_solve_pcg(self._h, C.c_double(rtol), C.c_double(atol), int(max_iter), _ptr(x), MEM_HOST, C.byref(it), C.byref(res)))
+        return x, it.value, res.value
 
     def inspector_timings(self):
         a, b = C.c_float(), C.c_float()

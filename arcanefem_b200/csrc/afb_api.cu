@@ -117,7 +117,7 @@ int afb_destroy(afb_ctx* ctx)
   p2p_destroy(ctx);
   DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,
                      &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
-                     &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback, &ctx->scan_state,
+                     &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback, &ctx->scan_state, &ctx->solver_work,
                      &ctx->plan.tile_desc, &ctx->plan.tile_nodes, &ctx->plan.tile_cells, &ctx->plan.unit_base, &ctx->plan.unit_len, &ctx->plan.emap, &ctx->plan.rowinfo, &ctx->plan.foot, &ctx->plan.lconn, &ctx->plan.lists,
                      &ctx->plan.rowf, &ctx->plan.inc, &ctx->plan.inc_grp, &ctx->plan.col_scratch, &ctx->plan.nn_deg, &ctx->plan.nn_local, &ctx->plan.nn_e0, &ctx->plan.emap_rows,
                      &ctx->plan.node_tile, &ctx->plan.node_lrow, &ctx->plan.scratch_a, &ctx->plan.scratch_b, &ctx->plan.scratch_c, &ctx->plan.stats };
@@ -690,6 +690,15 @@ int afb_last_timings(afb_ctx* ctx, float* connectivity_ms, float* pattern_ms, fl
     if (ctx->timed[p]) AFB_CUDA(cudaEventElapsedTime(out[p], ctx->ev[2 * p], ctx->ev[2 * p + 1]));
   }
   return AFB_OK;
+}
+
+int afb_solve_pcg(afb_ctx* ctx, double rtol, double atol, int max_iter, double* x, int mem_space, int* iterations, double* residual)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_pattern && ctx->assembled, AFB_ERR_INVALID, "afb_solve_pcg: assemble the matrix first");
+  AFB_REQUIRE(rtol >= 0.0 && atol >= 0.0 && max_iter >= 0, AFB_ERR_INVALID, "afb_solve_pcg: negative tolerance / iteration count");
+  AFB_TRY(verify_pending(ctx));
+  return solve_pcg(ctx, rtol, atol, max_iter, x, mem_space, iterations, residual);
 }
 
 int afb_inspector_timings(afb_ctx* ctx, float* mesh_tiling_ms, float* value_plan_ms)

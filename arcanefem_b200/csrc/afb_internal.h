@@ -165,7 +165,7 @@ struct afb_ctx {
   bool saved_valid = false;
 
   // scratch
-  afb::DevBuf tmp_i32a, tmp_i32b, tmp_scan, tmp_ids, tmp_vals, tmp_flag, tmp_lookback, scan_state;
+  afb::DevBuf tmp_i32a, tmp_i32b, tmp_scan, tmp_ids, tmp_vals, tmp_flag, tmp_lookback, scan_state, solver_work;
   uint64_t mesh_gen = 0;        // bumped by afb_set_mesh / afb_mesh_generate_box
   uint64_t pattern_mesh_gen = ~0ull; // mesh generation the column buffer was last sized for
 
@@ -213,6 +213,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags);
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags);
 bool pattern_tiled_ready(const afb_ctx* ctx);
 int rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* faces_dev, int kind, int nb_value, const double* values, int skip_dirichlet);
+int solve_pcg(afb_ctx* ctx, double rtol, double atol, int max_iter, double* x_out, int mem_space, int* iterations, double* residual);
 void p2p_destroy(afb_ctx* ctx);
 int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle);
 int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const int64_t* pull_first,

@@ -372,6 +372,18 @@ AFB_API int afb_p2p_disconnect(afb_ctx* ctx);
  */
 AFB_API int afb_renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_global, int32_t* out);
 
+/* ---- solve ---------------------------------------------------------------- */
+
+/*
+ * Jacobi-preconditioned conjugate gradient on the matrix and RHS of the context, as assembled (CSR, or BSR in either
+ * value layout): stands in for the HYPRE / PETSc solve the reference hands the same arrays to
+ * (femutils/HypreDoFLinearSystem.cc:461-520, PetscDoFLinearSystem.cc:329-398) so that golden solution files can be
+ * checked end to end on the GPU.  SPD systems only (Poisson, elasticity; Dirichlet by penalty or elimination).
+ * Stops when sqrt(r . D^-1 r) <= max(rtol * its initial value, atol) or after max_iter iterations (then an error is
+ * returned, x still holds the last iterate).  x: nb_row*b doubles, host or device (mem_space); may be NULL.
+ */
+AFB_API int afb_solve_pcg(afb_ctx* ctx, double rtol, double atol, int max_iter, double* x, int mem_space, int* iterations, double* residual);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 
 /* Milliseconds spent by the last call of each phase, measured with CUDA events on the

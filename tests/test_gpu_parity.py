@@ -555,6 +555,57 @@ def test_elasticity_traction_golden_solution(ctx):
     assert worst < 1.0e-4
 
 
+# ---------------------------------------------------------------------------------------------
+# in-repo Jacobi-PCG (afb_solve_pcg): the reference's golden solution files end to end on the device
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CS.POISSON_CASES) + [f"neumann:{k}" for k in CS.NEUMANN_CASES])
+def test_pcg_poisson_golden(ctx, name):
+    case = CS.NEUMANN_CASES[name[8:]] if name.startswith("neumann:") else CS.POISSON_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(1)
+    ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER, flags=A.FLAG_SIGNED_TRI_AREA)
+    ctx.set_dirichlet_nodes(ids)
+    ctx.rhs_reset()
+    ctx.rhs_source(case["f"], nodewise=False, signed_tri_area=True)
+    for group, q in case.get("neumann", []):
+        ctx.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), q, kind=A.NEUMANN_FLUX, skip_dirichlet=True)
+    ctx.dirichlet_penalty(ids, g, case["penalty"])
+    u, it, res = ctx.solve_pcg(rtol=1e-13, max_iter=5000)
+    assert 0 < it < 5000
+    rows, cols, vals, rhs = (ctx.to_host(w) for w in (A.ARRAY_ROWS, A.ARRAY_COLUMNS, A.ARRAY_VALUES, A.ARRAY_RHS))
+    u_ref = spla.spsolve(sp.csr_matrix((vals, cols, rows)).tocsc(), rhs)
+    assert np.abs(u - u_ref).max() <= 1e-9 * np.abs(u_ref).max()
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16)
+    assert worst < 1.0e-6
+    ctx.clear_dirichlet()
+
+
+@pytest.mark.parametrize("name", list(CS.ELASTICITY_CASES))
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_pcg_elasticity_golden(ctx, name, layout):
+    case = CS.ELASTICITY_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    b = m.dim
+    lam, mu = O.lame(case["E"], case["nu"])
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(b)
+    ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER, layout=layout)
+    ctx.rhs_reset()
+    ctx.rhs_source(case["f"])
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    ctx.dirichlet_penalty(ids, g, case["penalty"])
+    u, it, res = ctx.solve_pcg(rtol=1e-12, max_iter=20000)
+    assert 0 < it < 20000
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10)
+    assert worst < 1.0e-4
+    # an indefinite / non-assembled system is refused, not iterated on
+    ctx.build_pattern(b)
+    with pytest.raises(A.AfbError):
+        ctx.solve_pcg()
+
+
 def test_degenerate_meshes(ctx):
     """Ragged / empty inputs: a mesh without cells (every row is its diagonal), a single cell, and a re-used context
     going back to a regular mesh afterwards; every variant, pattern re-builds included."""
@@ -672,6 +723,21 @@ def test_full_size_poisson_properties(ctx):
     rowmax = torch.zeros(nbn, dtype=torch.float64, device="cuda").scatter_reduce(0, rid, a.abs(), "amax")
     for other in (A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER):
         assert float(((a - results[other]).abs() / rowmax[rid]).max()) < 1e-12
+    # idempotence of the steady-state BuildMatrix at full size: both re-build algorithms reproduce the first pattern bit for bit
+    rows0, cols0 = rows.clone(), cols.clone()
+    torch.cuda.synchronize()
+    for algo in (A.SPARSITY_FROM_CELLS, A.SPARSITY_FROM_CONNECTIVITY):
+        ctx.set_sparsity_algorithm(algo)
+        try:
+            assert ctx.build_pattern(1) == (nbn, nnz)
+            v2 = ctx.csr_view()
+            assert bool(torch.equal(A.as_torch(v2["rows"], nbn + 1, np.int32, 0).long(), rows0))
+            assert bool(torch.equal(A.as_torch(v2["columns"], nnz, np.int32, 0).long(), cols0))
+            ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+            ctx.synchronize()
+            assert bool(torch.equal(A.as_torch(v2["values"], nnz, np.float64, 0), results[A.VARIANT_TILED_GATHER]))
+        finally:
+            ctx.set_sparsity_algorithm(A.SPARSITY_AUTO)
 
 
 def test_full_size_elasticity_rigid_body_modes(ctx):
