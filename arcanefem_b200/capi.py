@@ -39,7 +39,7 @@ EXPORTS = [
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
     "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail",
-    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_status", "afb_p2p_disconnect", "afb_solve_pcg", "afb_last_timings", "afb_inspector_timings", "afb_launch_count",
+    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_exchange_async", "afb_p2p_wait", "afb_p2p_status", "afb_p2p_disconnect", "afb_solve_pcg", "afb_last_timings", "afb_inspector_timings", "afb_launch_count",
 ]
 
 
@@ -281,8 +281,11 @@ class Context:
         self._p2p_keep = list(slots)
         _check(lib().afb_p2p_connect(self._h, int(my_rank), n, pr, vh, fh, i64(pull_first), i64(pull_count), sl, i64(send_first), i64(send_count)))
 
-    def p2p_exchange(self):
-        _check(lib().afb_p2p_exchange(self._h))
+    def p2p_exchange(self, asynchronous=False):
+        _check(lib().afb_p2p_exchange_async(self._h) if asynchronous else lib().afb_p2p_exchange(self._h))
+
+    def p2p_wait(self):
+        _check(lib().afb_p2p_wait(self._h))
 
     def p2p_status(self):
         st = C.c_int()

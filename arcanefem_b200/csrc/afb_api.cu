@@ -203,7 +203,19 @@ int afb_p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_
 int afb_p2p_exchange(afb_ctx* ctx)
 {
   AFB_TRY(check_ctx(ctx));
-  return p2p_exchange(ctx);
+  return p2p_exchange(ctx, 0);
+}
+
+int afb_p2p_exchange_async(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  return p2p_exchange(ctx, 1);
+}
+
+int afb_p2p_wait(afb_ctx* ctx)
+{
+  AFB_TRY(check_ctx(ctx));
+  return p2p_wait(ctx);
 }
 
 int afb_p2p_status(afb_ctx* ctx, int* status)

@@ -218,7 +218,8 @@ void p2p_destroy(afb_ctx* ctx);
 int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle);
 int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const int64_t* pull_first,
                 const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count);
-int p2p_exchange(afb_ctx* ctx);
+int p2p_exchange(afb_ctx* ctx, int async);
+int p2p_wait(afb_ctx* ctx);
 int p2p_status(afb_ctx* ctx, int* status);
 int p2p_disconnect(afb_ctx* ctx);
 bool pattern_nn_ready(const afb_ctx* ctx);

@@ -50,6 +50,11 @@ struct P2PState {
   std::vector<void*> opened;
   int nb_peer = 0;
   const void* values_base = nullptr;
+  // asynchronous form: the kernel runs on a side stream (highest priority) so that work which does not touch `values`
+  // -- the next BuildMatrix of a time loop -- proceeds on the context stream while the ranks synchronise
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  bool inflight = false;
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
@@ -159,6 +164,8 @@ int p2p_disconnect(afb_ctx* ctx)
   if (!ctx->p2p) return AFB_OK;
   P2PState* S = static_cast<P2PState*>(ctx->p2p);
   cudaStreamSynchronize(ctx->stream);
+  if (S->side) cudaStreamSynchronize(S->side);
+  S->inflight = false;
   for (void* p : S->opened) cudaIpcCloseMemHandle(p);
   S->opened.clear();
   if (S->d_peers) cudaFree(S->d_peers);
@@ -176,6 +183,9 @@ void p2p_destroy(afb_ctx* ctx)
   p2p_disconnect(ctx);
   P2PState* S = static_cast<P2PState*>(ctx->p2p);
   if (S->flags) cudaFree(S->flags);
+  if (S->ev_ready) cudaEventDestroy(S->ev_ready);
+  if (S->ev_done) cudaEventDestroy(S->ev_done);
+  if (S->side) cudaStreamDestroy(S->side);
   delete S;
   ctx->p2p = nullptr;
 }
@@ -220,15 +230,42 @@ int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank
   return AFB_OK;
 }
 
-int p2p_exchange(afb_ctx* ctx)
+int p2p_wait(afb_ctx* ctx)
+{
+  P2PState* S = ctx->p2p ? static_cast<P2PState*>(ctx->p2p) : nullptr;
+  if (!S || !S->inflight) return AFB_OK;
+  AFB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_done, 0));
+  S->inflight = false;
+  return AFB_OK;
+}
+
+int p2p_exchange(afb_ctx* ctx, int async)
 {
   P2PState* S = ctx->p2p ? static_cast<P2PState*>(ctx->p2p) : nullptr;
   AFB_REQUIRE(S && S->connected, AFB_ERR_INVALID, "afb_p2p_exchange: not connected");
   AFB_REQUIRE(S->values_base == ctx->values.p, AFB_ERR_INVALID, "afb_p2p_exchange: the values array moved since afb_p2p_export (re-export and re-connect)");
+  AFB_TRY(p2p_wait(ctx)); // one exchange in flight at a time
   S->epoch++;
   if (S->nb_peer == 0) return AFB_OK;
-  k_p2p_exchange<<<S->nb_peer * P2P_BLOCKS_PER_PEER, P2P_THREADS, 0, ctx->stream>>>(S->d_peers, ctx->values.as<double>(), S->flags, S->my_rank, S->epoch, S->counters);
+  cudaStream_t st = ctx->stream;
+  if (async) {
+    if (!S->side) {
+      int lo = 0, hi = 0;
+      AFB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      AFB_CUDA(cudaStreamCreateWithPriority(&S->side, cudaStreamNonBlocking, hi));
+      AFB_CUDA(cudaEventCreateWithFlags(&S->ev_ready, cudaEventDisableTiming));
+      AFB_CUDA(cudaEventCreateWithFlags(&S->ev_done, cudaEventDisableTiming));
+    }
+    AFB_CUDA(cudaEventRecord(S->ev_ready, ctx->stream));
+    AFB_CUDA(cudaStreamWaitEvent(S->side, S->ev_ready, 0));
+    st = S->side;
+  }
+  k_p2p_exchange<<<S->nb_peer * P2P_BLOCKS_PER_PEER, P2P_THREADS, 0, st>>>(S->d_peers, ctx->values.as<double>(), S->flags, S->my_rank, S->epoch, S->counters);
   AFB_LAUNCH_CHECK(ctx);
+  if (async) {
+    AFB_CUDA(cudaEventRecord(S->ev_done, S->side));
+    S->inflight = true;
+  }
   return AFB_OK;
 }
 
@@ -239,6 +276,7 @@ int p2p_status(afb_ctx* ctx, int* status)
   *status = 0;
   if (!S || !S->flags) return AFB_OK;
   uint32_t e = 0;
+  AFB_TRY(p2p_wait(ctx));
   AFB_CUDA(cudaMemcpyAsync(&e, S->flags + 2 * P2P_MAX_RANK, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   AFB_CUDA(cudaStreamSynchronize(ctx->stream));
   *status = (int)e;

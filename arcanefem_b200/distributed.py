@@ -277,8 +277,8 @@ class ExchangePlan:
 class _P2P:
     """afb_p2p_* of one context behind the three calls ExchangePlan needs."""
 
-    def __init__(self, ctx):
-        self.ctx = ctx
+    def __init__(self, ctx, overlap=True):
+        self.ctx, self.overlap = ctx, overlap
 
     def export(self):
         return self.ctx.p2p_export()
@@ -287,7 +287,10 @@ class _P2P:
         self.ctx.p2p_connect(*a)
 
     def exchange(self):
-        self.ctx.p2p_exchange()
+        self.ctx.p2p_exchange(asynchronous=self.overlap)
+
+    def wait(self):
+        self.ctx.p2p_wait()
 
     def disconnect(self):
         self.ctx.p2p_disconnect()
@@ -296,12 +299,12 @@ class _P2P:
 class DistributedAssembly:
     """One rank's share of a domain-decomposed assembly on its GPU (context `ctx`)."""
 
-    def __init__(self, ctx, rank, world, node_gid, node_owner, nb_own_node, device_index, group=None, transport="p2p", comm_device=None):
+    def __init__(self, ctx, rank, world, node_gid, node_owner, nb_own_node, device_index, group=None, transport="p2p", comm_device=None, overlap=True):
         """transport "p2p": ghost rows travel in one kernel over NVLink peer memory (CUDA IPC, csrc/p2p.cu);
         "nccl": torch.distributed send/recv of the rows + accumulate kernels.  comm_device: where set-up tensors live
         (default the GPU, for the nccl backend; "cpu" with a gloo group)."""
         self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
-        self.transport, self.comm_device = transport, comm_device
+        self.transport, self.comm_device, self.overlap = transport, comm_device, overlap
         self.node_gid, self.node_owner, self.nb_own_node = node_gid, node_owner, int(nb_own_node)
         self.device_index = device_index
         self.plan = None
@@ -338,7 +341,7 @@ class DistributedAssembly:
                                  values_slice=lambda first, n: vals_t[first:first + n],
                                  add_at=lambda slots, buf: ctx.add_values_at(int(slots.numel()), slots, buf),
                                  make_buffer=lambda n: torch.empty(n, dtype=torch.float64, device=f"cuda:{dev}"), group=self.group,
-                                 comm_device=self.comm_device or f"cuda:{dev}", p2p=_P2P(ctx) if self.transport == "p2p" else None)
+                                 comm_device=self.comm_device or f"cuda:{dev}", p2p=_P2P(ctx, overlap=self.overlap) if self.transport == "p2p" else None)
 
     def assemble(self, op, params=None, fmt=None, variant=None, layout=None, mode="exchange", flags=0):
         """Fresh assembly of this rank's rows (call after ctx.build_pattern).  mode "exchange": own cells
@@ -348,6 +351,7 @@ class DistributedAssembly:
         fmt = A.FORMAT_CSR if fmt is None else fmt
         variant = A.VARIANT_TILED_GATHER if variant is None else variant
         layout = A.LAYOUT_PER_BLOCK if layout is None else layout
+        self.wait()  # the previous exchange (side stream) is done with `values` before they are overwritten
         if mode == "replicate":
             ctx.assemble(op, params=params, fmt=fmt, variant=variant, layout=layout, flags=flags)
             return
@@ -364,6 +368,12 @@ class DistributedAssembly:
                 raise
             self._build_plan(layout)  # collective: a re-allocation follows the pattern size, identical on the ranks' schedule
             self.plan.exchange()
+
+    def wait(self):
+        """Orders the context stream after the exchange of the last assemble() (transport p2p runs it on a side stream so that
+        the next BuildMatrix overlaps it).  Call before anything that reads or writes the matrix values."""
+        if self.plan is not None and self.plan.p2p is not None:
+            self.plan.p2p.wait()
 
     def numbering(self):
         if self.plan is None:

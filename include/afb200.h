@@ -352,6 +352,11 @@ AFB_API int afb_values_tail(afb_ctx* ctx, int32_t first_block_row, int64_t* firs
  *                      Neighbour relations must be symmetric (counts may be 0).  Ranks < 64.
  *   afb_p2p_exchange   stream-ordered after afb_assemble_bilinear(AFB_FLAG_OWN_CELLS_ONLY | AFB_FLAG_ALL_ROWS);
  *                      every rank of the decomposition must call it once per assembly
+ *   afb_p2p_exchange_async / afb_p2p_wait   the same kernel on an internal high-priority side stream, ordered after the
+ *                      work already queued on the context stream; afb_p2p_wait makes the context stream wait for it.
+ *                      Between the two the caller may queue work that does not touch `values` (in a time loop: the next
+ *                      afb_build_pattern), which then overlaps the ranks' synchronisation.  Everything reading or writing
+ *                      `values` must come after afb_p2p_wait (afb_p2p_status and a second exchange wait by themselves).
  *   afb_p2p_status     synchronises; 0 = fine, 1/2 = a neighbour did not show up within the kernel's time-out
  *   afb_p2p_disconnect closes the mappings (also done by afb_destroy); collective by convention
  * Re-export and re-connect after afb_build_pattern moved the values array (afb_p2p_exchange reports it).
@@ -361,6 +366,8 @@ AFB_API int afb_p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle
 AFB_API int afb_p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles,
                             const int64_t* pull_first, const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count);
 AFB_API int afb_p2p_exchange(afb_ctx* ctx);
+AFB_API int afb_p2p_exchange_async(afb_ctx* ctx);
+AFB_API int afb_p2p_wait(afb_ctx* ctx);
 AFB_API int afb_p2p_status(afb_ctx* ctx, int* status);
 AFB_API int afb_p2p_disconnect(afb_ctx* ctx);
 

@@ -30,6 +30,7 @@ for transport in ("p2p", "nccl"):
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         e1b = torch.cuda.Event(enable_timing=True); e1b.record(stream)
         da.plan.exchange()
+        da.wait()
         e2.record(stream)
         torch.cuda.synchronize()
         ta.append(e0.elapsed_time(e1)); ts.append(e1b.elapsed_time(e2))

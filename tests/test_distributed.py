@@ -312,6 +312,8 @@ def run_rank_p2p(rank, world, port, case, transport, errq):
             ctx.build_pattern(b)
             da.assemble(op, params=params, fmt=fmt, variant=A.VARIANT_TILED_GATHER, layout=layout, mode="exchange")
             if transport == "p2p":
+                if rep == 1:
+                    da.wait()  # explicit join; p2p_status below joins by itself in the other repetitions
                 assert ctx.p2p_status() == 0, "ghost-row exchange timed out"
             else:
                 ctx.synchronize()
