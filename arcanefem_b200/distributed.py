@@ -281,6 +281,9 @@ class _P2P:
         self.ctx, self.overlap = ctx, overlap
 
     def export(self):
+        import os
+        if os.environ.get("AFB_P2P_DISABLE"):  # exercises the collective fall-back to the torch.distributed transport
+            raise RuntimeError("peer-memory exchange disabled by AFB_P2P_DISABLE")
         return self.ctx.p2p_export()
 
     def connect(self, *a):
