@@ -400,10 +400,14 @@ static_assert(sizeof(VecSmem<3>) <= TG_SMEM_LIMIT, "TG_MINB vector-executor CTAs
 
 
 
-template <int NPC, int LAYOUT>
+// OP 0: isotropic elasticity; OP 1 (Tri3 only): the bilaplacian's mixed form, dofs (u1,u2) per node
+//   K_ab = [[0, s d_a.d_b], [s d_a.d_b, area (1 + delta_ab)]]   (modules/bilaplacian/ElementMatrix.h:37-45): the off-diagonal
+//   term is tr(M), the mass-like term sums a seventh cached plane (the cells' areas)
+template <int NPC, int LAYOUT, int OP = 0>
 __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(ExecArgs A, ElemParams prm)
 {
   constexpr int DIM = NPC - 1, B = DIM;
+  static_assert(OP == 0 || NPC == 3, "the bilaplacian executor is for Tri3");
   extern __shared__ __align__(16) unsigned char ex_raw[];
   VecSmem<DIM>& S = *reinterpret_cast<VecSmem<DIM>*>(ex_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -472,6 +476,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
           for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int k = 0; k < 2; ++k) S.G[(a * 2 + k) * TV_CS + lc] = g.c[a][k] * q;
+          if constexpr (OP == 1) S.G[6 * TV_CS + lc] = g.area;
         }
       }
     }
@@ -491,6 +496,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
       const uint32_t* l = l32 + (S.ubase[u] >> 1) + lane;
       const int len2 = S.ulen[u] >> 1;
       double M[DIM][DIM];
+      double asum = 0.0;
 #pragma unroll
       for (int i = 0; i < DIM; ++i)
 #pragma unroll
@@ -513,6 +519,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
           for (int i = 0; i < DIM; ++i)
 #pragma unroll
             for (int j = 0; j < DIM; ++j) M[i][j] = fma(ga[i], gb[j], M[i][j]);
+          if constexpr (OP == 1) asum = fma(S.G[6 * TV_CS + lc], a == b ? 2.0 : 1.0, asum);
         }
         w = wn;
       }
@@ -525,6 +532,12 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
         for (int i = 0; i < DIM; ++i)
 #pragma unroll
           for (int j = 0; j < DIM; ++j) blk[i * B + j] = lam * M[i][j] + mu * M[j][i] + (i == j ? mu * tr : 0.0);
+        if constexpr (OP == 1) {
+          blk[0] = 0.0;
+          blk[1] = tr;
+          blk[2] = tr;
+          blk[3] = asum;
+        }
         // (row, position) of the entry and of its mirror: rows from the plan, positions from the tile-local entry index
         auto emit = [&](int e, int lo, bool transpose) {
           const int e0 = rowinfo_erow(S.rowinfo[lo]);
@@ -579,8 +592,9 @@ static int scalar_executor_choice()
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags)
 {
   const bool vec = ctx->b > 1;
-  AFB_REQUIRE((ctx->npc == 3 || ctx->npc == 4) && ((op == AFB_OP_POISSON && !vec) || (op == AFB_OP_ELASTICITY && vec)), AFB_ERR_UNSUPPORTED,
-              "AFB_VARIANT_TILED_GATHER is not available for operator %d on %d-node cells (P1 Poisson and P1 elasticity only); use AFB_VARIANT_NODEWISE", op, ctx->npc);
+  AFB_REQUIRE((ctx->npc == 3 || ctx->npc == 4) && ((op == AFB_OP_POISSON && !vec) || (op == AFB_OP_ELASTICITY && vec) || (op == AFB_OP_BILAPLACIAN && vec && ctx->npc == 3)),
+              AFB_ERR_UNSUPPORTED,
+              "AFB_VARIANT_TILED_GATHER is not available for operator %d on %d-node cells (P1 Poisson, P1 elasticity, Tri3 bilaplacian only); use AFB_VARIANT_NODEWISE", op, ctx->npc);
   TilePlan& P = ctx->plan;
   const int mode = flags & (AFB_FLAG_ALL_ROWS | AFB_FLAG_OWN_CELLS_ONLY);
   if (!P.mesh_valid || P.mesh_gen != ctx->mesh_gen || P.mesh_b_class != (vec ? 1 : 0)) AFB_TRY(build_tile_mesh(ctx));
@@ -625,6 +639,8 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   if (!vec) e = ctx->npc == 4 ? go(k_assemble_tiled<4>, sizeof(ExecSmem)) : go(k_assemble_tiled<3>, sizeof(ExecSmem));
   else if (ctx->npc == 4)
     e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_tiled_vec<4, AFB_LAYOUT_PER_BLOCK>, sizeof(VecSmem<3>)) : go(k_assemble_tiled_vec<4, AFB_LAYOUT_PER_ROW>, sizeof(VecSmem<3>));
+  else if (op == AFB_OP_BILAPLACIAN)
+    e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_tiled_vec<3, AFB_LAYOUT_PER_BLOCK, 1>, sizeof(VecSmem<2>)) : go(k_assemble_tiled_vec<3, AFB_LAYOUT_PER_ROW, 1>, sizeof(VecSmem<2>));
   else
     e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_tiled_vec<3, AFB_LAYOUT_PER_BLOCK>, sizeof(VecSmem<2>)) : go(k_assemble_tiled_vec<3, AFB_LAYOUT_PER_ROW>, sizeof(VecSmem<2>));
   AFB_CUDA(e);

@@ -71,7 +71,8 @@ enum {
 enum {
   AFB_VARIANT_CELLWISE_ATOMIC = 0, /* thread per cell + fp64 atomics: csr-gpu / coo-gpu / bsr                       */
   AFB_VARIANT_NODEWISE = 1,        /* thread per row, no atomics: nwcsr / bsr-atomic-free (AF-CSR_GPU / AF-BSR_GPU)  */
-  AFB_VARIANT_TILED_GATHER = 2     /* B200 path: row tiles staged in shared memory, every row written exactly once   */
+  AFB_VARIANT_TILED_GATHER = 2     /* B200 path: row tiles staged in shared memory, every row written exactly once
+                                      (P1 Poisson, P1 elasticity, Tri3 bilaplacian; any format)                       */
 };
 
 /* sparsity algorithm of a re-build on an unchanged mesh (the first build of a mesh always starts from the cells) */

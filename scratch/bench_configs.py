@@ -50,5 +50,5 @@ if "c5" in which:
     run("C5 2-D Poisson P1 b=1 CSR", 4096, 1, A.OP_POISSON, T, dim=2, reps=3)
     run("C5 2-D Poisson P1 b=1 COO", 4096, 1, A.OP_POISSON, [T[0], T[2]], dim=2, reps=3, fmt=A.FORMAT_COO)
     run("C5 2-D elasticity P1 b=2 BSR", 4096, 2, A.OP_ELASTICITY, T, params=[1.0e6, 8.0e5], dim=2, reps=3)
-    run("C5 2-D bilaplacian P1 b=2 BSR", 4096, 2, A.OP_BILAPLACIAN, T[:2], dim=2, reps=3)
+    run("C5 2-D bilaplacian P1 b=2 BSR", 4096, 2, A.OP_BILAPLACIAN, T, dim=2, reps=3)
     run("C5 2-D Poisson P2 (Tri6) b=1 CSR", 1024, 1, A.OP_POISSON, T[:2], dim=2, reps=3, p2=True)

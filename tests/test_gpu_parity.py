@@ -312,8 +312,8 @@ def test_elasticity_values(ctx, name, variant, layout):
             ctx.csr_view()
 
 
-@pytest.mark.parametrize("name", ["L-shape_2D", "box2d_n17"])
-@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+@pytest.mark.parametrize("name", ["L-shape_2D", "box2d_n17", "porous_2D"])
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER], ids=["bsr", "af-bsr", "tiled"])
 @pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
 def test_bilaplacian_values(ctx, name, variant, layout):
     m = get_mesh(name)
