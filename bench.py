@@ -461,48 +461,51 @@ def run_b200(args):
     e2e_serial_ms = e0.elapsed_time(e1)
     e2e_ms, e2e_pipelined = e2e_serial_ms, False
     if world == 1 and not args.no_e2e_pipeline:
-        # Streaming form of the same step: two contexts on two streams, driven by two host threads (ctypes releases
-        # the GIL), so one step's H2D overlaps the other's D2H (PCIe is full duplex) and the kernels of either.
-        # Every step still copies its own inputs in and its own CSR arrays out.
-        import concurrent.futures
-        nl = max(2, args.e2e_lanes)
-        extra = []
-        for _ in range(nl - 1):
-            st_k = torch.cuda.Stream(device=dev)
-            extra.append((st_k, A.Context(local_rank, stream=st_k.cuda_stream),
-                          (torch.empty_like(rows_h).pin_memory(), torch.empty_like(cols_h).pin_memory(), torch.empty_like(vals_h).pin_memory())))
+        try:
+            # Streaming form of the same step: several contexts, each on its own stream and driven by its own host thread
+            # (ctypes releases the GIL), so one lane's H2D overlaps another's D2H (PCIe: 55 + 51 GB/s one way, 76 GB/s both
+            # ways on this box) and the kernels of either.  Every step still copies its own inputs in and its CSR arrays out.
+            import concurrent.futures
+            nl = max(2, args.e2e_lanes)
+            extra = []
+            for _ in range(nl - 1):
+                st_k = torch.cuda.Stream(device=dev)
+                extra.append((st_k, A.Context(local_rank, stream=st_k.cuda_stream),
+                              (torch.empty_like(rows_h).pin_memory(), torch.empty_like(cols_h).pin_memory(), torch.empty_like(vals_h).pin_memory())))
 
-        def lane_step(c, outs):
-            c.set_mesh(3, coords_h.numpy(), cells_h.numpy(), None)
-            c.set_own_cell_count(info["nb_own_cell"])
-            c.build_pattern(1)
-            c.assemble(A.OP_POISSON, variant=e2e_variant)
-            c.to_host(A.ARRAY_ROWS, outs[0].numpy())
-            c.to_host(A.ARRAY_COLUMNS, outs[1].numpy())
-            c.to_host(A.ARRAY_VALUES, outs[2].numpy())
+            def lane_step(c, outs):
+                c.set_mesh(3, coords_h.numpy(), cells_h.numpy(), None)
+                c.set_own_cell_count(info["nb_own_cell"])
+                c.build_pattern(1)
+                c.assemble(A.OP_POISSON, variant=e2e_variant)
+                c.to_host(A.ARRAY_ROWS, outs[0].numpy())
+                c.to_host(A.ARRAY_COLUMNS, outs[1].numpy())
+                c.to_host(A.ARRAY_VALUES, outs[2].numpy())
 
-        lanes = [(ctx2, (rows_h, cols_h, vals_h))] + [(c, o) for _, c, o in extra]
-        per_lane = 2 * e2e_steps
-        pipe_steps = nl * per_lane
-        step_s = 1e-3 * e2e_serial_ms / e2e_steps
-        with concurrent.futures.ThreadPoolExecutor(max_workers=nl) as pool:
-            def run_lane(k, count):
-                if count > 1:
-                    time.sleep(k * step_s / nl)  # lanes start out of phase (inside the timed region): uploads meet downloads
-                for _ in range(count):
-                    lane_step(*lanes[k])
-            list(pool.map(lambda k: run_lane(k, 1), range(nl)))  # warm-up of every lane
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            list(pool.map(lambda k: run_lane(k, per_lane), range(nl)))
-            torch.cuda.synchronize(dev)
-            pipe_ms = 1e3 * (time.perf_counter() - t0)
-        for _, c, o in extra:
-            assert torch.equal(o[2], vals_h) or e2e_variant == A.VARIANT_CELLWISE_ATOMIC, "pipelined lanes disagree"
-            assert torch.equal(o[1], cols_h) and torch.equal(o[0], rows_h), "pipelined lanes disagree (pattern)"
-            c.close()
-        if pipe_ms / pipe_steps < e2e_serial_ms / e2e_steps:
-            e2e_ms, e2e_pipelined = pipe_ms * e2e_steps / pipe_steps, True
+            lanes = [(ctx2, (rows_h, cols_h, vals_h))] + [(c, o) for _, c, o in extra]
+            per_lane = 2 * e2e_steps
+            pipe_steps = nl * per_lane
+            step_s = 1e-3 * e2e_serial_ms / e2e_steps
+            with concurrent.futures.ThreadPoolExecutor(max_workers=nl) as pool:
+                def run_lane(k, count):
+                    if count > 1:
+                        time.sleep(k * step_s / nl)  # lanes start out of phase (inside the timed region): uploads meet downloads
+                    for _ in range(count):
+                        lane_step(*lanes[k])
+                list(pool.map(lambda k: run_lane(k, 1), range(nl)))  # warm-up of every lane
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                list(pool.map(lambda k: run_lane(k, per_lane), range(nl)))
+                torch.cuda.synchronize(dev)
+                pipe_ms = 1e3 * (time.perf_counter() - t0)
+            for _, c, o in extra:
+                assert torch.equal(o[2], vals_h) or e2e_variant == A.VARIANT_CELLWISE_ATOMIC, "pipelined lanes disagree"
+                assert torch.equal(o[1], cols_h) and torch.equal(o[0], rows_h), "pipelined lanes disagree (pattern)"
+                c.close()
+            if pipe_ms / pipe_steps < e2e_serial_ms / e2e_steps:
+                e2e_ms, e2e_pipelined = pipe_ms * e2e_steps / pipe_steps, True
+        except Exception as exc:  # noqa: BLE001 -- the one-step-at-a-time number above stands
+            print(f"bench.py: pipelined e2e skipped ({type(exc).__name__}: {exc})", file=sys.stderr)
     h2d = coords_h.numel() * 8 + cells_h.numel() * 4 + (own_h.numel() if info["is_own"] else 0)
     d2h = rows_h.numel() * 4 + cols_h.numel() * 4 + vals_h.numel() * 8
     checksum = float(vals_h.sum())
