@@ -161,12 +161,40 @@ class DoFLinearSystem {
     return { p, n };
   }
   bool hasView() const { return m_has_view; }
+  //! DoFLinearSystem::solve (femutils/DoFLinearSystem.cc; HypreDoFLinearSystem.cc:461-520 behind it): here a Jacobi-PCG on the
+  //! arrays as assembled -- a stand-in for tests; a production build hands getCSRValues() to HYPRE / PETSc.
+  //! solution_host: nb_row*b doubles.  Returns the number of iterations.
+  Int32 solve(Real* solution_host, Real rtol = 1.0e-10, Real atol = 0.0, Int32 max_iter = 10000)
+  {
+    int it = 0;
+    double res = 0.0;
+    check(afb_solve_pcg(m_ctx.handle(), rtol, atol, max_iter, solution_host, AFB_MEM_HOST, &it, &res));
+    return it;
+  }
 
  private:
   Context& m_ctx;
   CSRFormatView m_view;
   bool m_has_view = false;
 };
+
+/*---------------------------------------------------------------------------*/
+//! RHS terms of femutils/ArcaneFemFunctionsGpu.h (BoundaryConditions::applyConstantSourceToRhs :675-708, applyNeumannToRhs,
+//! ArcaneFemFunctions.h applyTractionToRhs*): groups become plain face lists (faceNode order, outward-normal swap applied)
+namespace BoundaryConditions {
+inline void applyConstantSourceToRhs(Context& ctx, const Real* f, int nb_component, bool nodewise = true)
+{
+  check(afb_assemble_rhs_source(ctx.handle(), f, nb_component, nodewise ? 1 : 0, 0));
+}
+inline void applyNeumannToRhs(Context& ctx, Int64 nb_face, const Int32* face_nodes, int nb_value, const Real* values, bool skip_dirichlet_nodes = false)
+{
+  check(afb_assemble_rhs_neumann(ctx.handle(), nb_face, face_nodes, AFB_NEUMANN_FLUX, nb_value, values, skip_dirichlet_nodes ? 1 : 0, AFB_MEM_HOST));
+}
+inline void applyTractionToRhs(Context& ctx, Int64 nb_face, const Int32* face_nodes, int nb_dof_per_node, const Real* traction)
+{
+  check(afb_assemble_rhs_neumann(ctx.handle(), nb_face, face_nodes, AFB_NEUMANN_TRACTION, nb_dof_per_node, traction, 0, AFB_MEM_HOST));
+}
+} // namespace BoundaryConditions
 
 /*---------------------------------------------------------------------------*/
 //! femutils/CsrFormatMatrix.h:37-142 (one DoF per node: the testlab csr / csr-gpu / nwcsr back-ends)

@@ -2,7 +2,7 @@
 // makes (modules/testlab/FemModule.cc:349-399, modules/elasticity/FemModule.cc:236-271), on a mesh file
 // written by the pytest; results go back as a binary file and are compared with the oracle there.
 //   facade_driver <mesh.bin> <mode> <out.bin>
-//   modes: csr-gpu | nwcsr | coo-gpu | bsr | af-bsr | elasticity-bsr | elasticity-af-bsr-csr
+//   modes: csr-gpu | nwcsr | coo-gpu | bsr | af-bsr | elasticity-bsr | elasticity-af-bsr-csr | solve
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -55,6 +55,32 @@ int main(int argc, char** argv)
       csr.translateToLinearSystem(linear_system);
       if (!linear_system.hasView() || linear_system.getCSRValues().nbRow() != mesh.nb_node) return 4;
       extra.push_back(csr.m_nnz);
+    }
+    else if (mode == "solve") {
+      // assembly -> source term + flux on the faces of the first cell -> penalty on DoF 0 -> DoFLinearSystem::solve
+      CsrFormat csr(ctx);
+      csr.initialize(mesh);
+      csr.assembleBilinear(Operator::Poisson, true);
+      const double f = 1.0, g = 0.25, penalty = 1.0e30, q = 2.0;
+      BoundaryConditions::applyConstantSourceToRhs(ctx, &f, 1, false);
+      std::vector<int> face(cells.begin(), cells.begin() + mesh.dim); // one face: the first `dim` nodes of cell 0
+      BoundaryConditions::applyNeumannToRhs(ctx, 1, face.data(), 1, &q);
+      const int dof0 = 0;
+      check(afb_dirichlet_penalty(ctx.handle(), 0, penalty, 1, &dof0, &g, AFB_MEM_HOST));
+      csr.translateToLinearSystem(linear_system);
+      std::vector<double> sol((size_t)mesh.nb_node);
+      const int it = linear_system.solve(sol.data(), 1.0e-13, 0.0, 20000);
+      extra.push_back(it);
+      rows = ctx.copyToHost<int>(AFB_ARRAY_ROWS);
+      cols = ctx.copyToHost<int>(AFB_ARRAY_COLUMNS);
+      FILE* o = std::fopen(argv[3], "wb");
+      if (!o) return 2;
+      put(o, rows);
+      put(o, cols);
+      put(o, sol);
+      put(o, extra);
+      std::fclose(o);
+      return 0;
     }
     else if (mode == "coo-gpu") {
       CooFormat coo(ctx);

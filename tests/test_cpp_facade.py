@@ -96,3 +96,23 @@ def test_facade_matches_oracle(driver, tmp_path, mode, meshname):
         assert list(extra[:5]) == [m.nb_node, cols.size, cols.size * bb, b, 0 if per_row else 1]
         if per_row:
             assert list(extra[5:7]) == [m.nb_node * b, cols.size * bb]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("meshname", ["box3d", "L-shape.msh"])
+def test_facade_solve(driver, tmp_path, meshname):
+    """BoundaryConditions::applyConstantSourceToRhs / applyNeumannToRhs + DoFLinearSystem::solve through the facade."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    m = M.box_mesh(3, 6) if meshname == "box3d" else M.read_msh(os.path.join(ROOT, "tests", "golden", meshname))
+    write_mesh(tmp_path / "m.bin", m)
+    r = subprocess.run([driver, str(tmp_path / "m.bin"), "solve", str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows, cols, sol, extra = read_out(tmp_path / "o.bin")
+    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, form=O.FORM_BSR)
+    rhs = O.rhs_source_cellwise(m.dim, m.coords, m.cells, [1.0], signed_area=False)
+    O.rhs_neumann(m.dim, 1, m.coords, m.cells[:1, :m.dim], [2.0], rhs)
+    O.dirichlet_penalty(rows, cols, vals, rhs, np.array([0], dtype=np.int32), np.array([0.25]), 1.0e30)
+    ref = spla.spsolve(sp.csr_matrix((vals, cols, rows)).tocsc(), rhs)
+    assert 0 < extra[0] < 20000
+    assert np.abs(sol - ref).max() <= 1e-8 * np.abs(ref).max()
