@@ -159,19 +159,18 @@ k_pattern_nn_place(const TileDesc* __restrict__ desc, const int32_t* __restrict_
                    const uint16_t* __restrict__ nn_e0, const int32_t* __restrict__ foot, int32_t* __restrict__ cols, int32_t* __restrict__ nz_per_row,
                    int32_t nb_node, int32_t* __restrict__ check /* device-mapped host words: rows[nb_node], stale flag */)
 {
-  __shared__ int32_t s_foot[TG_FMAX];
   __shared__ int32_t s_dbase[TG_EMAX];
-  __shared__ int s_bad;
   const int32_t t = blockIdx.x;
   const TileDesc d = desc[t];
   const int R = d.nb_row, E = d.nb_entry;
   if (t == 0 && threadIdx.x == 0) check[0] = __ldg(rows + nb_node);
   if (R == 0) return;
   const int i = threadIdx.x;
-  if (i == 0) s_bad = 0;
-  // everything addressed by the descriptor alone is requested at once; rows[node] is the only dependent load
+  // everything addressed by the descriptor alone is requested at once; rows[node] and foot[local index] (the tile's
+  // footprint: 1.4 KB, L1-resident after the first touch) are the only dependent loads; one barrier per tile
   constexpr int PER = 12;
   const uint16_t* src = nn_local + d.ent_off;
+  const int32_t* ft = foot + d.foot_off;
   uint16_t loc[PER];
 #pragma unroll
   for (int q = 0; q < PER; ++q) {
@@ -185,26 +184,27 @@ k_pattern_nn_place(const TileDesc* __restrict__ desc, const int32_t* __restrict_
     e0 = __ldg(nn_e0 + d.node_off + i);
     e1 = i + 1 < R ? (int)__ldg(nn_e0 + d.node_off + i + 1) : E;
   }
-  for (int f = i; f < d.nb_foot; f += blockDim.x) s_foot[f] = __ldg(foot + d.foot_off + f);
-  __syncthreads();
+  int32_t col[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) col[q] = __ldg(ft + loc[q]);
+  int bad = 0;
   if (i < R) {
     const int rb = __ldg(rows + node), deg = __ldg(rows + node + 1) - rb;
     nz_per_row[node] = deg;
-    if (deg != e1 - e0) s_bad = 1; // the connectivity was built for another pattern
+    if (deg != e1 - e0) bad = 1; // the connectivity was built for another pattern
     else
       for (int e = e0; e < e1; ++e) s_dbase[e] = rb - e0;
   }
-  __syncthreads();
-  if (s_bad) {
+  if (__syncthreads_or(bad)) { // the one barrier of the tile
     if (i == 0) check[1] = 1;
     return;
   }
 #pragma unroll
   for (int q = 0; q < PER; ++q) {
     const int e = i + q * blockDim.x;
-    if (e < E) cols[s_dbase[e] + e] = s_foot[loc[q]];
+    if (e < E) cols[s_dbase[e] + e] = col[q];
   }
-  for (int e = i + PER * blockDim.x; e < E; e += blockDim.x) cols[s_dbase[e] + e] = s_foot[__ldg(src + e)];
+  for (int e = i + PER * blockDim.x; e < E; e += blockDim.x) cols[s_dbase[e] + e] = __ldg(ft + __ldg(src + e));
 }
 
 // pass 2 (after the scan of the degrees): the tile's columns move from the scratch to their rows;
