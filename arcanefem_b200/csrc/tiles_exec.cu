@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
       }
       if (gs >= 1) sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       if (gs >= 2) sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      __syncwarp(); // the row's other lanes have passed their (discarded) read of the diagonal slot
       if (q == 0 && ed >= 0) S.vout[ed] = -sum;
       __syncwarp();
       const int eb = rowinfo_erow(S.rowinfo[r0]), ee = rowinfo_erow(S.rowinfo[r1]);
