@@ -44,7 +44,12 @@ constexpr unsigned TG_NONE16 = 0xFFFFu;
 
 // vector (b = 2, 3) executor: cache of sqrt(s)*grad(phi_a) per cell, blocks accumulated in registers
 constexpr int TV_PLANES = 12;              // 4 nodes x 3 components
-constexpr int TV_CMAX = (TG_SMEM_LIMIT - 3 * 8 * TG_FMAX - 8 * TG_RMAX - 1024) / (8 * TV_PLANES) - 1 < 1024 ? (TG_SMEM_LIMIT - 3 * 8 * TG_FMAX - 8 * TG_RMAX - 1024) / (8 * TV_PLANES) - 1 : 1024;
+#ifndef AFB_TV_LMAX
+#define AFB_TV_LMAX 10240
+#endif
+constexpr int TV_LMAX = AFB_TV_LMAX;       // 16-bit list slots of a tile staged through the TMA engine (0: lists read from global memory)
+constexpr int TV_CMAX_RAW = (TG_SMEM_LIMIT - 3 * 8 * TG_FMAX - 8 * TG_RMAX - 1024 - 2 * TV_LMAX) / (8 * TV_PLANES) - 1;
+constexpr int TV_CMAX = TV_CMAX_RAW < 1024 ? TV_CMAX_RAW : 1024;
 constexpr int TV_CS = TV_CMAX + 1;
 
 struct TileDesc {

@@ -395,7 +395,9 @@ struct VecSmem {
   uint32_t rowinfo[TG_RMAX];
   uint32_t ubase[TG_UMAX];
   uint16_t ulen[TG_UMAX];
+  __align__(16) uint16_t lists[TV_LMAX > 0 ? TV_LMAX : 8]; // the tile's contribution lists (TMA bulk copy, in flight during phase A)
   __align__(16) TileDesc desc[4];
+  __align__(8) unsigned long long mbar;
 };
 static_assert(sizeof(VecSmem<3>) <= TG_SMEM_LIMIT, "TG_MINB vector-executor CTAs must fit one SM");
 
@@ -415,6 +417,12 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
   constexpr int NW = TG_THREADS / 32;
   constexpr int DW = sizeof(TileDesc) / 4;
   int32_t t = blockIdx.x;
+  const uint32_t mbar = smem_u32(&S.mbar);
+  unsigned parity = 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   // zero slot of every plane (list padding)
   if (threadIdx.x < TV_PLANES) S.G[threadIdx.x * TV_CS + TV_CS - 1] = 0.0;
   if (threadIdx.x < 3 * DW) {
@@ -433,6 +441,16 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
   const double lam = prm.p0, mu = prm.p1;
   while (t < A.nb_tile) {
     const TileDesc d = S.desc[slot];
+    // every warp is past the previous tile's phase B (end-of-loop barrier): the list buffer may be overwritten
+    const bool staged = TV_LMAX > 0 && d.list_len > 0 && d.list_len <= TV_LMAX;
+    if (threadIdx.x == 0 && staged) {
+      const uint32_t bytes = (uint32_t)d.list_len * 2u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(S.lists)), "l"(A.lists + d.list_off),
+                   "r"(bytes), "r"(mbar)
+                   : "memory");
+    }
     if ((int)threadIdx.x < d.nb_foot) {
       S.cx[3 * threadIdx.x] = pf.c0;
       S.cx[3 * threadIdx.x + 1] = pf.c1;
@@ -490,7 +508,12 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
     __syncthreads();
     // ---- phase B: one lane per block entry; M accumulated in registers, lists streamed from global
     //      (dynamic unit hand-out and deeper list prefetch were measured slower) ----
-    const uint32_t* l32 = reinterpret_cast<const uint32_t*>(A.lists + d.list_off);
+    if (staged) {
+      mbar_wait(mbar, parity);
+      parity ^= 1u;
+    }
+    // (generic loads below: the lists live in shared memory when staged, in global memory for an oversized tile)
+    const uint32_t* l32 = staged ? reinterpret_cast<const uint32_t*>(S.lists) : reinterpret_cast<const uint32_t*>(A.lists + d.list_off);
     for (int u = warp; u < d.nb_unit; u += NW) {
       const uint32_t em = __ldg(A.emap + (size_t)(d.unit_off + u) * 32 + lane);
       const uint32_t er = __ldg(A.emap_rows + (size_t)(d.unit_off + u) * 32 + lane);
@@ -502,9 +525,9 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
       for (int i = 0; i < DIM; ++i)
 #pragma unroll
         for (int j = 0; j < DIM; ++j) M[i][j] = 0.0;
-      uint32_t w = len2 > 0 ? __ldg(l) : 0u;
+      uint32_t w = len2 > 0 ? l[0] : 0u;
       for (int k = 0; k < len2; ++k) {
-        const uint32_t wn = (k + 1 < len2) ? __ldg(l + (k + 1) * 32) : 0u;
+        const uint32_t wn = (k + 1 < len2) ? l[(k + 1) * 32] : 0u;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint32_t code = h ? (w >> 16) : (w & 0xFFFFu);
