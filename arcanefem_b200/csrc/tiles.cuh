@@ -51,6 +51,10 @@ constexpr int TV_LMAX = AFB_TV_LMAX;       // 16-bit list slots of a tile staged
 constexpr int TV_CMAX_RAW = (TG_SMEM_LIMIT - 3 * 8 * TG_FMAX - 8 * TG_RMAX - 1024 - 2 * TV_LMAX) / (8 * TV_PLANES) - 1;
 constexpr int TV_CMAX = TV_CMAX_RAW < 1024 ? TV_CMAX_RAW : 1024;
 constexpr int TV_CS = TV_CMAX + 1;
+#ifndef AFB_TV_RT2
+#define AFB_TV_RT2 352
+#endif
+constexpr int TV_RT2 = AFB_TV_RT2;         // target rows per tile of the vector executor in 2-D (measured: 224 / 288 / 352 -> 2.23 / 2.39 / 2.20 ms at C5)
 
 struct TileDesc {
   int32_t node_off, nb_row;    // rows (node ids ascending) in tile_nodes / rowinfo

@@ -7,7 +7,7 @@ mkdir -p ../variants
 build() {
   name=$1; shift
   rm -rf build_$name; mkdir -p build_$name
-  for f in afb_api scan connectivity pattern_rows assemble tiles_plan tiles_exec tiles_pipe pattern_tiled linear mesh_gen; do
+  for f in $(ls *.cu | sed s/.cu//); do
     /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -I../../include -I. --expt-relaxed-constexpr $@ -c $f.cu -o build_$name/$f.o 2>/dev/null &
   done
   wait
