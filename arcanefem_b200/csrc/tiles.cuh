@@ -51,6 +51,12 @@ constexpr int TV_LMAX = AFB_TV_LMAX;       // 16-bit list slots of a tile staged
 constexpr int TV_CMAX_RAW = (TG_SMEM_LIMIT - 3 * 8 * TG_FMAX - 8 * TG_RMAX - 1024 - 2 * TV_LMAX) / (8 * TV_PLANES) - 1;
 constexpr int TV_CMAX = TV_CMAX_RAW < 1024 ? TV_CMAX_RAW : 1024;
 constexpr int TV_CS = TV_CMAX + 1;
+#ifndef AFB_TV_RT3
+#define AFB_TV_RT3 100
+#endif
+constexpr int TV_RT3 = AFB_TV_RT3 > 8 ? AFB_TV_RT3 : 8; // target rows per tile of the vector executor in 3-D (measured at n=140, b=3:
+                                                        // 60 / 75 / 88 / 100 / 112 / 125 / 150 rows -> 2.44 / 2.45 / 2.41 / 2.32 / 2.35 / 2.35 / 2.40 ms;
+                                                        // bricks over the cell limit are cut by the per-brick refinement)
 #ifndef AFB_TV_RT2
 #define AFB_TV_RT2 352
 #endif

@@ -796,7 +796,7 @@ int build_tile_mesh(afb_ctx* ctx)
   int32_t* brick_of = P.scratch_c.as<int32_t>();
 
   // bricks holding ~rtarget nodes on a uniform mesh
-  const int rtarget = dim == 3 ? (vec ? std::max(8, TG_RT3 * TV_CMAX / TG_CMAX) : TG_RT3) : (vec ? TV_RT2 : TG_RT2);
+  const int rtarget = dim == 3 ? (vec ? TV_RT3 : TG_RT3) : (vec ? TV_RT2 : TG_RT2);
   double vol = 1.0;
   int nd_ext = 0;
   for (int a = 0; a < 3; ++a)
