@@ -582,9 +582,17 @@ def main():
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1, exchange mode: one pull kernel over NVLink peer memory (CUDA IPC) or NCCL send/recv + accumulate kernels")
     ap.add_argument("--mode", default="exchange", choices=["exchange", "replicate"], help="N>1: ghost-row exchange over NCCL (north star) or the reference's ghost-cell replication")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    # stdout carries exactly one JSON line: everything native libraries print there (NCCL's version banner, ...) is sent
+    # to stderr for the duration of the run, the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    sys.stdout = real_stdout
+    try:
+        return run_reference(args) if args.impl == "reference" else run_b200(args)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
