@@ -111,6 +111,34 @@ def test_elasticity_traction_golden():
     assert worst < 1.0e-4
 
 
+@pytest.mark.parametrize("meshfile", ["circle_cut.msh", "sphere_cut.msh", "L-shape-3D.msh", "bar_dynamic_3D.msh"])
+def test_neumann_closed_surface_properties(meshfile):
+    """Size-independent checks of the flux term in 2-D and 3-D (no reference golden file has a 3-D flux): over the closed
+    boundary a constant flux vector integrates to zero (divergence theorem: the normals of orient_boundary_faces point
+    outward everywhere), a unit scalar flux integrates to the boundary's measure, and a traction distributes t * measure."""
+    m = M.read_msh(os.path.join(CS.GOLDEN, meshfile))
+    faces = M.orient_boundary_faces(m, np.concatenate([f for f in m.faces.values()], axis=0))
+    # every boundary face exactly once: each appears in exactly one cell
+    assert np.unique(np.sort(faces, axis=1), axis=0).shape[0] == faces.shape[0]
+    p = m.coords[faces]
+    if m.dim == 2:
+        meas = np.linalg.norm((p[:, 1] - p[:, 0])[:, :2], axis=1)
+    else:
+        meas = 0.5 * np.linalg.norm(np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), axis=1)
+    q = [2.9e4, -1.8e4, 0.7e4][:m.dim]
+    rhs = np.zeros(m.nb_node)
+    O.rhs_neumann(m.dim, 1, m.coords, faces, q, rhs, kind=O.NEUMANN_FLUX)
+    assert abs(rhs.sum()) <= 1e-10 * np.abs(q).max() * meas.sum()
+    rhs[:] = 0.0
+    O.rhs_neumann(m.dim, 1, m.coords, faces, [1.0], rhs, kind=O.NEUMANN_FLUX)
+    assert abs(rhs.sum() - meas.sum()) <= 1e-12 * meas.sum()
+    t = [1.0, -2.0, 0.5][:m.dim]
+    rhs = np.zeros(m.nb_node * m.dim)
+    O.rhs_neumann(m.dim, m.dim, m.coords, faces, t, rhs, kind=O.NEUMANN_TRACTION)
+    for k in range(m.dim):
+        assert abs(rhs[k::m.dim].sum() - t[k] * meas.sum()) <= 1e-12 * abs(t[k]) * meas.sum()
+
+
 def test_formulations_agree_to_rounding():
     m = _load(CS.POISSON_CASES["sphere_3D"])
     rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
