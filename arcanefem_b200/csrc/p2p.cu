@@ -18,6 +18,7 @@
 // resident at once, and every wait gives up after AFB_P2P_TIMEOUT_NS with an error flag instead of hanging.
 // This replaces what the reference delegates to the solver's parallel matrix assembly (HYPRE IJ off-processor
 // values); the NCCL path of arcanefem_b200/distributed.py stays as the portable fallback.
+#include <algorithm>
 #include <vector>
 
 #include "afb_internal.h"
@@ -25,7 +26,8 @@
 namespace afb {
 
 constexpr int P2P_MAX_RANK = 64;
-constexpr int P2P_BLOCKS_PER_PEER = 48;  // x peers (2 for slabs) stays below one block per SM: all blocks resident at once
+constexpr int P2P_BLOCKS_PER_PEER = 48;  // x peers (2 for slabs) stays below one block per SM: all blocks resident at once; fewer per peer
+                                         // when many peers would not fit the device together (every wait needs the whole grid resident)
 constexpr int P2P_THREADS = 512;
 constexpr int P2P_UNROLL = 8;           // remote loads in flight per thread: a pull is latency-bound (NVLink round trip), not bandwidth-bound
 constexpr unsigned long long AFB_P2P_TIMEOUT_NS = 4000000000ull;
@@ -45,7 +47,10 @@ struct P2PState {
   uint32_t epoch = 0;
   int my_rank = 0;
   uint32_t* flags = nullptr;   // [2][P2P_MAX_RANK] + error word, cudaMalloc (exported)
-  int* counters = nullptr;     // one per peer
+  int* counters = nullptr;     // two per peer: blocks done, blocks that gave up waiting for READY
+  int blocks_per_peer = P2P_BLOCKS_PER_PEER;
+  uint32_t* h_err = nullptr;   // sticky error word in mapped pinned host memory: read without a stream synchronisation
+  uint32_t* d_err = nullptr;   // its device address
   PeerDev* d_peers = nullptr;
   std::vector<void*> opened;
   int nb_peer = 0;
@@ -89,23 +94,32 @@ __device__ __forceinline__ bool wait_epoch(const uint32_t* flag, uint32_t epoch)
 }
 
 __global__ void __launch_bounds__(P2P_THREADS)
-k_p2p_exchange(const PeerDev* __restrict__ peers, double* __restrict__ values, uint32_t* __restrict__ flags, int my_rank, uint32_t epoch, int* __restrict__ counters)
+k_p2p_exchange(const PeerDev* __restrict__ peers, double* __restrict__ values, uint32_t* __restrict__ flags, int my_rank, uint32_t epoch, int* __restrict__ counters,
+               int bpp, uint32_t* __restrict__ host_err)
 {
   __shared__ int s_ok;
-  const int p = blockIdx.x / P2P_BLOCKS_PER_PEER, bb = blockIdx.x % P2P_BLOCKS_PER_PEER;
+  const int p = blockIdx.x / bpp, bb = blockIdx.x % bpp;
   const PeerDev P = peers[p];
   uint32_t* err = flags + 2 * P2P_MAX_RANK;
+  auto fail = [&](uint32_t code) {
+    atomicExch(err, code);
+    *reinterpret_cast<volatile uint32_t*>(host_err) = code;
+    __threadfence_system();
+  };
   if (threadIdx.x == 0) {
     if (bb == 0) {
       __threadfence_system();
       st_release_sys(P.peer_flags + my_rank, epoch); // READY
     }
     s_ok = wait_epoch(flags + P.rank, epoch) ? 1 : 0;
-    if (!s_ok) atomicExch(err, 1u);
+    if (!s_ok) {
+      fail(1u);
+      atomicAdd(counters + 2 * p + 1, 1);
+    }
   }
   __syncthreads();
   if (s_ok) {
-    const long long stride = (long long)P2P_BLOCKS_PER_PEER * P2P_THREADS;
+    const long long stride = (long long)bpp * P2P_THREADS;
     const double* src = P.peer_values + P.pull_first;
     long long i = (long long)bb * P2P_THREADS + threadIdx.x;
     for (; i + (P2P_UNROLL - 1) * stride < P.pull_n; i += P2P_UNROLL * stride) {
@@ -123,18 +137,21 @@ k_p2p_exchange(const PeerDev* __restrict__ peers, double* __restrict__ values, u
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(counters + p, 1) == P2P_BLOCKS_PER_PEER - 1) { // last block of this neighbour: everything is pulled
-      counters[p] = 0;
+    if (atomicAdd(counters + 2 * p, 1) == bpp - 1) { // last block of this neighbour
+      const int gave_up = atomicExch(counters + 2 * p + 1, 0);
+      counters[2 * p] = 0;
       __threadfence_system();
-      st_release_sys(P.peer_flags + P2P_MAX_RANK + my_rank, epoch); // PULLED
+      // PULLED only if every block pulled its share: after a READY timeout the neighbour must keep its slice
+      // (its own wait for PULLED then times out into status 2 instead of zeroing contributions nobody took)
+      if (gave_up == 0) st_release_sys(P.peer_flags + P2P_MAX_RANK + my_rank, epoch);
     }
     s_ok = wait_epoch(flags + P2P_MAX_RANK + P.rank, epoch) ? 1 : 0;
-    if (!s_ok) atomicExch(err, 2u);
+    if (!s_ok) fail(2u);
   }
   __syncthreads();
   if (s_ok) {
     double* dst = values + P.send_first;
-    for (long long i = (long long)bb * P2P_THREADS + threadIdx.x; i < P.send_n; i += (long long)P2P_BLOCKS_PER_PEER * P2P_THREADS) dst[i] = 0.0;
+    for (long long i = (long long)bb * P2P_THREADS + threadIdx.x; i < P.send_n; i += (long long)bpp * P2P_THREADS) dst[i] = 0.0;
   }
 }
 
@@ -151,6 +168,9 @@ int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle)
   if (!S->flags) {
     AFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&S->flags), sizeof(uint32_t) * (2 * P2P_MAX_RANK + 2)));
     AFB_CUDA(cudaMemset(S->flags, 0, sizeof(uint32_t) * (2 * P2P_MAX_RANK + 2)));
+    AFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&S->h_err), sizeof(uint32_t), cudaHostAllocMapped));
+    *S->h_err = 0u;
+    AFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&S->d_err), S->h_err, 0));
   }
   static_assert(sizeof(cudaIpcMemHandle_t) == AFB_P2P_HANDLE_BYTES, "IPC handle size");
   AFB_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(values_handle), ctx->values.p));
@@ -183,6 +203,7 @@ void p2p_destroy(afb_ctx* ctx)
   p2p_disconnect(ctx);
   P2PState* S = static_cast<P2PState*>(ctx->p2p);
   if (S->flags) cudaFree(S->flags);
+  if (S->h_err) cudaFreeHost(S->h_err);
   if (S->ev_ready) cudaEventDestroy(S->ev_ready);
   if (S->ev_done) cudaEventDestroy(S->ev_done);
   if (S->side) cudaStreamDestroy(S->side);
@@ -221,8 +242,14 @@ int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank
   if (nb_peer > 0) {
     AFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&S->d_peers), sizeof(PeerDev) * (size_t)nb_peer));
     AFB_CUDA(cudaMemcpy(S->d_peers, h.data(), sizeof(PeerDev) * (size_t)nb_peer, cudaMemcpyHostToDevice));
-    AFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&S->counters), sizeof(int) * (size_t)nb_peer));
-    AFB_CUDA(cudaMemset(S->counters, 0, sizeof(int) * (size_t)nb_peer));
+    AFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&S->counters), sizeof(int) * 2 * (size_t)nb_peer));
+    AFB_CUDA(cudaMemset(S->counters, 0, sizeof(int) * 2 * (size_t)nb_peer));
+    // the kernel spin-waits on remote progress: its whole grid must be resident at once
+    int per_sm = 0;
+    AFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_p2p_exchange, P2P_THREADS, 0));
+    const int resident = per_sm * ctx->sm_count;
+    S->blocks_per_peer = std::min(P2P_BLOCKS_PER_PEER, resident / nb_peer);
+    AFB_REQUIRE(S->blocks_per_peer >= 1, AFB_ERR_INVALID, "afb_p2p_connect: %d peers exceed the %d exchange blocks the device keeps resident", nb_peer, resident);
   }
   S->my_rank = my_rank;
   S->nb_peer = nb_peer;
@@ -233,9 +260,16 @@ int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank
 int p2p_wait(afb_ctx* ctx)
 {
   P2PState* S = ctx->p2p ? static_cast<P2PState*>(ctx->p2p) : nullptr;
-  if (!S || !S->inflight) return AFB_OK;
-  AFB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_done, 0));
-  S->inflight = false;
+  if (!S) return AFB_OK;
+  if (S->inflight) {
+    AFB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_done, 0));
+    S->inflight = false;
+  }
+  // sticky error word of the exchanges that have completed so far (mapped host memory: no synchronisation);
+  // afb_p2p_status reads it after draining the stream and clears it
+  if (S->h_err && *reinterpret_cast<volatile uint32_t*>(S->h_err) != 0u)
+    AFB_REQUIRE(false, AFB_ERR_CUDA, "ghost-row exchange timed out (status %u: %s); contributions of that step are incomplete -- afb_p2p_status reads and clears the error",
+                *S->h_err, *S->h_err == 1u ? "a neighbour's rows never became ready" : "a neighbour never acknowledged the pull");
   return AFB_OK;
 }
 
@@ -260,7 +294,8 @@ int p2p_exchange(afb_ctx* ctx, int async)
     AFB_CUDA(cudaStreamWaitEvent(S->side, S->ev_ready, 0));
     st = S->side;
   }
-  k_p2p_exchange<<<S->nb_peer * P2P_BLOCKS_PER_PEER, P2P_THREADS, 0, st>>>(S->d_peers, ctx->values.as<double>(), S->flags, S->my_rank, S->epoch, S->counters);
+  k_p2p_exchange<<<S->nb_peer * S->blocks_per_peer, P2P_THREADS, 0, st>>>(S->d_peers, ctx->values.as<double>(), S->flags, S->my_rank, S->epoch, S->counters,
+                                                                          S->blocks_per_peer, S->d_err);
   AFB_LAUNCH_CHECK(ctx);
   if (async) {
     AFB_CUDA(cudaEventRecord(S->ev_done, S->side));
@@ -276,9 +311,14 @@ int p2p_status(afb_ctx* ctx, int* status)
   *status = 0;
   if (!S || !S->flags) return AFB_OK;
   uint32_t e = 0;
-  AFB_TRY(p2p_wait(ctx));
+  if (S->inflight) {
+    AFB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_done, 0));
+    S->inflight = false;
+  }
   AFB_CUDA(cudaMemcpyAsync(&e, S->flags + 2 * P2P_MAX_RANK, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaMemsetAsync(S->flags + 2 * P2P_MAX_RANK, 0, sizeof(uint32_t), ctx->stream)); // read-and-clear
   AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (S->h_err) *S->h_err = 0u;
   *status = (int)e;
   return AFB_OK;
 }

@@ -599,20 +599,6 @@ int ensure_values_zeroed(afb_ctx* ctx)
   return AFB_OK;
 }
 
-int assemble_tiled_pipe(afb_ctx* ctx, const ElemParams& prm, int accumulate); // tiles_pipe.cu
-
-// scalar executor schedule: 0 = phase-separated, two CTAs per SM (k_assemble_tiled, the default: measured
-// faster); 1 = software-pipelined, one CTA per SM (k_assemble_tiled_pipe).  AFB_TILED_EXEC=phase|pipe.
-static int scalar_executor_choice()
-{
-  static const int choice = [] {
-    const char* env = getenv("AFB_TILED_EXEC");
-    if (env && !strcmp(env, "pipe")) return 1;
-    return 0;
-  }();
-  return choice;
-}
-
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags)
 {
   const bool vec = ctx->b > 1;
@@ -635,7 +621,6 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   const bool all_rows = ctx->all_own || (flags & AFB_FLAG_ALL_ROWS);
   if (accumulate || (vec && !all_rows)) AFB_TRY(ensure_values_zeroed(ctx));
   else ctx->values_dirty = false;
-  if (!vec && scalar_executor_choice() == 1) return assemble_tiled_pipe(ctx, prm, accumulate);
   ExecArgs A;
   A.desc = P.tile_desc.as<TileDesc>();
   A.nb_tile = P.nb_tile;

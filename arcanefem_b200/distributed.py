@@ -83,6 +83,7 @@ class ExchangePlan:
       values_slice(first, n)    -> tensor view of `values[first:first+n]` (zero-copy send buffer)
       add_at(slots, contrib)    -> values[slots] += contrib
       make_buffer(n)            -> float64 tensor for receiving
+      fence()                   -> orders the context's stream and the transport's stream against each other (both ways)
     comm_device: where the tensors handed to torch.distributed live ("cpu" for gloo, "cuda:i" for nccl).
     After the sends the ghost rows are zeroed (the reference's ghost rows are all-zero: isOwn gate).
     p2p: optional object with export() / connect(...) / exchange() (capi.Context: afb_p2p_*): the per-assembly
@@ -91,8 +92,9 @@ class ExchangePlan:
     """
 
     def __init__(self, rank, world, node_gid, node_owner, nb_own_node, b, layout_per_row, tail_pattern, lookup, values_slice, add_at, make_buffer,
-                 group=None, comm_device="cpu", p2p=None):
+                 group=None, comm_device="cpu", p2p=None, fence=None):
         import torch.distributed as dist
+        self.fence = fence or (lambda: None)
         self.dist, self.group, self.comm_device = dist, group, comm_device
         self.rank, self.world, self.b = rank, world, b
         self.node_gid = np.asarray(node_gid, dtype=np.int64)
@@ -224,6 +226,9 @@ class ExchangePlan:
             self.p2p.exchange()
             return
         dist = self.dist
+        # the assembly ran on the context's stream, the transport and the torch ops below run on torch's current
+        # stream: order them explicitly (host-side fences; this is the portable fall-back, not the fast path)
+        self.fence()
         ops = []
         for q, first, n in self.send:
             if n:
@@ -236,6 +241,7 @@ class ExchangePlan:
         for q, first, n in self.send:
             if n:
                 self.values_slice(first, n).zero_()
+        self.fence()  # receives and zero fills (torch stream) are complete before the accumulate kernels (context stream)
         for q, slots, buf in self.recv:
             self.add_at(slots, buf)
 
@@ -340,11 +346,16 @@ class DistributedAssembly:
                 ctx.synchronize()
             return slots
 
+        def fence():
+            ctx.synchronize()
+            torch.cuda.current_stream(dev).synchronize()
+
         self.plan = ExchangePlan(self.rank, self.world, self.node_gid, self.node_owner, own, b, layout == A.LAYOUT_PER_ROW, tail_pattern, lookup,
                                  values_slice=lambda first, n: vals_t[first:first + n],
                                  add_at=lambda slots, buf: ctx.add_values_at(int(slots.numel()), slots, buf),
                                  make_buffer=lambda n: torch.empty(n, dtype=torch.float64, device=f"cuda:{dev}"), group=self.group,
-                                 comm_device=self.comm_device or f"cuda:{dev}", p2p=_P2P(ctx, overlap=self.overlap) if self.transport == "p2p" else None)
+                                 comm_device=self.comm_device or f"cuda:{dev}", p2p=_P2P(ctx, overlap=self.overlap) if self.transport == "p2p" else None,
+                                 fence=fence)
 
     def assemble(self, op, params=None, fmt=None, variant=None, layout=None, mode="exchange", flags=0):
         """Fresh assembly of this rank's rows (call after ctx.build_pattern).  mode "exchange": own cells

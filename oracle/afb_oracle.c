@@ -1007,12 +1007,28 @@ ORC_API int64_t orc_build_pattern_host(int npc, int32_t nb_node, int64_t nb_cell
  * it owns, modules/testlab/CsrBiliAssembly.cc:23-92 (BuildMatrix) and :97-182
  * (AddAndCompute, isOwn gate :174); no communication during assembly).
  * Sub-domain = cells [cell_lo, cell_hi) (own + ghost layer) and owned nodes
- * [owner_lo, owner_hi).  The rank allocates its own row/column/value arrays like
- * CsrFormat::initialize does on every assembly (femutils/CsrFormatMatrix.cc:35-58),
- * fills them, and returns nnz of its owned rows; *checksum = sum of values so the
- * work cannot be elided.  If out_rows/out_cols/out_vals are non-NULL they receive the
- * rank's arrays (rows relative to the rank's first entry; tests compare them with the
- * global oracle).  seconds[0] = BuildMatrix, seconds[1] = AddAndCompute.
+ * [owner_lo, owner_hi).
+ *
+ * Init time (untimed, like FemModule::startInit, modules/testlab/FemModule.cc:124,136):
+ * orc_reference_init builds the node-node-via-edge connectivity of the owned nodes
+ * (Arcane's MeshUtils::computeNodeNodeViaEdgeConnectivity is external; the neighbour
+ * lists are emitted ascending here).
+ *
+ * Timed, per assembly:
+ *   BuildMatrix   CsrFormat::initialize (femutils/CsrFormatMatrix.cc:35-58: row / column /
+ *                 value / rows_nb_column arrays allocated and filled with -1 / -1 / 0 / 0 on
+ *                 every assembly) + the walk of _buildMatrixCsr (CsrBiliAssembly.cc:79-91):
+ *                 per node setCoordinates(diagonal) then setCoordinates(neighbour) for
+ *                 every entry of the node-node view -- no sort, no search.
+ *   AddAndCompute element matrix (host form) + matrixAddValue with the linear scan of
+ *                 indexValue (femutils/CsrFormatMatrix.h:58-87), exact zeros skipped.
+ * Returns nnz of the owned rows; *checksum = sum of values so the work cannot be elided.
+ * If out_rows/out_cols/out_vals are non-NULL they receive the rank's arrays (rows relative
+ * to the rank's first entry, columns in the reference's order: diagonal first).
+ * seconds[0] = BuildMatrix, seconds[1] = AddAndCompute.
+ *
+ * orc_reference_rank (no handle) is the first-assembly form: it builds the connectivity
+ * inside the timed BuildMatrix (what a run pays once), kept for the record.
  */
 #include <time.h>
 static double now_s(void)
@@ -1022,14 +1038,28 @@ static double now_s(void)
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-ORC_API int64_t orc_reference_rank(int npc, int dim, int64_t cell_lo, int64_t cell_hi, int32_t owner_lo, int32_t owner_hi,
-                                   const double* coords, const int32_t* conn, double* checksum, double* seconds,
-                                   int32_t* out_rows, int32_t* out_cols, double* out_vals, int64_t out_capacity)
+typedef struct {
+  int32_t owner_lo, owner_hi;
+  int64_t* ptr;  /* nb_own + 1 */
+  int32_t* list; /* neighbours (self excluded), ascending */
+} orc_nn_t;
+
+ORC_API void orc_reference_free(void* h)
 {
-  const double t0 = now_s();
+  orc_nn_t* nn = (orc_nn_t*)h;
+  if (!nn) return;
+  free(nn->ptr);
+  free(nn->list);
+  free(nn);
+}
+
+ORC_API void* orc_reference_init(int npc, int64_t cell_lo, int64_t cell_hi, int32_t owner_lo, int32_t owner_hi, const int32_t* conn)
+{
   const int32_t nb_own = owner_hi - owner_lo;
-  /* BuildMatrix: node -> cells of the sub-domain restricted to owned nodes, then per owned
-   * node the diagonal + neighbours (ascending) */
+  orc_nn_t* nn = (orc_nn_t*)calloc(1, sizeof(orc_nn_t));
+  nn->owner_lo = owner_lo;
+  nn->owner_hi = owner_hi;
+  /* node -> cells of the sub-domain restricted to owned nodes */
   int64_t* ptr = (int64_t*)calloc((size_t)nb_own + 1, sizeof(int64_t));
   for (int64_t c = cell_lo; c < cell_hi; ++c)
     for (int i = 0; i < npc; ++i) {
@@ -1046,34 +1076,61 @@ ORC_API int64_t orc_reference_rank(int npc, int dim, int64_t cell_lo, int64_t ce
       if (v >= owner_lo && v < owner_hi) list[fill[v - owner_lo]++] = (int32_t)c;
     }
   free(fill);
-  int32_t* rows = (int32_t*)malloc(sizeof(int32_t) * ((size_t)nb_own + 1));
   int64_t cap = 0;
-  for (int32_t n = 0; n < nb_own; ++n) cap += 1 + (ptr[n + 1] - ptr[n]) * (npc - 1); /* upper bound */
-  int32_t* cols = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cap > 0 ? cap : 1));
-  int64_t nnz = 0;
+  for (int32_t n = 0; n < nb_own; ++n) cap += (ptr[n + 1] - ptr[n]) * (npc - 1); /* upper bound */
+  nn->ptr = (int64_t*)malloc(sizeof(int64_t) * ((size_t)nb_own + 1));
+  nn->list = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cap > 0 ? cap : 1));
+  int64_t tot = 0;
   int32_t tmp[4096];
   for (int32_t n = 0; n < nb_own; ++n) {
     const int32_t r = owner_lo + n;
     int cnt = 0;
-    tmp[cnt++] = r;
     for (int64_t q = ptr[n]; q < ptr[n + 1]; ++q) {
       const int32_t* cn = conn + (int64_t)list[q] * npc;
       for (int i = 0; i < npc; ++i) {
         int32_t v = cn[i];
+        if (v == r) continue;
         int found = 0;
         for (int t = 0; t < cnt; ++t) if (tmp[t] == v) { found = 1; break; }
         if (!found && cnt < 4096) tmp[cnt++] = v;
       }
     }
     qsort(tmp, (size_t)cnt, sizeof(int32_t), cmp_i32);
-    rows[n] = (int32_t)nnz;
-    memcpy(cols + nnz, tmp, sizeof(int32_t) * (size_t)cnt);
-    nnz += cnt;
+    nn->ptr[n] = tot;
+    memcpy(nn->list + tot, tmp, sizeof(int32_t) * (size_t)cnt);
+    tot += cnt;
   }
-  rows[nb_own] = (int32_t)nnz;
+  nn->ptr[nb_own] = tot;
   free(ptr);
   free(list);
-  double* vals = (double*)calloc((size_t)(nnz > 0 ? nnz : 1), sizeof(double));
+  return nn;
+}
+
+ORC_API int64_t orc_reference_rank_nn(const void* handle, int npc, int dim, int64_t cell_lo, int64_t cell_hi, int32_t owner_lo, int32_t owner_hi,
+                                      const double* coords, const int32_t* conn, double* checksum, double* seconds,
+                                      int32_t* out_rows, int32_t* out_cols, double* out_vals, int64_t out_capacity)
+{
+  const orc_nn_t* nn = (const orc_nn_t*)handle;
+  if (!nn || nn->owner_lo != owner_lo || nn->owner_hi != owner_hi) return -3;
+  const double t0 = now_s();
+  const int32_t nb_own = owner_hi - owner_lo;
+  /* BuildMatrix: CsrFormat::initialize (allocate + 4 fills), then the append walk */
+  const int64_t nnz = (int64_t)nb_own + nn->ptr[nb_own]; /* nbNode + 2 nbEdge */
+  int32_t* rows = (int32_t*)malloc(sizeof(int32_t) * ((size_t)nb_own + 1));
+  int32_t* cols = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+  double* vals = (double*)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+  int32_t* rows_nb_column = (int32_t*)malloc(sizeof(int32_t) * ((size_t)nb_own + 1));
+  for (int32_t n = 0; n < nb_own; ++n) rows[n] = -1;
+  for (int64_t i = 0; i < nnz; ++i) cols[i] = -1;
+  for (int64_t i = 0; i < nnz; ++i) vals[i] = 0.0;
+  for (int32_t n = 0; n < nb_own; ++n) rows_nb_column[n] = 0;
+  int64_t last = 0;
+  for (int32_t n = 0; n < nb_own; ++n) {
+    if (rows[n] == -1) rows[n] = (int32_t)last; /* setCoordinates, femutils/CsrFormatMatrix.h:104-112 */
+    cols[last++] = owner_lo + n;
+    for (int64_t q = nn->ptr[n]; q < nn->ptr[n + 1]; ++q) cols[last++] = nn->list[q];
+  }
+  rows[nb_own] = (int32_t)last;
   const double t1 = now_s();
   /* AddAndCompute */
   double K[16];
@@ -1108,5 +1165,20 @@ ORC_API int64_t orc_reference_rank(int npc, int dim, int64_t cell_lo, int64_t ce
   free(rows);
   free(cols);
   free(vals);
+  free(rows_nb_column);
   return rc ? rc : nnz;
+}
+
+/* first-assembly form: connectivity built inside the timed BuildMatrix */
+ORC_API int64_t orc_reference_rank(int npc, int dim, int64_t cell_lo, int64_t cell_hi, int32_t owner_lo, int32_t owner_hi,
+                                   const double* coords, const int32_t* conn, double* checksum, double* seconds,
+                                   int32_t* out_rows, int32_t* out_cols, double* out_vals, int64_t out_capacity)
+{
+  const double t0 = now_s();
+  void* h = orc_reference_init(npc, cell_lo, cell_hi, owner_lo, owner_hi, conn);
+  const double t1 = now_s();
+  const int64_t r = orc_reference_rank_nn(h, npc, dim, cell_lo, cell_hi, owner_lo, owner_hi, coords, conn, checksum, seconds, out_rows, out_cols, out_vals, out_capacity);
+  if (seconds) seconds[0] += t1 - t0;
+  orc_reference_free(h);
+  return r;
 }

@@ -197,11 +197,30 @@ def assemble_csr_host_range(mesh_dim, coords, cells, rows, cols, values, cell_lo
     assert rc == 0, rc
 
 
-def reference_rank(mesh_dim, coords, cells, cell_lo, cell_hi, owner_lo, owner_hi, want_arrays=False, capacity=0):
+class ReferenceRank:
+    """Init-time state of one MPI-rank-equivalent of the reference's sequential CSR back-end: the node-node
+    connectivity of its owned nodes (built once, untimed, like FemModule::startInit)."""
+
+    def __init__(self, cells, cell_lo, cell_hi, owner_lo, owner_hi):
+        lib().orc_reference_init.restype = C.c_void_p
+        self.args = (cell_lo, cell_hi, owner_lo, owner_hi)
+        self.h = C.c_void_p(lib().orc_reference_init(cells.shape[1], C.c_int64(cell_lo), C.c_int64(cell_hi), C.c_int32(owner_lo), C.c_int32(owner_hi), _p(cells)))
+
+    def close(self):
+        if self.h:
+            lib().orc_reference_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def reference_rank(mesh_dim, coords, cells, cell_lo, cell_hi, owner_lo, owner_hi, want_arrays=False, capacity=0, init=None):
     """One MPI-rank-equivalent of the reference's sequential CSR back-end (BuildMatrix + AddAndCompute)
     on the sub-domain cells [cell_lo,cell_hi) / owned nodes [owner_lo,owner_hi).  ctypes releases the
-    GIL, so N python threads run N ranks concurrently.  Returns dict(nnz, checksum, seconds[, rows, cols, vals])."""
-    lib().orc_reference_rank.restype = C.c_int64
+    GIL, so N python threads run N ranks concurrently.  `init` = ReferenceRank of the same sub-domain: BuildMatrix
+    walks the init-time node-node connectivity as the reference does; without it the connectivity is built inside the
+    timed BuildMatrix (first assembly).  Returns dict(nnz, checksum, seconds[, rows, cols, vals])."""
     chk = C.c_double()
     sec = (C.c_double * 2)()
     rows = cols = vals = None
@@ -209,8 +228,15 @@ def reference_rank(mesh_dim, coords, cells, cell_lo, cell_hi, owner_lo, owner_hi
         rows = np.empty(owner_hi - owner_lo + 1, dtype=np.int32)
         cols = np.empty(capacity, dtype=np.int32)
         vals = np.empty(capacity, dtype=np.float64)
-    nnz = lib().orc_reference_rank(cells.shape[1], mesh_dim, C.c_int64(cell_lo), C.c_int64(cell_hi), C.c_int32(owner_lo), C.c_int32(owner_hi),
-                                   _p(coords), _p(cells), C.byref(chk), sec, _p(rows), _p(cols), _p(vals), C.c_int64(capacity))
+    tail = (C.c_int64(cell_lo), C.c_int64(cell_hi), C.c_int32(owner_lo), C.c_int32(owner_hi),
+            _p(coords), _p(cells), C.byref(chk), sec, _p(rows), _p(cols), _p(vals), C.c_int64(capacity))
+    if init is not None:
+        assert init.args == (cell_lo, cell_hi, owner_lo, owner_hi)
+        lib().orc_reference_rank_nn.restype = C.c_int64
+        nnz = lib().orc_reference_rank_nn(init.h, cells.shape[1], mesh_dim, *tail)
+    else:
+        lib().orc_reference_rank.restype = C.c_int64
+        nnz = lib().orc_reference_rank(cells.shape[1], mesh_dim, *tail)
     assert nnz >= 0, nnz
     out = dict(nnz=int(nnz), checksum=chk.value, seconds=(sec[0], sec[1]))
     if want_arrays:

@@ -747,7 +747,7 @@ def test_full_size_elasticity_rigid_body_modes(ctx):
     nbc, nbn, nbe, nnz = M.box_counts(3, n)
     lam, mu = O.lame(21.0e5, 0.28)
     ctx.build_pattern(3)
-    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE):
+    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER):
         ctx.reset_values()
         ctx.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=A.LAYOUT_PER_ROW)
         v = ctx.csr_view()
@@ -769,3 +769,62 @@ def test_full_size_elasticity_rigid_body_modes(ctx):
         for mode in modes:
             r = Acsr @ mode.reshape(-1)
             assert float(r.abs().max()) < 1e-11 * scale
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size comparison with the CPU oracle: digests (sum |a_ij|, trace) of the whole matrix and the values of a
+# fixed sample of rows, recorded by tests/golden/make_box_checksums.py (the oracle at the BASELINE sizes)
+# ---------------------------------------------------------------------------------------------
+def _golden_digest(key):
+    import json
+    with open(os.path.join(CS.GOLDEN, "box_checksums.json")) as f:
+        return json.load(f)[key]
+
+
+FULL_SIZE = [
+    ("poisson3d_n24", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER]),
+    ("poisson3d_n120", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER]),      # C2
+    ("poisson3d_n256", [A.VARIANT_TILED_GATHER]),                                                      # C4
+    ("elasticity3d_n24", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER]),
+    ("elasticity3d_n100", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_TILED_GATHER]),                        # 6 M cells, b=3
+    ("elasticity3d_n203", [A.VARIANT_TILED_GATHER]),                                                   # C3
+]
+
+
+@pytest.mark.parametrize("key,variants", FULL_SIZE, ids=[k for k, _ in FULL_SIZE])
+def test_full_size_against_oracle_digest(key, variants):
+    import torch
+    g = _golden_digest(key)
+    n, b, op = g["n"], g["b"], g["op"]
+    with A.Context(0) as c:
+        info = c.generate_box(3, n)
+        assert (info["nb_cell"], info["nb_node"]) == (g["nb_cell"], g["nb_node"])
+        nbr, nnz = c.build_pattern(b)
+        assert nnz == g["nnz"]
+        rows = A.as_torch((c.csr_view() if b == 1 else c.bsr_view())["rows" if b == 1 else "rows_index"], nbr + 1, np.int32, 0)
+        rows_h = rows.cpu().numpy()
+        sample = sorted(int(k) for k in g["sample_rows"])
+        for layout in ([A.LAYOUT_PER_BLOCK] if b == 1 else [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW]):
+            for variant in variants:
+                c.reset_values()
+                c.assemble(op, params=g["params"], fmt=A.FORMAT_CSR if b == 1 else A.FORMAT_BSR, variant=variant, layout=layout)
+                c.synchronize()
+                v = c.csr_view() if b == 1 else c.bsr_view()
+                cols = A.as_torch(v["columns"], nnz, np.int32, 0)
+                vals = A.as_torch(v["values"], nnz * b * b, np.float64, 0)
+                # whole-matrix digests
+                import bench
+                abs_sum, trace = bench.values_digest(torch, rows, cols, vals, nbr, b, layout)
+                assert abs(abs_sum - g["abs_sum"]) <= 1e-12 * g["abs_sum"], (key, variant, layout, abs_sum, g["abs_sum"])
+                assert abs(trace - g["trace"]) <= 1e-12 * abs(g["trace"]), (key, variant, layout, trace, g["trace"])
+                # sampled rows: columns bit-exact, values to the parity bar
+                for r in sample:
+                    ref = g["sample_rows"][str(r)]
+                    lo, hi = int(rows_h[r]), int(rows_h[r + 1])
+                    assert cols[lo:hi].cpu().tolist() == ref["cols"]
+                    got = vals[lo * b * b:hi * b * b].cpu().numpy()
+                    want = np.asarray(ref["vals"])
+                    if b > 1 and layout == A.LAYOUT_PER_ROW:  # per block (p, i, j) -> per row (i, p, j)
+                        want = want.reshape(hi - lo, b, b).transpose(1, 0, 2).reshape(-1)
+                    scale = np.abs(want).max()
+                    assert np.abs(got - want).max() <= TOL * scale, (key, variant, layout, r)

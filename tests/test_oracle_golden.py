@@ -239,3 +239,31 @@ def test_bilaplacian_golden(method):
     u = spla.spsolve(_csr(crow, ccol, vals).tocsc(), rhs)
     worst = CS.compare_to_golden(m, u, golden, b, eps=1.0e-3, min_value=1.0e-10)
     assert worst < 1.0e-4
+
+
+def test_reference_rank_legs_match_global_oracle():
+    """bench.py's CPU arm: the per-rank sequential CSR back-end (init-time node-node connectivity, BuildMatrix =
+    allocate + fill + append walk, AddAndCompute = host element matrix + linear-scan add) reproduces the global
+    oracle matrix on its owned rows; the first-assembly form (connectivity built inside BuildMatrix) is identical."""
+    n = 6
+    m = M.box_mesh(3, n)
+    rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    ref = O.assemble(3, m.coords, m.cells, rows, cols, form=O.FORM_HOST)
+    plane, layer = (n + 1) ** 2, 6 * n * n
+    for k0, k1 in ((0, 3), (3, 7)):
+        part = (layer * max(k0 - 1, 0), layer * min(k1, n), plane * k0, plane * k1)
+        init = O.ReferenceRank(m.cells, *part)
+        cap = int(rows[part[3]] - rows[part[2]])
+        for ini in (init, None):
+            r = O.reference_rank(3, m.coords, m.cells, *part, want_arrays=True, capacity=cap, init=ini)
+            assert r["nnz"] == cap
+            for lr in range(part[3] - part[2]):
+                g = part[2] + lr
+                lo, hi = r["rows"][lr], r["rows"][lr + 1]
+                c = r["cols"][lo:hi]
+                assert c[0] == g, "diagonal first (CsrBiliAssembly.cc:84)"
+                order = np.argsort(c)
+                assert np.array_equal(c[order], cols[rows[g]:rows[g + 1]])
+                want = ref[rows[g]:rows[g + 1]]
+                assert np.allclose(r["vals"][lo:hi][order], want, rtol=0, atol=1e-12 * np.abs(want).max())
+        init.close()
