@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "afb_internal.h"
@@ -105,6 +106,10 @@ int afb_create(int device, afb_ctx** out)
   AFB_CUDA(cudaEventCreateWithFlags(&ctx->check_event, cudaEventDisableTiming));
   AFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin_check), 2 * sizeof(int32_t), cudaHostAllocMapped));
   AFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->pin_check_dev), ctx->pin_check, 0));
+  if (const char* ex = getenv("AFB_TILED_EXEC")) { // default executor of the scalar tiled gather (afb_set_tiled_executor)
+    if (!strcmp(ex, "chain")) ctx->tiled_exec = AFB_TILED_EXEC_CHAIN;
+    else if (!strcmp(ex, "flow")) ctx->tiled_exec = AFB_TILED_EXEC_CHAIN_FLOW;
+  }
   *out = ctx;
   return AFB_OK;
 }
@@ -115,6 +120,7 @@ int afb_destroy(afb_ctx* ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   p2p_destroy(ctx);
+  chain_destroy(ctx);
   DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,
                      &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
                      &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback, &ctx->scan_state, &ctx->solver_work,
@@ -174,6 +180,22 @@ int afb_options_from_name(const char* name, int* format, int* variant, int* spar
     }
   set_error("afb_options_from_name: unknown matrix format option '%s'", name);
   return AFB_ERR_INVALID;
+}
+
+int afb_set_tiled_executor(afb_ctx* ctx, int executor)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(executor >= AFB_TILED_EXEC_BRICKS && executor <= AFB_TILED_EXEC_CHAIN_FLOW, AFB_ERR_INVALID, "afb_set_tiled_executor: unknown executor %d", executor);
+  ctx->tiled_exec = executor;
+  return AFB_OK;
+}
+
+int afb_set_tiled_stage_limit(afb_ctx* ctx, int64_t bytes)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(bytes >= 0, AFB_ERR_INVALID, "afb_set_tiled_stage_limit: negative limit");
+  ctx->tiled_stage_limit = bytes;
+  return AFB_OK;
 }
 
 int afb_set_sparsity_algorithm(afb_ctx* ctx, int algorithm)
@@ -309,6 +331,11 @@ int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_block_row, 
   AFB_REQUIRE(ctx->has_mesh, AFB_ERR_INVALID, "afb_build_pattern: no mesh set");
   // BSRMatrix::initialize argument checks (femutils/BSRFormat.cc:51-55)
   AFB_REQUIRE(nb_dof_per_node >= 1 && nb_dof_per_node <= 3, AFB_ERR_INVALID, "BSRMatrix(initialize): block_size must be 1, 2 or 3 (got %d)", nb_dof_per_node);
+  // a mesh that was assembled through the chained-slice executor and is built again: create the init-time node-node
+  // connectivity of the connectivity-based BuildMatrix now (once per mesh; the first assembly did not need it)
+  if (ctx->has_pattern && ctx->b == 1 && nb_dof_per_node == 1 && ctx->pattern_mesh_gen == ctx->mesh_gen && ctx->sparsity_algo != AFB_SPARSITY_FROM_CELLS &&
+      chain_plan_ms(ctx) >= 0.0f && !pattern_nn_ready(ctx) && (ctx->npc == 3 || ctx->npc == 4))
+    AFB_TRY(build_tile_mesh(ctx));
   invalidate_pattern(ctx);
   ctx->b = nb_dof_per_node;
   AFB_TRY(time_begin(ctx, 1));
@@ -719,6 +746,8 @@ int afb_inspector_timings(afb_ctx* ctx, float* mesh_tiling_ms, float* value_plan
   const TilePlan& P = ctx->plan;
   if (mesh_tiling_ms) *mesh_tiling_ms = (P.mesh_valid && P.mesh_gen == ctx->mesh_gen) ? P.mesh_ms : -1.0f;
   if (value_plan_ms) *value_plan_ms = (P.lists_valid && P.lists_mesh_gen == ctx->mesh_gen) ? P.lists_ms : -1.0f;
+  // scalar assemblies run on the chained-slice plan (chain_plan.cu): its inspector is the value plan of this context
+  if (value_plan_ms && chain_plan_ms(ctx) >= 0.0f) *value_plan_ms = chain_plan_ms(ctx);
   return AFB_OK;
 }
 

@@ -177,7 +177,10 @@ struct afb_ctx {
   cudaEvent_t check_event = nullptr;
   bool check_pending = false;
   int sparsity_algo = 0;            // AFB_SPARSITY_*
+  int tiled_exec = 0;               // AFB_TILED_EXEC_*
+  int64_t tiled_stage_limit = 1ll << 40; // afb_set_tiled_stage_limit
   void* p2p = nullptr;              // afb::P2PState (p2p.cu): ghost-row exchange over NVLink peer memory
+  void* chain = nullptr;            // afb::ChainPlan (chain_plan.cu): plan of the scalar tiled-gather executor
   unsigned scan_tickets = 0, scan_epoch = 0; // chained scan (scan.cu): tiles handed out so far, epoch of the last call
   uint64_t nnz_mesh_gen = ~0ull;    // mesh generation ctx->nnz was last read back for
 
@@ -215,6 +218,8 @@ bool pattern_tiled_ready(const afb_ctx* ctx);
 int rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* faces_dev, int kind, int nb_value, const double* values, int skip_dirichlet);
 int solve_pcg(afb_ctx* ctx, double rtol, double atol, int max_iter, double* x_out, int mem_space, int* iterations, double* residual);
 void p2p_destroy(afb_ctx* ctx);
+void chain_destroy(afb_ctx* ctx);
+float chain_plan_ms(const afb_ctx* ctx);
 int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle);
 int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const int64_t* pull_first,
                 const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count);

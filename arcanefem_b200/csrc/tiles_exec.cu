@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "chain.cuh"
 #include "element.cuh"
 #include "tiles.cuh"
 
@@ -112,6 +113,7 @@ struct ExecArgs {
   const uint16_t* lists;
   double* values;
   int accumulate;
+  int list_stage_max; // tiles with more 16-bit list slots read their lists from global memory (<= the staging buffer)
 };
 
 // The next tiles' inputs travel in two waves so that no warp ever waits on a dependent load:
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
     //      with the previous tile's phase C and write-out, so the row tables and the list region may be overwritten ----
     __syncthreads();
     const TileDesc d = S.desc[slot];
-    const bool staged = d.list_len <= TG_LMAX; // lists of an oversized tile are read from global memory
+    const bool staged = d.list_len <= A.list_stage_max; // lists of an oversized tile are read from global memory
     stage_rows(S, d, pf);
     if (threadIdx.x == 0 && staged && d.list_len > 0) {
       const uint32_t bytes = (uint32_t)d.list_len * 2u;
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
   while (t < A.nb_tile) {
     const TileDesc d = S.desc[slot];
     // every warp is past the previous tile's phase B (end-of-loop barrier): the list buffer may be overwritten
-    const bool staged = TV_LMAX > 0 && d.list_len > 0 && d.list_len <= TV_LMAX;
+    const bool staged = TV_LMAX > 0 && d.list_len > 0 && d.list_len <= A.list_stage_max;
     if (threadIdx.x == 0 && staged) {
       const uint32_t bytes = (uint32_t)d.list_len * 2u;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -607,6 +609,14 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
               "AFB_VARIANT_TILED_GATHER is not available for operator %d on %d-node cells (P1 Poisson, P1 elasticity, Tri3 bilaplacian only); use AFB_VARIANT_NODEWISE", op, ctx->npc);
   TilePlan& P = ctx->plan;
   const int mode = flags & (AFB_FLAG_ALL_ROWS | AFB_FLAG_OWN_CELLS_ONLY);
+  // scalar operators: the chained-slice executors when selected (afb_set_tiled_executor; chain_exec.cu, chain_flow.cu)
+  if (!vec && ctx->tiled_exec != AFB_TILED_EXEC_BRICKS) {
+    ElemParams prm;
+    prm.p0 = params ? params[0] : 0.0;
+    prm.p1 = params ? params[1] : 0.0;
+    prm.flags = flags;
+    return chain_assemble(ctx, prm, flags, ctx->assembled ? 1 : 0);
+  }
   if (!P.mesh_valid || P.mesh_gen != ctx->mesh_gen || P.mesh_b_class != (vec ? 1 : 0)) AFB_TRY(build_tile_mesh(ctx));
   if (!P.lists_valid || P.lists_mesh_gen != ctx->mesh_gen || P.lists_b != ctx->b || P.lists_mode != mode) AFB_TRY(build_tile_lists(ctx, mode));
   ElemParams prm;
@@ -637,6 +647,7 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   A.lists = P.lists.as<uint16_t>();
   A.values = ctx->values.as<double>();
   A.accumulate = accumulate;
+  A.list_stage_max = (int)std::min<int64_t>(vec ? TV_LMAX : TG_LMAX, ctx->tiled_stage_limit / 2);
   const int grid = std::min<int>(P.nb_tile, TG_MINB * ctx->sm_count);
   auto go = [&](auto kernel, size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -197,6 +197,25 @@ AFB_API int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_blo
 AFB_API int afb_set_sparsity_algorithm(afb_ctx* ctx, int algorithm);
 
 /*
+ * Executor behind AFB_VARIANT_TILED_GATHER for b = 1 (the node-wise, atomic-free back-ends of the reference:
+ * modules/testlab/NodeWiseCsrBiliAssembly.cc:157-297, femutils/BSRFormat.h:406-577).  All three write every row exactly
+ * once, bit-reproducibly, and agree to 1e-12; they differ in how the work is cut and scheduled on the SMs:
+ *   AFB_TILED_EXEC_BRICKS       spatial bricks of rows, one CTA per brick, halo cells recomputed (default: measured fastest)
+ *   AFB_TILED_EXEC_CHAIN        columns swept slice by slice, cells shared by consecutive slices stay in shared memory
+ *   AFB_TILED_EXEC_CHAIN_FLOW   the same slices through a warp-specialised mbarrier pipeline, one CTA per SM
+ * b > 1 always runs on bricks.  The setting persists until changed; AFB_TILED_EXEC in the environment sets the default
+ * ("bricks", "chain", "flow").
+ */
+enum { AFB_TILED_EXEC_BRICKS = 0, AFB_TILED_EXEC_CHAIN = 1, AFB_TILED_EXEC_CHAIN_FLOW = 2 };
+AFB_API int afb_set_tiled_executor(afb_ctx* ctx, int executor);
+/*
+ * Tuning / test knob of the tiled executors: plan records (contribution lists) larger than `bytes` are not staged in shared
+ * memory through the TMA engine but read from global memory (the branch oversized tiles take).  Default: the executor's
+ * staging capacity.  bytes = 0 sends every tile through the global-memory branch.
+ */
+AFB_API int afb_set_tiled_stage_limit(afb_ctx* ctx, int64_t bytes);
+
+/*
  * The reference's matrix-format options, kept as names: testlab's boolean options of modules/testlab/Fem.axl:42-95
  * ("legacy", "coo", "coo-sorting", "coo-gpu", "coo-sorting-gpu", "csr", "csr-gpu", "nwcsr", "blcsr", "bsr", "bsr-atomic-free")
  * and the production modules' <matrix-format> strings ("DOK", "BSR", "AF-BSR": modules/poisson/Fem.axl:31,

@@ -828,3 +828,132 @@ def test_full_size_against_oracle_digest(key, variants):
                         want = want.reshape(hi - lo, b, b).transpose(1, 0, 2).reshape(-1)
                     scale = np.abs(want).max()
                     assert np.abs(got - want).max() <= TOL * scale, (key, variant, layout, r)
+
+
+# ---------------------------------------------------------------------------------------------
+# the three executors behind VARIANT_TILED_GATHER (afb_set_tiled_executor) and their read-from-global-memory
+# branch (afb_set_tiled_stage_limit = 0: no tile stages its plan record in shared memory)
+# ---------------------------------------------------------------------------------------------
+EXECUTORS = [(A.TILED_EXEC_BRICKS, "bricks"), (A.TILED_EXEC_CHAIN, "chain"), (A.TILED_EXEC_CHAIN_FLOW, "flow")]
+
+
+@pytest.fixture
+def exec_ctx():
+    c = A.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", P1_POISSON)
+@pytest.mark.parametrize("executor", [e for e, _ in EXECUTORS], ids=[n for _, n in EXECUTORS])
+@pytest.mark.parametrize("stage_limit", [None, 0], ids=["staged", "from-global"])
+def test_tiled_executors_poisson(exec_ctx, name, executor, stage_limit):
+    c = exec_ctx
+    m = get_mesh(name)
+    c.set_tiled_executor(executor)
+    if stage_limit is not None:
+        c.set_tiled_stage_limit(stage_limit)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(1)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=O.FORM_BSR, nodewise=True)
+    c.assemble(A.OP_POISSON, fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER)
+    v1 = c.to_host(A.ARRAY_VALUES)
+    row_scaled_close(v1, ref, rows)
+    # steady state: pattern re-build (connectivity-based from the second build on) + assembly, bit-reproducible
+    for _ in range(2):
+        c.build_pattern(1)
+        c.assemble(A.OP_POISSON, fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER)
+        assert np.array_equal(c.to_host(A.ARRAY_VALUES), v1)
+    # a second operator on top accumulates
+    c.assemble(A.OP_POISSON, fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER)
+    row_scaled_close(c.to_host(A.ARRAY_VALUES), 2.0 * v1, rows)
+
+
+@pytest.mark.parametrize("executor", [e for e, _ in EXECUTORS], ids=[n for _, n in EXECUTORS])
+def test_tiled_executors_ownership_modes(exec_ctx, executor):
+    c = exec_ctx
+    c.set_tiled_executor(executor)
+    m = get_mesh("box3d_n9")
+    nb_own_cell = (m.nb_cell * 2) // 3
+    own = np.ones(m.nb_node, dtype=np.uint8)
+    own[::5] = 0
+    c.set_mesh(3, m.coords, m.cells, own)
+    c.set_own_cell_count(nb_own_cell)
+    c.build_pattern(1)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    full = O.assemble(3, m.coords, m.cells[:nb_own_cell], rows, cols, form=O.FORM_BSR)
+    seg = np.repeat(np.arange(m.nb_node), np.diff(rows))
+    for flags, ref in ((A.FLAG_OWN_CELLS_ONLY | A.FLAG_ALL_ROWS, full), (A.FLAG_OWN_CELLS_ONLY, np.where(own[seg] != 0, full, 0.0)), (0, None)):
+        if ref is None:  # ghost cells recomputed, owned rows only (the reference's scheme)
+            ref = np.where(own[seg] != 0, O.assemble(3, m.coords, m.cells, rows, cols, form=O.FORM_BSR), 0.0)
+        c.reset_values()
+        c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER, flags=flags)
+        row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows)
+
+
+@pytest.mark.parametrize("executor", [e for e, _ in EXECUTORS], ids=[n for _, n in EXECUTORS])
+def test_tiled_executors_limits_and_degenerate(exec_ctx, executor):
+    """High-valence fan: 300 triangles around one node fit a tile / slice; 3000 do not: an explicit error, no silent fallback."""
+    c = exec_ctx
+    c.set_tiled_executor(executor)
+    for k, ok in ((300, True), (3000, False)):
+        ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+        coords = np.zeros((k + 1, 3))
+        coords[1:, 0], coords[1:, 1] = np.cos(ang), np.sin(ang)
+        cells = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.int32)
+        c.set_mesh(2, coords, cells)
+        c.build_pattern(1)
+        rows_ref, cols_ref = O.build_pattern(3, k + 1, cells)
+        ref = O.assemble(2, coords, cells, rows_ref, cols_ref, form=O.FORM_BSR)
+        if ok:
+            c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+            row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows_ref)
+        else:
+            with pytest.raises(A.AfbError):
+                c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+            c.assemble(A.OP_POISSON, variant=A.VARIANT_NODEWISE)
+            row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows_ref)
+    # one cell, and a mesh with an isolated node
+    coords = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [5, 5, 5]], dtype=np.float64)
+    cells = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    c.set_mesh(3, coords, cells)
+    c.build_pattern(1)
+    rows_ref, cols_ref = O.build_pattern(4, 5, cells)
+    ref = O.assemble(3, coords, cells, rows_ref, cols_ref, form=O.FORM_BSR)
+    c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+    row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows_ref)
+
+
+@pytest.mark.parametrize("name", ["bar_3D", "box3d_n9", "box2d_n17"])
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_vector_executor_lists_from_global_memory(exec_ctx, name, layout):
+    """k_assemble_tiled_vec with every tile's contribution lists read from global memory (the branch oversized tiles take)."""
+    c = exec_ctx
+    c.set_tiled_stage_limit(0)
+    m = get_mesh(name)
+    b = m.dim
+    lam, mu = O.lame(21.0e5, 0.28)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(b)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[lam, mu], layout=layout, nodewise=True)
+    c.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER, layout=layout)
+    row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows, b=b, layout=layout)
+
+
+@pytest.mark.parametrize("executor", [A.TILED_EXEC_CHAIN, A.TILED_EXEC_CHAIN_FLOW], ids=["chain", "flow"])
+def test_chain_executors_full_size_digest(executor):
+    """C2 (10.4 M Tet4) through the chained-slice executors against the oracle's full-size digest."""
+    import torch
+    import bench
+    g = _golden_digest("poisson3d_n120")
+    with A.Context(0) as c:
+        c.set_tiled_executor(executor)
+        c.generate_box(3, 120)
+        nbr, nnz = c.build_pattern(1)
+        for _ in range(2):
+            c.build_pattern(1)
+            c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+        abs_sum, trace, _ = bench.matrix_digest(torch, A, c, 0, nbr)
+        assert abs(abs_sum - g["abs_sum"]) <= 1e-12 * g["abs_sum"] and abs(trace - g["trace"]) <= 1e-12 * g["trace"]
