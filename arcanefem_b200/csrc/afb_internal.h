@@ -223,6 +223,14 @@ float chain_plan_ms(const afb_ctx* ctx);
 int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle);
 int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const int64_t* pull_first,
                 const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count);
+struct P2PEndpoint { // what a rank tells its neighbours about its arrays (p2p_export_ex)
+  unsigned char values_handle[64], flags_handle[64]; // CUDA IPC handles (peers in other processes)
+  uint64_t pid, values_ptr, flags_ptr;               // raw pointers (peers in the same process)
+  int32_t device, pad;
+};
+int p2p_export_ex(afb_ctx* ctx, P2PEndpoint* ep);
+int p2p_connect_ex(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const P2PEndpoint* endpoints,
+                   const int64_t* pull_first, const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count);
 int p2p_exchange(afb_ctx* ctx, int async);
 int p2p_wait(afb_ctx* ctx);
 int p2p_status(afb_ctx* ctx, int* status);

@@ -35,6 +35,7 @@ __device__ __forceinline__ void load_cell_nodes(const int32_t* __restrict__ conn
 // ---------------------------------------------------------------------------------------------
 // cell-wise atomic
 // ---------------------------------------------------------------------------------------------
+// (vector reductions -- red.global.add.v2 -- exist for f32 / f16x2 / bf16x2 only: ptxas rejects .v2.f64, so b > 1 blocks stay scalar REDs)
 template <class E, int LAYOUT, bool COO>
 __global__ void __launch_bounds__(128)
 k_assemble_cellwise(const double* __restrict__ coords, const int32_t* __restrict__ conn, const uint8_t* __restrict__ is_own, int64_t nb_cell,
@@ -52,16 +53,12 @@ k_assemble_cellwise(const double* __restrict__ coords, const int32_t* __restrict
   for (int a = 0; a < NPC; ++a) {
     const int32_t r = nd[a];
     if (is_own && !is_own[r]) continue;
-    int rb, re;
-    if constexpr (COO) {
-      // COO back-end: locate the row segment by binary search over the COO row array
-      rb = (int)lower_bound_i32(coo_rows, nnz, r);
-      re = (int)lower_bound_i32(coo_rows, nnz, r + 1);
-    }
-    else {
-      rb = __ldg(rows + r);
-      re = __ldg(rows + r + 1);
-    }
+    // COO back-end: the reference locates the row segment by a binary search over the COO row array for every entry
+    // (femutils/CooFormatMatrix.h:308-353: ~28 dependent loads per entry at 100 M cells).  The COO row array here is the
+    // expansion of row_index, which the pattern build keeps: the segment is read directly, as in the CSR back-end.
+    (void)coo_rows;
+    (void)nnz;
+    const int rb = __ldg(rows + r), re = __ldg(rows + r + 1);
     const int nz = re - rb;
 #pragma unroll
     for (int bc = 0; bc < NPC; ++bc) {

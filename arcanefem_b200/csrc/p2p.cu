@@ -19,7 +19,10 @@
 // This replaces what the reference delegates to the solver's parallel matrix assembly (HYPRE IJ off-processor
 // values); the NCCL path of arcanefem_b200/distributed.py stays as the portable fallback.
 #include <algorithm>
+#include <cstring>
 #include <vector>
+
+#include <unistd.h>
 
 #include "afb_internal.h"
 
@@ -179,6 +182,20 @@ int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle)
   return AFB_OK;
 }
 
+// extended descriptor for peers that may live in the same process (several contexts driven by one host program:
+// afb_mgpu_*, tests/cpp): CUDA IPC handles cannot be opened by the process that created them, raw pointers can be used
+int p2p_export_ex(afb_ctx* ctx, P2PEndpoint* ep)
+{
+  memset(ep, 0, sizeof(*ep));
+  AFB_TRY(p2p_export(ctx, ep->values_handle, ep->flags_handle));
+  P2PState* S = state_of(ctx);
+  ep->pid = (uint64_t)getpid();
+  ep->values_ptr = (uint64_t)(uintptr_t)ctx->values.p;
+  ep->flags_ptr = (uint64_t)(uintptr_t)S->flags;
+  ep->device = ctx->device;
+  return AFB_OK;
+}
+
 int p2p_disconnect(afb_ctx* ctx)
 {
   if (!ctx->p2p) return AFB_OK;
@@ -214,6 +231,12 @@ void p2p_destroy(afb_ctx* ctx)
 int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const int64_t* pull_first,
                 const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count)
 {
+  return p2p_connect_ex(ctx, my_rank, nb_peer, peer_rank, values_handles, flags_handles, nullptr, pull_first, pull_count, slots, send_first, send_count);
+}
+
+int p2p_connect_ex(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank, const void* values_handles, const void* flags_handles, const P2PEndpoint* endpoints,
+                   const int64_t* pull_first, const int64_t* pull_count, const int64_t* const* slots, const int64_t* send_first, const int64_t* send_count)
+{
   P2PState* S = state_of(ctx);
   AFB_REQUIRE(S->flags && S->values_base == ctx->values.p, AFB_ERR_INVALID, "afb_p2p_connect: call afb_p2p_export first (and again after the values array moved)");
   AFB_REQUIRE(my_rank >= 0 && my_rank < P2P_MAX_RANK && nb_peer >= 0 && nb_peer <= P2P_MAX_RANK, AFB_ERR_INVALID, "afb_p2p_connect: rank/peer count out of range (max %d)", P2P_MAX_RANK);
@@ -224,10 +247,23 @@ int p2p_connect(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_rank
   for (int k = 0; k < nb_peer; ++k) {
     AFB_REQUIRE(peer_rank[k] >= 0 && peer_rank[k] < P2P_MAX_RANK && peer_rank[k] != my_rank, AFB_ERR_INVALID, "afb_p2p_connect: bad peer rank %d", peer_rank[k]);
     void *pv = nullptr, *pf = nullptr;
-    AFB_CUDA(cudaIpcOpenMemHandle(&pv, vh[k], cudaIpcMemLazyEnablePeerAccess));
-    S->opened.push_back(pv);
-    AFB_CUDA(cudaIpcOpenMemHandle(&pf, fh[k], cudaIpcMemLazyEnablePeerAccess));
-    S->opened.push_back(pf);
+    if (endpoints && endpoints[k].pid == (uint64_t)getpid()) { // same process: the peer's arrays are directly addressable
+      if (endpoints[k].device != ctx->device) {
+        cudaError_t pe = cudaDeviceEnablePeerAccess(endpoints[k].device, 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+        else AFB_CUDA(pe);
+      }
+      pv = reinterpret_cast<void*>((uintptr_t)endpoints[k].values_ptr);
+      pf = reinterpret_cast<void*>((uintptr_t)endpoints[k].flags_ptr);
+    }
+    else {
+      const cudaIpcMemHandle_t* hv = endpoints ? reinterpret_cast<const cudaIpcMemHandle_t*>(endpoints[k].values_handle) : vh + k;
+      const cudaIpcMemHandle_t* hf = endpoints ? reinterpret_cast<const cudaIpcMemHandle_t*>(endpoints[k].flags_handle) : fh + k;
+      AFB_CUDA(cudaIpcOpenMemHandle(&pv, *hv, cudaIpcMemLazyEnablePeerAccess));
+      S->opened.push_back(pv);
+      AFB_CUDA(cudaIpcOpenMemHandle(&pf, *hf, cudaIpcMemLazyEnablePeerAccess));
+      S->opened.push_back(pf);
+    }
     h[k].peer_values = static_cast<const double*>(pv);
     h[k].peer_flags = static_cast<uint32_t*>(pf);
     h[k].slots = slots[k];

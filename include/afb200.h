@@ -424,6 +424,74 @@ AFB_API int afb_inspector_timings(afb_ctx* ctx, float* mesh_tiling_ms, float* va
 /* number of kernels launched by this context so far (bench.py "gpu_launches") */
 AFB_API int64_t afb_launch_count(afb_ctx* ctx);
 
+
+/* =============================================================================================
+ * Domain decomposition behind the C ABI.  What the reference gets from Arcane's partitioner, from
+ * Arcane's variable synchronisation and from the solver's parallel matrix (femutils/HypreDoFLinearSystem.cc:209-249:
+ * allGather(nb_own_row) + ghost synchronize; :461-520: off-processor entries) is done here by the library; the host
+ * program only provides two communication primitives (MPI in the reference's world, torch.distributed in bench.py,
+ * shared memory in tests/cpp/mgpu_driver.cpp).
+ * ============================================================================================= */
+typedef struct afb_transport {
+  void* user;
+  int32_t rank, world;
+  /* every rank contributes `bytes` bytes; recv receives world * bytes, in rank order.  Collective. */
+  int (*allgather)(void* user, const void* send, int64_t bytes, void* recv);
+  /* for k < nb_peer: send send_bytes[k] bytes to rank peer[k] and receive recv_bytes[k] bytes from it (sizes are known on
+   * both sides; zero sizes allowed; peers are symmetric).  device_memory != 0: the buffers are device pointers. */
+  int (*exchange)(void* user, int32_t nb_peer, const int32_t* peer, const void* const* send, const int64_t* send_bytes, void* const* recv, const int64_t* recv_bytes,
+                  int device_memory);
+  int32_t exchange_takes_device_memory; /* the exchange callback can move device buffers (e.g. NCCL): the fall-back transport then sends the matrix rows in place */
+  int32_t pad;
+} afb_transport;
+
+/*
+ * Partition of a global mesh into `world` sub-domains by recursive coordinate bisection of the cell centroids (what the
+ * reference asks of Arcane's partitioner; structured boxes come out as slabs / bricks).  Semantics of an Arcane sub-domain
+ * as ArcaneFEM sees it: own cells + one layer of ghost cells, every node has exactly one owner (the lowest rank among the
+ * cells touching it), local numbering owned-first, ghosts grouped by ascending owner then global id.  Host arrays.
+ */
+typedef struct afb_partition afb_partition;
+AFB_API int afb_partition_create(int dim, int nodes_per_cell, int32_t nb_node, int64_t nb_cell, const double* xyz, const int32_t* cell_nodes, int world, afb_partition** out);
+AFB_API int afb_partition_destroy(afb_partition* p);
+/* sizes of rank's sub-domain */
+AFB_API int afb_partition_sizes(const afb_partition* p, int rank, int32_t* nb_node, int32_t* nb_own_node, int64_t* nb_cell, int64_t* nb_own_cell);
+/* arrays of rank's sub-domain (any pointer may be NULL): xyz [nb_node*3], cell_nodes [nb_cell*npc] local ids, is_own [nb_node], node_gid [nb_node],
+ * node_owner [nb_node], cell_gid [nb_cell] */
+AFB_API int afb_partition_get(const afb_partition* p, int rank, double* xyz, int32_t* cell_nodes, uint8_t* is_own, int64_t* node_gid, int32_t* node_owner, int64_t* cell_gid);
+
+/*
+ * Host-only index logic of the ghost-row exchange of one rank (no CUDA call: also used by the CPU tests).
+ * rows_tail [nb_ghost + 1]: block-row offsets (absolute, i.e. row_index[nb_own_node .. nb_node]) of the ghost rows;
+ * cols_tail: local column ids of those rows (columns[rows_tail[0] .. rows_tail[nb_ghost])).  Collective over the transport.
+ */
+typedef struct afb_xplan_host afb_xplan_host;
+AFB_API int afb_xplan_host_create(const afb_transport* t, int nb_dof_per_node, int value_layout, int32_t nb_node, int32_t nb_own_node, const int64_t* node_gid,
+                                  const int32_t* node_owner, const int32_t* rows_tail, const int32_t* cols_tail, afb_xplan_host** out);
+AFB_API int afb_xplan_host_destroy(afb_xplan_host* h);
+/* neighbours (ascending rank): the slice [send_first, +send_count) of this rank's values array each one receives, and the
+ * number of doubles it sends here */
+AFB_API int afb_xplan_host_peers(const afb_xplan_host* h, int32_t* nb_peer, const int32_t** peer, const int64_t** send_first, const int64_t** send_count, const int64_t** recv_count);
+/* (dof_row, dof_col) of every double neighbour k sends, in ITS memory order, as local DoF ids of this rank */
+AFB_API int afb_xplan_host_pairs(const afb_xplan_host* h, int32_t k, const int32_t** dof_rows, const int32_t** dof_cols);
+/* global numbering of the rows (HypreDoFLinearSystemImpl::_computeMatrixNumeration): first_dof [world + 1], dof_l2g [nb_node * b].  Collective. */
+AFB_API int afb_xplan_host_numbering(afb_xplan_host* h, int64_t* first_dof, int32_t* dof_l2g);
+
+/*
+ * The exchange itself on a context (after afb_build_pattern and a first afb_assemble_bilinear with
+ * AFB_FLAG_OWN_CELLS_ONLY | AFB_FLAG_ALL_ROWS, which fixes the value layout).  Collective.  Transport of the rows:
+ * one pull kernel over peer memory (NVLink; CUDA IPC between processes, plain pointers inside one) when every rank can map
+ * its neighbours -- agreed on collectively -- else the transport's exchange callback + accumulate kernels.
+ */
+typedef struct afb_xplan afb_xplan;
+AFB_API int afb_xplan_create(afb_ctx* ctx, const afb_transport* t, const int64_t* node_gid, const int32_t* node_owner, int32_t nb_own_node, int allow_peer_memory, afb_xplan** out);
+AFB_API int afb_xplan_destroy(afb_xplan* x);
+AFB_API int afb_xplan_exchange(afb_xplan* x);   /* after every such assembly; the peer-memory kernel runs on a side stream */
+AFB_API int afb_xplan_wait(afb_xplan* x);       /* orders the context stream after the exchange; reports a timed-out exchange */
+AFB_API int afb_xplan_numbering(afb_xplan* x, int64_t* first_dof, int32_t* dof_l2g);
+/* transport_kind: 0 none (single rank), 1 peer memory, 2 callback; bytes per exchange */
+AFB_API int afb_xplan_info(const afb_xplan* x, int32_t* nb_peer, int64_t* bytes_sent, int64_t* bytes_received, int32_t* transport_kind, const char** why_not_peer_memory);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,3 +116,96 @@ def test_facade_solve(driver, tmp_path, meshname):
     ref = spla.spsolve(sp.csr_matrix((vals, cols, rows)).tocsc(), rhs)
     assert 0 < extra[0] < 20000
     assert np.abs(sol - ref).max() <= 1e-8 * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# the domain-decomposition layer of the C ABI from C++ only (tests/cpp/mgpu_driver.cpp): afb_partition_* (RCB), per-rank
+# contexts, afb_xplan_* with an in-process transport, the peer-memory exchange kernel between contexts of one process
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def mgpu_driver(tmp_path_factory):
+    if not os.path.exists(os.path.join(LIBDIR, "libafb200.so")):
+        pytest.skip("libafb200.so not built")
+    out = str(tmp_path_factory.mktemp("cpp") / "mgpu_driver")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "mgpu_driver.cpp"), "-o", out,
+           "-L" + LIBDIR, "-lafb200", "-Wl,-rpath," + LIBDIR, "-pthread"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def test_mgpu_driver_compiles_and_has_no_cpu_fallback(mgpu_driver, tmp_path):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present: covered by the gpu tests")
+    m = M.box_mesh(3, 2)
+    write_mesh(tmp_path / "m.bin", m)
+    r = subprocess.run([mgpu_driver, str(tmp_path / "m.bin"), "2", "1", "0", "1", str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+def read_ranks(path, world):
+    out = []
+    with open(path, "rb") as f:
+        for _ in range(world):
+            arrs = []
+            for dt in (np.int32, np.int32, np.float64, np.int64, np.int32, np.int64, np.int32):
+                n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+                arrs.append(np.fromfile(f, dtype=dt, count=n))
+            out.append(arrs)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", [("box3d", 1, O.LAYOUT_PER_BLOCK), ("box3d", 3, O.LAYOUT_PER_ROW), ("sphere", 1, O.LAYOUT_PER_BLOCK), ("box3d", 3, O.LAYOUT_PER_BLOCK)],
+                         ids=["box-poisson", "box-elasticity-per-row", "sphere-poisson", "box-elasticity-per-block"])
+@pytest.mark.parametrize("p2p", [1, 0], ids=["peer-memory", "callback-transport"])
+def test_mgpu_driver_two_rank_exchange_without_python(mgpu_driver, tmp_path, world, case, p2p):
+    name, b, layout = case
+    m = M.box_mesh(3, 7) if name == "box3d" else M.read_msh(os.path.join(ROOT, "tests", "golden", "sphere_cut.msh"))
+    write_mesh(tmp_path / "m.bin", m)
+    r = subprocess.run([mgpu_driver, str(tmp_path / "m.bin"), str(world), str(b), str(layout), str(p2p), str(tmp_path / "o.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    op = O.OP_POISSON if b == 1 else O.OP_ELASTICITY
+    params = list(O.lame(21.0e5, 0.28)) if b > 1 else None
+    grows, gcols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    gvals = O.assemble(m.dim, m.coords, m.cells, grows, gcols, op=op, form=O.FORM_BSR, params=params, layout=layout)
+    bb = b * b
+    seen = np.zeros(m.nb_node, dtype=np.int32)
+    firsts = None
+    node_number = {}
+    for rank, (rows, cols, vals, gid, meta, first, l2g) in enumerate(read_ranks(tmp_path / "o.bin", world)):
+        nb_own, kind = int(meta[0]), int(meta[1])
+        assert kind == (1 if p2p else 2), "transport kind"
+        seen[gid[:nb_own]] += 1
+        firsts = first if firsts is None else firsts
+        assert np.array_equal(first, firsts) and first[rank + 1] - first[rank] == nb_own * b
+        assert np.array_equal(l2g[:nb_own * b], first[rank] + np.arange(nb_own * b))
+        for i in range(nb_own):
+            node_number[int(gid[i])] = int(l2g[i * b]) // b
+        for i in range(nb_own):  # owned rows equal the global matrix rows (columns through the gid map)
+            g = int(gid[i])
+            lo, hi = int(rows[i]), int(rows[i + 1])
+            glo, ghi = int(grows[g]), int(grows[g + 1])
+            assert hi - lo == ghi - glo
+            order = np.argsort(gid[cols[lo:hi]])
+            assert np.array_equal(gid[cols[lo:hi]][order], gcols[glo:ghi])
+            got = vals[lo * bb:hi * bb]
+            want = gvals[glo * bb:ghi * bb]
+            nz = hi - lo
+            if b > 1 and layout == O.LAYOUT_PER_ROW:
+                got = got.reshape(b, nz, b)[:, order, :].reshape(-1)
+            else:
+                got = got.reshape(nz, bb)[order].reshape(-1)
+            scale = np.abs(want).max()
+            assert np.abs(got - want).max() <= 1e-12 * scale, (rank, i)
+        assert not vals[int(rows[nb_own]) * bb:].any(), "ghost rows are zero after the exchange"
+    assert (seen == 1).all(), "every node has exactly one owner"
+    # ghosts learnt their global number from the owner
+    for rank, (rows, cols, vals, gid, meta, first, l2g) in enumerate(read_ranks(tmp_path / "o.bin", world)):
+        for i in range(int(meta[0]), gid.size):
+            assert int(l2g[i * b]) // b == node_number[int(gid[i])]

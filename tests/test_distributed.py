@@ -40,6 +40,31 @@ def numpy_lookup(rows, cols, b, per_row):
     return f
 
 
+def expand_block_entries(rows_local, cols_local, run_len, b, layout_per_row):
+    """Scalar (dof_row, dof_col) pairs of block entries in the memory order of the sender's values (BSRMatrix::findValueIndex
+    layouts, femutils/BSRFormat.cc:79-106) -- numpy restatement of what afb_xplan_host_create does in C++ (checker only)."""
+    rows_local = np.asarray(rows_local, dtype=np.int64)
+    cols_local = np.asarray(cols_local, dtype=np.int64)
+    if b == 1:
+        return rows_local.astype(np.int32), cols_local.astype(np.int32)
+    ii, jj = np.meshgrid(np.arange(b), np.arange(b), indexing="ij")
+    if not layout_per_row:
+        dr = (rows_local[:, None, None] * b + ii[None]).reshape(-1)
+        dc = (cols_local[:, None, None] * b + jj[None]).reshape(-1)
+        return dr.astype(np.int32), dc.astype(np.int32)
+    out_r, out_c = [], []
+    pos = 0
+    for nz in run_len:
+        r = rows_local[pos:pos + nz]
+        c = cols_local[pos:pos + nz]
+        dr = np.repeat(r[None, :, None] * b + np.arange(b)[:, None, None], b, axis=2)
+        dc = np.broadcast_to(c[None, :, None] * b + np.arange(b)[None, None, :], (b, nz, b))
+        out_r.append(dr.reshape(-1))
+        out_c.append(dc.reshape(-1))
+        pos += nz
+    return np.concatenate(out_r).astype(np.int32), np.concatenate(out_c).astype(np.int32)
+
+
 def global_reference(mesh, op, params, layout):
     rows, cols = O.build_pattern(mesh.npc, mesh.nb_node, mesh.cells)
     vals = O.assemble(mesh.dim, mesh.coords, mesh.cells, rows, cols, op=op, form=O.FORM_BSR, params=params, layout=layout)
@@ -208,7 +233,6 @@ def test_box_slab_matches_generic_partition():
                          ids=["box-poisson", "box-elasticity-per-row", "sphere-poisson"])
 def test_decomposed_assembly_gpu(case, variant):
     from arcanefem_b200 import capi as A
-    from arcanefem_b200.distributed import expand_block_entries
     name, op, layout = case
     mesh = M.box_mesh(3, 7) if name == "box3d" else M.read_msh(os.path.join(ROOT, "tests", "golden", name))
     world = 3
@@ -353,3 +377,45 @@ def test_ghost_rows_pulled_over_peer_memory(world, case):
             errs.append((-1, "rank timed out"))
     assert not errs, "\n".join(f"rank {r}:\n{t}" for r, t in errs)
     assert all(p.exitcode == 0 for p in procs)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("name", ["box3d", "box2d", "sphere_cut.msh"])
+def test_native_rcb_partition_semantics(name, world):
+    """afb_partition_* (recursive coordinate bisection, C++): Arcane sub-domain semantics as ArcaneFEM sees them -- every cell
+    owned once, every node owned once (lowest rank among its cells), one ghost-cell layer, owned-first numbering with the
+    ghosts grouped by ascending owner then global id, balanced cell counts."""
+    from arcanefem_b200.distributed import partition_mesh_native
+    mesh = M.box_mesh(3, 6) if name == "box3d" else (M.box_mesh(2, 12) if name == "box2d" else M.read_msh(os.path.join(ROOT, "tests", "golden", name)))
+    subs = partition_mesh_native(mesh, world)
+    cell_seen = np.zeros(mesh.nb_cell, dtype=np.int32)
+    node_seen = np.zeros(mesh.nb_node, dtype=np.int32)
+    owner_of = np.full(mesh.nb_node, -1)
+    for s in subs:
+        cell_seen[s.cell_gid[:s.nb_own_cell]] += 1
+        node_seen[s.node_gid[:s.nb_own_node]] += 1
+        owner_of[s.node_gid[:s.nb_own_node]] = s.rank
+    assert (cell_seen == 1).all() and (node_seen == 1).all()
+    counts = [s.nb_own_cell for s in subs]
+    assert max(counts) - min(counts) <= max(2, world)
+    cell_rank = np.empty(mesh.nb_cell, dtype=np.int32)
+    for s in subs:
+        cell_rank[s.cell_gid[:s.nb_own_cell]] = s.rank
+    low = np.full(mesh.nb_node, world)
+    np.minimum.at(low, mesh.cells.ravel(), np.repeat(cell_rank, mesh.npc))
+    assert np.array_equal(owner_of, np.where(low == world, 0, low))
+    for s in subs:
+        assert np.array_equal(s.node_owner, owner_of[s.node_gid]) and np.array_equal(s.is_own, (s.node_owner == s.rank).astype(np.uint8))
+        assert (s.node_owner[:s.nb_own_node] == s.rank).all() and (s.node_owner[s.nb_own_node:] != s.rank).all()
+        gh = s.node_owner[s.nb_own_node:]
+        assert (np.diff(gh) >= 0).all()
+        for q in np.unique(gh):
+            g = s.node_gid[s.nb_own_node:][gh == q]
+            assert (np.diff(g) > 0).all()
+        assert (np.diff(s.node_gid[:s.nb_own_node]) > 0).all()
+        # cells: connectivity maps back, ghost cells = the foreign cells touching an owned node
+        assert np.array_equal(s.node_gid[s.cells], mesh.cells[s.cell_gid])
+        touches = (owner_of[mesh.cells] == s.rank).any(axis=1)
+        expected_ghost = np.nonzero(touches & (cell_rank != s.rank))[0]
+        assert np.array_equal(np.sort(s.cell_gid[s.nb_own_cell:]), expected_ghost)
+        assert np.allclose(s.coords, mesh.coords[s.node_gid])
