@@ -290,6 +290,27 @@ int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cel
   return AFB_OK;
 }
 
+int afb_update_coordinates(afb_ctx* ctx, const double* xyz, int mem_space)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_mesh && xyz, AFB_ERR_INVALID, "afb_update_coordinates: no mesh / null coordinates");
+  const size_t bytes = sizeof(double) * 3 * (size_t)ctx->nb_node;
+  if (mem_space == AFB_MEM_DEVICE) {
+    if (xyz != ctx->coords.p) {
+      if (ctx->coords.owned) AFB_CUDA(cudaMemcpyAsync(ctx->coords.p, xyz, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+      else ctx->coords.alias(xyz, bytes);
+    }
+  }
+  else {
+    if (!ctx->coords.owned) { // the context aliased the caller's device array so far: own a copy from now on
+      ctx->coords.release();
+      AFB_TRY(ctx->coords.reserve(bytes));
+    }
+    AFB_CUDA(cudaMemcpyAsync(ctx->coords.p, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return AFB_OK;
+}
+
 int afb_set_own_cell_count(afb_ctx* ctx, int64_t nb_own_cell)
 {
   AFB_TRY(check_ctx(ctx));

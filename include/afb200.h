@@ -153,6 +153,14 @@ AFB_API int afb_synchronize(afb_ctx* ctx);
 AFB_API int afb_set_mesh(afb_ctx* ctx, int dim, int nodes_per_cell, int32_t nb_node, int64_t nb_cell,
                          const double* xyz, const int32_t* cell_nodes, const uint8_t* node_is_own, int mem_space);
 
+/*
+ * New node coordinates on the same topology (a time loop / moving mesh: what changes between two
+ * AssembleBilinearOperator calls of a reference module is the field data, not Arcane's connectivity).  Everything derived
+ * from the connectivity alone -- node->cell lists, the sparsity structures, the plans of the tiled executors -- stays valid.
+ * xyz: [nb_node][3] AoS like afb_set_mesh.
+ */
+AFB_API int afb_update_coordinates(afb_ctx* ctx, const double* xyz, int mem_space);
+
 /* Cells [0, nb_own_cell) belong to this sub-domain, cells [nb_own_cell, nb_cell) are ghost cells
  * (Arcane's one-layer ghost cells; Cell::isOwn()).  Default after afb_set_mesh: all cells own. */
 AFB_API int afb_set_own_cell_count(afb_ctx* ctx, int64_t nb_own_cell);

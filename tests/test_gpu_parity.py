@@ -957,3 +957,30 @@ def test_chain_executors_full_size_digest(executor):
             c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
         abs_sum, trace, _ = bench.matrix_digest(torch, A, c, 0, nbr)
         assert abs(abs_sum - g["abs_sum"]) <= 1e-12 * g["abs_sum"] and abs(trace - g["trace"]) <= 1e-12 * g["trace"]
+
+
+@pytest.mark.parametrize("executor", [e for e, _ in EXECUTORS], ids=[n for _, n in EXECUTORS])
+def test_update_coordinates_keeps_plans(exec_ctx, executor):
+    """afb_update_coordinates: new coordinates on the same topology (time loop); sparsity structures and executor plans
+    survive, every variant follows the new coordinates."""
+    c = exec_ctx
+    c.set_tiled_executor(executor)
+    m = get_mesh("box3d_n9")
+    c.set_mesh(3, m.coords, m.cells)
+    c.build_pattern(1)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+    c.build_pattern(1)  # (the second build of a mesh creates the init-time connectivity of the connectivity-based BuildMatrix)
+    c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+    t0 = c.inspector_timings()
+    rng = np.random.default_rng(7)
+    for step in range(2):
+        moved = m.coords * (1.0 + 0.1 * (step + 1)) + 0.02 / 9 * rng.standard_normal(m.coords.shape)
+        c.update_coordinates(moved)
+        ref = O.assemble(3, moved, m.cells, rows, cols, form=O.FORM_BSR)
+        for variant in (A.VARIANT_TILED_GATHER, A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE):
+            c.build_pattern(1)
+            assert np.array_equal(c.to_host(A.ARRAY_ROWS), rows) and np.array_equal(c.to_host(A.ARRAY_COLUMNS), cols)
+            c.assemble(A.OP_POISSON, variant=variant)
+            row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows)
+    assert c.inspector_timings() == t0, "the inspector must not run again"
