@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -42,6 +43,7 @@ static void invalidate_pattern(afb_ctx* ctx)
 {
   ctx->has_pattern = false;
   ctx->assembled = false;
+  ctx->values_touched = false;
   ctx->coo_rows_valid = false;
   ctx->csr_valid = false;
   ctx->saved_valid = false;
@@ -122,7 +124,7 @@ int afb_destroy(afb_ctx* ctx)
   p2p_destroy(ctx);
   chain_destroy(ctx);
   DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,
-                     &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
+                     &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->ij_rows, &ctx->ij_cols, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
                      &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback, &ctx->scan_state, &ctx->solver_work,
                      &ctx->plan.tile_desc, &ctx->plan.tile_nodes, &ctx->plan.tile_cells, &ctx->plan.unit_base, &ctx->plan.unit_len, &ctx->plan.emap, &ctx->plan.rowinfo, &ctx->plan.foot, &ctx->plan.lconn, &ctx->plan.lists,
                      &ctx->plan.rowf, &ctx->plan.inc, &ctx->plan.inc_grp, &ctx->plan.col_scratch, &ctx->plan.nn_deg, &ctx->plan.nn_local, &ctx->plan.nn_e0, &ctx->plan.emap_rows,
@@ -269,6 +271,9 @@ int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cel
               "unsupported cell type: %d nodes per cell in dimension %d (Tri3/Tri6/Tet4/Tet10 only)", npc, dim);
   AFB_REQUIRE(nb_node > 0 && nb_cell >= 0, AFB_ERR_INVALID, "bad mesh sizes nb_node=%d nb_cell=%lld", nb_node, (long long)nb_cell);
   AFB_REQUIRE(xyz && (cell_nodes || nb_cell == 0), AFB_ERR_INVALID, "null mesh arrays");
+  // device arrays are used in place (zero-copy) and read with vector loads: 16-byte aligned connectivity rows, 8-byte coordinates
+  AFB_REQUIRE(mem_space != AFB_MEM_DEVICE || ((reinterpret_cast<uintptr_t>(cell_nodes) & 15u) == 0 && (reinterpret_cast<uintptr_t>(xyz) & 7u) == 0), AFB_ERR_INVALID,
+              "afb_set_mesh(AFB_MEM_DEVICE): cell_nodes must be 16-byte aligned and xyz 8-byte aligned (pass a copy, or use AFB_MEM_HOST)");
   invalidate_pattern(ctx);
   ctx->has_mesh = false;
   ctx->dim = dim;
@@ -281,6 +286,11 @@ int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cel
   ctx->nb_own_node = nb_node;
   ctx->nb_own_cell = nb_cell;
   if (node_is_own) AFB_TRY(upload(ctx, ctx->is_own, node_is_own, (size_t)nb_node, mem_space));
+  if (node_is_own && mem_space == AFB_MEM_HOST) {
+    int32_t own = 0;
+    for (int32_t i = 0; i < nb_node; ++i) own += node_is_own[i] ? 1 : 0;
+    ctx->nb_own_node = own;
+  }
   ctx->has_dir_nodes = false;
   ctx->has_mesh = true;
   ctx->mesh_gen++;
@@ -378,6 +388,7 @@ int afb_reset_values(afb_ctx* ctx)
   AFB_CUDA(cudaMemsetAsync(ctx->values.p, 0, sizeof(double) * (size_t)ctx->nnz * ctx->b * ctx->b, ctx->stream));
   ctx->values_dirty = false;
   ctx->assembled = false;
+  ctx->values_touched = false;
   ctx->saved_valid = false;
   return AFB_OK;
 }
@@ -458,6 +469,7 @@ int afb_dirichlet_penalty(afb_ctx* ctx, int weak, double penalty, int32_t n, con
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_dirichlet_penalty: no pattern");
   if (n <= 0) return AFB_OK;
   AFB_TRY(ensure_values_zeroed(ctx));
+  ctx->values_touched = true;
   const void *ids = nullptr, *vals = nullptr;
   AFB_TRY(stage(ctx, ctx->tmp_ids, dof_ids, sizeof(int32_t) * (size_t)n, mem_space, &ids));
   AFB_TRY(stage(ctx, ctx->tmp_vals, g, sizeof(double) * (size_t)n, mem_space, &vals));
@@ -562,6 +574,8 @@ int afb_matrix_set_value(afb_ctx* ctx, int32_t dof_row, int32_t dof_col, double 
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_matrix_set_value: no pattern");
   int64_t slot = -1;
   AFB_TRY(single_slot(ctx, dof_row, dof_col, &slot));
+  AFB_TRY(ensure_values_zeroed(ctx));
+  ctx->values_touched = true; // a later tiled assembly adds on top instead of overwriting (the reference's += semantics)
   if (mode == 1) {
     double old = 0.0;
     AFB_CUDA(cudaMemcpyAsync(&old, ctx->values.as<double>() + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -714,6 +728,7 @@ int afb_add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, const doubl
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_add_values_at: no pattern");
   AFB_TRY(ensure_values_zeroed(ctx));
+  ctx->values_touched = true;
   return add_values_at(ctx, n, slots, contrib);
 }
 
@@ -749,6 +764,45 @@ int afb_last_timings(afb_ctx* ctx, float* connectivity_ms, float* pattern_ms, fl
     *out[p] = -1.0f;
     if (ctx->timed[p]) AFB_CUDA(cudaEventElapsedTime(out[p], ctx->ev[2 * p], ctx->ev[2 * p + 1]));
   }
+  return AFB_OK;
+}
+
+int afb_get_ij_arrays(afb_ctx* ctx, int32_t first_own_row, int32_t nb_own_row, const int32_t* dof_local_to_global, const int32_t** ncols, const int32_t** rows,
+                      const int32_t** cols, const double** values, int64_t* nb_values)
+{
+  AFB_TRY(check_ctx(ctx));
+  const int32_t *v_rows = nullptr, *v_nbc = nullptr, *v_cols = nullptr;
+  double* v_vals = nullptr;
+  int32_t nb_row = 0;
+  int64_t nnz = 0;
+  AFB_TRY(afb_get_csr_view(ctx, &v_rows, &v_nbc, &v_cols, &v_vals, &nb_row, &nnz));
+  AFB_REQUIRE(nb_own_row >= 0 && nb_own_row <= nb_row && first_own_row >= 0, AFB_ERR_INVALID, "afb_get_ij_arrays: nb_own_row %d outside [0,%d]", nb_own_row, nb_row);
+  AFB_TRY(ctx->ij_rows.reserve(sizeof(int32_t) * (size_t)std::max(nb_own_row, 1)));
+  AFB_TRY(fill_iota(ctx, first_own_row, nb_own_row, ctx->ij_rows.as<int32_t>()));
+  const int32_t* c = v_cols;
+  if (dof_local_to_global) {
+    AFB_TRY(ctx->ij_cols.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));
+    AFB_TRY(renumber_columns(ctx, dof_local_to_global, ctx->ij_cols.as<int32_t>()));
+    c = ctx->ij_cols.as<int32_t>();
+  }
+  int32_t own_end = 0; // values of the owned rows: rows[nb_own_row]
+  AFB_CUDA(cudaMemcpyAsync(&own_end, v_rows + nb_own_row, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ncols) *ncols = v_nbc;
+  if (rows) *rows = ctx->ij_rows.as<int32_t>();
+  if (cols) *cols = c;
+  if (values) *values = v_vals;
+  if (nb_values) *nb_values = own_end;
+  return AFB_OK;
+}
+
+int afb_memcpy_to_host(afb_ctx* ctx, void* dst_host, const void* src_device, size_t bytes)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(bytes == 0 || (dst_host && src_device), AFB_ERR_INVALID, "afb_memcpy_to_host: null pointer");
+  AFB_TRY(verify_pending(ctx));
+  if (bytes) AFB_CUDA(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
   return AFB_OK;
 }
 

@@ -151,8 +151,10 @@ struct afb_ctx {
   afb::DevBuf rhs;    // double[nb_node*b]
   int layout = AFB_LAYOUT_PER_BLOCK;
   bool assembled = false;
+  bool values_touched = false; // something other than an assembly wrote into `values` since the last reset / pattern build
   // expanded scalar CSR of a b>1 matrix (BSRMatrix::toCsr)
   afb::DevBuf csr_rows, csr_cols, csr_nbcol;
+  afb::DevBuf ij_rows, ij_cols;  // afb_get_ij_arrays: global row numbers, columns in the solver's numbering
   bool csr_valid = false;
 
   // Dirichlet state
@@ -252,6 +254,7 @@ int ensure_scalar_csr(afb_ctx* ctx);
 int lookup_value_slots(afb_ctx* ctx, int64_t n, const int32_t* dof_rows, const int32_t* dof_cols, int64_t* slots);
 int add_values_at(afb_ctx* ctx, int64_t n, const int64_t* slots, const double* contrib);
 int renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_global, int32_t* out);
+int fill_iota(afb_ctx* ctx, int32_t first, int32_t n, int32_t* out);
 int scatter_flags(afb_ctx* ctx, uint8_t* flags, double* vals, uint8_t flag, int32_t n, const int32_t* ids, const double* v);
 
 // ---- mesh_gen.cu -----------------------------------------------------------------------------

@@ -195,6 +195,20 @@ __global__ void k_renumber(int64_t n, const int32_t* __restrict__ cols, const in
   }
 }
 
+__global__ void k_iota(int32_t first, int32_t n, int32_t* __restrict__ out)
+{
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = first + i;
+}
+
+int fill_iota(afb_ctx* ctx, int32_t first, int32_t n, int32_t* out)
+{
+  if (n <= 0) return AFB_OK;
+  k_iota<<<grid_for(n, 256), 256, 0, ctx->stream>>>(first, n, out);
+  AFB_LAUNCH_CHECK(ctx);
+  return AFB_OK;
+}
+
 int renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_global, int32_t* out)
 {
   const int32_t* cols = ctx->cols.as<int32_t>();

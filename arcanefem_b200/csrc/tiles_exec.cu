@@ -615,7 +615,7 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
     prm.p0 = params ? params[0] : 0.0;
     prm.p1 = params ? params[1] : 0.0;
     prm.flags = flags;
-    return chain_assemble(ctx, prm, flags, ctx->assembled ? 1 : 0);
+    return chain_assemble(ctx, prm, flags, (ctx->assembled || ctx->values_touched) ? 1 : 0);
   }
   if (!P.mesh_valid || P.mesh_gen != ctx->mesh_gen || P.mesh_b_class != (vec ? 1 : 0)) AFB_TRY(build_tile_mesh(ctx));
   if (!P.lists_valid || P.lists_mesh_gen != ctx->mesh_gen || P.lists_b != ctx->b || P.lists_mode != mode) AFB_TRY(build_tile_lists(ctx, mode));
@@ -627,7 +627,7 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   // values already holding contributions (a second operator added on top) are accumulated into;
   // a fresh matrix is simply overwritten (every entry of every row is written exactly once; the
   // vector executor does not write the rows of non-owned nodes: those need the zero fill)
-  const int accumulate = ctx->assembled ? 1 : 0;
+  const int accumulate = (ctx->assembled || ctx->values_touched) ? 1 : 0;
   const bool all_rows = ctx->all_own || (flags & AFB_FLAG_ALL_ROWS);
   if (accumulate || (vec && !all_rows)) AFB_TRY(ensure_values_zeroed(ctx));
   else ctx->values_dirty = false;

@@ -811,6 +811,17 @@ def run_b200(args):
             line["configs"] = cfgs
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(args, n)
+        if args.time_stats:
+            # the reference's output/listing/time_stats.json (modules/testlab/FemModule.cc:19-56), for its own plotting scripts
+            from arcanefem_b200.timestats import write_time_stats
+            bm_cells = per_sparsity.get("cells", pattern_ms) * 1e-3
+            fm = {"nwcsr": (pattern_ms * 1e-3, values_ms * 1e-3)} if variant == A.VARIANT_TILED_GATHER else {}
+            if A.VARIANT_CELLWISE_ATOMIC in per_variant:
+                fm["csr-gpu"] = (bm_cells, per_variant[A.VARIANT_CELLWISE_ATOMIC] * 1e-3)
+                fm["coo-gpu"] = (bm_cells, per_variant[A.VARIANT_CELLWISE_ATOMIC] * 1e-3)  # same kernel: the COO back-end reads the row segment directly
+            if A.VARIANT_NODEWISE in per_variant:
+                fm["CsrNodeWise_ThreadPerRow"] = (bm_cells, per_variant[A.VARIANT_NODEWISE] * 1e-3)
+            write_time_stats(args.time_stats, args.steps, world, 3, (n + 1) ** 3, 12 * n * n, int(cells_all), fm)
         print(json.dumps(line))
     if ctx is not None:
         ctx.close()
@@ -828,6 +839,7 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="box size of the job (C4: 256 = 100 663 296 Tet4; C2: 120)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N>1: the same box cut in N slabs (north star) or a box growing with N")
     ap.add_argument("--n-c3", type=int, default=203, help="box size of the C3 (elasticity b=3) entry of the configs block")
+    ap.add_argument("--time-stats", default=None, help="also write the reference's time_stats.json (modules/testlab/FemModule.cc:19-56) to this path")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs block (C2, C3) at N=1")
     ap.add_argument("--no-first-step", action="store_true", help="skip the first-assembly (nothing amortised) measurement at N=1")
     ap.add_argument("--e2e-variant", default="auto", choices=["auto", "same", "atomic", "nodewise", "tiled"], help="e2e: cheaper of atomic / steady-state variant by trial, the steady-state variant, or a fixed one")

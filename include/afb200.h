@@ -148,7 +148,8 @@ AFB_API int afb_synchronize(afb_ctx* ctx);
  * femutils/ArcaneFemFunctions.h:3245-3262,3893-3911); xyz = AoS double[nb_node][3];
  * cell_nodes = int32[nb_cell][npc]; node_is_own = uint8[nb_node] or NULL (all owned).
  * Also builds the node->cell connectivity (Arcane's nodeCell view), ascending cell ids.
- * mem_space HOST copies to the device; DEVICE keeps the caller's pointers (zero-copy).
+ * mem_space HOST copies to the device; DEVICE keeps the caller's pointers (zero-copy): cell_nodes must then be 16-byte
+ * aligned (rows are read with 128-bit loads) and xyz 8-byte aligned, else AFB_ERR_INVALID.
  */
 AFB_API int afb_set_mesh(afb_ctx* ctx, int dim, int nodes_per_cell, int32_t nb_node, int64_t nb_cell,
                          const double* xyz, const int32_t* cell_nodes, const uint8_t* node_is_own, int mem_space);
@@ -406,6 +407,19 @@ AFB_API int afb_p2p_disconnect(afb_ctx* ctx);
  * m_dof_matrix_numbering when running in parallel (femutils/HypreDoFLinearSystem.cc:390-406).
  */
 AFB_API int afb_renumber_columns(afb_ctx* ctx, const int32_t* dof_local_to_global, int32_t* out);
+
+/*
+ * The arrays of HYPRE_IJMatrixSetValues(ij_A, nrows, ncols, rows, cols, values) exactly as HypreDoFLinearSystemImpl::solve
+ * passes them (femutils/HypreDoFLinearSystem.cc:501-514), as device pointers owned by the context: `ncols` = number of
+ * columns of every row, `rows` = global row numbers first_own_row + i, `cols` = columns in the solver's global numbering
+ * (dof_local_to_global: device array of nb_row entries, afb_xplan_numbering; NULL = sequential, columns unchanged),
+ * `values` = the assembled values in place.  nb_own_row rows are handed over (the owned rows come first).  Scalar CSR view:
+ * b > 1 needs the per-row value layout, like afb_get_csr_view.
+ */
+AFB_API int afb_get_ij_arrays(afb_ctx* ctx, int32_t first_own_row, int32_t nb_own_row, const int32_t* dof_local_to_global, const int32_t** ncols, const int32_t** rows,
+                              const int32_t** cols, const double** values, int64_t* nb_values);
+/* device -> host copy on the context's stream, synchronised (what UVM host access gives the reference) */
+AFB_API int afb_memcpy_to_host(afb_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
 
 /* ---- solve ---------------------------------------------------------------- */
 

@@ -984,3 +984,36 @@ def test_update_coordinates_keeps_plans(exec_ctx, executor):
             c.assemble(A.OP_POISSON, variant=variant)
             row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows)
     assert c.inspector_timings() == t0, "the inspector must not run again"
+
+
+@pytest.mark.parametrize("executor", [e for e, _ in EXECUTORS], ids=[n for _, n in EXECUTORS])
+def test_values_written_before_the_assembly_are_kept(exec_ctx, executor):
+    """matrixAddValue / weak penalty before assembleBilinear: every variant adds on top, as the reference's += does."""
+    c = exec_ctx
+    c.set_tiled_executor(executor)
+    m = get_mesh("box3d_n6_nojitter")
+    c.set_mesh(3, m.coords, m.cells)
+    c.build_pattern(1)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    ref = O.assemble(3, m.coords, m.cells, rows, cols, form=O.FORM_BSR)
+    dofs = np.array([0, 5, 11], dtype=np.int32)
+    for variant in (A.VARIANT_TILED_GATHER, A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE):
+        c.build_pattern(1)
+        c.dirichlet_penalty(dofs, np.zeros(3), 3.5, weak=True)  # A[i,i] += 3.5 before anything is assembled
+        c.assemble(A.OP_POISSON, variant=variant)
+        want = ref.copy()
+        for d in dofs:
+            lo, hi = rows[d], rows[d + 1]
+            want[lo + int(np.nonzero(cols[lo:hi] == d)[0][0])] += 3.5
+        row_scaled_close(c.to_host(A.ARRAY_VALUES), want, rows)
+
+
+def test_unaligned_device_connectivity_is_rejected(exec_ctx):
+    import torch
+    m = get_mesh("box3d_n6_nojitter")
+    xyz = torch.from_numpy(m.coords).cuda()
+    flat = torch.zeros(m.cells.size + 1, dtype=torch.int32, device="cuda")
+    flat[1:] = torch.from_numpy(m.cells.reshape(-1)).cuda()
+    shifted = flat[1:].view(-1, 4)  # 4 bytes off a 16-byte boundary
+    with pytest.raises(A.AfbError, match="aligned"):
+        exec_ctx.set_mesh(3, xyz, shifted, mem_space=A.MEM_DEVICE)
