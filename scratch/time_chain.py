@@ -12,6 +12,7 @@ stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 ctx = A.Context(0, stream=stream.cuda_stream)
 EXEC = {"bricks": 0, "tiles": 0, "chain": 1, "flow": 2}[os.environ.get("AFB_TILED_EXEC", "bricks")]
+ctx.set_tiled_executor(EXEC)
 info = ctx.generate_box(dim, n)
 nbr, nnz = ctx.build_pattern(1)
 ev = lambda: torch.cuda.Event(enable_timing=True)
