@@ -267,8 +267,8 @@ int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cel
 {
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(dim == 2 || dim == 3, AFB_ERR_UNSUPPORTED, "BSRFormat(initialize): Only supports 2D and 3D (dim=%d)", dim);
-  AFB_REQUIRE((dim == 2 && (npc == 3 || npc == 6)) || (dim == 3 && (npc == 4 || npc == 10)), AFB_ERR_UNSUPPORTED,
-              "unsupported cell type: %d nodes per cell in dimension %d (Tri3/Tri6/Tet4/Tet10 only)", npc, dim);
+  AFB_REQUIRE((dim == 2 && (npc == 3 || npc == 6 || npc == 4)) || (dim == 3 && (npc == 4 || npc == 10 || npc == 8)), AFB_ERR_UNSUPPORTED,
+              "unsupported cell type: %d nodes per cell in dimension %d (Tri3 / Tri6 / Quad4, Tet4 / Tet10 / Hexa8)", npc, dim);
   AFB_REQUIRE(nb_node > 0 && nb_cell >= 0, AFB_ERR_INVALID, "bad mesh sizes nb_node=%d nb_cell=%lld", nb_node, (long long)nb_cell);
   AFB_REQUIRE(xyz && (cell_nodes || nb_cell == 0), AFB_ERR_INVALID, "null mesh arrays");
   // device arrays are used in place (zero-copy) and read with vector loads: 16-byte aligned connectivity rows, 8-byte coordinates
@@ -365,7 +365,7 @@ int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_block_row, 
   // a mesh that was assembled through the chained-slice executor and is built again: create the init-time node-node
   // connectivity of the connectivity-based BuildMatrix now (once per mesh; the first assembly did not need it)
   if (ctx->has_pattern && ctx->b == 1 && nb_dof_per_node == 1 && ctx->pattern_mesh_gen == ctx->mesh_gen && ctx->sparsity_algo != AFB_SPARSITY_FROM_CELLS &&
-      chain_plan_ms(ctx) >= 0.0f && !pattern_nn_ready(ctx) && (ctx->npc == 3 || ctx->npc == 4))
+      chain_plan_ms(ctx) >= 0.0f && !pattern_nn_ready(ctx) && ctx->npc == ctx->dim + 1)
     AFB_TRY(build_tile_mesh(ctx));
   invalidate_pattern(ctx);
   ctx->b = nb_dof_per_node;
@@ -375,7 +375,7 @@ int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_block_row, 
   ctx->has_pattern = true;
   // explicit connectivity-based sparsity: the init-time connectivity is created right after the first build
   // of a mesh (AUTO creates it with the first tiled assembly)
-  if (ctx->sparsity_algo == AFB_SPARSITY_FROM_CONNECTIVITY && !pattern_nn_ready(ctx) && (ctx->npc == 3 || ctx->npc == 4)) AFB_TRY(build_tile_mesh(ctx));
+  if (ctx->sparsity_algo == AFB_SPARSITY_FROM_CONNECTIVITY && !pattern_nn_ready(ctx) && ctx->npc == ctx->dim + 1) AFB_TRY(build_tile_mesh(ctx));
   if (nb_block_row) *nb_block_row = ctx->nb_node;
   if (nb_block_nnz) *nb_block_nnz = ctx->nnz;
   return AFB_OK;

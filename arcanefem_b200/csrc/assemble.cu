@@ -214,6 +214,8 @@ int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, in
     if (npc == 3 && dim == 2) return launch<Tri3Poisson>(ctx, format, variant, layout, prm);
     if (npc == 6 && dim == 2) return launch<Tri6Poisson>(ctx, format, variant, layout, prm);
     if (npc == 10 && dim == 3) return launch<Tet10Poisson>(ctx, format, variant, layout, prm);
+    if (npc == 4 && dim == 2) return launch<Quad4Poisson>(ctx, format, variant, layout, prm);
+    if (npc == 8 && dim == 3) return launch<Hexa8Poisson>(ctx, format, variant, layout, prm);
   }
   else if (op == AFB_OP_ELASTICITY) {
     if (npc == 4 && dim == 3) return launch<Tet4Elasticity>(ctx, format, variant, layout, prm);

@@ -815,7 +815,7 @@ template <class F> static int ch_by_npc(int npc, F f)
 
 int chain_build(afb_ctx* ctx, int mode_flags, int geom, const ChainLimits& L, int grid)
 {
-  AFB_REQUIRE(ctx->npc == 3 || ctx->npc == 4, AFB_ERR_UNSUPPORTED, "the tiled path is not available for %d-node cells (P1 simplices only); use AFB_VARIANT_NODEWISE", ctx->npc);
+  AFB_REQUIRE(ctx->npc == ctx->dim + 1, AFB_ERR_UNSUPPORTED, "the tiled path is not available for %d-node cells in dimension %d (P1 simplices only); use AFB_VARIANT_NODEWISE", ctx->npc, ctx->dim);
   AFB_REQUIRE(ctx->has_pattern && ctx->b == 1, AFB_ERR_INVALID, "chain inspector: build a scalar pattern first");
   ChainPlan& P = *chain_of(ctx);
   P.valid = false;

@@ -142,6 +142,7 @@ int build_node_cells(afb_ctx* ctx)
     case 3: k_count_node_cells<3><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
     case 4: k_count_node_cells<4><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
     case 6: k_count_node_cells<6><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
+    case 8: k_count_node_cells<8><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
     case 10: k_count_node_cells<10><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, deg); break;
     }
     AFB_LAUNCH_CHECK(ctx);
@@ -155,6 +156,7 @@ int build_node_cells(afb_ctx* ctx)
     case 3: k_fill_node_cells<3><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
     case 4: k_fill_node_cells<4><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
     case 6: k_fill_node_cells<6><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
+    case 8: k_fill_node_cells<8><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
     case 10: k_fill_node_cells<10><<<grid, 256, 0, ctx->stream>>>(conn, nb_cell, ptr, deg, list); break;
     }
     AFB_LAUNCH_CHECK(ctx);
@@ -362,6 +364,7 @@ static int dispatch_row_unique(afb_ctx* ctx, bool write, int32_t* deg)
   case 3: return launch_row_unique<3>(ctx, write, deg);
   case 4: return launch_row_unique<4>(ctx, write, deg);
   case 6: return launch_row_unique<6>(ctx, write, deg);
+  case 8: return launch_row_unique<8>(ctx, write, deg);
   case 10: return launch_row_unique<10>(ctx, write, deg);
   }
   set_error("unsupported nodes_per_cell %d", ctx->npc);

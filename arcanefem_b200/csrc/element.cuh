@@ -278,6 +278,124 @@ struct Tet10Poisson {
 // ---------------------------------------------------------------------------------------------
 // slot search and value indexing
 // ---------------------------------------------------------------------------------------------
+// Q1 quadrilateral / hexahedron, Poisson (modules/poisson/ElementMatrixHexQuad.h:68-104, :197-236; geometry
+// femutils/ArcaneFemFunctionsGpu.h:296-349, :554-586; reference gradients femutils/ShapeFunctions.h:123-129, :314-346).
+// 2x2 (2x2x2) Gauss points at +-1/sqrt(3), weight 1: K_ab = sum_g detJ_g grad N_a . grad N_b.  The inverse Jacobian is applied
+// as adjugate / det: G_a = adj(J)^T dN_a / det, so K_ab = sum_g (A_a . A_b) / det_g with A_a = adj-transformed reference gradient.
+// ---------------------------------------------------------------------------------------------
+struct Quad4Poisson {
+  static constexpr int NPC = 4, B = 1, DIM = 2;
+  double K[4][4];
+  double area;
+  __device__ void init(const double* __restrict__ coords, const int32_t (&nd)[4], const ElemParams&)
+  {
+    double x[4], y[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { double z; load3(coords, nd[a], x[a], y[a], z); (void)z; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) K[a][b] = 0.0;
+    area = 0.0;
+    const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+#pragma unroll
+    for (int ixi = 0; ixi < 2; ++ixi)
+#pragma unroll
+      for (int ieta = 0; ieta < 2; ++ieta) {
+        const double xi = gp[ixi], eta = gp[ieta];
+        const double dxi[4] = { -0.25 * (1.0 - eta), 0.25 * (1.0 - eta), 0.25 * (1.0 + eta), -0.25 * (1.0 + eta) };
+        const double det_[4] = { -0.25 * (1.0 - xi), -0.25 * (1.0 + xi), 0.25 * (1.0 + xi), 0.25 * (1.0 - xi) };
+        double J00 = 0, J01 = 0, J10 = 0, J11 = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          J00 += dxi[a] * x[a]; J01 += dxi[a] * y[a];
+          J10 += det_[a] * x[a]; J11 += det_[a] * y[a];
+        }
+        const double det = J00 * J11 - J01 * J10;
+        const double inv = 1.0 / det;
+        double ax[4], ay[4]; // det * physical gradients
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          ax[a] = J11 * dxi[a] - J01 * det_[a];
+          ay[a] = J00 * det_[a] - J10 * dxi[a];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = a; b < 4; ++b) K[a][b] += (ax[a] * ax[b] + ay[a] * ay[b]) * inv;
+        area += det;
+      }
+#pragma unroll
+    for (int a = 1; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < a; ++b) K[a][b] = K[b][a];
+  }
+  __device__ __forceinline__ void block(int a, int b, double (&o)[1]) const { o[0] = K[a][b]; }
+  __device__ __forceinline__ double measure() const { return area; }
+};
+
+struct Hexa8Poisson {
+  static constexpr int NPC = 8, B = 1, DIM = 3;
+  double K[8][8];
+  double vol;
+  __device__ void init(const double* __restrict__ coords, const int32_t (&nd)[8], const ElemParams&)
+  {
+    double x[8], y[8], z[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) load3(coords, nd[a], x[a], y[a], z[a]);
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) K[a][b] = 0.0;
+    vol = 0.0;
+    const double sx[8] = { -1, 1, 1, -1, -1, 1, 1, -1 }, sy[8] = { -1, -1, 1, 1, -1, -1, 1, 1 }, sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+    const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+      const double xi = gp[(g >> 2) & 1], eta = gp[(g >> 1) & 1], zeta = gp[g & 1];
+      double dxi[8], det_[8], dze[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        dxi[a] = sx[a] * 0.125 * (1.0 + sy[a] * eta) * (1.0 + sz[a] * zeta);
+        det_[a] = sy[a] * 0.125 * (1.0 + sx[a] * xi) * (1.0 + sz[a] * zeta);
+        dze[a] = sz[a] * 0.125 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta);
+      }
+      double J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        J[0][0] += dxi[a] * x[a]; J[0][1] += dxi[a] * y[a]; J[0][2] += dxi[a] * z[a];
+        J[1][0] += det_[a] * x[a]; J[1][1] += det_[a] * y[a]; J[1][2] += det_[a] * z[a];
+        J[2][0] += dze[a] * x[a]; J[2][1] += dze[a] * y[a]; J[2][2] += dze[a] * z[a];
+      }
+      // adjugate (rows of det * J^-1)
+      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[0][2] * J[2][1] - J[0][1] * J[2][2], c02 = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+      const double c10 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c11 = J[0][0] * J[2][2] - J[0][2] * J[2][0], c12 = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+      const double c20 = J[1][0] * J[2][1] - J[1][1] * J[2][0], c21 = J[0][1] * J[2][0] - J[0][0] * J[2][1], c22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      const double det = J[0][0] * c00 + J[0][1] * c10 + J[0][2] * c20;
+      const double inv = 1.0 / det;
+      double ax[8], ay[8], az[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        ax[a] = c00 * dxi[a] + c01 * det_[a] + c02 * dze[a];
+        ay[a] = c10 * dxi[a] + c11 * det_[a] + c12 * dze[a];
+        az[a] = c20 * dxi[a] + c21 * det_[a] + c22 * dze[a];
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = a; b < 8; ++b) K[a][b] += (ax[a] * ax[b] + ay[a] * ay[b] + az[a] * az[b]) * inv;
+      vol += det;
+    }
+#pragma unroll
+    for (int a = 1; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < a; ++b) K[a][b] = K[b][a];
+  }
+  __device__ __forceinline__ void block(int a, int b, double (&o)[1]) const { o[0] = K[a][b]; }
+  __device__ __forceinline__ double measure() const { return vol; }
+};
+
+// ---------------------------------------------------------------------------------------------
 // position of `col` in the ascending segment cols[lo,hi) (present by construction)
 __device__ __forceinline__ int find_col(const int32_t* __restrict__ cols, int lo, int hi, int32_t col)
 {

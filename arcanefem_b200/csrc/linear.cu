@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) k_rhs_source_nodewise(const double* __res
 
 int rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed_area)
 {
-  AFB_REQUIRE(ctx->npc == 3 || ctx->npc == 4, AFB_ERR_UNSUPPORTED, "constant source term is implemented for P1 cells only (npc=%d)", ctx->npc);
+  AFB_REQUIRE(ctx->npc == ctx->dim + 1, AFB_ERR_UNSUPPORTED, "constant source term is implemented for P1 simplices only (%d-node cells in dimension %d)", ctx->npc, ctx->dim);
   AFB_REQUIRE(nb_f >= 1 && nb_f <= 3 && nb_f <= ctx->b, AFB_ERR_INVALID, "source has %d components, matrix has %d dof per node", nb_f, ctx->b);
   double ff[3] = { 0, 0, 0 };
   for (int k = 0; k < nb_f; ++k) ff[k] = f[k];

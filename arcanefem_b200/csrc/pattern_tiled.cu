@@ -269,7 +269,7 @@ bool pattern_nn_ready(const afb_ctx* ctx)
 bool pattern_tiled_ready(const afb_ctx* ctx)
 {
   const TilePlan& P = ctx->plan;
-  return P.mesh_valid && P.mesh_gen == ctx->mesh_gen && (ctx->npc == 3 || ctx->npc == 4);
+  return P.mesh_valid && P.mesh_gen == ctx->mesh_gen && ctx->npc == ctx->dim + 1;
 }
 
 static int pattern_threads(const TilePlan& P) { return std::max(32, (P.max_rows + 31) & ~31); }

@@ -604,7 +604,7 @@ int ensure_values_zeroed(afb_ctx* ctx)
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags)
 {
   const bool vec = ctx->b > 1;
-  AFB_REQUIRE((ctx->npc == 3 || ctx->npc == 4) && ((op == AFB_OP_POISSON && !vec) || (op == AFB_OP_ELASTICITY && vec) || (op == AFB_OP_BILAPLACIAN && vec && ctx->npc == 3)),
+  AFB_REQUIRE(ctx->npc == ctx->dim + 1 && ((op == AFB_OP_POISSON && !vec) || (op == AFB_OP_ELASTICITY && vec) || (op == AFB_OP_BILAPLACIAN && vec && ctx->npc == 3)),
               AFB_ERR_UNSUPPORTED,
               "AFB_VARIANT_TILED_GATHER is not available for operator %d on %d-node cells (P1 Poisson, P1 elasticity, Tri3 bilaplacian only); use AFB_VARIANT_NODEWISE", op, ctx->npc);
   TilePlan& P = ctx->plan;

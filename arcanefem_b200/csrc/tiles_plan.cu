@@ -750,7 +750,7 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static bool tiled_cells_supported(const afb_ctx* ctx) { return ctx->npc == 3 || ctx->npc == 4; }
+static bool tiled_cells_supported(const afb_ctx* ctx) { return ctx->npc == ctx->dim + 1; } // P1 simplices (4 nodes in 2-D is a quadrilateral)
 
 template <class F> static int launch_by_npc(int npc, F f)
 {

@@ -262,6 +262,24 @@ def box_mesh(dim: int, n: int, jitter: float = 0.2, seed: int = 12345) -> Mesh:
     return Mesh(dim=dim, coords=coords, cells=np.ascontiguousarray(cells.astype(np.int32)), node_uid=ids, groups=groups)
 
 
+def box_mesh_q1(dim: int, n: int, jitter: float = 0.2, seed: int = 12345) -> Mesh:
+    """The same jittered node grid as box_mesh, cut in n^dim Q1 cells: Quad4 (counter-clockwise) in 2-D, Hexa8 in 3-D (bottom face
+    counter-clockwise, then the top face: the node order of the reference's shape functions, femutils/ShapeFunctions.h:123-129,
+    :314-346)."""
+    base = box_mesh(dim, n, jitter, seed)
+    m = n + 1
+    if dim == 2:
+        cj, ci = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        v = (ci + m * cj).ravel()
+        cells = np.stack([v, v + 1, v + 1 + m, v + m], axis=1)
+    else:
+        ck, cj, ci = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+        v = (ci + m * (cj + m * ck)).ravel()
+        mm = m * m
+        cells = np.stack([v, v + 1, v + 1 + m, v + m, v + mm, v + 1 + mm, v + 1 + m + mm, v + m + mm], axis=1)
+    return Mesh(dim=dim, coords=base.coords, cells=np.ascontiguousarray(cells.astype(np.int32)), node_uid=base.node_uid, groups=base.groups)
+
+
 def to_p2(mesh: Mesh) -> Mesh:
     """P1 simplex mesh -> P2 (Tri6/Tet10): one node per edge, ids appended after the
     vertex ids in ascending (min,max) vertex-pair order; mid-edge coordinates are the

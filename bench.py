@@ -787,6 +787,7 @@ def run_b200(args):
             "check": check,
             "e2e": {"value": cells_all * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sm[6]), "d2h_bytes_per_step": int(sm[7]),
                     "steps": e2e_steps, "variant": VARIANT_NAMES[variant],
+                    "pcie_gbs_all_ranks": (float(sm[6]) + float(sm[7])) * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                     "pipelined": f"{nl} lanes (contexts / streams / host threads) out of phase: one lane's H2D overlaps another's D2H and kernels" if e2e_pipelined else "no (one step at a time)",
                     "one_step_at_a_time_value": cells_all * e2e_steps / (float(mx[10]) * 1e-3),
                     "what": "time loop on a resident mesh, as the reference's benchmark re-assembles the same mesh: afb_update_coordinates(host, pinned) + afb_build_pattern + "

@@ -6,7 +6,7 @@
 //   AFB_HAVE_PETSC   PetscDoFLinearSystemImpl's COO hand-off (femutils/PetscDoFLinearSystem.cc:329-345,398):
 //                    MatSetPreallocationCOOLocal(nnz, coo_rows, coo_cols) + MatSetValuesCOO(values, INSERT_VALUES)
 // Include HYPRE.h + HYPRE_IJ_mv.h / petscmat.h BEFORE this header (tests/cpp/mock_solvers.h provides the same names for the
-// image without the libraries and records the arguments, so the argument layout is tested on the GPU against the oracle).
+// image without the libraries and records the arguments, so the argument layout is checked on the GPU by the test-suite).
 // HYPRE_Int / HYPRE_BigInt / PetscInt must be 32-bit, as the reference assumes when it passes its Int32 arrays (:501-514).
 #pragma once
 

@@ -410,6 +410,89 @@ static void ke_tet10_poisson(const r3* m, double* K)
   }
 }
 
+
+/* ---------------------------------------------------------------------------
+ * Q1 quadrilateral / hexahedron, Poisson (modules/poisson/ElementMatrixHexQuad.h:33-66, :159-195):
+ * 2x2 (2x2x2) Gauss points at +-1/sqrt(3), weights 1; at every point the reference gradients
+ * (femutils/ShapeFunctions.h:123-129, :314-346), the Jacobian J = sum_a dN_a (x) x_a, its determinant and
+ * inverse (femutils/ArcaneFemFunctionsGpu.h:296-349, :554-586), physical gradients, and
+ *   ae += (dxU ^ dxU) * w + (dyU ^ dyU) * w (+ (dzU ^ dzU) * w),  w = detJ.
+ * ------------------------------------------------------------------------- */
+static void ke_quad4_poisson(const r3* m, double* K)
+{
+  const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+  for (int i = 0; i < 16; ++i) K[i] = 0.0;
+  for (int ixi = 0; ixi < 2; ++ixi)
+    for (int ieta = 0; ieta < 2; ++ieta) {
+      const double xi = gp[ixi], eta = gp[ieta];
+      const double dxi[4] = { -0.25 * (1.0 - eta), 0.25 * (1.0 - eta), 0.25 * (1.0 + eta), -0.25 * (1.0 + eta) };
+      const double det_[4] = { -0.25 * (1.0 - xi), -0.25 * (1.0 + xi), 0.25 * (1.0 + xi), 0.25 * (1.0 - xi) };
+      double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
+      for (int a = 0; a < 4; ++a) {
+        J00 += dxi[a] * m[a].x;
+        J01 += dxi[a] * m[a].y;
+        J10 += det_[a] * m[a].x;
+        J11 += det_[a] * m[a].y;
+      }
+      const double detJ = J00 * J11 - J01 * J10;
+      const double i00 = J11 / detJ, i01 = -J01 / detJ, i10 = -J10 / detJ, i11 = J00 / detJ;
+      double dx[4], dy[4];
+      for (int a = 0; a < 4; ++a) {
+        dx[a] = i00 * dxi[a] + i01 * det_[a];
+        dy[a] = i10 * dxi[a] + i11 * det_[a];
+      }
+      const double w = detJ * 1.0 * 1.0;
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) K[a * 4 + b] += (dx[a] * dx[b]) * w + (dy[a] * dy[b]) * w;
+    }
+}
+
+static void ke_hexa8_poisson(const r3* m, double* K)
+{
+  const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+  static const double sx[8] = { -1, 1, 1, -1, -1, 1, 1, -1 }, sy[8] = { -1, -1, 1, 1, -1, -1, 1, 1 }, sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+  for (int i = 0; i < 64; ++i) K[i] = 0.0;
+  for (int ixi = 0; ixi < 2; ++ixi)
+    for (int ieta = 0; ieta < 2; ++ieta)
+      for (int izeta = 0; izeta < 2; ++izeta) {
+        const double xi = gp[ixi], eta = gp[ieta], zeta = gp[izeta];
+        double dxi[8], det_[8], dze[8];
+        for (int a = 0; a < 8; ++a) { /* femutils/ShapeFunctions.h:317-346: +-0.125 (1 +- eta)(1 +- zeta) ... */
+          dxi[a] = sx[a] * 0.125 * (1.0 + sy[a] * eta) * (1.0 + sz[a] * zeta);
+          det_[a] = sy[a] * 0.125 * (1.0 + sx[a] * xi) * (1.0 + sz[a] * zeta);
+          dze[a] = sz[a] * 0.125 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta);
+        }
+        double J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+        for (int a = 0; a < 8; ++a) {
+          J[0][0] += dxi[a] * m[a].x; J[0][1] += dxi[a] * m[a].y; J[0][2] += dxi[a] * m[a].z;
+          J[1][0] += det_[a] * m[a].x; J[1][1] += det_[a] * m[a].y; J[1][2] += det_[a] * m[a].z;
+          J[2][0] += dze[a] * m[a].x; J[2][1] += dze[a] * m[a].y; J[2][2] += dze[a] * m[a].z;
+        }
+        const double detJ = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                            J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        double inv[3][3]; /* adjugate / det (Arcane math::inverseMatrix) */
+        inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / detJ;
+        inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / detJ;
+        inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / detJ;
+        inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / detJ;
+        inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / detJ;
+        inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / detJ;
+        inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / detJ;
+        inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / detJ;
+        inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / detJ;
+        double dx[8], dy[8], dz[8];
+        for (int a = 0; a < 8; ++a) {
+          dx[a] = inv[0][0] * dxi[a] + inv[0][1] * det_[a] + inv[0][2] * dze[a];
+          dy[a] = inv[1][0] * dxi[a] + inv[1][1] * det_[a] + inv[1][2] * dze[a];
+          dz[a] = inv[2][0] * dxi[a] + inv[2][1] * det_[a] + inv[2][2] * dze[a];
+        }
+        const double w = detJ * 1.0 * 1.0;
+        for (int a = 0; a < 8; ++a)
+          for (int b = 0; b < 8; ++b) K[a * 8 + b] += (dx[a] * dx[b]) * w + (dy[a] * dy[b]) * w + (dz[a] * dz[b]) * w;
+      }
+}
+
+
 /* ------------------------------------------------------------------------- */
 /* Element-matrix dispatcher: K is (npc*b) x (npc*b), row-major.              */
 /* params: ELASTICITY -> {lambda, mu}                                         */
@@ -453,6 +536,8 @@ static int element_matrix(int npc, int dim, int op, int form, const double* para
       }
       return 0;
     }
+    if (npc == 4 && dim == 2) { ke_quad4_poisson(m, K); return 0; }
+    if (npc == 8 && dim == 3) { ke_hexa8_poisson(m, K); return 0; }
     if (npc == 6 && dim == 2) { ke_tri6_poisson(m, K); return 0; }
     if (npc == 10 && dim == 3) { ke_tet10_poisson(m, K); return 0; }
     return -1;

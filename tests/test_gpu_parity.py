@@ -1017,3 +1017,32 @@ def test_unaligned_device_connectivity_is_rejected(exec_ctx):
     shifted = flat[1:].view(-1, 4)  # 4 bytes off a 16-byte boundary
     with pytest.raises(A.AfbError, match="aligned"):
         exec_ctx.set_mesh(3, xyz, shifted, mem_space=A.MEM_DEVICE)
+
+
+# ---------------------------------------------------------------------------------------------
+# Q1 cells: Quad4 / Hexa8 Poisson (modules/poisson/ElementMatrixHexQuad.h) with their all-pairs sparsity
+# (femutils/BSRFormat.cc:284-338: edges + face / body diagonals of every cell)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,n", [(2, 13), (3, 6)], ids=["quad4", "hexa8"])
+@pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_COO, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC),
+                                         (A.FORMAT_BSR, A.VARIANT_NODEWISE)], ids=["csr-gpu", "coo-gpu", "bsr", "af-bsr"])
+def test_q1_poisson_values(exec_ctx, dim, n, fmt, variant):
+    c = exec_ctx
+    m = M.box_mesh_q1(dim, n)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    nbr, nnz = c.build_pattern(1)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    rows_ref, cols_ref = O.build_pattern(m.npc, m.nb_node, m.cells)
+    assert np.array_equal(rows, rows_ref) and np.array_equal(cols, cols_ref)
+    # interior rows: 9 (quad) / 27 (hexa) entries = the node, its edges and the face / body diagonals of its cells
+    assert np.diff(rows).max() == 3 ** dim
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=O.FORM_HOST, nodewise=variant == A.VARIANT_NODEWISE)
+    for rep in range(2):  # second round: steady-state BuildMatrix
+        c.build_pattern(1)
+        assert np.array_equal(c.to_host(A.ARRAY_ROWS), rows) and np.array_equal(c.to_host(A.ARRAY_COLUMNS), cols)
+        c.assemble(A.OP_POISSON, fmt=fmt, variant=variant)
+        row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows)
+    with pytest.raises(A.AfbError, match="P1"):
+        c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+    with pytest.raises(A.AfbError):
+        c.rhs_source(1.0)
