@@ -25,6 +25,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_SIGNED_TRI_AREA, FLAG_OWN_CELLS_ONLY, FLAG_ALL_ROWS = 1, 2, 4
 SPARSITY_AUTO, SPARSITY_FROM_CELLS, SPARSITY_FROM_CONNECTIVITY = 0, 1, 2
 TILED_EXEC_BRICKS, TILED_EXEC_CHAIN, TILED_EXEC_CHAIN_FLOW = 0, 1, 2
+VEC_EXEC_AUTO, VEC_EXEC_ROWS, VEC_EXEC_UNITS = 0, 1, 2
 NEUMANN_FLUX, NEUMANN_TRACTION = 0, 1
 ELIMINATE_ROW, ELIMINATE_ROW_COLUMN = 1, 2
 (ARRAY_ROWS, ARRAY_COLUMNS, ARRAY_VALUES, ARRAY_NZ_PER_ROW, ARRAY_RHS, ARRAY_COO_ROWS, ARRAY_CSR_ROWS, ARRAY_CSR_COLUMNS,
@@ -36,7 +37,7 @@ _ARRAY_DTYPE = {ARRAY_ROWS: np.int32, ARRAY_COLUMNS: np.int32, ARRAY_VALUES: np.
 
 EXPORTS = [
     "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_update_coordinates", "afb_set_own_cell_count", "afb_get_own_cell_count", "afb_renumber_columns", "afb_get_ij_arrays", "afb_memcpy_to_host", "afb_mesh_generate_box",
-    "afb_build_pattern", "afb_set_sparsity_algorithm", "afb_set_tiled_executor", "afb_set_tiled_stage_limit", "afb_options_from_name", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_assemble_rhs_neumann", "afb_set_dirichlet_nodes",
+    "afb_build_pattern", "afb_set_sparsity_algorithm", "afb_set_tiled_executor", "afb_set_vector_executor", "afb_set_tiled_stage_limit", "afb_options_from_name", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_assemble_rhs_neumann", "afb_set_dirichlet_nodes",
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
     "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail",
@@ -179,6 +180,10 @@ class Context:
     def set_sparsity_algorithm(self, algorithm):
         """SPARSITY_FROM_CELLS = computeSparsityAtomic, SPARSITY_FROM_CONNECTIVITY = computeSparsityAtomicFree (re-builds on an unchanged mesh)."""
         _check(lib().afb_set_sparsity_algorithm(self._h, int(algorithm)))
+
+    def set_vector_executor(self, executor):
+        """VEC_EXEC_AUTO (default: rows on Tet4, units on Tri3), VEC_EXEC_ROWS, VEC_EXEC_UNITS: how VARIANT_TILED_GATHER runs for elasticity."""
+        _check(lib().afb_set_vector_executor(self._h, int(executor)))
 
     def set_tiled_executor(self, executor):
         """TILED_EXEC_BRICKS (default), TILED_EXEC_CHAIN, TILED_EXEC_CHAIN_FLOW: how VARIANT_TILED_GATHER runs for b = 1."""

@@ -108,6 +108,7 @@ int afb_create(int device, afb_ctx** out)
   AFB_CUDA(cudaEventCreateWithFlags(&ctx->check_event, cudaEventDisableTiming));
   AFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin_check), 2 * sizeof(int32_t), cudaHostAllocMapped));
   AFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->pin_check_dev), ctx->pin_check, 0));
+  if (const char* ex = getenv("AFB_VEC_EXEC")) ctx->vec_exec = !strcmp(ex, "units") ? AFB_VEC_EXEC_UNITS : !strcmp(ex, "rows") ? AFB_VEC_EXEC_ROWS : AFB_VEC_EXEC_AUTO; // afb_set_vector_executor
   if (const char* ex = getenv("AFB_TILED_EXEC")) { // default executor of the scalar tiled gather (afb_set_tiled_executor)
     if (!strcmp(ex, "chain")) ctx->tiled_exec = AFB_TILED_EXEC_CHAIN;
     else if (!strcmp(ex, "flow")) ctx->tiled_exec = AFB_TILED_EXEC_CHAIN_FLOW;
@@ -189,6 +190,14 @@ int afb_set_tiled_executor(afb_ctx* ctx, int executor)
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(executor >= AFB_TILED_EXEC_BRICKS && executor <= AFB_TILED_EXEC_CHAIN_FLOW, AFB_ERR_INVALID, "afb_set_tiled_executor: unknown executor %d", executor);
   ctx->tiled_exec = executor;
+  return AFB_OK;
+}
+
+int afb_set_vector_executor(afb_ctx* ctx, int executor)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(executor >= AFB_VEC_EXEC_AUTO && executor <= AFB_VEC_EXEC_UNITS, AFB_ERR_INVALID, "afb_set_vector_executor: unknown executor %d", executor);
+  ctx->vec_exec = executor;
   return AFB_OK;
 }
 

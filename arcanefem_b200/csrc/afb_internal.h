@@ -83,7 +83,7 @@ struct TilePlan {
   // ---- mesh tiling ----
   bool mesh_valid = false;
   uint64_t mesh_gen = ~0ull;
-  int mesh_b_class = 0;        // 0: scalar limits (TG_CMAX), 1: vector limits (TV_CMAX)
+  int mesh_b_class = 0;        // 0: scalar limits (TG_CMAX), 1: vector limits (TV_CMAX), 2: row-ordered vector executor (VR_CMAX)
   int32_t nb_tile = 0;
   int max_rows = 0;
   int64_t nb_tile_cell = 0, nb_foot = 0, nb_inc = 0, nb_entry = 0;
@@ -108,13 +108,14 @@ struct TilePlan {
   // ---- value plan ----
   bool lists_valid = false;
   uint64_t lists_mesh_gen = ~0ull;
-  int lists_b = 0, lists_mode = 0;
+  int lists_b = 0, lists_mode = 0, lists_kind = 0; // kind 0: units of equally long lists (+ mirrors); 1: row-ordered units (vr_units)
   int64_t nb_unit = 0, nb_list = 0;
   DevBuf rowinfo;     // uint32 per tile row: first entry | diagonal position << 16 | owned << 31
   DevBuf unit_base;   // uint32 per unit: offset (16-bit slots) of the unit's index slab inside the tile's list region
   DevBuf unit_len;    // uint16 per unit: contributions per entry of the unit (even)
   DevBuf emap;        // uint32 per (unit, lane): tile-local entry | mirror entry << 16; 0xFFFFFFFF = padding lane
   DevBuf emap_rows;   // uint32 per (unit, lane), vector plans only: tile row of the entry | tile row of the mirror << 16
+  DevBuf vr_units;    // uint2 per unit of a row-ordered plan (tiles.cuh: vr_pack_unit)
   DevBuf lists;       // uint16: cache indices, per unit [len/2][32 lanes][2]; one contiguous region per tile (TMA bulk copy)
   DevBuf col_scratch; // int32[nb_entry]: columns in tile order between the two BuildMatrix passes (pattern_tiled.cu)
   DevBuf scratch_a, scratch_b, scratch_c, stats; // builder scratch
@@ -180,6 +181,8 @@ struct afb_ctx {
   bool check_pending = false;
   int sparsity_algo = 0;            // AFB_SPARSITY_*
   int tiled_exec = 0;               // AFB_TILED_EXEC_*
+  int vec_exec = 0;                 // AFB_VEC_EXEC_* (afb_set_vector_executor)
+  bool vec_rows() const { return vec_exec == 1 /*ROWS*/ || (vec_exec == 0 /*AUTO*/ && npc == 4); }
   int64_t tiled_stage_limit = 1ll << 40; // afb_set_tiled_stage_limit
   void* p2p = nullptr;              // afb::P2PState (p2p.cu): ghost-row exchange over NVLink peer memory
   void* chain = nullptr;            // afb::ChainPlan (chain_plan.cu): plan of the scalar tiled-gather executor
@@ -213,8 +216,9 @@ int pattern_rows_fused(afb_ctx* ctx, int* exceeded, int32_t* nnz_out);
 int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, int variant, int layout, int flags);
 
 // ---- tiles_plan.cu / tiles_exec.cu / pattern_tiled.cu ----------------------------------------
-int build_tile_mesh(afb_ctx* ctx);
+int build_tile_mesh(afb_ctx* ctx, int cls = -1); // cls: TilePlan::mesh_b_class wanted (-1: from the context)
 int build_tile_lists(afb_ctx* ctx, int mode_flags);
+int build_tile_rowlists(afb_ctx* ctx, int mode_flags);
 int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int flags);
 bool pattern_tiled_ready(const afb_ctx* ctx);
 int rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* faces_dev, int kind, int nb_value, const double* values, int skip_dirichlet);

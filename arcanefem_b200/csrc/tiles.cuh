@@ -62,6 +62,40 @@ constexpr int TV_RT3 = AFB_TV_RT3 > 8 ? AFB_TV_RT3 : 8; // target rows per tile 
 #endif
 constexpr int TV_RT2 = AFB_TV_RT2;         // target rows per tile of the vector executor in 2-D (measured: 224 / 288 / 352 -> 2.23 / 2.39 / 2.20 ms at C5)
 
+// row-ordered vector executor (elasticity): lanes = consecutive entries of whole rows, blocks staged per warp and written as
+// contiguous runs, the diagonal block derived from the row's off-diagonal blocks (zero block row sums)
+constexpr int VR_BSTRIDE3 = 9, VR_BSTRIDE2 = 5;      // doubles per staged block (odd: conflict-free half-warps)
+constexpr int VR_UMAX = TG_THREADS;                  // units per tile (one thread stages one unit record)
+constexpr int VR_FIXED = 3 * 8 * TG_FMAX + (TG_THREADS / 32) * 304 * 8 + 8 * TG_RMAX + 4 * (TG_RMAX + 1) + 8 * VR_UMAX + 2 * TG_EMAX + 4 * 64 + 64;
+constexpr int VR_CMAX_RAW = (TG_SMEM_LIMIT - VR_FIXED) / (8 * TV_PLANES) - 1;
+#ifndef AFB_VR_CS_MOD
+#define AFB_VR_CS_MOD 1
+#endif
+// cache plane stride: the largest value that fits with VR_CS % 16 == AFB_VR_CS_MOD (1: consecutive planes shift by one 8-byte
+// bank, so the gathers of different nodes of one cell never collide)
+constexpr int VR_CS_FIT = (VR_CMAX_RAW < 1023 ? VR_CMAX_RAW : 1023) + 1;
+constexpr int VR_CS = VR_CS_FIT - ((VR_CS_FIT - AFB_VR_CS_MOD) & 15);
+constexpr int VR_CMAX = VR_CS - 1;
+constexpr int VR_LC_BITS = 10;                       // list code = (a * 4 + b) << 10 | cache slot of the cell (a, b: nodes of the cell)
+constexpr unsigned VR_LC_MASK = (1u << VR_LC_BITS) - 1u;
+static_assert(VR_CS <= (1 << VR_LC_BITS), "cache slots must fit the list code");
+constexpr int VR_PSTRIDE3 = 99, VR_PSTRIDE2 = 66;    // per-row value layout: staged as [block row][entry][column], plane stride
+constexpr int VR_STAGE = 3 * VR_PSTRIDE3 + 7;        // doubles of staging per warp (>= 32 * VR_BSTRIDE3)
+#ifndef AFB_VR_RT3
+#define AFB_VR_RT3 80
+#endif
+#ifndef AFB_VR_RT2
+#define AFB_VR_RT2 320
+#endif
+constexpr int VR_RT3 = AFB_VR_RT3, VR_RT2 = AFB_VR_RT2;
+#ifndef AFB_VR_SLACK
+#define AFB_VR_SLACK 0
+#endif
+constexpr int VR_SLACK = AFB_VR_SLACK; // extra (padding) steps per unit: room for the plan to dodge shared-memory bank conflicts
+// unit record (uint2): x = first 16-bit slot of the unit's lists inside the tile's list region;
+// y = first tile-local entry | (entries - 1) << 12 | list length (contributions per lane, even) << 17
+__host__ __device__ __forceinline__ uint32_t vr_pack_unit(int first, int cnt, int len) { return (uint32_t)first | ((uint32_t)(cnt - 1) << 12) | ((uint32_t)len << 17); }
+
 struct TileDesc {
   int32_t node_off, nb_row;    // rows (node ids ascending) in tile_nodes / rowinfo
   int32_t cell_off, nb_cell;   // tile_cells / lconn

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "chain.cuh"
 #include "element.cuh"
@@ -95,6 +96,7 @@ struct TilePrefetch {
   uint32_t rowinfo;
   int32_t fidx, node;     // level-1 indices (footprint node, row node) of the tile after that
   uint32_t em[TG_UPW];    // entry map words of this warp's units (scalar executor)
+  uint2 unit;             // unit record `threadIdx.x` (row-ordered vector executor)
 };
 
 struct ExecArgs {
@@ -111,6 +113,7 @@ struct ExecArgs {
   const uint32_t* emap;
   const uint32_t* emap_rows; // vector plans only
   const uint16_t* lists;
+  const uint2* vr_units;     // row-ordered vector plans only
   double* values;
   int accumulate;
   int list_stage_max; // tiles with more 16-bit list slots read their lists from global memory (<= the staging buffer)
@@ -591,6 +594,299 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
 }
 
 // ---------------------------------------------------------------------------------------------
+// row-ordered vector executor (isotropic elasticity, b = DIM)
+//   Same cache as above (g_a = sqrt(s) grad phi_a per tile cell), different division of phase B: a unit is up to 32
+//   CONSECUTIVE entries of whole rows (tiles_plan.cu: k_tile_rowlists), one lane per entry, M = sum g_a (x) g_b in
+//   registers.  The blocks of a unit go to a per-warp staging buffer; the diagonal block is minus the sum of the row's
+//   other blocks (block row sums of the stiffness matrix are zero: sum_b g_b = 0 in every cell), so it needs neither a list
+//   nor the longest loop of the tile; then the warp writes the unit as a few contiguous runs (a row's blocks are
+//   contiguous in both value layouts).  No mirror writes, no per-entry maps.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+struct RowsSmem {
+  static constexpr int BS = DIM == 3 ? VR_BSTRIDE3 : VR_BSTRIDE2;
+  double G[TV_PLANES * VR_CS];
+  double cx[3 * TG_FMAX];
+  double stage[(TG_THREADS / 32) * VR_STAGE];
+  int2 rowtab[TG_RMAX];          // value offset of (row, entry e, block row i, column j) = x + EB * e + i * y + j
+  uint32_t rowinfo[TG_RMAX + 1]; // + sentinel (first entry = nb_entry)
+  uint2 units[VR_UMAX];
+  uint16_t erow_of[TG_EMAX];     // tile row of every entry
+  __align__(16) TileDesc desc[4];
+};
+static_assert(sizeof(RowsSmem<3>) <= TG_SMEM_LIMIT, "TG_MINB row-ordered executor CTAs must fit one SM");
+constexpr int VR_ROUNDS = (VR_CMAX + TG_THREADS - 1) / TG_THREADS;
+static_assert(VR_ROUNDS <= TG_PF_ROUNDS, "prefetch registers");
+
+template <int ROUNDS>
+__device__ __forceinline__ void prefetch_rows_level2(const TileDesc& d, const ExecArgs& A, TilePrefetch& pf)
+{
+  if ((int)threadIdx.x < d.nb_foot) {
+    const double* p = A.coords + 3 * (int64_t)pf.fidx;
+    pf.c0 = __ldg(p);
+    pf.c1 = __ldg(p + 1);
+    pf.c2 = __ldg(p + 2);
+  }
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int lc = min(r * TG_THREADS + (int)threadIdx.x, d.nb_cell - 1);
+    if (d.nb_cell > 0) pf.ln[r] = __ldg(reinterpret_cast<const uint2*>(A.lconn) + d.cell_off + lc);
+  }
+  if ((int)threadIdx.x < d.nb_unit) pf.unit = __ldg(A.vr_units + d.unit_off + threadIdx.x);
+  if ((int)threadIdx.x < d.nb_row) {
+    pf.rowbeg = __ldg(A.rows + pf.node);
+    pf.rowinfo = __ldg(A.rowinfo + d.node_off + threadIdx.x);
+  }
+}
+
+template <int NPC, int LAYOUT>
+__global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_rows_vec(ExecArgs A, ElemParams prm)
+{
+  constexpr int DIM = NPC - 1, B = DIM, BB = B * B, BS = RowsSmem<DIM>::BS;
+  extern __shared__ __align__(16) unsigned char ex_raw[];
+  RowsSmem<DIM>& S = *reinterpret_cast<RowsSmem<DIM>*>(ex_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = TG_THREADS / 32;
+  constexpr int DW = sizeof(TileDesc) / 4;
+  int32_t t = blockIdx.x;
+  if (threadIdx.x < TV_PLANES) S.G[threadIdx.x * VR_CS + VR_CS - 1] = 0.0; // zero slot of every plane (list padding)
+  if (threadIdx.x < 3 * DW) {
+    const int k = threadIdx.x / DW, w = threadIdx.x % DW;
+    const int64_t tt = (int64_t)t + (int64_t)k * gridDim.x;
+    if (tt < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[k])[w] = __ldg(reinterpret_cast<const int32_t*>(A.desc + tt) + w);
+  }
+  __syncthreads();
+  int slot = 0;
+  TilePrefetch pf;
+  if (t < A.nb_tile) {
+    prefetch_level1(S.desc[0], A, pf);
+    prefetch_rows_level2<VR_ROUNDS>(S.desc[0], A, pf);
+    if ((int64_t)t + gridDim.x < A.nb_tile) prefetch_level1(S.desc[1], A, pf);
+  }
+  const double lam = prm.p0, mu = prm.p1;
+  double* const stg = S.stage + warp * VR_STAGE;
+  while (t < A.nb_tile) {
+    const TileDesc d = S.desc[slot];
+    if ((int)threadIdx.x < d.nb_foot) {
+      S.cx[3 * threadIdx.x] = pf.c0;
+      S.cx[3 * threadIdx.x + 1] = pf.c1;
+      S.cx[3 * threadIdx.x + 2] = pf.c2;
+    }
+    if ((int)threadIdx.x < d.nb_unit) S.units[threadIdx.x] = pf.unit;
+    if ((int)threadIdx.x < d.nb_row) S.rowinfo[threadIdx.x] = pf.rowinfo;
+    else if ((int)threadIdx.x == d.nb_row) S.rowinfo[threadIdx.x] = pack_rowinfo(d.nb_entry, 0, false);
+    __syncthreads();
+    // the next tile's contribution lists start their way from DRAM to L2 now (one bulk prefetch): phase B reads them from L2
+    if (threadIdx.x == 0 && (int64_t)t + gridDim.x < A.nb_tile) {
+      const TileDesc& dn = S.desc[(slot + 1) & 3];
+      if (dn.list_len > 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.lists + dn.list_off), "r"((uint32_t)dn.list_len * 2u) : "memory");
+    }
+    // ---- phase A: g_a = sqrt(s) * cofactor gradients ----
+#pragma unroll
+    for (int r = 0; r < VR_ROUNDS; ++r) {
+      const int lc = r * TG_THREADS + threadIdx.x;
+      if (lc < d.nb_cell) {
+        const uint2 ln = pf.ln[r];
+        if constexpr (NPC == 4) {
+          const double* p0 = S.cx + 3 * (ln.x & 0xFFFFu);
+          const double* p1 = S.cx + 3 * (ln.x >> 16);
+          const double* p2 = S.cx + 3 * (ln.y & 0xFFFFu);
+          const double* p3 = S.cx + 3 * (ln.y >> 16);
+          Tet4Geom g;
+          g.init_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+          const double q = sqrt(g.s);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) S.G[(a * 3 + k) * VR_CS + lc] = g.c[a][k] * q;
+        }
+        else {
+          const double* p0 = S.cx + 3 * (ln.x & 0xFFFFu);
+          const double* p1 = S.cx + 3 * (ln.x >> 16);
+          const double* p2 = S.cx + 3 * (ln.y & 0xFFFFu);
+          Tri3Geom g;
+          g.init_xy(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], false);
+          const double q = sqrt(g.s);
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) S.G[(a * 2 + k) * VR_CS + lc] = g.c[a][k] * q;
+        }
+      }
+    }
+    // row tables (thread per row): where the row's values live, and the row of each of its entries
+    if ((int)threadIdx.x < d.nb_row) {
+      const int e0 = rowinfo_erow(pf.rowinfo), nz = rowinfo_erow(S.rowinfo[threadIdx.x + 1]) - e0;
+      if constexpr (LAYOUT == AFB_LAYOUT_PER_BLOCK) S.rowtab[threadIdx.x] = make_int2(BB * (pf.rowbeg - e0), B);
+      else S.rowtab[threadIdx.x] = make_int2(BB * pf.rowbeg - B * e0, B * nz);
+      for (int x = 0; x < nz; ++x) S.erow_of[e0 + x] = (uint16_t)threadIdx.x;
+    }
+    const int64_t tn = (int64_t)t + gridDim.x, tnn = tn + gridDim.x, tnnn = tnn + gridDim.x;
+    const int nslot = (slot + 1) & 3, nnslot = (slot + 2) & 3, nnnslot = (slot + 3) & 3;
+    if (tn < A.nb_tile) prefetch_rows_level2<VR_ROUNDS>(S.desc[nslot], A, pf);
+    if (tnn < A.nb_tile) prefetch_level1(S.desc[nnslot], A, pf);
+    int32_t desc_word = 0;
+    if (threadIdx.x < DW && tnnn < A.nb_tile) desc_word = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnnn) + threadIdx.x);
+    __syncthreads();
+    // ---- phase B: one lane per entry of the unit ----
+    // staged block of lane el, element (i, j): per-block layout [entry][i][j] (stride BS, odd); per-row layout [i][entry][j]
+    // (plane stride PS): either way the write-out below reads consecutive words
+    constexpr int PS = DIM == 3 ? VR_PSTRIDE3 : VR_PSTRIDE2;
+    auto sidx = [](int el, int i, int j) { return LAYOUT == AFB_LAYOUT_PER_BLOCK ? el * BS + i * B + j : i * PS + el * B + j; };
+    const uint32_t* l32 = reinterpret_cast<const uint32_t*>(A.lists + d.list_off);
+    constexpr int LW = 4; // list words (2 contributions each) held in registers per unit; longer lists continue from memory
+    uint32_t wq[LW];
+    uint2 U = make_uint2(0u, 0u);
+    auto fetch = [&](int u) {
+      if (u < d.nb_unit) {
+        U = S.units[u];
+        const uint32_t* l = l32 + (U.x >> 1) + lane;
+        const int len2 = (int)(U.y >> 18);
+#pragma unroll
+        for (int k = 0; k < LW; ++k) wq[k] = k < len2 ? __ldg(l + k * 32) : (uint32_t)(VR_CS - 1) * 0x10001u;
+      }
+    };
+    fetch(warp);
+    for (int u = warp; u < d.nb_unit; u += NW) {
+      const int first = (int)(U.y & 0xFFFu), cnt = (int)((U.y >> 12) & 31u) + 1, len2 = (int)(U.y >> 18);
+      const uint32_t* l = l32 + (U.x >> 1) + lane;
+      uint32_t wc[LW];
+#pragma unroll
+      for (int k = 0; k < LW; ++k) wc[k] = wq[k];
+      fetch(u + NW); // the next unit's words travel while this one is summed
+      // where this lane's entry goes (read back through shuffles by the write-out)
+      int my_base = 0, my_y = 0;
+      if (lane < cnt) {
+        const int2 T = S.rowtab[S.erow_of[first + lane]];
+        my_base = T.x + (LAYOUT == AFB_LAYOUT_PER_BLOCK ? BB : B) * (first + lane);
+        my_y = T.y;
+      }
+      double M[DIM][DIM];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) M[i][j] = 0.0;
+      auto add2 = [&](uint32_t w) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t code = h ? (w >> 16) : (w & 0xFFFFu);
+          const uint32_t lc = code & VR_LC_MASK, a = code >> (VR_LC_BITS + 2), b = (code >> VR_LC_BITS) & 3u;
+          const double* pa = S.G + (a * (DIM * VR_CS) + lc);
+          const double* pb = S.G + (b * (DIM * VR_CS) + lc);
+          double ga[DIM], gb[DIM];
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) {
+            ga[i] = pa[i * VR_CS];
+            gb[i] = pb[i * VR_CS];
+          }
+#pragma unroll
+          for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) M[i][j] = fma(ga[i], gb[j], M[i][j]);
+        }
+      };
+      if (len2 <= LW) {
+#pragma unroll
+        for (int k = 0; k < LW; ++k)
+          if (k < len2) add2(wc[k]);
+      }
+      else {
+#pragma unroll
+        for (int k = 0; k < LW; ++k) add2(wc[k]);
+        for (int k = LW; k < len2; ++k) add2(__ldg(l + k * 32));
+      }
+      {
+        double tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) tr += M[i][i];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+          for (int j = 0; j < DIM; ++j) stg[sidx(lane, i, j)] = lam * M[i][j] + mu * M[j][i] + (i == j ? mu * tr : 0.0);
+      }
+      __syncwarp();
+      // diagonal blocks of the rows that lie wholly inside the unit: minus the sum of the row's other blocks (zero block row
+      // sums; the diagonal's own slot was staged as zero, so the whole row is summed).  The block is symmetric: its upper
+      // triangle is summed and mirrored.  Lanes: NS components x 2 halves of the row x RPP rows per pass.
+      {
+        constexpr int NS = B * (B + 1) / 2, RPP = (32 / NS) / 2;
+        const int r0 = S.erow_of[first], r1 = S.erow_of[first + cnt - 1];
+        const int g = lane / NS, c = lane - g * NS, q = g >> 1, h = g & 1;
+        const int ci = B == 3 ? (c < 3 ? 0 : (c < 5 ? 1 : 2)) : (c < 2 ? 0 : 1), cj = B == 3 ? (c < 3 ? c : (c < 5 ? c - 2 : 2)) : (c < 2 ? c : 1);
+        constexpr int XS = LAYOUT == AFB_LAYOUT_PER_BLOCK ? BS : B; // stride between the entries of a row
+        for (int rb = r0; rb <= r1; rb += RPP) {
+          const int rr = rb + q;
+          double sum = 0.0;
+          int dslot = -1;
+          if (g < 2 * RPP && rr <= r1) {
+            const uint32_t ri = S.rowinfo[rr];
+            const int e0 = rowinfo_erow(ri), nz = rowinfo_erow(S.rowinfo[rr + 1]) - e0;
+            if (nz <= 32) {
+              const int half = (nz + 1) >> 1, xe = h ? nz : half;
+              const double* src = stg + sidx(e0 - first, ci, cj);
+              double s0 = 0.0, s1 = 0.0;
+              int x = h ? half : 0;
+              for (; x + 1 < xe; x += 2) {
+                s0 += src[x * XS];
+                s1 += src[(x + 1) * XS];
+              }
+              if (x < xe) s0 += src[x * XS];
+              sum = s0 + s1;
+              dslot = e0 - first + rowinfo_pdiag(ri);
+            }
+          }
+          const double other = __shfl_down_sync(0xffffffffu, sum, NS); // the second half of the row sits NS lanes above
+          __syncwarp();
+          if (h == 0 && dslot >= 0) {
+            const double v = -(sum + other);
+            stg[sidx(dslot, ci, cj)] = v;
+            if (ci != cj) stg[sidx(dslot, cj, ci)] = v;
+          }
+        }
+      }
+      __syncwarp();
+      // write-out: contiguous runs
+      auto put = [&](auto acc) {
+        constexpr bool ACC = decltype(acc)::value;
+        if constexpr (LAYOUT == AFB_LAYOUT_PER_BLOCK) {
+          for (int x0 = 0; x0 < cnt * BB; x0 += 32) {
+            const int x = x0 + lane, el = x / BB, c = x - el * BB;
+            const int base = __shfl_sync(0xffffffffu, my_base, el & 31);
+            if (x < cnt * BB) {
+              double* dst = A.values + ((int64_t)base + c);
+              const double v = stg[el * BS + c];
+              if (ACC) *dst += v; else *dst = v;
+            }
+          }
+        }
+        else {
+          for (int x0 = 0; x0 < cnt * B; x0 += 32) {
+            const int x = x0 + lane, el = x / B, j = x - el * B;
+            const int base = __shfl_sync(0xffffffffu, my_base, el & 31), ys = __shfl_sync(0xffffffffu, my_y, el & 31);
+            if (x < cnt * B) {
+              double* dst = A.values + ((int64_t)base + j);
+#pragma unroll
+              for (int i = 0; i < B; ++i) {
+                const double v = stg[i * PS + x];
+                if (ACC) dst[i * ys] += v; else dst[i * ys] = v;
+              }
+            }
+          }
+        }
+      };
+      if (A.accumulate) put(std::true_type()); else put(std::false_type());
+      __syncwarp();
+    }
+    if (threadIdx.x < DW && tnnn < A.nb_tile) reinterpret_cast<int32_t*>(&S.desc[nnnslot])[threadIdx.x] = desc_word;
+    __syncthreads();
+    t = (int32_t)tn;
+    slot = nslot;
+    if (tn >= A.nb_tile) break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 int ensure_values_zeroed(afb_ctx* ctx)
@@ -617,8 +913,11 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
     prm.flags = flags;
     return chain_assemble(ctx, prm, flags, (ctx->assembled || ctx->values_touched) ? 1 : 0);
   }
-  if (!P.mesh_valid || P.mesh_gen != ctx->mesh_gen || P.mesh_b_class != (vec ? 1 : 0)) AFB_TRY(build_tile_mesh(ctx));
-  if (!P.lists_valid || P.lists_mesh_gen != ctx->mesh_gen || P.lists_b != ctx->b || P.lists_mode != mode) AFB_TRY(build_tile_lists(ctx, mode));
+  const bool rows_exec = vec && op == AFB_OP_ELASTICITY && ctx->vec_rows(); // row-ordered units (k_assemble_rows_vec)
+  const int cls = !vec ? 0 : (rows_exec ? 2 : 1);
+  if (!P.mesh_valid || P.mesh_gen != ctx->mesh_gen || P.mesh_b_class != cls) AFB_TRY(build_tile_mesh(ctx, cls));
+  if (!P.lists_valid || P.lists_mesh_gen != ctx->mesh_gen || P.lists_b != ctx->b || P.lists_mode != mode || P.lists_kind != (rows_exec ? 1 : 0))
+    AFB_TRY(rows_exec ? build_tile_rowlists(ctx, mode) : build_tile_lists(ctx, mode));
   ElemParams prm;
   prm.p0 = params ? params[0] : 0.0;
   prm.p1 = params ? params[1] : 0.0;
@@ -645,6 +944,7 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   A.emap = P.emap.as<uint32_t>();
   A.emap_rows = vec ? P.emap_rows.as<uint32_t>() : nullptr;
   A.lists = P.lists.as<uint16_t>();
+  A.vr_units = rows_exec ? P.vr_units.as<uint2>() : nullptr;
   A.values = ctx->values.as<double>();
   A.accumulate = accumulate;
   A.list_stage_max = (int)std::min<int64_t>(vec ? TV_LMAX : TG_LMAX, ctx->tiled_stage_limit / 2);
@@ -657,6 +957,10 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   };
   cudaError_t e;
   if (!vec) e = ctx->npc == 4 ? go(k_assemble_tiled<4>, sizeof(ExecSmem)) : go(k_assemble_tiled<3>, sizeof(ExecSmem));
+  else if (rows_exec && ctx->npc == 4)
+    e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_rows_vec<4, AFB_LAYOUT_PER_BLOCK>, sizeof(RowsSmem<3>)) : go(k_assemble_rows_vec<4, AFB_LAYOUT_PER_ROW>, sizeof(RowsSmem<3>));
+  else if (rows_exec)
+    e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_rows_vec<3, AFB_LAYOUT_PER_BLOCK>, sizeof(RowsSmem<2>)) : go(k_assemble_rows_vec<3, AFB_LAYOUT_PER_ROW>, sizeof(RowsSmem<2>));
   else if (ctx->npc == 4)
     e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_tiled_vec<4, AFB_LAYOUT_PER_BLOCK>, sizeof(VecSmem<3>)) : go(k_assemble_tiled_vec<4, AFB_LAYOUT_PER_ROW>, sizeof(VecSmem<3>));
   else if (op == AFB_OP_BILAPLACIAN)

@@ -748,6 +748,258 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// value plan of the row-ordered vector executor (k_assemble_rows_vec)
+//   entries in tile order (row by row, columns ascending); a unit = up to 32 consecutive entries made of whole rows (a
+//   row longer than 32 entries is cut into units of its own); every off-diagonal entry carries the list of its cells
+//   (both orientations of a pair are computed: no mirror writes, so a unit's output is a few contiguous runs); the
+//   diagonal block is derived from the row's blocks (zero block row sums) unless the row was cut, then it has a list.
+//   FILL = false: only the sizes (desc.nb_unit, desc.list_len) -- the host turns them into offsets.
+// ---------------------------------------------------------------------------------------------
+struct RowListSmem {
+  int erow[TG_RMAX + 1];
+  int cnt[TG_EMAX];
+  int eoff[TG_EMAX + 1];
+  uint16_t clist[16 * TG_CMAX];
+  int ufirst[VR_UMAX + 1], ucnt[VR_UMAX + 1], ubase[VR_UMAX + 2];
+  uint8_t own[TG_RMAX];
+  int tmp[40];
+};
+
+template <int NPC, bool FILL>
+__global__ void __launch_bounds__(TB_THREADS, 1)
+k_tile_rowlists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __restrict__ tnodes, const int32_t* __restrict__ tile_cells, const int32_t* __restrict__ conn,
+                const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, const int32_t* __restrict__ node_tile, const int32_t* __restrict__ node_lrow,
+                const uint8_t* __restrict__ is_own, int64_t nb_own_cell, uint32_t* __restrict__ rowinfo, uint2* __restrict__ units, uint16_t* __restrict__ lists,
+                int* __restrict__ error)
+{
+  extern __shared__ unsigned char tl_raw[];
+  RowListSmem& S = *reinterpret_cast<RowListSmem*>(tl_raw);
+  constexpr int CS = VR_CS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int32_t t = blockIdx.x; t < nb_tile; t += gridDim.x) {
+    const TileDesc d = desc[t];
+    const int R = d.nb_row, C = d.nb_cell;
+    for (int i = threadIdx.x; i <= R; i += blockDim.x) {
+      int deg = 0;
+      if (i < R) {
+        const int32_t r = tnodes[d.node_off + i];
+        deg = rows[r + 1] - rows[r];
+        S.own[i] = (!is_own || is_own[r]) ? 1 : 0;
+      }
+      S.erow[i] = deg;
+    }
+    __syncthreads();
+    const int E = smem_exclusive_scan(S.erow, R + 1, S.tmp);
+    if (E != d.nb_entry || E > TG_EMAX) {
+      if (threadIdx.x == 0) atomicExch(error, 1);
+      __syncthreads();
+      continue;
+    }
+    for (int e = threadIdx.x; e < E; e += blockDim.x) S.cnt[e] = 0;
+    // ---- row words: first entry, position of the diagonal, ownership ----
+    for (int i = warp; i < R; i += nwarp) {
+      const int32_t r = tnodes[d.node_off + i];
+      const int rb = rows[r], deg = rows[r + 1] - rb;
+      int pdiag = 0;
+      for (int p0 = 0; p0 < deg; p0 += 32) {
+        const int p = p0 + lane;
+        const unsigned hit = __ballot_sync(0xffffffffu, p < deg && cols[rb + p] == r);
+        if (hit) pdiag = p0 + __ffs(hit) - 1;
+      }
+      if (FILL && lane == 0) rowinfo[d.node_off + i] = pack_rowinfo(S.erow[i], pdiag, S.own[i] != 0);
+    }
+    __syncthreads();
+    // ---- contribution lists (count, scan, fill) ----
+    for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
+      for (int lc = threadIdx.x; lc < C; lc += blockDim.x) {
+        const int32_t cell = tile_cells[d.cell_off + lc];
+        if ((int64_t)cell >= nb_own_cell) continue; // ghost cells contribute nothing (domain-decomposition mode B)
+        const int32_t* cn = conn + (int64_t)cell * NPC;
+        int32_t nd[NPC];
+        int li[NPC];
+#pragma unroll
+        for (int a = 0; a < NPC; ++a) {
+          nd[a] = __ldg(cn + a);
+          li[a] = (__ldg(node_tile + nd[a]) == t) ? __ldg(node_lrow + nd[a]) : -1;
+          if (li[a] >= 0 && !S.own[li[a]]) li[a] = -1;
+        }
+#pragma unroll
+        for (int a = 0; a < NPC; ++a) {
+          if (li[a] < 0) continue;
+          const int rb = __ldg(rows + nd[a]), re = __ldg(rows + nd[a] + 1);
+          const bool cut = re - rb > 32; // the row spans several units: its diagonal block has a list of its own
+#pragma unroll
+          for (int bq = 0; bq < NPC; ++bq) {
+            if (bq == a && !cut) continue;
+            const int e = S.erow[li[a]] + (find_col(cols, rb, re, nd[bq]) - rb);
+            if (pass == 0) atomicAdd(&S.cnt[e], 1);
+            else {
+              const int slot = atomicSub(&S.cnt[e], 1) - 1; // countdown cursor, restored from eoff below
+              S.clist[S.eoff[e] + slot] = (uint16_t)(((a * 4 + bq) << VR_LC_BITS) | lc);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (pass == 0) {
+        if (FILL) {
+          for (int e = threadIdx.x; e <= E; e += blockDim.x) S.eoff[e] = e < E ? S.cnt[e] : 0;
+          __syncthreads();
+          smem_exclusive_scan(S.eoff, E + 1, S.tmp);
+        }
+      }
+      else {
+        for (int e = threadIdx.x; e < E; e += blockDim.x) S.cnt[e] = S.eoff[e + 1] - S.eoff[e];
+        __syncthreads();
+      }
+    }
+    // ---- units: whole rows packed greedily in tile order ----
+    if (threadIdx.x == 0) {
+      int nu = 0, first = -1, cnt = 0;
+      auto close = [&]() {
+        if (cnt > 0) {
+          if (nu < VR_UMAX) { S.ufirst[nu] = first; S.ucnt[nu] = cnt; }
+          ++nu;
+        }
+        cnt = 0;
+      };
+      for (int i = 0; i < R; ++i) {
+        const int e0 = S.erow[i], nz = S.erow[i + 1] - e0;
+        if (!S.own[i] || nz == 0) { close(); continue; }
+        if (nz > 32) {
+          close();
+          for (int x = 0; x < nz; x += 32) { first = e0 + x; cnt = min(32, nz - x); close(); }
+          continue;
+        }
+        if (cnt + nz > 32) close();
+        if (cnt == 0) first = e0;
+        cnt += nz;
+      }
+      close();
+      S.tmp[34] = nu;
+    }
+    __syncthreads();
+    const int nunit = S.tmp[34];
+    if (nunit > VR_UMAX) {
+      if (threadIdx.x == 0) atomicExch(error, 2);
+      __syncthreads();
+      continue;
+    }
+    for (int u = threadIdx.x; u <= nunit; u += blockDim.x) {
+      int len = 0;
+      if (u < nunit) {
+        const int f = S.ufirst[u], n = S.ucnt[u];
+        for (int x = 0; x < n; ++x) len = max(len, S.cnt[f + x]);
+        if (len > 0) len = (len + VR_SLACK + 1) & ~1;
+        S.ucnt[u] |= len << 8;
+      }
+      S.ubase[u] = len * 32;
+    }
+    __syncthreads();
+    const int list_total = (smem_exclusive_scan(S.ubase, nunit + 1, S.tmp) + 7) & ~7;
+    if (!FILL) {
+      if (threadIdx.x == 0) {
+        desc[t].nb_unit = nunit;
+        desc[t].list_len = list_total;
+      }
+      __syncthreads();
+      continue;
+    }
+    if (nunit != d.nb_unit || list_total != d.list_len) {
+      if (threadIdx.x == 0) atomicExch(error, 3);
+      __syncthreads();
+      continue;
+    }
+    // canonical order inside a list: ascending local cell index (= ascending global cell id): fixed summation order
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      uint16_t* l = S.clist + S.eoff[e];
+      const int n = S.cnt[e];
+      for (int i = 1; i < n; ++i) {
+        const uint16_t x = l[i];
+        const unsigned kx = ((unsigned)(x & VR_LC_MASK) << 16) | x;
+        int j = i - 1;
+        while (j >= 0) {
+          const uint16_t y = l[j];
+          if ((((unsigned)(y & VR_LC_MASK) << 16) | y) <= kx) break;
+          l[j + 1] = y;
+          --j;
+        }
+        l[j + 1] = x;
+      }
+    }
+    __syncthreads();
+    constexpr uint16_t PAD = (uint16_t)(CS - 1);
+    for (int u = threadIdx.x; u < nunit; u += blockDim.x)
+      units[d.unit_off + u] = make_uint2((uint32_t)S.ubase[u], vr_pack_unit(S.ufirst[u], S.ucnt[u] & 0xFF, S.ucnt[u] >> 8));
+    for (int x = S.ubase[nunit] + threadIdx.x; x < list_total; x += blockDim.x) lists[d.list_off + x] = PAD;
+    // Lists of a unit, one thread per half-warp of lanes.  The executor reads contribution k of its 16 lanes with one
+    // shared-memory instruction per gradient component: the k-th slots of the 16 lists are chosen (greedily) so that both
+    // gradients (node a, node b of the cell) fall into different 8-byte banks across the lanes whenever possible.  The
+    // order inside an entry's list is therefore plan-defined (not ascending cell id), but fixed: sums stay reproducible.
+    for (int hx = threadIdx.x; hx < nunit * 2; hx += blockDim.x) {
+      const int u = hx >> 1, l0 = (hx & 1) * 16;
+      const int f = S.ufirst[u], n = S.ucnt[u] & 0xFF, len = S.ucnt[u] >> 8;
+      unsigned taken[16];
+      bool simple = false;
+      for (int j = 0; j < 16; ++j) {
+        taken[j] = 0u;
+        if (l0 + j < n && S.cnt[f + l0 + j] > 32) simple = true;
+      }
+      uint16_t* out0 = lists + d.list_off + S.ubase[u] + l0 * 2; // [len/2][32 lanes][2]
+      unsigned char used[16];
+      for (int j = 0; j < 16; ++j) used[j] = 0;
+      for (int k = 0; k < len; ++k) {
+        short ownA[16], ownB[16]; // 8-byte bank -> cache word read from it in this step (-1: free); equal words are broadcast
+        for (int q = 0; q < 16; ++q) ownA[q] = ownB[q] = -1;
+        // lanes that have no step to spare choose first; a lane whose list is shorter than the unit's may sit a step out
+        // (padding slot) when every remaining contribution of it would collide
+        unsigned must_mask = 0u;
+        for (int j = 0; j < 16; ++j) {
+          const int c = l0 + j < n ? S.cnt[f + l0 + j] : 0;
+          if (simple || c - used[j] >= len - k) must_mask |= 1u << j;
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int j = 0; j < 16; ++j) {
+            const int lj = l0 + j;
+            const int c = lj < n ? S.cnt[f + lj] : 0;
+            const int rem = c - used[j];
+            const bool must = (must_mask >> j) & 1u;
+            if (must != (pass == 0)) continue;
+            uint16_t code = PAD;
+            if (rem > 0) {
+              const uint16_t* src = S.clist + S.eoff[f + lj];
+              if (simple) code = k < c ? src[k] : PAD;
+              else {
+                int best = -1, best_score = -1;
+                for (int q = 0; q < c; ++q) {
+                  if ((taken[j] >> q) & 1u) continue;
+                  const unsigned cd = src[q], pl = cd >> VR_LC_BITS, lc = cd & VR_LC_MASK;
+                  const int wa = (int)((pl >> 2) * (NPC - 1) * CS + lc), wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
+                  const int score = ((ownA[wa & 15] < 0 || ownA[wa & 15] == wa) ? 1 : 0) + ((ownB[wb & 15] < 0 || ownB[wb & 15] == wb) ? 1 : 0);
+                  if (score > best_score) { best_score = score; best = q; }
+                  if (score == 2) break;
+                }
+                if (must || best_score == 2) {
+                  code = src[best];
+                  taken[j] |= 1u << best;
+                  ++used[j];
+                  const unsigned pl = (unsigned)code >> VR_LC_BITS, lc = code & VR_LC_MASK;
+                  const int wa = (int)((pl >> 2) * (NPC - 1) * CS + lc), wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
+                  if (ownA[wa & 15] < 0) ownA[wa & 15] = (short)wa;
+                  if (ownB[wb & 15] < 0) ownB[wb & 15] = (short)wb;
+                }
+              }
+            }
+            out0[j * 2 + (k >> 1) * 64 + (k & 1)] = code;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static bool tiled_cells_supported(const afb_ctx* ctx) { return ctx->npc == ctx->dim + 1; } // P1 simplices (4 nodes in 2-D is a quadrilateral)
@@ -758,7 +1010,7 @@ template <class F> static int launch_by_npc(int npc, F f)
   return f(std::integral_constant<int, 3>());
 }
 
-int build_tile_mesh(afb_ctx* ctx)
+int build_tile_mesh(afb_ctx* ctx, int cls)
 {
   AFB_REQUIRE(tiled_cells_supported(ctx), AFB_ERR_UNSUPPORTED, "the tiled path is not available for %d-node cells (P1 simplices only); use AFB_VARIANT_NODEWISE", ctx->npc);
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "tile inspector: build the pattern first");
@@ -769,7 +1021,8 @@ int build_tile_mesh(afb_ctx* ctx)
   const int32_t nb_node = ctx->nb_node;
   const int dim = ctx->dim, npc = ctx->npc;
   const bool vec = ctx->b > 1;
-  const int cmax = vec ? TV_CMAX : TG_CMAX;
+  if (cls < 0) cls = !vec ? 0 : (ctx->vec_rows() ? 2 : 1);
+  const int cmax = cls == 2 ? VR_CMAX : cls == 1 ? TV_CMAX : TG_CMAX;
   cudaEvent_t e0, e1;
   AFB_CUDA(cudaEventCreate(&e0));
   AFB_CUDA(cudaEventCreate(&e1));
@@ -796,7 +1049,7 @@ int build_tile_mesh(afb_ctx* ctx)
   int32_t* brick_of = P.scratch_c.as<int32_t>();
 
   // bricks holding ~rtarget nodes on a uniform mesh
-  const int rtarget = dim == 3 ? (vec ? TV_RT3 : TG_RT3) : (vec ? TV_RT2 : TG_RT2);
+  const int rtarget = dim == 3 ? (cls == 2 ? VR_RT3 : cls == 1 ? TV_RT3 : TG_RT3) : (cls == 2 ? VR_RT2 : cls == 1 ? TV_RT2 : TG_RT2);
   double vol = 1.0;
   int nd_ext = 0;
   for (int a = 0; a < 3; ++a)
@@ -947,7 +1200,7 @@ int build_tile_mesh(afb_ctx* ctx)
   AFB_REQUIRE(err == 0, AFB_ERR_CUDA, "tile inspector: mesh tiling inconsistency (code %d)", err);
   P.hdesc_host.assign(reinterpret_cast<const int32_t*>(hdesc.data()), reinterpret_cast<const int32_t*>(hdesc.data()) + 16 * (size_t)nb_tile);
   P.mesh_gen = ctx->mesh_gen;
-  P.mesh_b_class = vec ? 1 : 0;
+  P.mesh_b_class = cls;
   P.mesh_valid = true;
   AFB_TRY(pattern_nn_build(ctx)); // tile-local node-node connectivity of the connectivity-based BuildMatrix
   return AFB_OK;
@@ -1023,6 +1276,79 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
   P.lists_b = ctx->b;
   P.lists_mode = mode_flags & (AFB_FLAG_ALL_ROWS | AFB_FLAG_OWN_CELLS_ONLY);
   P.lists_mesh_gen = ctx->mesh_gen;
+  P.lists_kind = 0;
+  P.lists_valid = true;
+  return AFB_OK;
+}
+
+int build_tile_rowlists(afb_ctx* ctx, int mode_flags)
+{
+  TilePlan& P = ctx->plan;
+  AFB_REQUIRE(P.mesh_valid && P.mesh_b_class == 2, AFB_ERR_INVALID, "tile inspector: no mesh tiling for the row-ordered executor");
+  P.lists_valid = false;
+  cudaStream_t st = ctx->stream;
+  const int npc = ctx->npc;
+  const int32_t nb_tile = P.nb_tile;
+  cudaEvent_t e0, e1;
+  AFB_CUDA(cudaEventCreate(&e0));
+  AFB_CUDA(cudaEventCreate(&e1));
+  AFB_CUDA(cudaEventRecord(e0, st));
+  TileDesc* hdesc = reinterpret_cast<TileDesc*>(P.hdesc_host.data());
+  AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
+  AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), st));
+  const uint8_t* own = (ctx->all_own || (mode_flags & AFB_FLAG_ALL_ROWS)) ? nullptr : ctx->is_own.as<uint8_t>();
+  const int64_t nb_own_cell = (mode_flags & AFB_FLAG_OWN_CELLS_ONLY) ? ctx->nb_own_cell : ctx->nb_cell;
+  AFB_TRY(P.rowinfo.reserve(sizeof(uint32_t) * (size_t)ctx->nb_node));
+  const size_t smem = sizeof(RowListSmem);
+  const int grid = std::min<int>(std::max(nb_tile, 1), 2 * ctx->sm_count);
+  auto go = [&](auto kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, TB_THREADS, smem, st>>>(P.tile_desc.as<TileDesc>(), nb_tile, P.tile_nodes.as<int32_t>(), P.tile_cells.as<int32_t>(), ctx->conn.as<int32_t>(),
+                                           ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(), P.node_tile.as<int32_t>(), P.node_lrow.as<int32_t>(), own, nb_own_cell,
+                                           P.rowinfo.as<uint32_t>(), P.vr_units.as<uint2>(), P.lists.as<uint16_t>(), ctx->tmp_flag.as<int>());
+    return cudaGetLastError();
+  };
+  int64_t unit_off = 0, list_off = 0;
+  if (nb_tile > 0) {
+    // pass 1: sizes
+    AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
+    AFB_CUDA(npc == 4 ? go(k_tile_rowlists<4, false>) : go(k_tile_rowlists<3, false>));
+    ctx->launches++;
+    AFB_CUDA(cudaMemcpyAsync(hdesc, P.tile_desc.p, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyDeviceToHost, st));
+    AFB_CUDA(cudaStreamSynchronize(st));
+    for (int32_t t = 0; t < nb_tile; ++t) {
+      TileDesc& d = hdesc[t];
+      d.unit_off = (int32_t)unit_off;
+      d.list_off = (uint32_t)list_off;
+      unit_off += d.nb_unit;
+      list_off += d.list_len;
+      AFB_REQUIRE(list_off < (1ll << 32) && unit_off < (1ll << 30), AFB_ERR_OVERFLOW, "tile inspector: value plan exceeds 32-bit offsets");
+    }
+  }
+  P.nb_unit = unit_off;
+  P.nb_list = list_off;
+  AFB_TRY(P.vr_units.reserve(sizeof(uint2) * (size_t)std::max<int64_t>(unit_off, 1)));
+  AFB_TRY(P.lists.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
+  if (nb_tile > 0) {
+    // pass 2: unit records and lists
+    AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
+    AFB_CUDA(npc == 4 ? go(k_tile_rowlists<4, true>) : go(k_tile_rowlists<3, true>));
+    ctx->launches++;
+  }
+  int err = 0;
+  AFB_CUDA(cudaMemcpyAsync(&err, ctx->tmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  AFB_CUDA(cudaEventRecord(e1, st));
+  AFB_CUDA(cudaEventSynchronize(e1));
+  AFB_CUDA(cudaEventElapsedTime(&P.lists_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  AFB_REQUIRE(err != 2, AFB_ERR_UNSUPPORTED, "tiled path: a tile has more than %d units of rows; use AFB_VARIANT_NODEWISE", VR_UMAX);
+  AFB_REQUIRE(err == 0, AFB_ERR_CUDA, "tile inspector: value plan inconsistency (code %d)", err);
+  P.lists_b = ctx->b;
+  P.lists_mode = mode_flags & (AFB_FLAG_ALL_ROWS | AFB_FLAG_OWN_CELLS_ONLY);
+  P.lists_mesh_gen = ctx->mesh_gen;
+  P.lists_kind = 1;
   P.lists_valid = true;
   return AFB_OK;
 }

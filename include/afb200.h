@@ -218,6 +218,19 @@ AFB_API int afb_set_sparsity_algorithm(afb_ctx* ctx, int algorithm);
 enum { AFB_TILED_EXEC_BRICKS = 0, AFB_TILED_EXEC_CHAIN = 1, AFB_TILED_EXEC_CHAIN_FLOW = 2 };
 AFB_API int afb_set_tiled_executor(afb_ctx* ctx, int executor);
 /*
+ * Executor behind AFB_VARIANT_TILED_GATHER for elasticity (b = 2, 3; BSRFormat::assembleBilinearAtomicFree with a b x b
+ * block per node pair, femutils/BSRFormat.h:406-577).  Both write every block exactly once and agree to 1e-12:
+ *   AFB_VEC_EXEC_ROWS    lanes = consecutive entries of whole rows; blocks staged per warp and written as contiguous runs;
+ *                        the diagonal block is minus the sum of the row's other blocks (measured fastest on Tet4, b = 3)
+ *   AFB_VEC_EXEC_UNITS   entries grouped by list length, symmetric twins summed once, blocks written from registers
+ *                        (measured fastest on Tri3, b = 2, where a row has 7 short lists)
+ *   AFB_VEC_EXEC_AUTO    rows for Tet4, units for Tri3 (default)
+ * The bilaplacian always runs on AFB_VEC_EXEC_UNITS (its blocks have no zero row sums).  The setting persists until changed;
+ * AFB_VEC_EXEC in the environment sets the default ("auto", "rows", "units").
+ */
+enum { AFB_VEC_EXEC_AUTO = 0, AFB_VEC_EXEC_ROWS = 1, AFB_VEC_EXEC_UNITS = 2 };
+AFB_API int afb_set_vector_executor(afb_ctx* ctx, int executor);
+/*
  * Tuning / test knob of the tiled executors: plan records (contribution lists) larger than `bytes` are not staged in shared
  * memory through the TMA engine but read from global memory (the branch oversized tiles take).  Default: the executor's
  * staging capacity.  bytes = 0 sends every tile through the global-memory branch.

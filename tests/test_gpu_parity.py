@@ -312,6 +312,40 @@ def test_elasticity_values(ctx, name, variant, layout):
             ctx.csr_view()
 
 
+@pytest.mark.parametrize("name", ["bar_3D", "sphere_3D", "box3d_n9", "L-shape_2D", "box2d_n17"])
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_elasticity_vector_executors_agree(name, layout):
+    """afb_set_vector_executor: the row-ordered executor (default) and the unit executor against the oracle and each other,
+    fresh / accumulated / after a reset, also when the contribution lists are read from global memory"""
+    m = get_mesh(name)
+    b = m.dim
+    lam, mu = O.lame(21.0e5, 0.28)
+    out = {}
+    with A.Context(0) as c:
+        c.set_mesh(m.dim, m.coords, m.cells)
+        c.build_pattern(b)
+        rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+        ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[lam, mu], layout=layout, nodewise=True)
+        for ex in (A.VEC_EXEC_ROWS, A.VEC_EXEC_UNITS, A.VEC_EXEC_ROWS):
+            c.set_vector_executor(ex)
+            for limit in (None, 0):
+                if limit is not None:
+                    c.set_tiled_stage_limit(limit)
+                c.reset_values()
+                c.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER, layout=layout)
+                v1 = c.to_host(A.ARRAY_VALUES)
+                row_scaled_close(v1, ref, rows, b=b, layout=layout)
+                c.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER, layout=layout)
+                row_scaled_close(c.to_host(A.ARRAY_VALUES), 2.0 * v1, rows, b=b, layout=layout)
+                if ex in out:
+                    assert np.array_equal(out[ex], v1), "bit-reproducible per executor"
+                out[ex] = v1
+            c.set_tiled_stage_limit(1 << 30)
+        with pytest.raises(A.AfbError):
+            c.set_vector_executor(7)
+    row_scaled_close(out[A.VEC_EXEC_ROWS], out[A.VEC_EXEC_UNITS], rows, b=b, layout=layout)
+
+
 @pytest.mark.parametrize("name", ["L-shape_2D", "box2d_n17", "porous_2D"])
 @pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER], ids=["bsr", "af-bsr", "tiled"])
 @pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
@@ -804,8 +838,13 @@ def test_full_size_against_oracle_digest(key, variants):
         rows = A.as_torch((c.csr_view() if b == 1 else c.bsr_view())["rows" if b == 1 else "rows_index"], nbr + 1, np.int32, 0)
         rows_h = rows.cpu().numpy()
         sample = sorted(int(k) for k in g["sample_rows"])
+        UNITS = 100 + A.VARIANT_TILED_GATHER  # the tiled gather through the other vector executor (afb_set_vector_executor)
+        if b > 1 and n <= 100 and A.VARIANT_TILED_GATHER in variants:
+            variants = variants + [UNITS]
         for layout in ([A.LAYOUT_PER_BLOCK] if b == 1 else [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW]):
             for variant in variants:
+                c.set_vector_executor(A.VEC_EXEC_UNITS if variant == UNITS else A.VEC_EXEC_AUTO)
+                variant = A.VARIANT_TILED_GATHER if variant == UNITS else variant
                 c.reset_values()
                 c.assemble(op, params=g["params"], fmt=A.FORMAT_CSR if b == 1 else A.FORMAT_BSR, variant=variant, layout=layout)
                 c.synchronize()
