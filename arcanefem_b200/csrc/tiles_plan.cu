@@ -486,6 +486,7 @@ struct ListBuilderSmem {
   int cnt[TG_EMAX];
   int eoff[TG_EMAX + 1];
   unsigned keys[TL_KEYS];
+  unsigned scol[TG_EMAX]; // columns of the tile's rows, in tile entry order (the searches below stay in shared memory)
   uint16_t e2[TG_EMAX];
   uint16_t clist[16 * TG_CMAX];
   int ulen[TG_UMAX + 1], ubase[TG_UMAX + 2];
@@ -521,10 +522,9 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
       __syncthreads();
       continue;
     }
-    // ---- entries: class, mirror ----
+    // ---- columns of the tile's rows -> shared memory; position of the diagonal ----
     for (int i = warp; i < R; i += nwarp) {
       const int32_t r = tnodes[d.node_off + i];
-      const bool own_i = !is_own || is_own[r];
       const int rb = rows[r], deg = rows[r + 1] - rb, e0 = S.erow[i];
       int pdiag = 0;
       for (int p0 = 0; p0 < deg; p0 += 32) {
@@ -532,25 +532,33 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
         int32_t c = -1;
         if (p < deg) {
           c = cols[rb + p];
-          int cls = 0;
-          unsigned m = TG_NONE16;
-          if (!own_i) cls = CLS_ZERO;
-          else if (c == r) cls = VEC ? 0 : CLS_DERIVED;
-          else if (__ldg(node_tile + c) == t && (!is_own || is_own[c])) {
-            const int j = __ldg(node_lrow + c);
-            if (j < i) cls = CLS_MIRROR;
-            else {
-              const int cb = rows[c], ce = rows[c + 1];
-              m = (unsigned)(S.erow[j] + (find_col(cols, cb, ce, r) - cb));
-            }
-          }
-          S.cnt[e0 + p] = cls;
-          S.e2[e0 + p] = (uint16_t)m;
+          S.scol[e0 + p] = (unsigned)c;
         }
         const unsigned hit = __ballot_sync(0xffffffffu, c == r);
         if (hit) pdiag = p0 + __ffs(hit) - 1;
       }
-      if (lane == 0) rowinfo[d.node_off + i] = pack_rowinfo(e0, pdiag, own_i);
+      if (lane == 0) rowinfo[d.node_off + i] = pack_rowinfo(e0, pdiag, !is_own || is_own[r]);
+    }
+    __syncthreads();
+    // ---- entries: class, mirror ----
+    for (int i = warp; i < R; i += nwarp) {
+      const int32_t r = tnodes[d.node_off + i];
+      const bool own_i = !is_own || is_own[r];
+      const int e0 = S.erow[i], deg = S.erow[i + 1] - e0;
+      for (int p = lane; p < deg; p += 32) {
+        const int32_t c = (int32_t)S.scol[e0 + p];
+        int cls = 0;
+        unsigned m = TG_NONE16;
+        if (!own_i) cls = CLS_ZERO;
+        else if (c == r) cls = VEC ? 0 : CLS_DERIVED;
+        else if (__ldg(node_tile + c) == t && (!is_own || is_own[c])) {
+          const int j = __ldg(node_lrow + c);
+          if (j < i) cls = CLS_MIRROR;
+          else m = (unsigned)(S.erow[j] + smem_find(S.scol + S.erow[j], S.erow[j + 1] - S.erow[j], (unsigned)r));
+        }
+        S.cnt[e0 + p] = cls;
+        S.e2[e0 + p] = (uint16_t)m;
+      }
     }
     __syncthreads();
     // ---- contribution lists of the computed entries (count, scan, fill) ----
@@ -569,12 +577,12 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
 #pragma unroll
         for (int a = 0; a < NPC; ++a) {
           if (li[a] < 0) continue;
-          const int rb = __ldg(rows + nd[a]), re = __ldg(rows + nd[a] + 1);
+          const int ea = S.erow[li[a]], dega = S.erow[li[a] + 1] - ea;
 #pragma unroll
           for (int bq = 0; bq < NPC; ++bq) {
             if (!VEC && bq == a) continue;                         // derived diagonal
             if (bq != a && li[bq] >= 0 && li[bq] < li[a]) continue; // the twin entry (li[bq], li[a]) takes it
-            const int e = S.erow[li[a]] + (find_col(cols, rb, re, nd[bq]) - rb);
+            const int e = ea + smem_find(S.scol + ea, dega, (unsigned)nd[bq]);
             if (pass == 0) atomicAdd(&S.cnt[e], 1);
             else {
               const int slot = atomicSub(&S.cnt[e], 1) - 1; // countdown cursor, restored from eoff below
@@ -669,81 +677,170 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
         emap_rows[(size_t)(d.unit_off + (x >> 5)) * 32 + (x & 31)] = w;
       }
     }
-    // Lists of a unit, one thread per half-warp of lanes.  The executor reads contribution k of its 16
-    // lanes with one shared-memory instruction: the k-th slots of the 16 lists are chosen so that they fall
-    // into different banks (8-byte bank = cache index mod 16) whenever possible -- greedy choice with
-    // one-step augmentation (a lane that finds all its banks taken may move an earlier lane to another
-    // free bank of that lane's remaining contributions).  The order inside an entry's list is therefore
-    // plan-defined (not ascending cell id), but fixed: the sums stay bit-reproducible.
-    for (int hx = threadIdx.x; hx < nunit * 2; hx += blockDim.x) {
-      const int u = hx >> 1, l0 = (hx & 1) * 16;
-      const int len = S.ulen[u];
-      int cnt_l[16];
-      const uint16_t* src_l[16];
-      unsigned long long taken[16];
-      bool simple = false;
-      for (int j = 0; j < 16; ++j) {
-        const int x = u * 32 + l0 + j;
-        const bool valid = x < EC;
-        const int e = valid ? (int)(S.keys[x] & 0xFFFFu) : 0;
-        cnt_l[j] = valid ? S.cnt[e] : 0;
-        src_l[j] = S.clist + (valid ? S.eoff[e] : 0);
-        taken[j] = 0ull;
-        if (cnt_l[j] > 64) simple = true;
-      }
-      uint16_t* out0 = lists + d.list_off + S.ubase[u] + l0 * 2; // [len/2][32 lanes][2]
-      for (int k = 0; k < len; ++k) {
-        signed char owner[16];  // bank -> lane
-        signed char choice[16]; // lane -> index into its list
-        for (int j = 0; j < 16; ++j) { owner[j] = -1; choice[j] = -1; }
-        if (!simple) {
-          for (int j = 0; j < 16; ++j) {
-            if (k >= cnt_l[j]) continue;
-            const int n = cnt_l[j];
-            int first = -1;
-            for (int q = 0; q < n && choice[j] < 0; ++q) {
-              if ((taken[j] >> q) & 1ull) continue;
-              if (first < 0) first = q;
-              const int bk = src_l[j][q] & 15;
-              if (owner[bk] < 0) { owner[bk] = (signed char)j; choice[j] = (signed char)q; }
-            }
-            if (choice[j] >= 0) continue;
-            // all banks of this lane's remaining contributions are taken: try to move one of their owners
-            for (int q = 0; q < n && choice[j] < 0; ++q) {
-              if ((taken[j] >> q) & 1ull) continue;
-              const int bk = src_l[j][q] & 15;
-              const int j2 = owner[bk];
-              if (j2 < 0 || j2 == j) continue;
-              const int n2 = cnt_l[j2];
-              for (int q2 = 0; q2 < n2; ++q2) {
-                if (((taken[j2] >> q2) & 1ull) || q2 == choice[j2]) continue;
-                const int b2 = src_l[j2][q2] & 15;
-                if (owner[b2] < 0) {
-                  owner[b2] = (signed char)j2;
-                  choice[j2] = (signed char)q2;
-                  owner[bk] = (signed char)j;
-                  choice[j] = (signed char)q;
-                  break;
-                }
+    // the lists in canonical order ([len/2][32 lanes][2], padded); k_bank_order below fixes the order inside each list
+    for (int x = threadIdx.x; x < nunit * 32; x += blockDim.x) {
+      const int u = x >> 5, ln = x & 31, len = S.ulen[u];
+      const bool valid = x < EC;
+      const int e = valid ? (int)(S.keys[x] & 0xFFFFu) : 0;
+      const int c = valid ? S.cnt[e] : 0;
+      const uint16_t* src = S.clist + (valid ? S.eoff[e] : 0);
+      uint16_t* out = lists + d.list_off + S.ubase[u] + ln * 2;
+      for (int k = 0; k < len; ++k) out[(k >> 1) * 64 + (k & 1)] = k < c ? src[k] : PAD;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Order inside the lists of a unit (second kernel of the value plan: one thread per half-unit over the whole grid).
+// The executor reads contribution k of its 16 lanes (a half-warp) with one shared-memory instruction: the k-th slots of
+// the 16 lists are chosen so that they fall into different banks (8-byte bank = cache index mod 16) whenever possible --
+// greedy choice in lane order with one-step augmentation (a lane that finds all its banks taken may move an earlier lane
+// to another free bank of that lane's remaining contributions).  The order inside an entry's list is therefore
+// plan-defined (not ascending cell id), but fixed: the sums stay bit-reproducible.
+//   canon: the lists in canonical order (same layout as the result), padded with `pad`
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bank_order(const TileDesc* __restrict__ desc, const uint32_t* __restrict__ unit_base, const uint16_t* __restrict__ unit_len,
+                                                    const uint16_t* __restrict__ canon, uint16_t* __restrict__ lists, uint16_t pad)
+{
+  const TileDesc d = desc[blockIdx.x];
+  for (int hx = threadIdx.x; hx < d.nb_unit * 2; hx += blockDim.x) {
+    const int u = hx >> 1, l0 = (hx & 1) * 16;
+    const int len = unit_len[d.unit_off + u];
+    const size_t base = (size_t)d.list_off + unit_base[d.unit_off + u] + l0 * 2;
+    const uint16_t* in0 = canon + base; // [len/2][32 lanes][2]
+    uint16_t* out0 = lists + base;
+    auto cand = [&](int j, int q) { return in0[j * 2 + (q >> 1) * 64 + (q & 1)]; };
+    int cnt_l[16];
+    unsigned long long taken[16];
+    bool simple = false;
+    for (int j = 0; j < 16; ++j) {
+      int c = 0;
+      while (c < len && cand(j, c) != pad) ++c;
+      cnt_l[j] = c;
+      taken[j] = 0ull;
+      if (c > 64) simple = true;
+    }
+    for (int k = 0; k < len; ++k) {
+      signed char owner[16];  // bank -> lane
+      signed char choice[16]; // lane -> index into its list
+      for (int j = 0; j < 16; ++j) { owner[j] = -1; choice[j] = -1; }
+      if (!simple) {
+        for (int j = 0; j < 16; ++j) {
+          if (k >= cnt_l[j]) continue;
+          const int n = cnt_l[j];
+          int first = -1;
+          for (int q = 0; q < n && choice[j] < 0; ++q) {
+            if ((taken[j] >> q) & 1ull) continue;
+            if (first < 0) first = q;
+            const int bk = cand(j, q) & 15;
+            if (owner[bk] < 0) { owner[bk] = (signed char)j; choice[j] = (signed char)q; }
+          }
+          if (choice[j] >= 0) continue;
+          // all banks of this lane's remaining contributions are taken: try to move one of their owners
+          for (int q = 0; q < n && choice[j] < 0; ++q) {
+            if ((taken[j] >> q) & 1ull) continue;
+            const int bk = cand(j, q) & 15;
+            const int j2 = owner[bk];
+            if (j2 < 0 || j2 == j) continue;
+            const int n2 = cnt_l[j2];
+            for (int q2 = 0; q2 < n2; ++q2) {
+              if (((taken[j2] >> q2) & 1ull) || q2 == choice[j2]) continue;
+              const int b2 = cand(j2, q2) & 15;
+              if (owner[b2] < 0) {
+                owner[b2] = (signed char)j2;
+                choice[j2] = (signed char)q2;
+                owner[bk] = (signed char)j;
+                choice[j] = (signed char)q;
+                break;
               }
             }
-            if (choice[j] < 0) choice[j] = (signed char)first; // a bank conflict remains
+          }
+          if (choice[j] < 0) choice[j] = (signed char)first; // a bank conflict remains
+        }
+      }
+      for (int j = 0; j < 16; ++j) {
+        uint16_t code = pad;
+        if (k < cnt_l[j]) {
+          if (simple) code = cand(j, k);
+          else {
+            code = cand(j, choice[j]);
+            taken[j] |= 1ull << choice[j];
           }
         }
+        out0[j * 2 + (k >> 1) * 64 + (k & 1)] = code;
+      }
+    }
+  }
+}
+
+// the same for the row-ordered plans (k_tile_rowlists): two gradients are read per contribution (node a and node b of the
+// cell), both should fall into different banks across the 16 lanes; equal words are broadcast and do not collide; lists
+// that have no step to spare choose first, a list shorter than the unit's may sit a step out (padding slot) when every
+// remaining contribution of it would collide
+template <int NPC>
+__global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restrict__ desc, const uint2* __restrict__ units, const uint16_t* __restrict__ canon,
+                                                         uint16_t* __restrict__ lists)
+{
+  constexpr int CS = VR_CS;
+  constexpr uint16_t PAD = (uint16_t)(CS - 1);
+  const TileDesc d = desc[blockIdx.x];
+  for (int hx = threadIdx.x; hx < d.nb_unit * 2; hx += blockDim.x) {
+    const int u = hx >> 1, l0 = (hx & 1) * 16;
+    const uint2 U = units[d.unit_off + u];
+    const int len = (int)(U.y >> 17);
+    const size_t base = (size_t)d.list_off + U.x + l0 * 2;
+    const uint16_t* in0 = canon + base;
+    uint16_t* out0 = lists + base;
+    auto cand = [&](int j, int q) { return in0[j * 2 + (q >> 1) * 64 + (q & 1)]; };
+    unsigned taken[16];
+    unsigned char cnt_l[16], used[16];
+    bool simple = false;
+    for (int j = 0; j < 16; ++j) {
+      int c = 0;
+      while (c < len && cand(j, c) != PAD) ++c;
+      if (c > 32) simple = true;
+      cnt_l[j] = (unsigned char)min(c, 255);
+      taken[j] = 0u;
+      used[j] = 0;
+    }
+    for (int k = 0; k < len; ++k) {
+      short ownA[16], ownB[16]; // 8-byte bank -> cache word read from it in this step (-1: free)
+      for (int q = 0; q < 16; ++q) ownA[q] = ownB[q] = -1;
+      unsigned must_mask = 0u;
+      for (int j = 0; j < 16; ++j)
+        if (simple || (int)cnt_l[j] - (int)used[j] >= len - k) must_mask |= 1u << j;
+      for (int pass = 0; pass < 2; ++pass) {
         for (int j = 0; j < 16; ++j) {
+          const bool must = (must_mask >> j) & 1u;
+          if (must != (pass == 0)) continue;
+          const int c = cnt_l[j], rem = c - used[j];
           uint16_t code = PAD;
-          if (k < cnt_l[j]) {
-            if (simple) code = src_l[j][k];
-            else {
-              code = src_l[j][choice[j]];
-              taken[j] |= 1ull << choice[j];
+          if (simple) code = cand(j, k);
+          else if (rem > 0) {
+            int best = -1, best_score = -1;
+            for (int q = 0; q < c; ++q) {
+              if ((taken[j] >> q) & 1u) continue;
+              const unsigned cd = cand(j, q), pl = cd >> VR_LC_BITS, lc = cd & VR_LC_MASK;
+              const int wa = (int)((pl >> 2) * (NPC - 1) * CS + lc), wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
+              const int score = ((ownA[wa & 15] < 0 || ownA[wa & 15] == wa) ? 1 : 0) + ((ownB[wb & 15] < 0 || ownB[wb & 15] == wb) ? 1 : 0);
+              if (score > best_score) { best_score = score; best = q; }
+              if (score == 2) break;
+            }
+            if (must || best_score == 2) {
+              code = cand(j, best);
+              taken[j] |= 1u << best;
+              ++used[j];
+              const unsigned pl = (unsigned)code >> VR_LC_BITS, lc = code & VR_LC_MASK;
+              const int wa = (int)((pl >> 2) * (NPC - 1) * CS + lc), wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
+              if (ownA[wa & 15] < 0) ownA[wa & 15] = (short)wa;
+              if (ownB[wb & 15] < 0) ownB[wb & 15] = (short)wb;
             }
           }
           out0[j * 2 + (k >> 1) * 64 + (k & 1)] = code;
         }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -932,68 +1029,14 @@ k_tile_rowlists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __r
     for (int u = threadIdx.x; u < nunit; u += blockDim.x)
       units[d.unit_off + u] = make_uint2((uint32_t)S.ubase[u], vr_pack_unit(S.ufirst[u], S.ucnt[u] & 0xFF, S.ucnt[u] >> 8));
     for (int x = S.ubase[nunit] + threadIdx.x; x < list_total; x += blockDim.x) lists[d.list_off + x] = PAD;
-    // Lists of a unit, one thread per half-warp of lanes.  The executor reads contribution k of its 16 lanes with one
-    // shared-memory instruction per gradient component: the k-th slots of the 16 lists are chosen (greedily) so that both
-    // gradients (node a, node b of the cell) fall into different 8-byte banks across the lanes whenever possible.  The
-    // order inside an entry's list is therefore plan-defined (not ascending cell id), but fixed: sums stay reproducible.
-    for (int hx = threadIdx.x; hx < nunit * 2; hx += blockDim.x) {
-      const int u = hx >> 1, l0 = (hx & 1) * 16;
+    // the lists in canonical order ([len/2][32 lanes][2], padded); k_bank_order_rows fixes the order inside each list
+    for (int x = threadIdx.x; x < nunit * 32; x += blockDim.x) {
+      const int u = x >> 5, ln = x & 31;
       const int f = S.ufirst[u], n = S.ucnt[u] & 0xFF, len = S.ucnt[u] >> 8;
-      unsigned taken[16];
-      bool simple = false;
-      for (int j = 0; j < 16; ++j) {
-        taken[j] = 0u;
-        if (l0 + j < n && S.cnt[f + l0 + j] > 32) simple = true;
-      }
-      uint16_t* out0 = lists + d.list_off + S.ubase[u] + l0 * 2; // [len/2][32 lanes][2]
-      unsigned char used[16];
-      for (int j = 0; j < 16; ++j) used[j] = 0;
-      for (int k = 0; k < len; ++k) {
-        short ownA[16], ownB[16]; // 8-byte bank -> cache word read from it in this step (-1: free); equal words are broadcast
-        for (int q = 0; q < 16; ++q) ownA[q] = ownB[q] = -1;
-        // lanes that have no step to spare choose first; a lane whose list is shorter than the unit's may sit a step out
-        // (padding slot) when every remaining contribution of it would collide
-        unsigned must_mask = 0u;
-        for (int j = 0; j < 16; ++j) {
-          const int c = l0 + j < n ? S.cnt[f + l0 + j] : 0;
-          if (simple || c - used[j] >= len - k) must_mask |= 1u << j;
-        }
-        for (int pass = 0; pass < 2; ++pass) {
-          for (int j = 0; j < 16; ++j) {
-            const int lj = l0 + j;
-            const int c = lj < n ? S.cnt[f + lj] : 0;
-            const int rem = c - used[j];
-            const bool must = (must_mask >> j) & 1u;
-            if (must != (pass == 0)) continue;
-            uint16_t code = PAD;
-            if (rem > 0) {
-              const uint16_t* src = S.clist + S.eoff[f + lj];
-              if (simple) code = k < c ? src[k] : PAD;
-              else {
-                int best = -1, best_score = -1;
-                for (int q = 0; q < c; ++q) {
-                  if ((taken[j] >> q) & 1u) continue;
-                  const unsigned cd = src[q], pl = cd >> VR_LC_BITS, lc = cd & VR_LC_MASK;
-                  const int wa = (int)((pl >> 2) * (NPC - 1) * CS + lc), wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
-                  const int score = ((ownA[wa & 15] < 0 || ownA[wa & 15] == wa) ? 1 : 0) + ((ownB[wb & 15] < 0 || ownB[wb & 15] == wb) ? 1 : 0);
-                  if (score > best_score) { best_score = score; best = q; }
-                  if (score == 2) break;
-                }
-                if (must || best_score == 2) {
-                  code = src[best];
-                  taken[j] |= 1u << best;
-                  ++used[j];
-                  const unsigned pl = (unsigned)code >> VR_LC_BITS, lc = code & VR_LC_MASK;
-                  const int wa = (int)((pl >> 2) * (NPC - 1) * CS + lc), wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
-                  if (ownA[wa & 15] < 0) ownA[wa & 15] = (short)wa;
-                  if (ownB[wb & 15] < 0) ownB[wb & 15] = (short)wb;
-                }
-              }
-            }
-            out0[j * 2 + (k >> 1) * 64 + (k & 1)] = code;
-          }
-        }
-      }
+      const int c = ln < n ? S.cnt[f + ln] : 0;
+      const uint16_t* src = S.clist + (ln < n ? S.eoff[f + ln] : 0);
+      uint16_t* out = lists + d.list_off + S.ubase[u] + ln * 2;
+      for (int k = 0; k < len; ++k) out[(k >> 1) * 64 + (k & 1)] = k < c ? src[k] : PAD;
     }
     __syncthreads();
   }
@@ -1242,6 +1285,9 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
   AFB_TRY(P.emap.reserve(sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(unit_off, 1)));
   if (vec) AFB_TRY(P.emap_rows.reserve(sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(unit_off, 1)));
   AFB_TRY(P.lists.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
+  DevBuf canon; // the lists in canonical order, between the two kernels (released on return)
+  struct Scoped { DevBuf& b; ~Scoped() { b.release(); } } canon_guard{ canon };
+  AFB_TRY(canon.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
   AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
   AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
   AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), st));
@@ -1255,7 +1301,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
       if (e != cudaSuccess) return e;
       kernel<<<grid, TB_THREADS, smem, st>>>(P.tile_desc.as<TileDesc>(), nb_tile, P.tile_nodes.as<int32_t>(), P.tile_cells.as<int32_t>(), ctx->conn.as<int32_t>(),
                                              ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(), P.node_tile.as<int32_t>(), P.node_lrow.as<int32_t>(), own, nb_own_cell,
-                                             P.rowinfo.as<uint32_t>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), P.emap.as<uint32_t>(), P.emap_rows.as<uint32_t>(), P.lists.as<uint16_t>(),
+                                             P.rowinfo.as<uint32_t>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), P.emap.as<uint32_t>(), P.emap_rows.as<uint32_t>(), canon.as<uint16_t>(),
                                              list_max, ctx->tmp_flag.as<int>());
       return cudaGetLastError();
     };
@@ -1263,7 +1309,11 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
     if (npc == 4) e = vec ? go(k_tile_lists<4, true>, 1 << 30) : go(k_tile_lists<4, false>, 1 << 30);
     else e = vec ? go(k_tile_lists<3, true>, 1 << 30) : go(k_tile_lists<3, false>, 1 << 30);
     AFB_CUDA(e);
-    ctx->launches++;
+    // order inside the lists (shared-memory banks of the executor's gathers): one thread per half-unit, whole grid
+    k_bank_order<<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), canon.as<uint16_t>(), P.lists.as<uint16_t>(),
+                                          (uint16_t)(vec ? (TV_CS - 1) : TG_ZERO));
+    AFB_LAUNCH_CHECK(ctx);
+    ctx->launches += 2;
   }
   int err = 0;
   AFB_CUDA(cudaMemcpyAsync(&err, ctx->tmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1299,6 +1349,8 @@ int build_tile_rowlists(afb_ctx* ctx, int mode_flags)
   const uint8_t* own = (ctx->all_own || (mode_flags & AFB_FLAG_ALL_ROWS)) ? nullptr : ctx->is_own.as<uint8_t>();
   const int64_t nb_own_cell = (mode_flags & AFB_FLAG_OWN_CELLS_ONLY) ? ctx->nb_own_cell : ctx->nb_cell;
   AFB_TRY(P.rowinfo.reserve(sizeof(uint32_t) * (size_t)ctx->nb_node));
+  DevBuf canon; // the lists in canonical order, between the kernels (released on return)
+  struct Scoped { DevBuf& b; ~Scoped() { b.release(); } } canon_guard{ canon };
   const size_t smem = sizeof(RowListSmem);
   const int grid = std::min<int>(std::max(nb_tile, 1), 2 * ctx->sm_count);
   auto go = [&](auto kernel) {
@@ -1306,7 +1358,7 @@ int build_tile_rowlists(afb_ctx* ctx, int mode_flags)
     if (e != cudaSuccess) return e;
     kernel<<<grid, TB_THREADS, smem, st>>>(P.tile_desc.as<TileDesc>(), nb_tile, P.tile_nodes.as<int32_t>(), P.tile_cells.as<int32_t>(), ctx->conn.as<int32_t>(),
                                            ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(), P.node_tile.as<int32_t>(), P.node_lrow.as<int32_t>(), own, nb_own_cell,
-                                           P.rowinfo.as<uint32_t>(), P.vr_units.as<uint2>(), P.lists.as<uint16_t>(), ctx->tmp_flag.as<int>());
+                                           P.rowinfo.as<uint32_t>(), P.vr_units.as<uint2>(), canon.as<uint16_t>(), ctx->tmp_flag.as<int>());
     return cudaGetLastError();
   };
   int64_t unit_off = 0, list_off = 0;
@@ -1330,11 +1382,15 @@ int build_tile_rowlists(afb_ctx* ctx, int mode_flags)
   P.nb_list = list_off;
   AFB_TRY(P.vr_units.reserve(sizeof(uint2) * (size_t)std::max<int64_t>(unit_off, 1)));
   AFB_TRY(P.lists.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
+  AFB_TRY(canon.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
   if (nb_tile > 0) {
-    // pass 2: unit records and lists
+    // pass 2: unit records and lists in canonical order; then the order inside the lists (one thread per half-unit)
     AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
     AFB_CUDA(npc == 4 ? go(k_tile_rowlists<4, true>) : go(k_tile_rowlists<3, true>));
-    ctx->launches++;
+    if (npc == 4) k_bank_order_rows<4><<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.vr_units.as<uint2>(), canon.as<uint16_t>(), P.lists.as<uint16_t>());
+    else k_bank_order_rows<3><<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.vr_units.as<uint2>(), canon.as<uint16_t>(), P.lists.as<uint16_t>());
+    AFB_LAUNCH_CHECK(ctx);
+    ctx->launches += 2;
   }
   int err = 0;
   AFB_CUDA(cudaMemcpyAsync(&err, ctx->tmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
