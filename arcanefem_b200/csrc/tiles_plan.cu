@@ -711,15 +711,25 @@ __global__ void __launch_bounds__(128) k_bank_order(const TileDesc* __restrict__
     const uint16_t* in0 = canon + base; // [len/2][32 lanes][2]
     uint16_t* out0 = lists + base;
     auto cand = [&](int j, int q) { return in0[j * 2 + (q >> 1) * 64 + (q & 1)]; };
+    // the banks of a list's contributions, 4 bits each (lists of up to 16: the searches below run on registers / local
+    // words; a longer list keeps its canonical order)
     int cnt_l[16];
-    unsigned long long taken[16];
+    unsigned long long bw[16];
+    unsigned taken[16];
     bool simple = false;
     for (int j = 0; j < 16; ++j) {
       int c = 0;
-      while (c < len && cand(j, c) != pad) ++c;
+      unsigned long long w = 0ull;
+      while (c < len) {
+        const unsigned cd = cand(j, c);
+        if (cd == pad) break;
+        if (c < 16) w |= (unsigned long long)(cd & 15u) << (4 * c);
+        ++c;
+      }
       cnt_l[j] = c;
-      taken[j] = 0ull;
-      if (c > 64) simple = true;
+      bw[j] = w;
+      taken[j] = 0u;
+      if (c > 16) simple = true;
     }
     for (int k = 0; k < len; ++k) {
       signed char owner[16];  // bank -> lane
@@ -729,24 +739,28 @@ __global__ void __launch_bounds__(128) k_bank_order(const TileDesc* __restrict__
         for (int j = 0; j < 16; ++j) {
           if (k >= cnt_l[j]) continue;
           const int n = cnt_l[j];
+          const unsigned long long wj = bw[j];
+          const unsigned tj = taken[j];
           int first = -1;
           for (int q = 0; q < n && choice[j] < 0; ++q) {
-            if ((taken[j] >> q) & 1ull) continue;
+            if ((tj >> q) & 1u) continue;
             if (first < 0) first = q;
-            const int bk = cand(j, q) & 15;
+            const int bk = (int)((wj >> (4 * q)) & 15ull);
             if (owner[bk] < 0) { owner[bk] = (signed char)j; choice[j] = (signed char)q; }
           }
           if (choice[j] >= 0) continue;
           // all banks of this lane's remaining contributions are taken: try to move one of their owners
           for (int q = 0; q < n && choice[j] < 0; ++q) {
-            if ((taken[j] >> q) & 1ull) continue;
-            const int bk = cand(j, q) & 15;
+            if ((tj >> q) & 1u) continue;
+            const int bk = (int)((wj >> (4 * q)) & 15ull);
             const int j2 = owner[bk];
             if (j2 < 0 || j2 == j) continue;
             const int n2 = cnt_l[j2];
+            const unsigned long long w2 = bw[j2];
+            const unsigned t2 = taken[j2];
             for (int q2 = 0; q2 < n2; ++q2) {
-              if (((taken[j2] >> q2) & 1ull) || q2 == choice[j2]) continue;
-              const int b2 = cand(j2, q2) & 15;
+              if (((t2 >> q2) & 1u) || q2 == choice[j2]) continue;
+              const int b2 = (int)((w2 >> (4 * q2)) & 15ull);
               if (owner[b2] < 0) {
                 owner[b2] = (signed char)j2;
                 choice[j2] = (signed char)q2;
@@ -765,7 +779,7 @@ __global__ void __launch_bounds__(128) k_bank_order(const TileDesc* __restrict__
           if (simple) code = cand(j, k);
           else {
             code = cand(j, choice[j]);
-            taken[j] |= 1ull << choice[j];
+            taken[j] |= 1u << choice[j];
           }
         }
         out0[j * 2 + (k >> 1) * 64 + (k & 1)] = code;
@@ -793,14 +807,35 @@ __global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restr
     const uint16_t* in0 = canon + base;
     uint16_t* out0 = lists + base;
     auto cand = [&](int j, int q) { return in0[j * 2 + (q >> 1) * 64 + (q & 1)]; };
+    // per list: the two banks (8-byte bank of the word of node a / node b) of every contribution, 4 bits each, and the low
+    // 12 bits of the two words (equal words are broadcast): lists of up to 16; a longer list keeps its canonical order
     unsigned taken[16];
     unsigned char cnt_l[16], used[16];
+    unsigned long long bwa[16], bwb[16];
     bool simple = false;
+    auto words = [&](unsigned cd, int& wa, int& wb) {
+      const unsigned pl = cd >> VR_LC_BITS, lc = cd & VR_LC_MASK;
+      wa = (int)((pl >> 2) * (NPC - 1) * CS + lc);
+      wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
+    };
     for (int j = 0; j < 16; ++j) {
       int c = 0;
-      while (c < len && cand(j, c) != PAD) ++c;
-      if (c > 32) simple = true;
+      unsigned long long a = 0ull, b = 0ull;
+      while (c < len) {
+        const unsigned cd = cand(j, c);
+        if (cd == PAD) break;
+        int wa, wb;
+        words(cd, wa, wb);
+        if (c < 16) {
+          a |= (unsigned long long)(wa & 15) << (4 * c);
+          b |= (unsigned long long)(wb & 15) << (4 * c);
+        }
+        ++c;
+      }
+      if (c > 16) simple = true;
       cnt_l[j] = (unsigned char)min(c, 255);
+      bwa[j] = a;
+      bwb[j] = b;
       taken[j] = 0u;
       used[j] = 0;
     }
@@ -818,12 +853,20 @@ __global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restr
           uint16_t code = PAD;
           if (simple) code = cand(j, k);
           else if (rem > 0) {
+            // a free bank is certainly no collision; an occupied one may hold the same word (checked on the few that tie)
+            const unsigned long long wa_j = bwa[j], wb_j = bwb[j];
             int best = -1, best_score = -1;
             for (int q = 0; q < c; ++q) {
               if ((taken[j] >> q) & 1u) continue;
-              const unsigned cd = cand(j, q), pl = cd >> VR_LC_BITS, lc = cd & VR_LC_MASK;
-              const int wa = (int)((pl >> 2) * (NPC - 1) * CS + lc), wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
-              const int score = ((ownA[wa & 15] < 0 || ownA[wa & 15] == wa) ? 1 : 0) + ((ownB[wb & 15] < 0 || ownB[wb & 15] == wb) ? 1 : 0);
+              const int ba = (int)((wa_j >> (4 * q)) & 15ull), bb = (int)((wb_j >> (4 * q)) & 15ull);
+              int sa = ownA[ba] < 0 ? 1 : 0, sb = ownB[bb] < 0 ? 1 : 0;
+              if (sa + sb < 2) {
+                int wa, wb;
+                words(cand(j, q), wa, wb);
+                if (!sa && ownA[ba] == wa) sa = 1;
+                if (!sb && ownB[bb] == wb) sb = 1;
+              }
+              const int score = sa + sb;
               if (score > best_score) { best_score = score; best = q; }
               if (score == 2) break;
             }
@@ -831,8 +874,8 @@ __global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restr
               code = cand(j, best);
               taken[j] |= 1u << best;
               ++used[j];
-              const unsigned pl = (unsigned)code >> VR_LC_BITS, lc = code & VR_LC_MASK;
-              const int wa = (int)((pl >> 2) * (NPC - 1) * CS + lc), wb = (int)((pl & 3u) * (NPC - 1) * CS + lc);
+              int wa, wb;
+              words(code, wa, wb);
               if (ownA[wa & 15] < 0) ownA[wa & 15] = (short)wa;
               if (ownB[wb & 15] < 0) ownB[wb & 15] = (short)wb;
             }

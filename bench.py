@@ -285,16 +285,16 @@ VARIANT_KERNEL = {0: "k_assemble_cellwise", 1: "k_assemble_nodewise", 2: "k_asse
 E_MOD, NU = 21e5, 0.28  # modules/elasticity/inputs/bar.3D.Dirichlet.bodyForce.arc:25-26
 
 
-def committed_traffic(kernel, n):
+def committed_traffic(kernel, n, exact_key=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the value kernel, from the committed
-    `ncu --set full` capture of the same kernel on the same box size (profiles/traffic.json); None otherwise
+    ncu capture of the same kernel on the same box size (profiles/traffic.json); None otherwise
     (a bench run is never taken under the profiler)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if kernel is None or n is None or not os.path.exists(p):
+    if (kernel is None and exact_key is None) or n is None or not os.path.exists(p):
         return None, None
     with open(p) as f:
         t = json.load(f)
-    e = t.get(f"{kernel}:n={n}")
+    e = t.get(exact_key if exact_key else f"{kernel}:n={n}")
     if not e:
         return None, None
     return float(e["dram_bytes_read"] + e["dram_bytes_write"]), e["source"]
@@ -388,10 +388,13 @@ def side_config(torch, A, device, stream, ev, name, n, op, b, layouts, peak):
             key = ("poisson3d_n%d" if op == A.OP_POISSON else "elasticity3d_n%d") % n
             ga, gt, _ = matrix_digest(torch, A, ctx, device, nbr, b, layout)
             ach = bytes_values / (vm * 1e-3) / 1e9
+            tkey = f"k_assemble_tiled<4>:3d:n={n}:b=1" if b == 1 else f"k_assemble_rows_vec<4, {layout}>:3d:n={n}:b={b}"
+            traffic, traffic_src = committed_traffic(None, n, exact_key=tkey)
             out.append({"config": name, "workload": f"box n={n} ({info['nb_cell']} Tet4), " + ("Poisson b=1 CSR" if b == 1 else f"elasticity b={b} BSR, values {'per block (BSR)' if layout == 0 else 'per row (AF-BSR / CSR hand-off)'}"),
                         "variant": VARIANT_NAMES[2], "build_matrix_ms": bm, "add_and_compute_ms": vm, "ms_per_step": bm + vm,
                         "elements_per_s": info["nb_cell"] / ((bm + vm) * 1e-3),
-                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": float(bytes_values)},
+                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": float(bytes_values),
+                                     "traffic": traffic, "traffic_source": traffic_src},
                         "inspector_ms_once_per_mesh": ctx.inspector_timings(),
                         "check": check_digest(name, ga, gt, key)})
     finally:

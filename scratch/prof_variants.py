@@ -7,6 +7,21 @@ import numpy as np
 from arcanefem_b200 import capi as A
 import bench
 
+def run_tiled_only(dim, n, b):
+    """large configurations (C4, C3): the tiled gather and the connectivity-based BuildMatrix only"""
+    ctx = A.Context(0)
+    ctx.generate_box(dim, n)
+    lam = bench.E_MOD * bench.NU / ((1 + bench.NU) * (1 - 2 * bench.NU)); mu = bench.E_MOD / (2 * (1 + bench.NU))
+    op, params, fmt = (A.OP_POISSON, None, A.FORMAT_CSR) if b == 1 else (A.OP_ELASTICITY, [lam, mu], A.FORMAT_BSR)
+    ctx.build_pattern(b)
+    for layout in ([A.LAYOUT_PER_BLOCK] if b == 1 else [A.LAYOUT_PER_ROW, A.LAYOUT_PER_BLOCK]):
+        for _ in range(3):
+            ctx.build_pattern(b)
+            ctx.assemble(op, params=params, fmt=fmt, variant=A.VARIANT_TILED_GATHER, layout=layout)
+    ctx.synchronize()
+    ctx.close()
+
+
 def run(dim, n, b, tag):
     ctx = A.Context(0)
     info = ctx.generate_box(dim, n)
@@ -19,6 +34,12 @@ def run(dim, n, b, tag):
             for _ in range(2):
                 ctx.reset_values()
                 ctx.assemble(op, params=params, fmt=fmt, variant=variant, layout=layout)
+        if b > 1:  # the other vector executor
+            ctx.set_vector_executor(A.VEC_EXEC_UNITS if dim == 3 else A.VEC_EXEC_ROWS)
+            for _ in range(2):
+                ctx.reset_values()
+                ctx.assemble(op, params=params, fmt=fmt, variant=A.VARIANT_TILED_GATHER, layout=layout)
+            ctx.set_vector_executor(A.VEC_EXEC_AUTO)
     if b == 1:
         ctx.reset_values()
         ctx.assemble(op, fmt=A.FORMAT_COO, variant=A.VARIANT_CELLWISE_ATOMIC)
@@ -36,4 +57,4 @@ def run(dim, n, b, tag):
     ctx.close()
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c2"
-{"c2": lambda: run(3, 120, 1, "c2"), "e3": lambda: run(3, 100, 3, "e3"), "e2": lambda: run(2, 2048, 2, "e2"), "p2d": lambda: run(2, 2048, 1, "p2d")}[which]()
+{"c4": lambda: run_tiled_only(3, 256, 1), "c3": lambda: run_tiled_only(3, 203, 3), "c2": lambda: run(3, 120, 1, "c2"), "e3": lambda: run(3, 100, 3, "e3"), "e2": lambda: run(2, 2048, 2, "e2"), "p2d": lambda: run(2, 2048, 1, "p2d")}[which]()

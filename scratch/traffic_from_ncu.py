@@ -4,7 +4,7 @@ import csv, json, os, re, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02t"
-CFG = {"c2": (3, 120, 1), "e3": (3, 100, 3), "e2": (2, 2048, 2), "p2d": (2, 2048, 1)}
+CFG = {"c4": (3, 256, 1), "c3": (3, 203, 3), "c2": (3, 120, 1), "e3": (3, 100, 3), "e2": (2, 2048, 2), "p2d": (2, 2048, 1)}
 out = {}
 for w, (dim, n, b) in CFG.items():
     path = f"gpurun_out/{tag}_traffic_{w}.csv"
@@ -46,8 +46,9 @@ for w, (dim, n, b) in CFG.items():
         out[f"{short}:{dim}d:n={n}:b={b}"] = e
 # the key bench.py looks up for the bench line of a same-size run (bricks executor)
 for k, e in list(out.items()):
-    if k.startswith("k_assemble_tiled<4>:3d:n=120"):
-        out["k_assemble_tiled:n=120"] = e
+    for n in (120, 256):
+        if k.startswith(f"k_assemble_tiled<4>:3d:n={n}"):
+            out[f"k_assemble_tiled:n={n}"] = e
 json.dump(out, open("profiles/traffic.json", "w"), indent=1, sort_keys=True)
 for k, e in sorted(out.items()):
     print(f"{k[:70]:70s} {e['time_us']:9.1f} us  R {e['dram_bytes_read']/1e6:8.1f} MB  W {e['dram_bytes_write']/1e6:8.1f} MB  x{e['traffic_over_algorithmic']:.2f} alg  {e['dram_gbs']:7.0f} GB/s")
