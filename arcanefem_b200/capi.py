@@ -41,7 +41,7 @@ EXPORTS = [
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
     "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail",
-    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_exchange_async", "afb_p2p_wait", "afb_p2p_status", "afb_p2p_disconnect", "afb_partition_create", "afb_partition_destroy", "afb_partition_sizes", "afb_partition_get",
+    "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_exchange_async", "afb_p2p_wait", "afb_p2p_status", "afb_p2p_wait_stats", "afb_p2p_disconnect", "afb_partition_create", "afb_partition_destroy", "afb_partition_sizes", "afb_partition_get",
     "afb_xplan_host_create", "afb_xplan_host_destroy", "afb_xplan_host_peers", "afb_xplan_host_pairs", "afb_xplan_host_numbering",
     "afb_xplan_create", "afb_xplan_destroy", "afb_xplan_exchange", "afb_xplan_wait", "afb_xplan_numbering", "afb_xplan_info", "afb_solve_pcg", "afb_last_timings", "afb_inspector_timings", "afb_launch_count",
 ]
@@ -309,6 +309,12 @@ class Context:
 
     def p2p_wait(self):
         _check(lib().afb_p2p_wait(self._h))
+
+    def p2p_wait_stats(self):
+        """(ready_wait_us, pulled_wait_us, nb_exchange) since the last call: time the exchange kernels waited for the neighbours."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        _check(lib().afb_p2p_wait_stats(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     def p2p_status(self):
         st = C.c_int()

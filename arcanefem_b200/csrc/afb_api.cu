@@ -251,6 +251,13 @@ int afb_p2p_wait(afb_ctx* ctx)
   return p2p_wait(ctx);
 }
 
+int afb_p2p_wait_stats(afb_ctx* ctx, double* ready_wait_us, double* pulled_wait_us, int64_t* nb_exchange)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ready_wait_us && pulled_wait_us && nb_exchange, AFB_ERR_INVALID, "afb_p2p_wait_stats: null");
+  return p2p_wait_stats(ctx, ready_wait_us, pulled_wait_us, nb_exchange);
+}
+
 int afb_p2p_status(afb_ctx* ctx, int* status)
 {
   AFB_TRY(check_ctx(ctx));

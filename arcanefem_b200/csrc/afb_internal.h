@@ -240,6 +240,7 @@ int p2p_connect_ex(afb_ctx* ctx, int my_rank, int nb_peer, const int32_t* peer_r
 int p2p_exchange(afb_ctx* ctx, int async);
 int p2p_wait(afb_ctx* ctx);
 int p2p_status(afb_ctx* ctx, int* status);
+int p2p_wait_stats(afb_ctx* ctx, double* ready_wait_us, double* pulled_wait_us, int64_t* nb_exchange);
 int p2p_disconnect(afb_ctx* ctx);
 bool pattern_nn_ready(const afb_ctx* ctx);
 int pattern_nn_build(afb_ctx* ctx);

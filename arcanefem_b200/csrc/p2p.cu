@@ -51,6 +51,8 @@ struct P2PState {
   int my_rank = 0;
   uint32_t* flags = nullptr;   // [2][P2P_MAX_RANK] + error word, cudaMalloc (exported)
   int* counters = nullptr;     // two per peer: blocks done, blocks that gave up waiting for READY
+  unsigned long long* wait_ns = nullptr; // [2]: ns the kernels spent waiting for the neighbours' READY / PULLED flags (first block of each neighbour)
+  long long stats_epoch0 = 0;  // epoch at the last afb_p2p_wait_stats
   int blocks_per_peer = P2P_BLOCKS_PER_PEER;
   uint32_t* h_err = nullptr;   // sticky error word in mapped pinned host memory: read without a stream synchronisation
   uint32_t* d_err = nullptr;   // its device address
@@ -98,7 +100,7 @@ __device__ __forceinline__ bool wait_epoch(const uint32_t* flag, uint32_t epoch)
 
 __global__ void __launch_bounds__(P2P_THREADS)
 k_p2p_exchange(const PeerDev* __restrict__ peers, double* __restrict__ values, uint32_t* __restrict__ flags, int my_rank, uint32_t epoch, int* __restrict__ counters,
-               int bpp, uint32_t* __restrict__ host_err)
+               int bpp, uint32_t* __restrict__ host_err, unsigned long long* __restrict__ wait_ns)
 {
   __shared__ int s_ok;
   const int p = blockIdx.x / bpp, bb = blockIdx.x % bpp;
@@ -114,7 +116,9 @@ k_p2p_exchange(const PeerDev* __restrict__ peers, double* __restrict__ values, u
       __threadfence_system();
       st_release_sys(P.peer_flags + my_rank, epoch); // READY
     }
+    const unsigned long long tw = globaltimer_ns();
     s_ok = wait_epoch(flags + P.rank, epoch) ? 1 : 0;
+    if (bb == 0) atomicAdd(wait_ns, globaltimer_ns() - tw); // rank skew, as seen from this rank
     if (!s_ok) {
       fail(1u);
       atomicAdd(counters + 2 * p + 1, 1);
@@ -148,7 +152,9 @@ k_p2p_exchange(const PeerDev* __restrict__ peers, double* __restrict__ values, u
       // (its own wait for PULLED then times out into status 2 instead of zeroing contributions nobody took)
       if (gave_up == 0) st_release_sys(P.peer_flags + P2P_MAX_RANK + my_rank, epoch);
     }
+    const unsigned long long tw = globaltimer_ns();
     s_ok = wait_epoch(flags + P2P_MAX_RANK + P.rank, epoch) ? 1 : 0;
+    if (bb == 0) atomicAdd(wait_ns + 1, globaltimer_ns() - tw);
     if (!s_ok) fail(2u);
   }
   __syncthreads();
@@ -171,6 +177,8 @@ int p2p_export(afb_ctx* ctx, void* values_handle, void* flags_handle)
   if (!S->flags) {
     AFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&S->flags), sizeof(uint32_t) * (2 * P2P_MAX_RANK + 2)));
     AFB_CUDA(cudaMemset(S->flags, 0, sizeof(uint32_t) * (2 * P2P_MAX_RANK + 2)));
+    AFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&S->wait_ns), 2 * sizeof(unsigned long long)));
+    AFB_CUDA(cudaMemset(S->wait_ns, 0, 2 * sizeof(unsigned long long)));
     AFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&S->h_err), sizeof(uint32_t), cudaHostAllocMapped));
     *S->h_err = 0u;
     AFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&S->d_err), S->h_err, 0));
@@ -331,12 +339,34 @@ int p2p_exchange(afb_ctx* ctx, int async)
     st = S->side;
   }
   k_p2p_exchange<<<S->nb_peer * S->blocks_per_peer, P2P_THREADS, 0, st>>>(S->d_peers, ctx->values.as<double>(), S->flags, S->my_rank, S->epoch, S->counters,
-                                                                          S->blocks_per_peer, S->d_err);
+                                                                          S->blocks_per_peer, S->d_err, S->wait_ns);
   AFB_LAUNCH_CHECK(ctx);
   if (async) {
     AFB_CUDA(cudaEventRecord(S->ev_done, S->side));
     S->inflight = true;
   }
+  return AFB_OK;
+}
+
+// time the exchange kernels since the last call spent waiting for the neighbours (synchronises; read and clear)
+int p2p_wait_stats(afb_ctx* ctx, double* ready_wait_us, double* pulled_wait_us, int64_t* nb_exchange)
+{
+  P2PState* S = ctx->p2p ? static_cast<P2PState*>(ctx->p2p) : nullptr;
+  *ready_wait_us = *pulled_wait_us = 0.0;
+  *nb_exchange = 0;
+  if (!S || !S->wait_ns) return AFB_OK;
+  if (S->inflight) {
+    AFB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_done, 0));
+    S->inflight = false;
+  }
+  unsigned long long w[2] = { 0ull, 0ull };
+  AFB_CUDA(cudaMemcpyAsync(w, S->wait_ns, sizeof(w), cudaMemcpyDeviceToHost, ctx->stream));
+  AFB_CUDA(cudaMemsetAsync(S->wait_ns, 0, sizeof(w), ctx->stream));
+  AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *ready_wait_us = 1e-3 * (double)w[0];
+  *pulled_wait_us = 1e-3 * (double)w[1];
+  *nb_exchange = (int64_t)S->epoch - S->stats_epoch0;
+  S->stats_epoch0 = (long long)S->epoch;
   return AFB_OK;
 }
 

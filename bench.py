@@ -539,6 +539,8 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.25)
     evs = [[ev(), ev(), ev()] for _ in range(args.steps)]
+    if world > 1 and mode == "exchange":
+        ctx.p2p_wait_stats()  # clear: the counters below cover the timed steps only
     barrier()
     t_start, t_end = ev(), ev()
     t_start.record(stream)
@@ -558,10 +560,13 @@ def run_b200(args):
         transport = "p2p" if da.plan.p2p is not None else "nccl"
         if args.transport == "p2p" and transport != "p2p" and rank == 0:
             print(f"bench.py: peer-memory exchange unavailable ({da.plan.p2p_error}); NCCL send/recv used instead", file=sys.stderr)
+    wait_ready_us = wait_pulled_us = 0.0
     if world > 1 and mode == "exchange" and transport == "p2p":
         st = ctx.p2p_status()
         if st != 0:
             raise SystemExit(f"bench.py: ghost-row exchange timed out on rank {rank} (status {st})")
+        wr, wp, nex = ctx.p2p_wait_stats()  # rank skew as seen by this rank's exchange kernels, per step
+        wait_ready_us, wait_pulled_us = wr / max(nex, 1), wp / max(nex, 1)
     total_ms = t_start.elapsed_time(t_end)
     pattern_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     values_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
@@ -739,7 +744,8 @@ def run_b200(args):
 
     # --- reduce over ranks (max time, summed work) ---------------------------------------------
     stats = torch.tensor([total_ms, pattern_ms, values_ms, e2e_ms, float(nb_cell_local), float(launches), float(h2d), float(d2h),
-                          float(bytes_values), float(bytes_pattern), e2e_serial_ms, dev_abs, dev_trace, float(dev_nnz), e2e_abs, e2e_trace, new_mesh_ms, float(h2d_new)],
+                          float(bytes_values), float(bytes_pattern), e2e_serial_ms, dev_abs, dev_trace, float(dev_nnz), e2e_abs, e2e_trace, new_mesh_ms, float(h2d_new),
+                          wait_ready_us, wait_pulled_us],
                          dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
@@ -781,7 +787,8 @@ def run_b200(args):
                        "inspector_ms_once_per_mesh": inspector,
                        "first_step_ms": first_step_ms,
                        "decomposition": mode, "exchange_bytes_sent_recv_rank0": list(exch_bytes),
-                       "per_rank_ms": [{"step": float(p[0]) / args.steps, "build_matrix": float(p[1]), "add_and_compute": float(p[2])} for p in per_rank] if world > 1 else None,
+                       "per_rank_ms": [{"step": float(p[0]) / args.steps, "build_matrix": float(p[1]), "add_and_compute": float(p[2]),
+                                        "exchange_wait_ready_us": float(p[18]), "exchange_wait_pulled_us": float(p[19])} for p in per_rank] if world > 1 else None,
                        "other_scheme_ms_per_step": None if other_ms is None else {other_ms[0]: other_ms[1]}},
             "roofline": {"bound": "hbm", "kernel": "value assembly (AddAndCompute)", "achieved": ach_values, "peak": peak, "unit": "GB/s", "frac": ach_values / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": float(mx[8])},

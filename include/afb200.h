@@ -411,6 +411,10 @@ AFB_API int afb_p2p_exchange(afb_ctx* ctx);
 AFB_API int afb_p2p_exchange_async(afb_ctx* ctx);
 AFB_API int afb_p2p_wait(afb_ctx* ctx);
 AFB_API int afb_p2p_status(afb_ctx* ctx, int* status);
+/* Rank skew as a number: microseconds the exchange kernels since the last call spent waiting for the neighbours' rows to
+ * become ready, and for the neighbours to acknowledge their pulls (first block of each neighbour, summed over neighbours
+ * and exchanges), and the number of exchanges.  Synchronises; read and clear. */
+AFB_API int afb_p2p_wait_stats(afb_ctx* ctx, double* ready_wait_us, double* pulled_wait_us, int64_t* nb_exchange);
 AFB_API int afb_p2p_disconnect(afb_ctx* ctx);
 
 /*

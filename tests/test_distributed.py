@@ -343,6 +343,10 @@ def run_rank_p2p(rank, world, port, case, transport, errq):
                 ctx.synchronize()
             lrows, lcols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
             check_owned_rows(s, b, layout, lrows, lcols, ctx.to_host(A.ARRAY_VALUES), grows, gcols, gvals)
+        if transport == "p2p":  # rank skew as a number (afb_p2p_wait_stats): read and clear
+            ready_us, pulled_us, nex = ctx.p2p_wait_stats()
+            assert nex == 3 and ready_us >= 0.0 and pulled_us >= 0.0 and ready_us + pulled_us < 3 * 60e6
+            assert ctx.p2p_wait_stats()[2] == 0
             dist.barrier()
         if transport == "p2p":
             ctx.p2p_disconnect()
