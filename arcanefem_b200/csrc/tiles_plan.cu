@@ -698,19 +698,18 @@ k_tile_lists(TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* __rest
 // greedy choice in lane order with one-step augmentation (a lane that finds all its banks taken may move an earlier lane
 // to another free bank of that lane's remaining contributions).  The order inside an entry's list is therefore
 // plan-defined (not ascending cell id), but fixed: the sums stay bit-reproducible.
-//   canon: the lists in canonical order (same layout as the result), padded with `pad`
+//   lists: in canonical order on entry (padded with `pad`), reordered in place
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_bank_order(const TileDesc* __restrict__ desc, const uint32_t* __restrict__ unit_base, const uint16_t* __restrict__ unit_len,
-                                                    const uint16_t* __restrict__ canon, uint16_t* __restrict__ lists, uint16_t pad)
+                                                    uint16_t* __restrict__ lists, uint16_t pad)
 {
   const TileDesc d = desc[blockIdx.x];
   for (int hx = threadIdx.x; hx < d.nb_unit * 2; hx += blockDim.x) {
     const int u = hx >> 1, l0 = (hx & 1) * 16;
     const int len = unit_len[d.unit_off + u];
     const size_t base = (size_t)d.list_off + unit_base[d.unit_off + u] + l0 * 2;
-    const uint16_t* in0 = canon + base; // [len/2][32 lanes][2]
-    uint16_t* out0 = lists + base;
-    auto cand = [&](int j, int q) { return in0[j * 2 + (q >> 1) * 64 + (q & 1)]; };
+    uint16_t* out0 = lists + base; // [len/2][32 lanes][2], canonical order on entry, reordered in place
+    auto cand = [&](int j, int q) { return out0[j * 2 + (q >> 1) * 64 + (q & 1)]; };
     // the banks of a list's contributions, 4 bits each (lists of up to 16: the searches below run on registers / local
     // words; a longer list keeps its canonical order)
     int cnt_l[16];
@@ -731,11 +730,14 @@ __global__ void __launch_bounds__(128) k_bank_order(const TileDesc* __restrict__
       taken[j] = 0u;
       if (c > 16) simple = true;
     }
+    if (simple) continue; // canonical order stays
+    unsigned long long perm[16]; // list -> its contribution of step k, 4 bits per step
+    for (int j = 0; j < 16; ++j) perm[j] = 0ull;
     for (int k = 0; k < len; ++k) {
       signed char owner[16];  // bank -> lane
       signed char choice[16]; // lane -> index into its list
       for (int j = 0; j < 16; ++j) { owner[j] = -1; choice[j] = -1; }
-      if (!simple) {
+      {
         for (int j = 0; j < 16; ++j) {
           if (k >= cnt_l[j]) continue;
           const int n = cnt_l[j];
@@ -773,17 +775,19 @@ __global__ void __launch_bounds__(128) k_bank_order(const TileDesc* __restrict__
           if (choice[j] < 0) choice[j] = (signed char)first; // a bank conflict remains
         }
       }
-      for (int j = 0; j < 16; ++j) {
-        uint16_t code = pad;
+      for (int j = 0; j < 16; ++j)
         if (k < cnt_l[j]) {
-          if (simple) code = cand(j, k);
-          else {
-            code = cand(j, choice[j]);
-            taken[j] |= 1u << choice[j];
-          }
+          taken[j] |= 1u << choice[j];
+          perm[j] |= (unsigned long long)choice[j] << (4 * k);
         }
-        out0[j * 2 + (k >> 1) * 64 + (k & 1)] = code;
-      }
+    }
+    // apply: every list is permuted in place
+    for (int j = 0; j < 16; ++j) {
+      const int n = cnt_l[j];
+      if (n < 2) continue;
+      uint16_t c[16];
+      for (int q = 0; q < n; ++q) c[q] = cand(j, q);
+      for (int k = 0; k < n; ++k) out0[j * 2 + (k >> 1) * 64 + (k & 1)] = c[(perm[j] >> (4 * k)) & 15ull];
     }
   }
 }
@@ -793,8 +797,7 @@ __global__ void __launch_bounds__(128) k_bank_order(const TileDesc* __restrict__
 // that have no step to spare choose first, a list shorter than the unit's may sit a step out (padding slot) when every
 // remaining contribution of it would collide
 template <int NPC>
-__global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restrict__ desc, const uint2* __restrict__ units, const uint16_t* __restrict__ canon,
-                                                         uint16_t* __restrict__ lists)
+__global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restrict__ desc, const uint2* __restrict__ units, uint16_t* __restrict__ lists)
 {
   constexpr int CS = VR_CS;
   constexpr uint16_t PAD = (uint16_t)(CS - 1);
@@ -804,9 +807,8 @@ __global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restr
     const uint2 U = units[d.unit_off + u];
     const int len = (int)(U.y >> 17);
     const size_t base = (size_t)d.list_off + U.x + l0 * 2;
-    const uint16_t* in0 = canon + base;
-    uint16_t* out0 = lists + base;
-    auto cand = [&](int j, int q) { return in0[j * 2 + (q >> 1) * 64 + (q & 1)]; };
+    uint16_t* out0 = lists + base; // canonical order on entry, reordered in place
+    auto cand = [&](int j, int q) { return out0[j * 2 + (q >> 1) * 64 + (q & 1)]; };
     // per list: the two banks (8-byte bank of the word of node a / node b) of every contribution, 4 bits each, and the low
     // 12 bits of the two words (equal words are broadcast): lists of up to 16; a longer list keeps its canonical order
     unsigned taken[16];
@@ -839,6 +841,10 @@ __global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restr
       taken[j] = 0u;
       used[j] = 0;
     }
+    if (simple || len > 16) continue; // canonical order stays
+    unsigned long long perm[16]; // list -> its contribution of step k (4 bits per step)
+    unsigned short sits[16];     // list -> steps it sits out (padding slot)
+    for (int j = 0; j < 16; ++j) { perm[j] = 0ull; sits[j] = 0; }
     for (int k = 0; k < len; ++k) {
       short ownA[16], ownB[16]; // 8-byte bank -> cache word read from it in this step (-1: free)
       for (int q = 0; q < 16; ++q) ownA[q] = ownB[q] = -1;
@@ -850,9 +856,8 @@ __global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restr
           const bool must = (must_mask >> j) & 1u;
           if (must != (pass == 0)) continue;
           const int c = cnt_l[j], rem = c - used[j];
-          uint16_t code = PAD;
-          if (simple) code = cand(j, k);
-          else if (rem > 0) {
+          bool took = false;
+          if (rem > 0) {
             // a free bank is certainly no collision; an occupied one may hold the same word (checked on the few that tie)
             const unsigned long long wa_j = bwa[j], wb_j = bwb[j];
             int best = -1, best_score = -1;
@@ -871,18 +876,27 @@ __global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restr
               if (score == 2) break;
             }
             if (must || best_score == 2) {
-              code = cand(j, best);
+              took = true;
               taken[j] |= 1u << best;
               ++used[j];
+              perm[j] |= (unsigned long long)best << (4 * k);
               int wa, wb;
-              words(code, wa, wb);
+              words(cand(j, best), wa, wb);
               if (ownA[wa & 15] < 0) ownA[wa & 15] = (short)wa;
               if (ownB[wb & 15] < 0) ownB[wb & 15] = (short)wb;
             }
           }
-          out0[j * 2 + (k >> 1) * 64 + (k & 1)] = code;
+          if (!took) sits[j] |= (unsigned short)(1u << k);
         }
       }
+    }
+    // apply: every list is permuted in place (padding slots where it sits out)
+    for (int j = 0; j < 16; ++j) {
+      const int n = cnt_l[j];
+      if (n == 0) continue;
+      uint16_t c[16];
+      for (int q = 0; q < n; ++q) c[q] = cand(j, q);
+      for (int k = 0; k < len; ++k) out0[j * 2 + (k >> 1) * 64 + (k & 1)] = ((sits[j] >> k) & 1u) ? PAD : c[(perm[j] >> (4 * k)) & 15ull];
     }
   }
 }
@@ -1328,9 +1342,6 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
   AFB_TRY(P.emap.reserve(sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(unit_off, 1)));
   if (vec) AFB_TRY(P.emap_rows.reserve(sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(unit_off, 1)));
   AFB_TRY(P.lists.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
-  DevBuf canon; // the lists in canonical order, between the two kernels (released on return)
-  struct Scoped { DevBuf& b; ~Scoped() { b.release(); } } canon_guard{ canon };
-  AFB_TRY(canon.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
   AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
   AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
   AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), st));
@@ -1344,7 +1355,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
       if (e != cudaSuccess) return e;
       kernel<<<grid, TB_THREADS, smem, st>>>(P.tile_desc.as<TileDesc>(), nb_tile, P.tile_nodes.as<int32_t>(), P.tile_cells.as<int32_t>(), ctx->conn.as<int32_t>(),
                                              ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(), P.node_tile.as<int32_t>(), P.node_lrow.as<int32_t>(), own, nb_own_cell,
-                                             P.rowinfo.as<uint32_t>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), P.emap.as<uint32_t>(), P.emap_rows.as<uint32_t>(), canon.as<uint16_t>(),
+                                             P.rowinfo.as<uint32_t>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), P.emap.as<uint32_t>(), P.emap_rows.as<uint32_t>(), P.lists.as<uint16_t>(),
                                              list_max, ctx->tmp_flag.as<int>());
       return cudaGetLastError();
     };
@@ -1353,7 +1364,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
     else e = vec ? go(k_tile_lists<3, true>, 1 << 30) : go(k_tile_lists<3, false>, 1 << 30);
     AFB_CUDA(e);
     // order inside the lists (shared-memory banks of the executor's gathers): one thread per half-unit, whole grid
-    k_bank_order<<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), canon.as<uint16_t>(), P.lists.as<uint16_t>(),
+    k_bank_order<<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.unit_base.as<uint32_t>(), P.unit_len.as<uint16_t>(), P.lists.as<uint16_t>(),
                                           (uint16_t)(vec ? (TV_CS - 1) : TG_ZERO));
     AFB_LAUNCH_CHECK(ctx);
     ctx->launches += 2;
@@ -1392,8 +1403,6 @@ int build_tile_rowlists(afb_ctx* ctx, int mode_flags)
   const uint8_t* own = (ctx->all_own || (mode_flags & AFB_FLAG_ALL_ROWS)) ? nullptr : ctx->is_own.as<uint8_t>();
   const int64_t nb_own_cell = (mode_flags & AFB_FLAG_OWN_CELLS_ONLY) ? ctx->nb_own_cell : ctx->nb_cell;
   AFB_TRY(P.rowinfo.reserve(sizeof(uint32_t) * (size_t)ctx->nb_node));
-  DevBuf canon; // the lists in canonical order, between the kernels (released on return)
-  struct Scoped { DevBuf& b; ~Scoped() { b.release(); } } canon_guard{ canon };
   const size_t smem = sizeof(RowListSmem);
   const int grid = std::min<int>(std::max(nb_tile, 1), 2 * ctx->sm_count);
   auto go = [&](auto kernel) {
@@ -1401,7 +1410,7 @@ int build_tile_rowlists(afb_ctx* ctx, int mode_flags)
     if (e != cudaSuccess) return e;
     kernel<<<grid, TB_THREADS, smem, st>>>(P.tile_desc.as<TileDesc>(), nb_tile, P.tile_nodes.as<int32_t>(), P.tile_cells.as<int32_t>(), ctx->conn.as<int32_t>(),
                                            ctx->rows.as<int32_t>(), ctx->cols.as<int32_t>(), P.node_tile.as<int32_t>(), P.node_lrow.as<int32_t>(), own, nb_own_cell,
-                                           P.rowinfo.as<uint32_t>(), P.vr_units.as<uint2>(), canon.as<uint16_t>(), ctx->tmp_flag.as<int>());
+                                           P.rowinfo.as<uint32_t>(), P.vr_units.as<uint2>(), P.lists.as<uint16_t>(), ctx->tmp_flag.as<int>());
     return cudaGetLastError();
   };
   int64_t unit_off = 0, list_off = 0;
@@ -1425,13 +1434,12 @@ int build_tile_rowlists(afb_ctx* ctx, int mode_flags)
   P.nb_list = list_off;
   AFB_TRY(P.vr_units.reserve(sizeof(uint2) * (size_t)std::max<int64_t>(unit_off, 1)));
   AFB_TRY(P.lists.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
-  AFB_TRY(canon.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
   if (nb_tile > 0) {
     // pass 2: unit records and lists in canonical order; then the order inside the lists (one thread per half-unit)
     AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
     AFB_CUDA(npc == 4 ? go(k_tile_rowlists<4, true>) : go(k_tile_rowlists<3, true>));
-    if (npc == 4) k_bank_order_rows<4><<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.vr_units.as<uint2>(), canon.as<uint16_t>(), P.lists.as<uint16_t>());
-    else k_bank_order_rows<3><<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.vr_units.as<uint2>(), canon.as<uint16_t>(), P.lists.as<uint16_t>());
+    if (npc == 4) k_bank_order_rows<4><<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.vr_units.as<uint2>(), P.lists.as<uint16_t>());
+    else k_bank_order_rows<3><<<nb_tile, 128, 0, st>>>(P.tile_desc.as<TileDesc>(), P.vr_units.as<uint2>(), P.lists.as<uint16_t>());
     AFB_LAUNCH_CHECK(ctx);
     ctx->launches += 2;
   }
