@@ -122,6 +122,8 @@ int afb_destroy(afb_ctx* ctx)
   if (!ctx) return AFB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (afb_xplan* x : std::vector<afb_xplan*>(ctx->xplans)) xplan_detach(x); // plans outliving their context must not touch it
+  ctx->xplans.clear();
   p2p_destroy(ctx);
   chain_destroy(ctx);
   DevBuf* bufs[] = { &ctx->coords, &ctx->conn, &ctx->is_own, &ctx->nc_ptr, &ctx->nc_list, &ctx->rows, &ctx->cols, &ctx->nz_per_row, &ctx->coo_rows, &ctx->values,

@@ -123,6 +123,9 @@ struct TilePlan {
 
 } // namespace afb
 
+struct afb_xplan;
+void xplan_detach(afb_xplan* x); // mgpu.cu: the plan's context is going away
+
 struct afb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -185,6 +188,7 @@ struct afb_ctx {
   bool vec_rows() const { return vec_exec == 1 /*ROWS*/ || (vec_exec == 0 /*AUTO*/ && npc == 4); }
   int64_t tiled_stage_limit = 1ll << 40; // afb_set_tiled_stage_limit
   void* p2p = nullptr;              // afb::P2PState (p2p.cu): ghost-row exchange over NVLink peer memory
+  std::vector<afb_xplan*> xplans;   // exchange plans living on this context (mgpu.cu): detached by afb_destroy
   void* chain = nullptr;            // afb::ChainPlan (chain_plan.cu): plan of the scalar tiled-gather executor
   unsigned scan_tickets = 0, scan_epoch = 0; // chained scan (scan.cu): tiles handed out so far, epoch of the last call
   uint64_t nnz_mesh_gen = ~0ull;    // mesh generation ctx->nnz was last read back for

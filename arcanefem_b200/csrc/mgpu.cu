@@ -424,12 +424,28 @@ struct afb_xplan {
   const void* values_base = nullptr;
 };
 
+// afb_destroy of the plan's context: release what lives on that context now, keep the host part for afb_xplan_destroy
+void xplan_detach(afb_xplan* x)
+{
+  if (!x || !x->ctx) return;
+  if (x->kind == 1) p2p_disconnect(x->ctx);
+  for (auto& b : x->slots) b.release();
+  for (auto& b : x->recvbuf) b.release();
+  x->ctx = nullptr;
+  x->kind = 0;
+}
+
 extern "C" {
 
 int afb_xplan_destroy(afb_xplan* x)
 {
   if (!x) return AFB_OK;
-  if (x->kind == 1) p2p_disconnect(x->ctx);
+  if (x->ctx) {
+    auto& v = x->ctx->xplans;
+    v.erase(std::remove(v.begin(), v.end(), x), v.end());
+    cudaSetDevice(x->ctx->device);
+    if (x->kind == 1) p2p_disconnect(x->ctx);
+  }
   for (auto& b : x->slots) b.release();
   for (auto& b : x->recvbuf) b.release();
   afb_xplan_host_destroy(x->host);
@@ -559,6 +575,7 @@ int afb_xplan_create(afb_ctx* ctx, const afb_transport* t, const int64_t* node_g
       }
     }
   }
+  ctx->xplans.push_back(X);
   *out = X;
   return AFB_OK;
 }
@@ -566,6 +583,7 @@ int afb_xplan_create(afb_ctx* ctx, const afb_transport* t, const int64_t* node_g
 int afb_xplan_exchange(afb_xplan* x)
 {
   AFB_REQUIRE(x, AFB_ERR_INVALID, "afb_xplan_exchange: null plan");
+  AFB_REQUIRE(x->ctx, AFB_ERR_INVALID, "afb_xplan_exchange: the plan's context was destroyed");
   afb_ctx* ctx = x->ctx;
   AFB_REQUIRE(ctx->values.p == x->values_base, AFB_ERR_INVALID, "afb_xplan_exchange: the values array moved since afb_xplan_create (create the plan again)");
   if (x->kind == 0) return AFB_OK;

@@ -246,6 +246,7 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+    sys.stdout.flush()
     return 0
 
 
@@ -739,6 +740,8 @@ def run_b200(args):
     h2d_new = coords_h.numel() * 8 + cells_h.numel() * 4 + (own_h.numel() if has_own else 0)
     h2d = coords_h.numel() * 8
     d2h = rows_h.numel() * 4 + cols_h.numel() * 4 + vals_h.numel() * 8
+    if da2 is not None:
+        da2.close()  # the exchange plan goes before its context
     ctx2.close()
     del coords_h, cells_h, rows_h, cols_h, vals_h
 
@@ -834,6 +837,9 @@ def run_b200(args):
                 fm["CsrNodeWise_ThreadPerRow"] = (bm_cells, per_variant[A.VARIANT_NODEWISE] * 1e-3)
             write_time_stats(args.time_stats, args.steps, world, 3, (n + 1) ** 3, 12 * n * n, int(cells_all), fm)
         print(json.dumps(line))
+        sys.stdout.flush()
+    if da is not None:
+        da.close()  # the exchange plan goes before its context
     if ctx is not None:
         ctx.close()
     if world > 1:
@@ -842,6 +848,8 @@ def run_b200(args):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()  # a crash inside native code prints the Python stack of every thread
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

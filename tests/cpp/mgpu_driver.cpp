@@ -185,10 +185,19 @@ int main(int argc, char** argv)
     R.first.resize(world + 1);
     R.l2g.resize((size_t)nn * b);
     CHECK(afb_xplan_numbering(x, R.first.data(), R.l2g.data()));
+    // odd ranks destroy the context first: the plan must survive that (afb_destroy detaches it) and still be destroyable
     sh.barrier();
-    CHECK(afb_xplan_destroy(x));
+    if (rank & 1) CHECK(afb_destroy(ctx));
+    else CHECK(afb_xplan_destroy(x));
     sh.barrier();
-    CHECK(afb_destroy(ctx));
+    if (rank & 1) {
+      if (afb_xplan_exchange(x) == 0) {
+        std::fprintf(stderr, "rank %d: exchange on a plan whose context is gone did not fail\n", rank);
+        failed = true;
+      }
+      CHECK(afb_xplan_destroy(x));
+    }
+    else CHECK(afb_destroy(ctx));
   };
   {
     // no GPU: afb_create fails on every rank before anything collective -- report like the facade driver does
