@@ -403,6 +403,26 @@ def side_config(torch, A, device, stream, ev, name, n, op, b, layouts, peak):
     return out
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal CPU affinity) before any pinned host buffer is allocated,
+    so that the e2e host<->device copies of N ranks do not all cross the socket interconnect.  Returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        if not target or target == allowed:
+            return "unchanged (%d CPUs allowed, %d next to the GPU)" % (len(allowed), len(cpus))
+        os.sched_setaffinity(0, target)
+        return "%d of %d allowed CPUs (next to GPU %d)" % (len(target), len(allowed), device_index)
+    except Exception as exc:  # noqa: BLE001 -- the placement is an optimisation, never a requirement
+        return "unchanged (%s)" % type(exc).__name__
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -418,6 +438,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the assembly path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    cpus_at_start = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    affinity = bind_to_gpu_numa(local_rank) if not args.no_bind else "unchanged (--no-bind)"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -800,6 +822,7 @@ def run_b200(args):
             "check": check,
             "e2e": {"value": cells_all * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sm[6]), "d2h_bytes_per_step": int(sm[7]),
                     "steps": e2e_steps, "variant": VARIANT_NAMES[variant],
+                    "host_cpus_rank0": affinity,
                     "pcie_gbs_all_ranks": (float(sm[6]) + float(sm[7])) * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                     "pipelined": f"{nl} lanes (contexts / streams / host threads) out of phase: one lane's H2D overlaps another's D2H and kernels" if e2e_pipelined else "no (one step at a time)",
                     "one_step_at_a_time_value": cells_all * e2e_steps / (float(mx[10]) * 1e-3),
@@ -823,6 +846,8 @@ def run_b200(args):
                 cfgs += side_config(torch, A, local_rank, stream, ev, "C2", 120, A.OP_POISSON, 1, [A.LAYOUT_PER_BLOCK], peak)
             cfgs += side_config(torch, A, local_rank, stream, ev, "C3", args.n_c3, A.OP_ELASTICITY, 3, [A.LAYOUT_PER_ROW, A.LAYOUT_PER_BLOCK], peak)
             line["configs"] = cfgs
+        if cpus_at_start is not None:
+            os.sched_setaffinity(0, cpus_at_start)  # the CPU baseline uses every host core again
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(args, n)
         if args.time_stats:
@@ -866,6 +891,7 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "atomic", "nodewise", "tiled"])
     ap.add_argument("--sparsity", default="auto", choices=["auto", "cells", "connectivity"], help="steady-state BuildMatrix algorithm (auto: by variant, as the reference pairs them)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the CPUs next to its GPU")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e: one step at a time only")
     ap.add_argument("--e2e-lanes", type=int, default=4, help="e2e: pipelined lanes (independent problems in flight)")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1, exchange mode: one pull kernel over NVLink peer memory (CUDA IPC) or NCCL send/recv + accumulate kernels")
