@@ -91,6 +91,10 @@ constexpr int VR_RT3 = AFB_VR_RT3, VR_RT2 = AFB_VR_RT2;
 #ifndef AFB_VR_SLACK
 #define AFB_VR_SLACK 0
 #endif
+#ifndef AFB_VR_SHARE
+#define AFB_VR_SHARE 1
+#endif
+constexpr bool VR_SHARE = AFB_VR_SHARE != 0; // list ordering prefers cells another lane of the half-warp reads in the same step
 constexpr int VR_SLACK = AFB_VR_SLACK; // extra (padding) steps per unit: room for the plan to dodge shared-memory bank conflicts
 // unit record (uint2): x = first 16-bit slot of the unit's lists inside the tile's list region;
 // y = first tile-local entry | (entries - 1) << 12 | list length (contributions per lane, even) << 17

@@ -864,18 +864,20 @@ __global__ void __launch_bounds__(128) k_bank_order_rows(const TileDesc* __restr
             for (int q = 0; q < c; ++q) {
               if ((taken[j] >> q) & 1u) continue;
               const int ba = (int)((wa_j >> (4 * q)) & 15ull), bb = (int)((wb_j >> (4 * q)) & 15ull);
-              int sa = ownA[ba] < 0 ? 1 : 0, sb = ownB[bb] < 0 ? 1 : 0;
+              int sa = ownA[ba] < 0 ? 1 : 0, sb = ownB[bb] < 0 ? 1 : 0, shared = 0;
               if (sa + sb < 2) {
                 int wa, wb;
                 words(cand(j, q), wa, wb);
-                if (!sa && ownA[ba] == wa) sa = 1;
-                if (!sb && ownB[bb] == wb) sb = 1;
+                if (!sa && ownA[ba] == wa) { sa = 1; ++shared; }
+                if (!sb && ownB[bb] == wb) { sb = 1; ++shared; }
               }
-              const int score = sa + sb;
+              // no collision first; among those, words another lane reads anyway (a cell shared by several entries of the
+              // row is read once for all of them and takes no further bank)
+              const int score = VR_SHARE ? 4 * (sa + sb) + shared : sa + sb;
               if (score > best_score) { best_score = score; best = q; }
-              if (score == 2) break;
+              if (!VR_SHARE && score == 2) break;
             }
-            if (must || best_score == 2) {
+            if (must || best_score >= (VR_SHARE ? 8 : 2)) {
               took = true;
               taken[j] |= 1u << best;
               ++used[j];
