@@ -332,6 +332,7 @@ struct MeshBuilderSmem {
   unsigned htab[TB_HASH];
   unsigned sfoot[1024];
   int gmax[TG_GMAX], goff[TG_GMAX + 1];
+  uint16_t rowfs[TG_RMAX]; // footprint index of every row
   int nb_cell, nb_foot;
 };
 
@@ -412,7 +413,11 @@ k_tile_mesh(const TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* _
       for (int a = 0; a < NPC; ++a) loc[a] = (unsigned short)smem_find(S.sfoot, F, (unsigned)__ldg(cn + a));
       lconn[d.cell_off + lc] = make_ushort4(loc[0], loc[1], loc[2], loc[3]);
     }
-    for (int i = threadIdx.x; i < R; i += blockDim.x) rowf[d.node_off + i] = (uint16_t)smem_find(S.sfoot, F, (unsigned)tnodes[d.node_off + i]);
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+      const uint16_t f = (uint16_t)smem_find(S.sfoot, F, (unsigned)tnodes[d.node_off + i]);
+      rowf[d.node_off + i] = f;
+      S.rowfs[i] = f;
+    }
     // ---- incidence lists: groups of 32 rows, padded to the group's largest valence ----
     const int ngroup = (R + 31) >> 5;
     for (int g = warp; g < ngroup; g += nwarp) {
@@ -437,20 +442,17 @@ k_tile_mesh(const TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* _
     __syncthreads();
     for (int g = threadIdx.x; g < TG_GMAX; g += blockDim.x)
       inc_grp[(size_t)t * TG_GMAX + g] = g < ngroup ? make_uint2((unsigned)S.goff[g], (unsigned)S.gmax[g]) : make_uint2(0u, 0u);
-    for (int g = warp; g < ngroup; g += nwarp) {
-      const int i = g * 32 + lane;
-      int32_t r = -1;
-      int qb = 0, v = 0;
-      unsigned self = 0;
+    // one thread per (row, incident-cell slot): all warps of the CTA work on the lists of all groups
+    const int total = S.goff[ngroup];
+    for (int x = threadIdx.x; x < total; x += blockDim.x) {
+      int g = 0;
+      while (g + 1 < ngroup && x >= S.goff[g + 1]) ++g;
+      const int y = x - S.goff[g], k = y >> 5, i = g * 32 + (y & 31);
+      unsigned w = 0u;
       if (i < R) {
-        r = tnodes[d.node_off + i];
-        qb = nc_ptr[r];
-        v = nc_ptr[r + 1] - qb;
-        self = (unsigned)smem_find(S.sfoot, F, (unsigned)r);
-      }
-      uint32_t* out = inc + d.inc_off + S.goff[g] + lane;
-      const int len = S.gmax[g];
-      for (int k = 0; k < len; ++k) {
+        const int32_t r = tnodes[d.node_off + i];
+        const int qb = nc_ptr[r], v = nc_ptr[r + 1] - qb;
+        const unsigned self = S.rowfs[i];
         unsigned f[3] = { self, self, self };
         if (k < v) {
           const int32_t* cn = conn + (int64_t)nc_list[qb + k] * NPC;
@@ -461,8 +463,9 @@ k_tile_mesh(const TileDesc* __restrict__ desc, int32_t nb_tile, const int32_t* _
             if (n != r && m < 3) f[m++] = (unsigned)smem_find(S.sfoot, F, (unsigned)n);
           }
         }
-        out[k * 32] = f[0] | (f[1] << 10) | (f[2] << 20);
+        w = f[0] | (f[1] << 10) | (f[2] << 20);
       }
+      inc[d.inc_off + x] = w;
     }
     __syncthreads();
   }

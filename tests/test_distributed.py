@@ -363,11 +363,23 @@ def run_rank_p2p(rank, world, port, case, transport, errq):
 @pytest.mark.parametrize("case", [("box3d", O.OP_POISSON, O.LAYOUT_PER_BLOCK), ("box3d", O.OP_ELASTICITY, O.LAYOUT_PER_ROW), ("sphere_cut.msh", O.OP_POISSON, O.LAYOUT_PER_BLOCK)],
                          ids=["box-poisson", "box-elasticity-per-row", "sphere-poisson"])
 def test_ghost_rows_pulled_over_peer_memory(world, case):
+    _run_exchange_processes(world, case, "p2p")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [("box3d", O.OP_POISSON, O.LAYOUT_PER_BLOCK), ("box3d", O.OP_ELASTICITY, O.LAYOUT_PER_ROW)], ids=["box-poisson", "box-elasticity-per-row"])
+def test_ghost_rows_through_the_transport_callbacks(case):
+    """the fall-back of the exchange (no peer memory): the rows travel through the two transport callbacks (torch.distributed
+    here) on contexts with their own streams -- everything is ordered on the context stream by the library"""
+    _run_exchange_processes(2, case, "nccl")
+
+
+def _run_exchange_processes(world, case, transport):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     errq = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=run_rank_p2p, args=(r, world, port, case, "p2p", errq)) for r in range(world)]
+    procs = [ctx.Process(target=run_rank_p2p, args=(r, world, port, case, transport, errq)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
