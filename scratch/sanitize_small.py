@@ -14,6 +14,14 @@ for dim, n in ((3, 7), (2, 20)):
             for rep in range(3):
                 ctx.build_pattern(b)
                 ctx.assemble(op, params=[1.0e6, 8.0e5], fmt=fmt, variant=A.VARIANT_TILED_GATHER)
+        if op == A.OP_ELASTICITY:  # both vector executors, both value layouts
+            for ex in (A.VEC_EXEC_ROWS, A.VEC_EXEC_UNITS, A.VEC_EXEC_AUTO):
+                ctx.set_vector_executor(ex)
+                for layout in (A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW):
+                    ctx.build_pattern(b)
+                    ctx.assemble(op, params=[1.0e6, 8.0e5], fmt=fmt, variant=A.VARIANT_TILED_GATHER, layout=layout)
+            ctx.build_pattern(b)
+            ctx.assemble(op, params=[1.0e6, 8.0e5], fmt=fmt, variant=A.VARIANT_TILED_GATHER)
         ctx.set_sparsity_algorithm(A.SPARSITY_AUTO)
         if op != A.OP_BILAPLACIAN:
             ids = np.nonzero(m.coords[:, dim - 1] == 0.0)[0].astype(np.int32)
