@@ -215,6 +215,35 @@ def test_tiled_gather_limits(ctx):
             row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows_ref)
 
 
+@pytest.mark.parametrize("k", [20, 40, 70])
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_row_ordered_executor_with_cut_rows(k, layout):
+    """rows longer than a unit (32 entries) are cut into units of their own and their diagonal block is summed from a list
+    instead of the row's other blocks: an "orange" of k tetrahedra around an axis (3-D, the two axis nodes have k + 2
+    entries) and a fan of k triangles (2-D, the centre has k + 1), both vector executors"""
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    lam, mu = O.lame(21.0e5, 0.28)
+    c3 = np.zeros((k + 2, 3))
+    c3[0, 2], c3[1, 2] = -0.7, 0.9
+    c3[2:, 0], c3[2:, 1], c3[2:, 2] = np.cos(ang), 1.1 * np.sin(ang), 0.05 * np.cos(3 * ang)
+    t3 = np.array([[0, 1, 2 + i, 2 + (i + 1) % k] for i in range(k)], dtype=np.int32)
+    c2 = np.zeros((k + 1, 3))
+    c2[1:, 0], c2[1:, 1] = np.cos(ang), 0.8 * np.sin(ang)
+    t2 = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.int32)
+    with A.Context(0) as c:
+        for dim, coords, cells in ((3, c3, t3), (2, c2, t2)):
+            c.set_mesh(dim, coords, cells)
+            c.build_pattern(dim)
+            rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+            assert int(np.diff(rows).max()) == k + (2 if dim == 3 else 1)
+            ref = O.assemble(dim, coords, cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[lam, mu], layout=layout, nodewise=True)
+            for ex in (A.VEC_EXEC_ROWS, A.VEC_EXEC_UNITS):
+                c.set_vector_executor(ex)
+                c.reset_values()
+                c.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER, layout=layout)
+                row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows, b=dim, layout=layout)
+
+
 def test_device_box_generator_bit_identical(ctx):
     for dim, n in ((3, 7), (2, 13)):
         ref = M.box_mesh(dim, n)
