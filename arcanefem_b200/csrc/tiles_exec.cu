@@ -849,7 +849,20 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_rows_vec(ExecA
       // write-out: contiguous runs
       auto put = [&](auto acc) {
         constexpr bool ACC = decltype(acc)::value;
-        if constexpr (LAYOUT == AFB_LAYOUT_PER_BLOCK) {
+        if constexpr (LAYOUT == AFB_LAYOUT_PER_BLOCK && BS == BB) {
+          // a row's blocks are one contiguous run, in the staging buffer and in `values`: copied row by row
+          const int r0 = S.erow_of[first], r1 = S.erow_of[first + cnt - 1];
+          for (int rr = r0; rr <= r1; ++rr) {
+            const int e0 = rowinfo_erow(S.rowinfo[rr]), e1 = rowinfo_erow(S.rowinfo[rr + 1]);
+            const int lo = max(e0, first), hi = min(e1, first + cnt);
+            double* dst = A.values + ((int64_t)S.rowtab[rr].x + (int64_t)BB * lo);
+            const double* src = stg + (lo - first) * BS;
+            for (int x = lane; x < (hi - lo) * BB; x += 32) {
+              if (ACC) dst[x] += src[x]; else dst[x] = src[x];
+            }
+          }
+        }
+        else if constexpr (LAYOUT == AFB_LAYOUT_PER_BLOCK) {
           for (int x0 = 0; x0 < cnt * BB; x0 += 32) {
             const int x = x0 + lane, el = x / BB, c = x - el * BB;
             const int base = __shfl_sync(0xffffffffu, my_base, el & 31);
