@@ -454,7 +454,9 @@ int afb_assemble_rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* face_
 {
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern && (nb_face == 0 || face_nodes) && values, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: no pattern / null argument");
-  AFB_REQUIRE(ctx->npc == ctx->dim + 1, AFB_ERR_UNSUPPORTED, "afb_assemble_rhs_neumann: P1 simplex meshes only (edges of Tri3, triangles of Tet4)");
+  // faces: 2-node edges (any 2-D mesh with straight edges: Tri3, Quad4) or 3-node triangles (Tet4)
+  AFB_REQUIRE(ctx->npc == ctx->dim + 1 || (ctx->dim == 2 && ctx->npc == 4), AFB_ERR_UNSUPPORTED,
+              "afb_assemble_rhs_neumann: 2-node edges of Tri3 / Quad4 meshes and 3-node triangles of Tet4 meshes only");
   AFB_REQUIRE(kind == AFB_NEUMANN_FLUX || kind == AFB_NEUMANN_TRACTION, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: unknown kind %d", kind);
   if (kind == AFB_NEUMANN_FLUX)
     AFB_REQUIRE(nb_value == 1 || nb_value == ctx->dim, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: a flux takes 1 value or one per space dimension (got %d)", nb_value);

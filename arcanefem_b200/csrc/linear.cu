@@ -66,9 +66,121 @@ __global__ void __launch_bounds__(128) k_rhs_source_nodewise(const double* __res
   if (b > 2) rhs[(int64_t)r * b + 2] = s2;
 }
 
+// Quad4 / Hexa8: integral of every shape function over the cell by the 2x2 / 2x2x2 Gauss rule, w_i = sum_gp N_i detJ
+// (femutils/ArcaneFemFunctions.cc:222-290, 437-483; device twin femutils/ArcaneFemFunctionsGpu.cc:393-470, 875-960)
+template <int NPC>
+__device__ __forceinline__ void q1_source_weights(const double* __restrict__ coords, const int32_t* __restrict__ cn, double (&w)[NPC])
+{
+  constexpr int DIM = NPC == 4 ? 2 : 3;
+  const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+  double x[NPC], y[NPC], z[NPC];
+#pragma unroll
+  for (int a = 0; a < NPC; ++a) {
+    load3(coords, __ldg(cn + a), x[a], y[a], z[a]);
+    w[a] = 0.0;
+  }
+  // node a of the reference element sits at (sx, sy, sz)[a]: counter-clockwise, bottom face then top face
+  auto sx = [](int a) { return ((a & 3) == 1 || (a & 3) == 2) ? 1.0 : -1.0; };
+  auto sy = [](int a) { return (a & 2) ? 1.0 : -1.0; };
+  auto sz = [](int a) { return (a & 4) ? 1.0 : -1.0; };
+#pragma unroll
+  for (int g = 0; g < (1 << DIM); ++g) {
+    const double xi = gp[(g >> (DIM - 1)) & 1], eta = gp[(g >> (DIM - 2)) & 1], zeta = DIM == 3 ? gp[g & 1] : 0.0;
+    double N[NPC], J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+#pragma unroll
+    for (int a = 0; a < NPC; ++a) {
+      const double fx = 1.0 + sx(a) * xi, fy = 1.0 + sy(a) * eta, fz = DIM == 3 ? 1.0 + sz(a) * zeta : 1.0;
+      const double s = DIM == 3 ? 0.125 : 0.25;
+      N[a] = s * fx * fy * fz;
+      const double dxi = sx(a) * s * fy * fz, det_ = sy(a) * s * fx * fz;
+      J[0][0] += dxi * x[a]; J[0][1] += dxi * y[a];
+      J[1][0] += det_ * x[a]; J[1][1] += det_ * y[a];
+      if constexpr (DIM == 3) {
+        const double dze = sz(a) * s * fx * fy;
+        J[0][2] += dxi * z[a]; J[1][2] += det_ * z[a];
+        J[2][0] += dze * x[a]; J[2][1] += dze * y[a]; J[2][2] += dze * z[a];
+      }
+    }
+    const double detJ = DIM == 2 ? J[0][0] * J[1][1] - J[0][1] * J[1][0]
+                                 : J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                                     J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+#pragma unroll
+    for (int a = 0; a < NPC; ++a) w[a] += N[a] * detJ;
+  }
+}
+
+template <int NPC>
+__global__ void __launch_bounds__(256) k_rhs_source_q1_cellwise(const double* __restrict__ coords, const int32_t* __restrict__ conn, const uint8_t* __restrict__ is_own,
+                                                                 const uint8_t* __restrict__ dir_node, int64_t nb_cell, int b, double f0, double f1, double f2,
+                                                                 double* __restrict__ rhs)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb_cell) return;
+  const int32_t* cn = conn + c * NPC;
+  double w[NPC];
+  q1_source_weights<NPC>(coords, cn, w);
+  const double f[3] = { f0, f1, f2 };
+#pragma unroll
+  for (int i = 0; i < NPC; ++i) {
+    const int32_t nd = __ldg(cn + i);
+    if ((dir_node && dir_node[nd]) || (is_own && !is_own[nd])) continue;
+    for (int k = 0; k < b; ++k)
+      if (f[k] != 0.0) atomicAdd(rhs + (int64_t)nd * b + k, w[i] * f[k]);
+  }
+}
+
+// node-wise (no atomics): every owned node sums its share of its incident cells, ascending cell ids
+template <int NPC>
+__global__ void __launch_bounds__(128) k_rhs_source_q1_nodewise(const double* __restrict__ coords, const int32_t* __restrict__ conn, const uint8_t* __restrict__ is_own,
+                                                                 const int32_t* __restrict__ nc_ptr, const int32_t* __restrict__ nc_list, int32_t nb_node, int b,
+                                                                 double f0, double f1, double f2, double* __restrict__ rhs)
+{
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nb_node) return;
+  if (is_own && !is_own[r]) return;
+  double s = 0.0;
+  for (int q = nc_ptr[r]; q < nc_ptr[r + 1]; ++q) {
+    const int32_t* cn = conn + (int64_t)nc_list[q] * NPC;
+    double w[NPC];
+    q1_source_weights<NPC>(coords, cn, w);
+#pragma unroll
+    for (int i = 0; i < NPC; ++i)
+      if (__ldg(cn + i) == r) s += w[i];
+  }
+  rhs[(int64_t)r * b] = f0 * s;
+  if (b > 1) rhs[(int64_t)r * b + 1] = f1 * s;
+  if (b > 2) rhs[(int64_t)r * b + 2] = f2 * s;
+}
+
 int rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed_area)
 {
-  AFB_REQUIRE(ctx->npc == ctx->dim + 1, AFB_ERR_UNSUPPORTED, "constant source term is implemented for P1 simplices only (%d-node cells in dimension %d)", ctx->npc, ctx->dim);
+  const bool q1 = (ctx->dim == 2 && ctx->npc == 4) || (ctx->dim == 3 && ctx->npc == 8);
+  AFB_REQUIRE(ctx->npc == ctx->dim + 1 || q1, AFB_ERR_UNSUPPORTED, "constant source term is implemented for P1 simplices, Quad4 and Hexa8 (%d-node cells in dimension %d)", ctx->npc,
+              ctx->dim);
+  if (q1) {
+    AFB_REQUIRE(nb_f >= 1 && nb_f <= 3 && nb_f <= ctx->b, AFB_ERR_INVALID, "source has %d components, matrix has %d dof per node", nb_f, ctx->b);
+    double ff[3] = { 0, 0, 0 };
+    for (int k = 0; k < nb_f; ++k) ff[k] = f[k];
+    const uint8_t* own = ctx->all_own ? nullptr : ctx->is_own.as<uint8_t>();
+    if (!nodewise) {
+      if (ctx->nb_cell == 0) return AFB_OK;
+      const uint8_t* dir = ctx->has_dir_nodes ? ctx->dir_node.as<uint8_t>() : nullptr;
+      const int grid = grid_for(ctx->nb_cell, 256);
+      if (ctx->npc == 4)
+        k_rhs_source_q1_cellwise<4><<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), ctx->conn.as<int32_t>(), own, dir, ctx->nb_cell, ctx->b, ff[0], ff[1], ff[2], ctx->rhs.as<double>());
+      else
+        k_rhs_source_q1_cellwise<8><<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), ctx->conn.as<int32_t>(), own, dir, ctx->nb_cell, ctx->b, ff[0], ff[1], ff[2], ctx->rhs.as<double>());
+    }
+    else {
+      const int grid = grid_for(ctx->nb_node, 128);
+      if (ctx->npc == 4)
+        k_rhs_source_q1_nodewise<4><<<grid, 128, 0, ctx->stream>>>(ctx->coords.as<double>(), ctx->conn.as<int32_t>(), own, ctx->nc_ptr.as<int32_t>(), ctx->nc_list.as<int32_t>(), ctx->nb_node, ctx->b, ff[0], ff[1], ff[2], ctx->rhs.as<double>());
+      else
+        k_rhs_source_q1_nodewise<8><<<grid, 128, 0, ctx->stream>>>(ctx->coords.as<double>(), ctx->conn.as<int32_t>(), own, ctx->nc_ptr.as<int32_t>(), ctx->nc_list.as<int32_t>(), ctx->nb_node, ctx->b, ff[0], ff[1], ff[2], ctx->rhs.as<double>());
+    }
+    AFB_LAUNCH_CHECK(ctx);
+    return AFB_OK;
+  }
   AFB_REQUIRE(nb_f >= 1 && nb_f <= 3 && nb_f <= ctx->b, AFB_ERR_INVALID, "source has %d components, matrix has %d dof per node", nb_f, ctx->b);
   double ff[3] = { 0, 0, 0 };
   for (int k = 0; k < nb_f; ++k) ff[k] = f[k];

@@ -269,7 +269,8 @@ AFB_API int afb_assemble_bilinear(afb_ctx* ctx, int op, const double* params, in
 AFB_API int afb_rhs_reset(afb_ctx* ctx);
 
 /*
- * Constant source term, b components f[0..b): rhs[dof(n,k)] += f[k]*meas/npc.
+ * Constant source term, b components f[0..b): rhs[dof(n,k)] += f[k]*meas/npc on P1 simplices; on Quad4 / Hexa8
+ * rhs[dof(n,k)] += f[k] * integral of N_n by the 2x2 / 2x2x2 Gauss rule (femutils/ArcaneFemFunctions.cc:222-290,437-483).
  * nodewise=0: cell-wise with atomics, skips nodes flagged by afb_set_dirichlet_nodes
  *   (modules/testlab/FemModule.cc:836-868,1358-1532; modules/elasticity/BodyForce.h:93-104);
  * nodewise=1: per-node sum over incident cells, rhs = sum

@@ -812,10 +812,80 @@ ORC_API void orc_bsr_to_csr(int32_t nb_block_row, int b, const int32_t* rows, co
  * elasticity body force: modules/elasticity/BodyForce.h:93-104 (tri, area/3) and
  *   the Tetra4 branch (volume/4); bilaplacian: modules/bilaplacian/FemModule.cc:157-172
  *   (component 0 only: pass f={f,0}); meas = UNSIGNED area (cross norm). */
+/* Quad4 / Hexa8: the source term is integrated with the 2x2 / 2x2x2 Gauss rule, rhs_i += N_i(gp) * qdot * w * detJ
+ * (femutils/ArcaneFemFunctions.cc:222-290 applyConstantSourceToRhsQuad4, :437-483 applyConstantSourceToRhsHexa8;
+ * shape functions femutils/ShapeFunctions.h, nodes counter-clockwise, bottom face then top face). */
+static void q1_source_weights(int dim, const r3* m, double* w /* [npc]: integral of N_i over the cell */)
+{
+  const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+  static const double sx[8] = { -1, 1, 1, -1, -1, 1, 1, -1 }, sy[8] = { -1, -1, 1, 1, -1, -1, 1, 1 }, sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+  const int npc = dim == 2 ? 4 : 8;
+  for (int i = 0; i < npc; ++i) w[i] = 0.0;
+  if (dim == 2) {
+    for (int ixi = 0; ixi < 2; ++ixi)
+      for (int ieta = 0; ieta < 2; ++ieta) {
+        const double xi = gp[ixi], eta = gp[ieta];
+        double N[4], dxi[4], det_[4];
+        for (int a = 0; a < 4; ++a) {
+          N[a] = 0.25 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta);
+          dxi[a] = sx[a] * 0.25 * (1.0 + sy[a] * eta);
+          det_[a] = sy[a] * 0.25 * (1.0 + sx[a] * xi);
+        }
+        double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
+        for (int a = 0; a < 4; ++a) {
+          J00 += dxi[a] * m[a].x;
+          J01 += dxi[a] * m[a].y;
+          J10 += det_[a] * m[a].x;
+          J11 += det_[a] * m[a].y;
+        }
+        const double iw = 1.0 * (J00 * J11 - J01 * J10);
+        for (int a = 0; a < 4; ++a) w[a] += N[a] * iw;
+      }
+    return;
+  }
+  for (int ixi = 0; ixi < 2; ++ixi)
+    for (int ieta = 0; ieta < 2; ++ieta)
+      for (int izeta = 0; izeta < 2; ++izeta) {
+        const double xi = gp[ixi], eta = gp[ieta], zeta = gp[izeta];
+        double N[8], dxi[8], det_[8], dze[8];
+        for (int a = 0; a < 8; ++a) {
+          N[a] = 0.125 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta) * (1.0 + sz[a] * zeta);
+          dxi[a] = sx[a] * 0.125 * (1.0 + sy[a] * eta) * (1.0 + sz[a] * zeta);
+          det_[a] = sy[a] * 0.125 * (1.0 + sx[a] * xi) * (1.0 + sz[a] * zeta);
+          dze[a] = sz[a] * 0.125 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta);
+        }
+        double J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+        for (int a = 0; a < 8; ++a) {
+          J[0][0] += dxi[a] * m[a].x; J[0][1] += dxi[a] * m[a].y; J[0][2] += dxi[a] * m[a].z;
+          J[1][0] += det_[a] * m[a].x; J[1][1] += det_[a] * m[a].y; J[1][2] += det_[a] * m[a].z;
+          J[2][0] += dze[a] * m[a].x; J[2][1] += dze[a] * m[a].y; J[2][2] += dze[a] * m[a].z;
+        }
+        const double detJ = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                            J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        for (int a = 0; a < 8; ++a) w[a] += N[a] * detJ;
+      }
+}
+
 ORC_API void orc_rhs_source_cellwise(int npc, int dim, int b, int signed_area, int32_t nb_node, int64_t nb_cell, const double* coords, const int32_t* conn,
                                      const uint8_t* is_own, const uint8_t* is_dirichlet, const double* f, double* rhs)
 {
   (void)nb_node;
+  if (npc == (dim == 2 ? 4 : 8)) { /* Quad4 / Hexa8 */
+    for (int64_t c = 0; c < nb_cell; ++c) {
+      const int32_t* cn = conn + c * npc;
+      r3 m[8];
+      double w[8];
+      for (int a = 0; a < npc; ++a) m[a] = r3_load(coords, cn[a]);
+      q1_source_weights(dim, m, w);
+      for (int i = 0; i < npc; ++i) {
+        const int32_t nd = cn[i];
+        if ((is_dirichlet && is_dirichlet[nd]) || (is_own && !is_own[nd])) continue;
+        for (int k = 0; k < b; ++k)
+          if (f[k] != 0.0) rhs[(int64_t)nd * b + k] += w[i] * f[k];
+      }
+    }
+    return;
+  }
   for (int64_t c = 0; c < nb_cell; ++c) {
     const int32_t* cn = conn + c * npc;
     double meas;

@@ -32,6 +32,12 @@ FILES = {
     "modules/elasticity/check/bar.2D.Dirichlet.bodyForce.txt": "elasticity_bar.2D.Dirichlet.bodyForce.txt",
     "modules/elasticity/check/bar.3D.Dirichlet.bodyForce.txt": "elasticity_bar.3D.Dirichlet.bodyForce.txt",
     "modules/bilaplacian/check/2d_test.txt": "bilaplacian_2d_test.txt",
+    # Quad4 / Hexa8 Poisson (modules/poisson: inputs/circle.2D.quad.arc, circle.neumann.2D.quad.arc with value=2, sphere.3D.hexa.arc)
+    "meshes/msh/circle_cut.quad.msh": "circle_cut.quad.msh",
+    "meshes/msh/sphere_cut.hexa.msh": "sphere_cut.hexa.msh",
+    "modules/poisson/check/poisson_test_ref_circle_2D_quad.txt": "poisson_test_ref_circle_2D_quad.txt",
+    "modules/poisson/check/poisson_test_ref_circle_scalar_neumann_2D_quad.txt": "poisson_test_ref_circle_scalar_neumann_2D_quad.txt",
+    "modules/poisson/check/poisson_test_ref_sphere_3D_hexa.txt": "poisson_test_ref_sphere_3D_hexa.txt",
 }
 
 if __name__ == "__main__":

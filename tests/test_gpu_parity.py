@@ -1112,5 +1112,35 @@ def test_q1_poisson_values(exec_ctx, dim, n, fmt, variant):
         row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows)
     with pytest.raises(A.AfbError, match="P1"):
         c.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
-    with pytest.raises(A.AfbError):
-        c.rhs_source(1.0)
+    # source term by the 2x2 / 2x2x2 Gauss rule, cell-wise (atomics) and node-wise
+    ref_rhs = O.rhs_source_cellwise(m.dim, m.coords, m.cells, 5.5)
+    for nodewise in (False, True):
+        c.rhs_reset()
+        c.rhs_source(5.5, nodewise=nodewise)
+        assert np.all(np.abs(c.to_host(A.ARRAY_RHS) - ref_rhs) <= 1e-12 * np.abs(ref_rhs).max())
+
+
+@pytest.mark.parametrize("name", list(CS.Q1_CASES))
+@pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
+                         ids=["csr-gpu", "bsr", "af-bsr"])
+def test_q1_poisson_golden_solution(exec_ctx, name, fmt, variant):
+    """Quad4 / Hexa8 Poisson of the production module against its own golden solution files (modules/poisson/check/*quad*, *hexa*):
+    matrix, source term, scalar Neumann flux and penalty through the C ABI, solved by the PCG stand-in and by a direct solve"""
+    c = exec_ctx
+    case = CS.Q1_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(1)
+    c.assemble(A.OP_POISSON, fmt=fmt, variant=variant)
+    c.rhs_reset()
+    c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
+    for group, q in case.get("neumann", []):
+        c.rhs_neumann(m.faces[group], q, kind=A.NEUMANN_FLUX)
+    c.dirichlet_penalty(ids, g, case["penalty"])
+    rows, cols, vals, rhs = (c.to_host(w) for w in (A.ARRAY_ROWS, A.ARRAY_COLUMNS, A.ARRAY_VALUES, A.ARRAY_RHS))
+    golden = CS.load_golden(case["golden"], 1)
+    u = spla.spsolve(sp.csr_matrix((vals, cols, rows)).tocsc(), rhs)
+    assert CS.compare_to_golden(m, u, golden, 1, eps=1.0e-4, min_value=1.0e-16, subset=True) < 1.0e-7
+    x, it, res = c.solve_pcg(rtol=1e-12, max_iter=20000)
+    assert CS.compare_to_golden(m, x, golden, 1, eps=1.0e-4, min_value=1.0e-16, subset=True) < 1.0e-6

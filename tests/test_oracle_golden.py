@@ -79,6 +79,25 @@ def test_poisson_golden(name, variant):
     assert worst < 1.0e-7
 
 
+@pytest.mark.parametrize("name", list(CS.Q1_CASES))
+@pytest.mark.parametrize("nodewise", [False, True], ids=["bsr", "af-bsr"])
+def test_q1_poisson_golden(name, nodewise):
+    """Quad4 / Hexa8 Poisson of the production module (modules/poisson/ElementMatrixHexQuad.h, source term
+    femutils/ArcaneFemFunctions.cc:222-290,437-483) against the module's own golden solution files."""
+    case = CS.Q1_CASES[name]
+    m = _load(case)
+    rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=O.FORM_BSR, nodewise=nodewise)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    rhs = O.rhs_source_cellwise(m.dim, m.coords, m.cells, case["f"])
+    for group, q in case.get("neumann", []):  # scalar flux on 2-node edges: no normal involved
+        O.rhs_neumann(m.dim, 1, m.coords, m.faces[group], q, rhs, kind=O.NEUMANN_FLUX)
+    O.dirichlet_penalty(rows, cols, vals, rhs, ids, g, case["penalty"])
+    u = spla.spsolve(_csr(rows, cols, vals).tocsc(), rhs)
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True)
+    assert worst < 1.0e-7
+
+
 @pytest.mark.parametrize("name", list(CS.NEUMANN_CASES))
 def test_poisson_neumann_golden(name):
     """Constant flux term (modules/testlab/FemModule.cc:1534-1706): scalar value and q.n with the outward normal."""
