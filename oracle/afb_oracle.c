@@ -12,7 +12,8 @@
  * function below restates the reference arithmetic and cites the file:line it
  * follows (paths relative to the reference root).  The oracle is pinned against
  * the reference's own golden solution vectors (modules/testlab/tests/ *.txt,
- * modules/elasticity/check/ *.txt, modules/bilaplacian/check/2d_test.txt) by
+ * modules/elasticity/check/ *.txt, modules/bilaplacian/check/2d_test.txt,
+ * modules/poisson/check/ *quad*.txt and *hexa.txt for Quad4 / Hexa8) by
  * tests/test_oracle_golden.py.  Pieces that no reference test pins (intra-row
  * column order, P2 tri/tet stiffness assembled into CSR) are marked
  * "parity unpinned" where they are defined.
