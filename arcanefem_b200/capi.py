@@ -203,7 +203,8 @@ class Context:
 
     # -- rhs / dirichlet -----------------------------------------------------------------------
     def rhs_neumann(self, faces, values, kind=NEUMANN_FLUX, skip_dirichlet=False):
-        """faces: int32 [nb_face, dim] oriented boundary faces (mesh.orient_boundary_faces); values: flux value, flux vector or traction."""
+        """faces: int32 [nb_face, dim] oriented boundary faces (mesh.orient_boundary_faces), [nb_face, 4] on Hexa8 meshes
+        (mesh.arcane_face_node_order for a flux vector); values: flux value, flux vector or traction."""
         faces = np.ascontiguousarray(faces, dtype=np.int32)
         values = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64)
         _check(lib().afb_assemble_rhs_neumann(self._h, C.c_int64(faces.shape[0]), _ptr(faces), int(kind), int(values.size), _ptr(values), int(skip_dirichlet), MEM_HOST))

@@ -454,9 +454,11 @@ int afb_assemble_rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* face_
 {
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern && (nb_face == 0 || face_nodes) && values, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: no pattern / null argument");
-  // faces: 2-node edges (any 2-D mesh with straight edges: Tri3, Quad4) or 3-node triangles (Tet4)
-  AFB_REQUIRE(ctx->npc == ctx->dim + 1 || (ctx->dim == 2 && ctx->npc == 4), AFB_ERR_UNSUPPORTED,
-              "afb_assemble_rhs_neumann: 2-node edges of Tri3 / Quad4 meshes and 3-node triangles of Tet4 meshes only");
+  // faces: 2-node edges (any 2-D mesh with straight edges: Tri3, Quad4), 3-node triangles (Tet4), 4-node quadrilaterals (Hexa8)
+  const bool hexa = ctx->dim == 3 && ctx->npc == 8;
+  AFB_REQUIRE(ctx->npc == ctx->dim + 1 || (ctx->dim == 2 && ctx->npc == 4) || hexa, AFB_ERR_UNSUPPORTED,
+              "afb_assemble_rhs_neumann: edges of Tri3 / Quad4 meshes, triangles of Tet4 meshes and quadrilaterals of Hexa8 meshes only");
+  AFB_REQUIRE(!hexa || kind == AFB_NEUMANN_FLUX, AFB_ERR_UNSUPPORTED, "afb_assemble_rhs_neumann: Hexa8 faces take a flux (no traction term)");
   AFB_REQUIRE(kind == AFB_NEUMANN_FLUX || kind == AFB_NEUMANN_TRACTION, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: unknown kind %d", kind);
   if (kind == AFB_NEUMANN_FLUX)
     AFB_REQUIRE(nb_value == 1 || nb_value == ctx->dim, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: a flux takes 1 value or one per space dimension (got %d)", nb_value);
@@ -464,7 +466,7 @@ int afb_assemble_rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* face_
     AFB_REQUIRE(nb_value == ctx->b, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: a traction takes one value per DoF of a node (%d, got %d)", ctx->b, nb_value);
   if (nb_face <= 0) return AFB_OK;
   const void* faces = nullptr;
-  AFB_TRY(stage(ctx, ctx->tmp_ids, face_nodes, sizeof(int32_t) * (size_t)nb_face * (size_t)ctx->dim, mem_space, &faces));
+  AFB_TRY(stage(ctx, ctx->tmp_ids, face_nodes, sizeof(int32_t) * (size_t)nb_face * (size_t)(hexa ? 4 : ctx->dim), mem_space, &faces));
   return rhs_neumann(ctx, nb_face, static_cast<const int32_t*>(faces), kind, nb_value, values, skip_dirichlet);
 }
 

@@ -253,6 +253,46 @@ __global__ void __launch_bounds__(256) k_rhs_neumann(const double* __restrict__ 
   }
 }
 
+// Quad4 faces of a Hexa8 mesh: 2x2 Gauss rule on the bilinear patch, detJ = |dr/dxi x dr/deta|, the unit normal taken at every
+// Gauss point from the face's node order (femutils/ArcaneFemFunctions.h:1843-1953; device twin ArcaneFemFunctionsGpu.cc:1146-1260)
+__global__ void __launch_bounds__(256) k_rhs_neumann_quad4(const double* __restrict__ coords, const int32_t* __restrict__ faces, int64_t nb_face,
+                                                            const uint8_t* __restrict__ is_own, const uint8_t* __restrict__ dir_node, int b, int nb_value, double v0, double v1,
+                                                            double v2, double* __restrict__ rhs)
+{
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nb_face) return;
+  const int32_t* fn = faces + f * 4;
+  double x[4], y[4], z[4], acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) load3(coords, __ldg(fn + i), x[i], y[i], z[i]);
+  const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const double xi = gp[g >> 1], eta = gp[g & 1];
+    double N[4], t1x = 0, t1y = 0, t1z = 0, t2x = 0, t2y = 0, t2z = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double sx = (i == 1 || i == 2) ? 1.0 : -1.0, sy = (i & 2) ? 1.0 : -1.0;
+      N[i] = 0.25 * (1.0 + sx * xi) * (1.0 + sy * eta);
+      const double dxi = sx * 0.25 * (1.0 + sy * eta), det_ = sy * 0.25 * (1.0 + sx * xi);
+      t1x += dxi * x[i]; t1y += dxi * y[i]; t1z += dxi * z[i];
+      t2x += det_ * x[i]; t2y += det_ * y[i]; t2z += det_ * z[i];
+    }
+    double nx = t1y * t2z - t1z * t2y, ny = t1z * t2x - t1x * t2z, nz = t1x * t2y - t1y * t2x;
+    const double detJ = sqrt(nx * nx + ny * ny + nz * nz);
+    nx /= detJ; ny /= detJ; nz /= detJ;
+    const double q = nb_value == 1 ? v0 : nx * v0 + ny * v1 + nz * v2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += q * N[j] * detJ;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int32_t nd = __ldg(fn + j);
+    if ((dir_node && dir_node[nd]) || (is_own && !is_own[nd])) continue;
+    atomicAdd(rhs + (int64_t)nd * b, acc[j]);
+  }
+}
+
 int rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* faces_dev, int kind, int nb_value, const double* values, int skip_dirichlet)
 {
   if (nb_face <= 0) return AFB_OK;
@@ -261,7 +301,9 @@ int rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* faces_dev, int kin
   const uint8_t* own = ctx->all_own ? nullptr : ctx->is_own.as<uint8_t>();
   const uint8_t* dir = (skip_dirichlet && ctx->has_dir_nodes) ? ctx->dir_node.as<uint8_t>() : nullptr;
   const int grid = grid_for(nb_face, 256);
-  if (ctx->dim == 2)
+  if (ctx->dim == 3 && ctx->npc == 8)
+    k_rhs_neumann_quad4<<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), faces_dev, nb_face, own, dir, ctx->b, nb_value, v[0], v[1], v[2], ctx->rhs.as<double>());
+  else if (ctx->dim == 2)
     k_rhs_neumann<2><<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), faces_dev, nb_face, own, dir, ctx->b, kind, nb_value, v[0], v[1], v[2], ctx->rhs.as<double>());
   else
     k_rhs_neumann<3><<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), faces_dev, nb_face, own, dir, ctx->b, kind, nb_value, v[0], v[1], v[2], ctx->rhs.as<double>());

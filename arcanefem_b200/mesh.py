@@ -178,6 +178,8 @@ def orient_boundary_faces(mesh: Mesh, faces: np.ndarray) -> np.ndarray:
     not "subdomain boundary outside"; here the side is found from the cell the face belongs to."""
     faces = np.array(faces, dtype=np.int32, copy=True)
     nn = faces.shape[1]
+    if mesh.cells.shape[1] == 2 ** mesh.dim:  # Quad4 (edges) / Hexa8 (Quad4 faces): side found from the cell's centroid
+        return _orient_q1_faces(mesh, faces)
     corner = mesh.cells[:, :mesh.dim + 1]
     key = lambda a: tuple(sorted(int(x) for x in a))
     owner = {}
@@ -194,6 +196,49 @@ def orient_boundary_faces(mesh: Mesh, faces: np.ndarray) -> np.ndarray:
         if np.dot(n, mesh.coords[opp] - p0) > 0.0:
             faces[f, [0, 1]] = faces[f, [1, 0]]
     assert nn == mesh.dim
+    return faces
+
+
+def arcane_face_node_order(mesh: Mesh, faces: np.ndarray) -> np.ndarray:
+    """Faces with their nodes in the order Arcane stores them: the node with the smallest unique id first, then round the
+    face towards its neighbour with the smaller unique id.  The reference's Quad4-face flux integral (Hexa8 meshes,
+    femutils/ArcaneFemFunctions.h:1843-1953) takes its normal dr/dxi x dr/deta from that order without the
+    outside-of-the-domain test the P1 helpers make: its q.n term follows the numbering, not the geometry."""
+    faces = np.asarray(faces, dtype=np.int32)
+    out = np.empty_like(faces)
+    nn = faces.shape[1]
+    for f in range(faces.shape[0]):
+        u = mesh.node_uid[faces[f]]
+        k = int(np.argmin(u))
+        step = 1 if u[(k + 1) % nn] < u[(k - 1) % nn] else -1
+        out[f] = [faces[f, (k + step * i) % nn] for i in range(nn)]
+    return out
+
+
+_HEXA_FACES = ((0, 3, 2, 1), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7))
+
+
+def _orient_q1_faces(mesh: Mesh, faces: np.ndarray) -> np.ndarray:
+    """Edges of a Quad4 mesh / Quad4 faces of a Hexa8 mesh, node order such that N = (y1-y0, x0-x1) resp. the patch normal
+    dr/dxi x dr/deta (femutils/ArcaneFemFunctions.h:1895-1915) points out of the cell the face belongs to."""
+    key = lambda a: tuple(sorted(int(x) for x in a))
+    owner = {}
+    local = ((0, 1), (1, 2), (2, 3), (3, 0)) if mesh.dim == 2 else _HEXA_FACES
+    for c, cn in enumerate(mesh.cells):
+        for lf in local:
+            owner.setdefault(key(cn[list(lf)]), c)
+    for f in range(faces.shape[0]):
+        c = owner[key(faces[f])]
+        centre = mesh.coords[mesh.cells[c]].mean(axis=0)
+        p = mesh.coords[faces[f]]
+        if mesh.dim == 2:
+            n = np.array([p[1][1] - p[0][1], p[0][0] - p[1][0], 0.0])
+        else:  # patch normal at the face centre: (dr/dxi) x (dr/deta)
+            t1 = 0.25 * (-p[0] + p[1] + p[2] - p[3])
+            t2 = 0.25 * (-p[0] - p[1] + p[2] + p[3])
+            n = np.cross(t1, t2)
+        if np.dot(n, p.mean(axis=0) - centre) < 0.0:
+            faces[f] = faces[f, ::-1] if mesh.dim == 2 else faces[f, [0, 3, 2, 1]]
     return faces
 
 

@@ -291,6 +291,11 @@ AFB_API int afb_assemble_rhs_source(afb_ctx* ctx, const double* f, int nb_f, int
  * face_nodes[nb_face][dim]: Arcane's faceNode order of the group's faces, with the first two nodes swapped for faces that
  * are not "subdomain boundary outside" -- the swap computeNormalFace / computeNormalTriangle apply
  * (femutils/ArcaneFemFunctionsGpu.h:159-214), so that N = (y1-y0, x0-x1)/|.| resp. (n1-n0)x(n2-n0)/|.| points outward.
+ * Edges of a Quad4 mesh are taken like those of a Tri3 mesh (the 2-point rule of applyNeumannToRhsQuad4,
+ * femutils/ArcaneFemFunctions.h:2762-2825, integrates the same linear functions).  Hexa8 meshes: face_nodes[nb_face][4],
+ * flux only; 2x2 Gauss rule on the bilinear patch, detJ = |dr/dxi x dr/deta| and the unit normal at every Gauss point from the
+ * face's node order AS ARCANE STORES IT (smallest unique id first, then towards its smaller neighbour) -- upstream makes no
+ * outside-of-the-domain test there (femutils/ArcaneFemFunctions.h:1843-1953), so its q.n term follows the numbering.
  * skip_dirichlet != 0: nodes marked by afb_set_dirichlet_nodes receive nothing (testlab: FemModule.cc:1577).
  */
 enum { AFB_NEUMANN_FLUX = 0, AFB_NEUMANN_TRACTION = 1 };

@@ -945,6 +945,43 @@ ORC_API void orc_rhs_source_nodewise(int npc, int dim, int b, int32_t nb_node, i
  * kind 1 (traction, b DoFs per node): rhs[dof(node,k)] += t[k]*measure/nn
  *          (femutils/ArcaneFemFunctions.h:2188-2220, 2854-2885).
  * Gates: owned nodes only; testlab additionally skips Dirichlet nodes (FemModule.cc:1577). */
+/* Quad4 faces of a Hexa8 mesh (femutils/ArcaneFemFunctions.h:1843-1953 applyNeumannToRhsHexa8): 2x2 Gauss rule on the
+ * bilinear patch, tangents t1 = dr/dxi, t2 = dr/deta, detJ = |t1 x t2|, unit normal (t1 x t2)/detJ at every Gauss point;
+ * rhs_j += value * N_j * detJ (scalar) or (normal . q) * N_j * detJ (vector).  The faces come oriented (outward t1 x t2). */
+ORC_API void orc_rhs_neumann_quad4(int b, int nb_value, int64_t nb_face, const double* coords, const int32_t* faces, const double* values, const uint8_t* is_own,
+                                   const uint8_t* is_dirichlet, double* rhs)
+{
+  const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+  static const double sx[4] = { -1, 1, 1, -1 }, sy[4] = { -1, -1, 1, 1 };
+  for (int64_t f = 0; f < nb_face; ++f) {
+    const int32_t* fn = faces + f * 4;
+    r3 c[4];
+    for (int i = 0; i < 4; ++i) c[i] = r3_load(coords, fn[i]);
+    for (int ixi = 0; ixi < 2; ++ixi)
+      for (int ieta = 0; ieta < 2; ++ieta) {
+        const double xi = gp[ixi], eta = gp[ieta];
+        double N[4];
+        r3 t1 = { 0, 0, 0 }, t2 = { 0, 0, 0 };
+        for (int i = 0; i < 4; ++i) {
+          N[i] = 0.25 * (1.0 + sx[i] * xi) * (1.0 + sy[i] * eta);
+          const double dxi = sx[i] * 0.25 * (1.0 + sy[i] * eta), det_ = sy[i] * 0.25 * (1.0 + sx[i] * xi);
+          t1.x += dxi * c[i].x; t1.y += dxi * c[i].y; t1.z += dxi * c[i].z;
+          t2.x += det_ * c[i].x; t2.y += det_ * c[i].y; t2.z += det_ * c[i].z;
+        }
+        r3 nr = r3_cross(t1, t2);
+        const double detJ = sqrt(nr.x * nr.x + nr.y * nr.y + nr.z * nr.z);
+        nr.x /= detJ; nr.y /= detJ; nr.z /= detJ;
+        const double iw = 1.0 * 1.0 * detJ;
+        for (int j = 0; j < 4; ++j) {
+          const int32_t nd = fn[j];
+          if ((is_dirichlet && is_dirichlet[nd]) || (is_own && !is_own[nd])) continue;
+          const double v = nb_value == 1 ? values[0] * N[j] * iw : (nr.x * values[0] + nr.y * values[1] + nr.z * values[2]) * N[j] * iw;
+          rhs[(int64_t)nd * b] += v;
+        }
+      }
+  }
+}
+
 ORC_API void orc_rhs_neumann(int dim, int b, int kind, int nb_value, int64_t nb_face, const double* coords, const int32_t* faces, const double* values,
                              const uint8_t* is_own, const uint8_t* is_dirichlet, double* rhs)
 {

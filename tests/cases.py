@@ -32,6 +32,15 @@ Q1_CASES = {
                                           golden="poisson_test_ref_circle_scalar_neumann_2D_quad.txt"),
     "sphere_3D_hexa": dict(mesh="sphere_cut.hexa.msh", f=5.5, dirichlet=[("horizontal", 0.5)], penalty=1.0e30,
                            golden="poisson_test_ref_sphere_3D_hexa.txt"),
+    # inputs/circle.neumann.2D.quad.arc, sphere.neumann.3D.hexa.arc (flux vector q: q.n with the outward normal) and the
+    # latter with neumann value=3.1 (CMakeLists.txt:188-198)
+    "circle_neumann_2D_quad": dict(mesh="circle_cut.quad.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("curved", [-0.35, 1.65])], penalty=1.0e30,
+                                   golden="poisson_test_ref_circle_neumann_2D_quad.txt"),
+    "sphere_neumann_3D_hexa": dict(mesh="sphere_cut.hexa.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("curved", [0.35, 1.65, 3.75])], penalty=1.0e30,
+                                   face_order="arcane",  # upstream takes the Quad4-face normal from Arcane's node order (see mesh.arcane_face_node_order)
+                                   golden="poisson_test_ref_sphere_neumann_3D_hexa.txt"),
+    "sphere_scalar_neumann_3D_hexa": dict(mesh="sphere_cut.hexa.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("curved", [3.1])], penalty=1.0e30,
+                                          golden="poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt"),
 }
 
 # Neumann flux cases of testlab (circle_cut.msh; modules/testlab/inputs/Test.circle.2D.trac*.arc): value = scalar flux,
@@ -64,6 +73,14 @@ ELASTICITY_CASES = {
 # modules/bilaplacian/inputs/direct.arc
 BILAPLACIAN_CASE = dict(mesh="bilap.msh", f=-786.25, dirichlet=[("boundary", [145.5, None])], penalty=1.0e30,
                         golden="bilaplacian_2d_test.txt")
+
+
+def boundary_faces(mesh, case, group):
+    """the group's faces in the node order the case's reference run saw"""
+    from arcanefem_b200 import mesh as M
+    if case.get("face_order") == "arcane":
+        return M.arcane_face_node_order(mesh, mesh.faces[group])
+    return M.orient_boundary_faces(mesh, mesh.faces[group])
 
 
 def load_golden(name, ncomp):

@@ -38,6 +38,9 @@ FILES = {
     "modules/poisson/check/poisson_test_ref_circle_2D_quad.txt": "poisson_test_ref_circle_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_circle_scalar_neumann_2D_quad.txt": "poisson_test_ref_circle_scalar_neumann_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_sphere_3D_hexa.txt": "poisson_test_ref_sphere_3D_hexa.txt",
+    "modules/poisson/check/poisson_test_ref_circle_neumann_2D_quad.txt": "poisson_test_ref_circle_neumann_2D_quad.txt",
+    "modules/poisson/check/poisson_test_ref_sphere_neumann_3D_hexa.txt": "poisson_test_ref_sphere_neumann_3D_hexa.txt",
+    "modules/poisson/check/poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt": "poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt",
 }
 
 if __name__ == "__main__":

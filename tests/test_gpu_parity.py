@@ -1136,7 +1136,7 @@ def test_q1_poisson_golden_solution(exec_ctx, name, fmt, variant):
     c.rhs_reset()
     c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
     for group, q in case.get("neumann", []):
-        c.rhs_neumann(m.faces[group], q, kind=A.NEUMANN_FLUX)
+        c.rhs_neumann(CS.boundary_faces(m, case, group), q, kind=A.NEUMANN_FLUX)
     c.dirichlet_penalty(ids, g, case["penalty"])
     rows, cols, vals, rhs = (c.to_host(w) for w in (A.ARRAY_ROWS, A.ARRAY_COLUMNS, A.ARRAY_VALUES, A.ARRAY_RHS))
     golden = CS.load_golden(case["golden"], 1)

@@ -90,8 +90,8 @@ def test_q1_poisson_golden(name, nodewise):
     vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=O.FORM_BSR, nodewise=nodewise)
     ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
     rhs = O.rhs_source_cellwise(m.dim, m.coords, m.cells, case["f"])
-    for group, q in case.get("neumann", []):  # scalar flux on 2-node edges: no normal involved
-        O.rhs_neumann(m.dim, 1, m.coords, m.faces[group], q, rhs, kind=O.NEUMANN_FLUX)
+    for group, q in case.get("neumann", []):  # edges of the Quad4 mesh / Quad4 faces of the Hexa8 mesh, outward
+        O.rhs_neumann(m.dim, 1, m.coords, CS.boundary_faces(m, case, group), q, rhs, kind=O.NEUMANN_FLUX)
     O.dirichlet_penalty(rows, cols, vals, rhs, ids, g, case["penalty"])
     u = spla.spsolve(_csr(rows, cols, vals).tocsc(), rhs)
     worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True)
