@@ -220,6 +220,8 @@ int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, in
   else if (op == AFB_OP_ELASTICITY) {
     if (npc == 4 && dim == 3) return launch<Tet4Elasticity>(ctx, format, variant, layout, prm);
     if (npc == 3 && dim == 2) return launch<Tri3Elasticity>(ctx, format, variant, layout, prm);
+    if (npc == 4 && dim == 2) return launch<Quad4Elasticity>(ctx, format, variant, layout, prm);
+    if (npc == 8 && dim == 3) return launch<Hexa8Elasticity>(ctx, format, variant, layout, prm);
   }
   else if (op == AFB_OP_BILAPLACIAN) {
     if (npc == 3 && dim == 2) return launch<Tri3Bilaplacian>(ctx, format, variant, layout, prm);

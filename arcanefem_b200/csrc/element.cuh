@@ -395,6 +395,97 @@ struct Hexa8Poisson {
   __device__ __forceinline__ double measure() const { return vol; }
 };
 
+// Quad4 / Hexa8 isotropic elasticity (modules/elasticity/ElementMatrixHexQuad.h:computeElementMatrix{Quad4,Hexa8}Base summed
+// over the 2x2 / 2x2x2 Gauss rule): per Gauss point the block of nodes (a, b) is w [lambda g_a g_b^T + mu g_b g_a^T + mu (g_a.g_b) I]
+// with the physical gradients g at the point and w = detJ -- the same block as on simplices, once per point.  The gradients of
+// all points are kept (a 24 x 24 element matrix is never formed); these cells run through the cell-wise and node-wise variants.
+template <int DIM_>
+struct Q1Elasticity {
+  static constexpr int DIM = DIM_, NPC = DIM_ == 2 ? 4 : 8, B = DIM_, NG = 1 << DIM_;
+  double G[NG][NPC][DIM_]; // physical gradients
+  double w[NG];            // detJ (Gauss weights are 1)
+  double lam, mu, meas;
+  __device__ void init(const double* __restrict__ coords, const int32_t (&nd)[NPC], const ElemParams& p)
+  {
+    lam = p.p0;
+    mu = p.p1;
+    meas = 0.0;
+    double x[NPC], y[NPC], z[NPC];
+#pragma unroll
+    for (int a = 0; a < NPC; ++a) load3(coords, nd[a], x[a], y[a], z[a]);
+    const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g) {
+      const double xi = gp[(g >> (DIM - 1)) & 1], eta = gp[(g >> (DIM - 2)) & 1], zeta = DIM == 3 ? gp[g & 1] : 0.0;
+      double dxi[NPC], det_[NPC], dze[NPC];
+#pragma unroll
+      for (int a = 0; a < NPC; ++a) {
+        const double sx = ((a & 3) == 1 || (a & 3) == 2) ? 1.0 : -1.0, sy = (a & 2) ? 1.0 : -1.0, sz = (a & 4) ? 1.0 : -1.0;
+        const double fx = 1.0 + sx * xi, fy = 1.0 + sy * eta, fz = DIM == 3 ? 1.0 + sz * zeta : 1.0, s = DIM == 3 ? 0.125 : 0.25;
+        dxi[a] = sx * s * fy * fz;
+        det_[a] = sy * s * fx * fz;
+        dze[a] = DIM == 3 ? sz * s * fx * fy : 0.0;
+      }
+      if constexpr (DIM == 2) {
+        double J00 = 0, J01 = 0, J10 = 0, J11 = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          J00 += dxi[a] * x[a]; J01 += dxi[a] * y[a];
+          J10 += det_[a] * x[a]; J11 += det_[a] * y[a];
+        }
+        const double det = J00 * J11 - J01 * J10, inv = 1.0 / det;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          G[g][a][0] = (J11 * dxi[a] - J01 * det_[a]) * inv;
+          G[g][a][1] = (J00 * det_[a] - J10 * dxi[a]) * inv;
+        }
+        w[g] = det;
+        meas += det;
+      }
+      else {
+        double J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          J[0][0] += dxi[a] * x[a]; J[0][1] += dxi[a] * y[a]; J[0][2] += dxi[a] * z[a];
+          J[1][0] += det_[a] * x[a]; J[1][1] += det_[a] * y[a]; J[1][2] += det_[a] * z[a];
+          J[2][0] += dze[a] * x[a]; J[2][1] += dze[a] * y[a]; J[2][2] += dze[a] * z[a];
+        }
+        const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[0][2] * J[2][1] - J[0][1] * J[2][2], c02 = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+        const double c10 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c11 = J[0][0] * J[2][2] - J[0][2] * J[2][0], c12 = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+        const double c20 = J[1][0] * J[2][1] - J[1][1] * J[2][0], c21 = J[0][1] * J[2][0] - J[0][0] * J[2][1], c22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        const double det = J[0][0] * c00 + J[0][1] * c10 + J[0][2] * c20, inv = 1.0 / det;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          G[g][a][0] = (c00 * dxi[a] + c01 * det_[a] + c02 * dze[a]) * inv;
+          G[g][a][1] = (c10 * dxi[a] + c11 * det_[a] + c12 * dze[a]) * inv;
+          G[g][a][2] = (c20 * dxi[a] + c21 * det_[a] + c22 * dze[a]) * inv;
+        }
+        w[g] = det;
+        meas += det;
+      }
+    }
+  }
+  __device__ void block(int a, int b, double (&o)[DIM_ * DIM_]) const
+  {
+#pragma unroll
+    for (int k = 0; k < DIM * DIM; ++k) o[k] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g) {
+      double dd = 0.0;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) dd += G[g][a][i] * G[g][b][i];
+      const double lw = lam * w[g], mw = mu * w[g];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) o[i * DIM + j] += lw * G[g][a][i] * G[g][b][j] + mw * G[g][a][j] * G[g][b][i] + (i == j ? mw * dd : 0.0);
+    }
+  }
+  __device__ __forceinline__ double measure() const { return meas; }
+};
+using Quad4Elasticity = Q1Elasticity<2>;
+using Hexa8Elasticity = Q1Elasticity<3>;
+
 // ---------------------------------------------------------------------------------------------
 // position of `col` in the ascending segment cols[lo,hi) (present by construction)
 __device__ __forceinline__ int find_col(const int32_t* __restrict__ cols, int lo, int hi, int32_t col)

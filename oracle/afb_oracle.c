@@ -448,6 +448,105 @@ static void ke_quad4_poisson(const r3* m, double* K)
     }
 }
 
+/* physical gradients and detJ of Quad4 / Hexa8 at one Gauss point (femutils/ArcaneFemFunctions.h computeGradientsAndJacobianQuad4 /
+ * ...Hexa8: J = sum dN/dxi x, inverse Jacobian applied to the reference gradients) */
+static double q1_gradients(int dim, const r3* m, double xi, double eta, double zeta, double* dx, double* dy, double* dz)
+{
+  static const double sx[8] = { -1, 1, 1, -1, -1, 1, 1, -1 }, sy[8] = { -1, -1, 1, 1, -1, -1, 1, 1 }, sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+  if (dim == 2) {
+    double dxi[4], det_[4];
+    for (int a = 0; a < 4; ++a) {
+      dxi[a] = sx[a] * 0.25 * (1.0 + sy[a] * eta);
+      det_[a] = sy[a] * 0.25 * (1.0 + sx[a] * xi);
+    }
+    double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
+    for (int a = 0; a < 4; ++a) {
+      J00 += dxi[a] * m[a].x; J01 += dxi[a] * m[a].y;
+      J10 += det_[a] * m[a].x; J11 += det_[a] * m[a].y;
+    }
+    const double detJ = J00 * J11 - J01 * J10;
+    const double i00 = J11 / detJ, i01 = -J01 / detJ, i10 = -J10 / detJ, i11 = J00 / detJ;
+    for (int a = 0; a < 4; ++a) {
+      dx[a] = i00 * dxi[a] + i01 * det_[a];
+      dy[a] = i10 * dxi[a] + i11 * det_[a];
+    }
+    return detJ;
+  }
+  double dxi[8], det_[8], dze[8];
+  for (int a = 0; a < 8; ++a) {
+    dxi[a] = sx[a] * 0.125 * (1.0 + sy[a] * eta) * (1.0 + sz[a] * zeta);
+    det_[a] = sy[a] * 0.125 * (1.0 + sx[a] * xi) * (1.0 + sz[a] * zeta);
+    dze[a] = sz[a] * 0.125 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta);
+  }
+  double J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+  for (int a = 0; a < 8; ++a) {
+    J[0][0] += dxi[a] * m[a].x; J[0][1] += dxi[a] * m[a].y; J[0][2] += dxi[a] * m[a].z;
+    J[1][0] += det_[a] * m[a].x; J[1][1] += det_[a] * m[a].y; J[1][2] += det_[a] * m[a].z;
+    J[2][0] += dze[a] * m[a].x; J[2][1] += dze[a] * m[a].y; J[2][2] += dze[a] * m[a].z;
+  }
+  const double detJ = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                      J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  double inv[3][3];
+  inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / detJ;
+  inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / detJ;
+  inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / detJ;
+  inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / detJ;
+  inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / detJ;
+  inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / detJ;
+  inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / detJ;
+  inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / detJ;
+  inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / detJ;
+  for (int a = 0; a < 8; ++a) {
+    dx[a] = inv[0][0] * dxi[a] + inv[0][1] * det_[a] + inv[0][2] * dze[a];
+    dy[a] = inv[1][0] * dxi[a] + inv[1][1] * det_[a] + inv[1][2] * dze[a];
+    dz[a] = inv[2][0] * dxi[a] + inv[2][1] * det_[a] + inv[2][2] * dze[a];
+  }
+  return detJ;
+}
+
+/* modules/elasticity/ElementMatrixHexQuad.h: computeElementMatrixQuad4Base / Hexa8Base summed over the 2x2 / 2x2x2 Gauss rule
+ * (_computeElementMatrixQuad4 / Hexa8), interleaved DoFs, the three energy terms grouped as upstream */
+static void ke_q1_elasticity(int dim, const r3* m, double lambda, double mu, double* K)
+{
+  const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+  const int npc = dim == 2 ? 4 : 8, n = npc * dim;
+  for (int i = 0; i < n * n; ++i) K[i] = 0.0;
+  for (int ixi = 0; ixi < 2; ++ixi)
+    for (int ieta = 0; ieta < 2; ++ieta)
+      for (int izeta = 0; izeta < (dim == 3 ? 2 : 1); ++izeta) {
+        double dxu[8], dyu[8], dzu[8];
+        const double detJ = q1_gradients(dim, m, gp[ixi], gp[ieta], dim == 3 ? gp[izeta] : 0.0, dxu, dyu, dzu);
+        const double w = detJ * 1.0 * 1.0 * 1.0;
+        /* d{x,y,z}U{x,y,z}[dof]: gradient component of the shape function in the slot of the displacement component */
+        double g[3][3][24]; /* [derivative][component][dof] */
+        for (int d = 0; d < 3; ++d)
+          for (int c = 0; c < 3; ++c)
+            for (int q = 0; q < n; ++q) g[d][c][q] = 0.0;
+        for (int a = 0; a < npc; ++a)
+          for (int c = 0; c < dim; ++c) {
+            g[0][c][dim * a + c] = dxu[a];
+            g[1][c][dim * a + c] = dyu[a];
+            if (dim == 3) g[2][c][dim * a + c] = dzu[a];
+          }
+        for (int i = 0; i < n; ++i)
+          for (int j = 0; j < n; ++j) {
+            double nse, ce, se;
+            if (dim == 2) {
+              nse = (lambda + 2 * mu) * ((g[0][0][i] * g[0][0][j]) + (g[1][1][i] * g[1][1][j])) * w;
+              ce = (lambda) * ((g[1][1][i] * g[0][0][j]) + (g[0][0][i] * g[1][1][j])) * w;
+              se = (mu) * ((g[0][1][i] + g[1][0][i]) * (g[1][0][j] + g[0][1][j])) * w;
+            }
+            else {
+              nse = (lambda + 2 * mu) * ((g[0][0][i] * g[0][0][j]) + (g[1][1][i] * g[1][1][j]) + (g[2][2][i] * g[2][2][j])) * w;
+              ce = lambda * ((g[0][0][i] * (g[1][1][j] + g[2][2][j])) + (g[1][1][i] * (g[0][0][j] + g[2][2][j])) + (g[2][2][i] * (g[0][0][j] + g[1][1][j]))) * w;
+              se = mu * (((g[1][0][i] + g[0][1][i]) * (g[1][0][j] + g[0][1][j])) + ((g[2][0][i] + g[0][2][i]) * (g[2][0][j] + g[0][2][j])) +
+                         ((g[2][1][i] + g[1][2][i]) * (g[2][1][j] + g[1][2][j]))) * w;
+            }
+            K[i * n + j] += (nse + ce) + se;
+          }
+      }
+}
+
 static void ke_hexa8_poisson(const r3* m, double* K)
 {
   const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
@@ -546,6 +645,7 @@ static int element_matrix(int npc, int dim, int op, int form, const double* para
   if (op == ORC_OP_ELASTICITY) {
     if (npc == 3 && dim == 2) { ke_tri3_elasticity(m[0], m[1], m[2], params[0], params[1], K); return 0; }
     if (npc == 4 && dim == 3) { ke_tet4_elasticity(m[0], m[1], m[2], m[3], params[0], params[1], K); return 0; }
+    if ((npc == 4 && dim == 2) || (npc == 8 && dim == 3)) { ke_q1_elasticity(dim, m, params[0], params[1], K); return 0; }
     return -1;
   }
   if (op == ORC_OP_BILAPLACIAN) {
@@ -685,7 +785,7 @@ ORC_API int orc_assemble_cellwise(int npc, int dim, int op, int form, const doub
   (void)nb_node;
   int b = op_block_size(op, dim);
   int n = npc * b;
-  double K[144];
+  double K[576];
   for (int64_t c = 0; c < nb_cell; ++c) {
     const int32_t* cn = conn + c * npc;
     if (element_matrix(npc, dim, op, form, params, coords, cn, K)) return -1;
@@ -744,7 +844,7 @@ ORC_API int orc_assemble_nodewise(int npc, int dim, int op, int form, const doub
   int64_t* ptr;
   int32_t* list;
   build_node_cells(npc, nb_node, nb_cell, conn, &ptr, &list);
-  double K[144];
+  double K[576];
   int rc = 0;
   for (int32_t r = 0; r < nb_node && !rc; ++r) {
     if (is_own && !is_own[r]) continue;

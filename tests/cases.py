@@ -70,6 +70,18 @@ ELASTICITY_CASES = {
                    golden="elasticity_bar.3D.Dirichlet.bodyForce.txt"),
 }
 
+# Quad4 / Hexa8 elasticity (modules/elasticity/ElementMatrixHexQuad.h): inputs/2D.dirichlet.bodyforce.quad.arc,
+# bar.2D.Dirichlet.bodyForce.quad.arc, 3D.dirichlet.bodyforce.hexa.arc
+Q1_ELASTICITY_CASES = {
+    "five_quads": dict(mesh="five_quads.msh", E=200e9, nu=0.3, f=[-9818949214245.0, -7818949234281.0],
+                       dirichlet=[("bot", [0.0, 0.0]), ("top", [1.9, 14.5])], penalty=1.0e30, golden="elasticity_2D.dirichlet.bodyforce.quad.txt"),
+    "plate_quad": dict(mesh="plate.quad.msh", E=21.0e5, nu=0.28, f=[0.0, -1.0], dirichlet=[("left", [0.0, 0.0])], penalty=1.0e30,
+                       golden="elasticity_bar.2D.Dirichlet.bodyForce.quad.txt"),
+    "truncated_cube_hexa": dict(mesh="truncated_cube.hexa.msh", E=200e9, nu=0.3, f=[-9.8e12, -7.5e12, 5.9e12],
+                                dirichlet=[("top", [1.0, 2.0, 8.0]), ("bottom", [12.9, -14.5, -18.8])], penalty=1.0e30,
+                                golden="elasticity_3D.dirichlet.bodyforce.hexa.txt"),
+}
+
 # modules/bilaplacian/inputs/direct.arc
 BILAPLACIAN_CASE = dict(mesh="bilap.msh", f=-786.25, dirichlet=[("boundary", [145.5, None])], penalty=1.0e30,
                         golden="bilaplacian_2d_test.txt")

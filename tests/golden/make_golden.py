@@ -38,6 +38,13 @@ FILES = {
     "modules/poisson/check/poisson_test_ref_circle_2D_quad.txt": "poisson_test_ref_circle_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_circle_scalar_neumann_2D_quad.txt": "poisson_test_ref_circle_scalar_neumann_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_sphere_3D_hexa.txt": "poisson_test_ref_sphere_3D_hexa.txt",
+    # Quad4 / Hexa8 elasticity (modules/elasticity)
+    "meshes/msh/five_quads.msh": "five_quads.msh",
+    "meshes/msh/plate.quad.msh": "plate.quad.msh",
+    "meshes/msh/truncated_cube.hexa.msh": "truncated_cube.hexa.msh",
+    "modules/elasticity/check/2D.dirichlet.bodyforce.quad.txt": "elasticity_2D.dirichlet.bodyforce.quad.txt",
+    "modules/elasticity/check/bar.2D.Dirichlet.bodyForce.quad.txt": "elasticity_bar.2D.Dirichlet.bodyForce.quad.txt",
+    "modules/elasticity/check/3D.dirichlet.bodyforce.hexa.txt": "elasticity_3D.dirichlet.bodyforce.hexa.txt",
     "modules/poisson/check/poisson_test_ref_circle_neumann_2D_quad.txt": "poisson_test_ref_circle_neumann_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_sphere_neumann_3D_hexa.txt": "poisson_test_ref_sphere_neumann_3D_hexa.txt",
     "modules/poisson/check/poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt": "poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt",

@@ -1120,6 +1120,49 @@ def test_q1_poisson_values(exec_ctx, dim, n, fmt, variant):
         assert np.all(np.abs(c.to_host(A.ARRAY_RHS) - ref_rhs) <= 1e-12 * np.abs(ref_rhs).max())
 
 
+@pytest.mark.parametrize("dim,n", [(2, 9), (3, 5)], ids=["quad4", "hexa8"])
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_q1_elasticity_values(exec_ctx, dim, n, variant, layout):
+    c = exec_ctx
+    m = M.box_mesh_q1(dim, n)
+    lam, mu = O.lame(21.0e5, 0.28)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(dim)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[lam, mu], layout=layout, nodewise=variant == A.VARIANT_NODEWISE)
+    c.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=layout)
+    row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows, b=dim, layout=layout)
+    ref_rhs = O.rhs_source_cellwise(m.dim, m.coords, m.cells, [1.5, -2.0, 0.5][:dim])
+    for nodewise in (False, True):
+        c.rhs_reset()
+        c.rhs_source([1.5, -2.0, 0.5][:dim], nodewise=nodewise)
+        assert np.all(np.abs(c.to_host(A.ARRAY_RHS) - ref_rhs) <= 1e-12 * np.abs(ref_rhs).max())
+    with pytest.raises(A.AfbError):
+        c.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER, layout=layout)
+
+
+@pytest.mark.parametrize("name", list(CS.Q1_ELASTICITY_CASES))
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+def test_q1_elasticity_golden_solution(exec_ctx, name, variant):
+    """Quad4 / Hexa8 elasticity against the elasticity module's own golden solution files (modules/elasticity/check/*quad*, *hexa*)"""
+    c = exec_ctx
+    case = CS.Q1_ELASTICITY_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    b = m.dim
+    lam, mu = O.lame(case["E"], case["nu"])
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(b)
+    c.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=A.LAYOUT_PER_ROW)
+    c.rhs_reset()
+    c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
+    c.dirichlet_penalty(ids, g, case["penalty"])
+    crow, ccol, vals, rhs = (c.to_host(w) for w in (A.ARRAY_CSR_ROWS, A.ARRAY_CSR_COLUMNS, A.ARRAY_VALUES, A.ARRAY_RHS))
+    u = spla.spsolve(sp.csr_matrix((vals, ccol, crow)).tocsc(), rhs)
+    assert CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10, subset=True) < 1.0e-4
+
+
 @pytest.mark.parametrize("name", list(CS.Q1_CASES))
 @pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
                          ids=["csr-gpu", "bsr", "af-bsr"])

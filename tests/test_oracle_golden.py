@@ -193,6 +193,20 @@ def test_elasticity_golden_per_row_layout(name, nodewise):
     assert worst < 1.0e-4
 
 
+@pytest.mark.parametrize("name", list(CS.Q1_ELASTICITY_CASES))
+@pytest.mark.parametrize("nodewise", [False, True], ids=["bsr", "af-bsr"])
+def test_q1_elasticity_golden(name, nodewise):
+    """Quad4 / Hexa8 elasticity (modules/elasticity/ElementMatrixHexQuad.h; body force modules/elasticity/BodyForce.h, Gauss rule)
+    against the elasticity module's own golden solution files"""
+    case = CS.Q1_ELASTICITY_CASES[name]
+    m, b, rows, cols, vals, rhs, ids, g = _elasticity_system(case, O.LAYOUT_PER_ROW, nodewise)
+    crow, ccol, nbc = O.bsr_to_csr(b, rows, cols)
+    O.dirichlet_penalty(crow, ccol, vals, rhs, ids, g, case["penalty"])
+    u = spla.spsolve(_csr(crow, ccol, vals).tocsc(), rhs)
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10, subset=True)
+    assert worst < 1.0e-4
+
+
 def test_elasticity_per_block_layout_equals_per_row():
     case = CS.ELASTICITY_CASES["bar_3D"]
     m, b, rows, cols, v_row, *_ = _elasticity_system(case, O.LAYOUT_PER_ROW, False)
