@@ -458,7 +458,6 @@ int afb_assemble_rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* face_
   const bool hexa = ctx->dim == 3 && ctx->npc == 8;
   AFB_REQUIRE(ctx->npc == ctx->dim + 1 || (ctx->dim == 2 && ctx->npc == 4) || hexa, AFB_ERR_UNSUPPORTED,
               "afb_assemble_rhs_neumann: edges of Tri3 / Quad4 meshes, triangles of Tet4 meshes and quadrilaterals of Hexa8 meshes only");
-  AFB_REQUIRE(!hexa || kind == AFB_NEUMANN_FLUX, AFB_ERR_UNSUPPORTED, "afb_assemble_rhs_neumann: Hexa8 faces take a flux (no traction term)");
   AFB_REQUIRE(kind == AFB_NEUMANN_FLUX || kind == AFB_NEUMANN_TRACTION, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: unknown kind %d", kind);
   if (kind == AFB_NEUMANN_FLUX)
     AFB_REQUIRE(nb_value == 1 || nb_value == ctx->dim, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: a flux takes 1 value or one per space dimension (got %d)", nb_value);

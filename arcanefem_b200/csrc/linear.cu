@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(256) k_rhs_neumann(const double* __restrict__ 
 // Quad4 faces of a Hexa8 mesh: 2x2 Gauss rule on the bilinear patch, detJ = |dr/dxi x dr/deta|, the unit normal taken at every
 // Gauss point from the face's node order (femutils/ArcaneFemFunctions.h:1843-1953; device twin ArcaneFemFunctionsGpu.cc:1146-1260)
 __global__ void __launch_bounds__(256) k_rhs_neumann_quad4(const double* __restrict__ coords, const int32_t* __restrict__ faces, int64_t nb_face,
-                                                            const uint8_t* __restrict__ is_own, const uint8_t* __restrict__ dir_node, int b, int nb_value, double v0, double v1,
-                                                            double v2, double* __restrict__ rhs)
+                                                            const uint8_t* __restrict__ is_own, const uint8_t* __restrict__ dir_node, int b, int kind, int nb_value, double v0,
+                                                            double v1, double v2, double* __restrict__ rhs)
 {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nb_face) return;
@@ -281,15 +281,20 @@ __global__ void __launch_bounds__(256) k_rhs_neumann_quad4(const double* __restr
     double nx = t1y * t2z - t1z * t2y, ny = t1z * t2x - t1x * t2z, nz = t1x * t2y - t1y * t2x;
     const double detJ = sqrt(nx * nx + ny * ny + nz * nz);
     nx /= detJ; ny /= detJ; nz /= detJ;
-    const double q = nb_value == 1 ? v0 : nx * v0 + ny * v1 + nz * v2;
+    // flux: value or q.n; traction (applyTractionToRhsHexa8, femutils/ArcaneFemFunctions.h:2222-2315): the shape-function integral, times t[k] below
+    const double q = kind == AFB_NEUMANN_TRACTION ? 1.0 : (nb_value == 1 ? v0 : nx * v0 + ny * v1 + nz * v2);
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] += q * N[j] * detJ;
   }
+  const double t[3] = { v0, v1, v2 };
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int32_t nd = __ldg(fn + j);
     if ((dir_node && dir_node[nd]) || (is_own && !is_own[nd])) continue;
-    atomicAdd(rhs + (int64_t)nd * b, acc[j]);
+    if (kind == AFB_NEUMANN_TRACTION) {
+      for (int k = 0; k < b; ++k) atomicAdd(rhs + (int64_t)nd * b + k, t[k] * acc[j]);
+    }
+    else atomicAdd(rhs + (int64_t)nd * b, acc[j]);
   }
 }
 
@@ -302,7 +307,7 @@ int rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* faces_dev, int kin
   const uint8_t* dir = (skip_dirichlet && ctx->has_dir_nodes) ? ctx->dir_node.as<uint8_t>() : nullptr;
   const int grid = grid_for(nb_face, 256);
   if (ctx->dim == 3 && ctx->npc == 8)
-    k_rhs_neumann_quad4<<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), faces_dev, nb_face, own, dir, ctx->b, nb_value, v[0], v[1], v[2], ctx->rhs.as<double>());
+    k_rhs_neumann_quad4<<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), faces_dev, nb_face, own, dir, ctx->b, kind, nb_value, v[0], v[1], v[2], ctx->rhs.as<double>());
   else if (ctx->dim == 2)
     k_rhs_neumann<2><<<grid, 256, 0, ctx->stream>>>(ctx->coords.as<double>(), faces_dev, nb_face, own, dir, ctx->b, kind, nb_value, v[0], v[1], v[2], ctx->rhs.as<double>());
   else

@@ -1048,9 +1048,9 @@ ORC_API void orc_rhs_source_nodewise(int npc, int dim, int b, int32_t nb_node, i
 /* Quad4 faces of a Hexa8 mesh (femutils/ArcaneFemFunctions.h:1843-1953 applyNeumannToRhsHexa8): 2x2 Gauss rule on the
  * bilinear patch, tangents t1 = dr/dxi, t2 = dr/deta, detJ = |t1 x t2|, unit normal (t1 x t2)/detJ at every Gauss point;
  * rhs_j += value * N_j * detJ (scalar) or (normal . q) * N_j * detJ (vector).  The faces come oriented (outward t1 x t2). */
-ORC_API void orc_rhs_neumann_quad4(int b, int nb_value, int64_t nb_face, const double* coords, const int32_t* faces, const double* values, const uint8_t* is_own,
+ORC_API void orc_rhs_neumann_quad4(int b, int kind, int nb_value, int64_t nb_face, const double* coords, const int32_t* faces, const double* values, const uint8_t* is_own,
                                    const uint8_t* is_dirichlet, double* rhs)
-{
+{ /* kind 1: traction, rhs[dof(j,k)] += t[k] * N_j * detJ (femutils/ArcaneFemFunctions.h:2222-2315 applyTractionToRhsHexa8) */
   const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
   static const double sx[4] = { -1, 1, 1, -1 }, sy[4] = { -1, -1, 1, 1 };
   for (int64_t f = 0; f < nb_face; ++f) {
@@ -1075,6 +1075,10 @@ ORC_API void orc_rhs_neumann_quad4(int b, int nb_value, int64_t nb_face, const d
         for (int j = 0; j < 4; ++j) {
           const int32_t nd = fn[j];
           if ((is_dirichlet && is_dirichlet[nd]) || (is_own && !is_own[nd])) continue;
+          if (kind == 1) {
+            for (int k = 0; k < b; ++k) rhs[(int64_t)nd * b + k] += values[k] * N[j] * iw;
+            continue;
+          }
           const double v = nb_value == 1 ? values[0] * N[j] * iw : (nr.x * values[0] + nr.y * values[1] + nr.z * values[2]) * N[j] * iw;
           rhs[(int64_t)nd * b] += v;
         }

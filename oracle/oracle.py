@@ -164,9 +164,8 @@ def rhs_neumann(mesh_dim, b, coords, faces, values, rhs, kind=NEUMANN_FLUX, is_o
     """rhs += boundary integral over P1 faces (oriented: see orc_rhs_neumann); in place."""
     faces = np.ascontiguousarray(faces, dtype=np.int32)
     values = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64)
-    if mesh_dim == 3 and faces.ndim == 2 and faces.shape[1] == 4:  # Quad4 faces of a Hexa8 mesh: flux only
-        assert kind == NEUMANN_FLUX
-        lib().orc_rhs_neumann_quad4(int(b), int(values.size), C.c_int64(faces.shape[0]), _p(_f64(coords)), _p(faces), _p(values), _p(_u8(is_own)), _p(_u8(is_dirichlet)), _p(rhs))
+    if mesh_dim == 3 and faces.ndim == 2 and faces.shape[1] == 4:  # Quad4 faces of a Hexa8 mesh
+        lib().orc_rhs_neumann_quad4(int(b), int(kind), int(values.size), C.c_int64(faces.shape[0]), _p(_f64(coords)), _p(faces), _p(values), _p(_u8(is_own)), _p(_u8(is_dirichlet)), _p(rhs))
         return rhs
     coords = np.ascontiguousarray(coords, dtype=np.float64)
     assert faces.shape[1] == mesh_dim and rhs.dtype == np.float64

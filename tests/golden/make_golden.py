@@ -45,6 +45,9 @@ FILES = {
     "modules/elasticity/check/2D.dirichlet.bodyforce.quad.txt": "elasticity_2D.dirichlet.bodyforce.quad.txt",
     "modules/elasticity/check/bar.2D.Dirichlet.bodyForce.quad.txt": "elasticity_bar.2D.Dirichlet.bodyForce.quad.txt",
     "modules/elasticity/check/3D.dirichlet.bodyforce.hexa.txt": "elasticity_3D.dirichlet.bodyforce.hexa.txt",
+    "modules/elasticity/check/2D.dirichlet.traction.bodyforce.quad.txt": "elasticity_2D.dirichlet.traction.bodyforce.quad.txt",
+    "modules/elasticity/check/bar.2D.traction.bodyforce.quad.txt": "elasticity_bar.2D.traction.bodyforce.quad.txt",
+    "modules/elasticity/check/3D.dirichlet.traction.bodyforce.hexa.txt": "elasticity_3D.dirichlet.traction.bodyforce.hexa.txt",
     "modules/poisson/check/poisson_test_ref_circle_neumann_2D_quad.txt": "poisson_test_ref_circle_neumann_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_sphere_neumann_3D_hexa.txt": "poisson_test_ref_sphere_neumann_3D_hexa.txt",
     "modules/poisson/check/poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt": "poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt",

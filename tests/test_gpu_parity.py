@@ -1157,6 +1157,8 @@ def test_q1_elasticity_golden_solution(exec_ctx, name, variant):
     c.assemble(A.OP_ELASTICITY, params=[lam, mu], fmt=A.FORMAT_BSR, variant=variant, layout=A.LAYOUT_PER_ROW)
     c.rhs_reset()
     c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
+    for group, t in case.get("traction", []):
+        c.rhs_neumann(m.faces[group], t, kind=A.NEUMANN_TRACTION)
     c.dirichlet_penalty(ids, g, case["penalty"])
     crow, ccol, vals, rhs = (c.to_host(w) for w in (A.ARRAY_CSR_ROWS, A.ARRAY_CSR_COLUMNS, A.ARRAY_VALUES, A.ARRAY_RHS))
     u = spla.spsolve(sp.csr_matrix((vals, ccol, crow)).tocsc(), rhs)

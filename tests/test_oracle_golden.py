@@ -200,6 +200,8 @@ def test_q1_elasticity_golden(name, nodewise):
     against the elasticity module's own golden solution files"""
     case = CS.Q1_ELASTICITY_CASES[name]
     m, b, rows, cols, vals, rhs, ids, g = _elasticity_system(case, O.LAYOUT_PER_ROW, nodewise)
+    for group, t in case.get("traction", []):  # edges of the Quad4 mesh / Quad4 faces of the Hexa8 mesh (no normal involved)
+        O.rhs_neumann(m.dim, b, m.coords, m.faces[group], t, rhs, kind=O.NEUMANN_TRACTION)
     crow, ccol, nbc = O.bsr_to_csr(b, rows, cols)
     O.dirichlet_penalty(crow, ccol, vals, rhs, ids, g, case["penalty"])
     u = spla.spsolve(_csr(crow, ccol, vals).tocsc(), rhs)
