@@ -43,6 +43,17 @@ Q1_CASES = {
                                           golden="poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt"),
 }
 
+# Laplace module (modules/laplace: no source term; inputs/ring.dirichlet-neumann.quad.arc, truncated-cube.neumann.3D.hexa.arc,
+# L-shape.3D.arc run as BSR and AF-BSR, CMakeLists.txt:71-89,112-123)
+Q1_CASES.update({
+    "laplace_ring_quad": dict(mesh="ring.quad.msh", f=0.0, dirichlet=[("inner", 50.0)], neumann=[("outer", [17.8])], penalty=1.0e30,
+                              golden="laplace_test_ring_quad.txt"),
+    "laplace_truncated_cube_hexa": dict(mesh="truncated_cube.hexa.msh", f=0.0, dirichlet=[("horizontal", 1.8)], neumann=[("bottom", [3.1])], penalty=1.0e30,
+                                        golden="laplace_test_trucated-cube_hexa.txt"),
+    "laplace_L-shape_3D": dict(mesh="L-shape-3D.msh", f=0.0, dirichlet=[("bot", 50.0), ("bc", 10.0)], penalty=1.0e30,
+                               golden="laplace_test_3D_L-shape.txt"),
+})
+
 # Neumann flux cases of testlab (circle_cut.msh; modules/testlab/inputs/Test.circle.2D.trac*.arc): value = scalar flux,
 # valueX/valueY = flux vector q (q.n with the outward normal)
 NEUMANN_CASES = {

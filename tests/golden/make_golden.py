@@ -38,6 +38,11 @@ FILES = {
     "modules/poisson/check/poisson_test_ref_circle_2D_quad.txt": "poisson_test_ref_circle_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_circle_scalar_neumann_2D_quad.txt": "poisson_test_ref_circle_scalar_neumann_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_sphere_3D_hexa.txt": "poisson_test_ref_sphere_3D_hexa.txt",
+    # Laplace module (Quad4, Hexa8, Tet4 through the BSR back-ends)
+    "meshes/msh/ring.quad.msh": "ring.quad.msh",
+    "modules/laplace/check/test_ring_quad.txt": "laplace_test_ring_quad.txt",
+    "modules/laplace/check/test_trucated-cube_hexa.txt": "laplace_test_trucated-cube_hexa.txt",
+    "modules/laplace/check/test_3D_L-shape.txt": "laplace_test_3D_L-shape.txt",
     # Quad4 / Hexa8 elasticity (modules/elasticity)
     "meshes/msh/five_quads.msh": "five_quads.msh",
     "meshes/msh/plate.quad.msh": "plate.quad.msh",
