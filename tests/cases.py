@@ -54,6 +54,17 @@ Q1_CASES.update({
                                golden="laplace_test_3D_L-shape.txt"),
 })
 
+# Production poisson module on P1 cells (BSR-lambda element matrices, BC-service source and flux terms; modules/poisson/inputs/
+# circle.2D.arc, circle.neumann.2D.arc, sphere.3D.arc, sphere.neumann.3D.arc; CMakeLists.txt:65-75,173-182)
+Q1_CASES.update({
+    "poissonmod_circle_2D": dict(mesh="circle_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], penalty=1.0e30, golden="poissonmod_test_ref_circle_2D.txt"),
+    "poissonmod_circle_neumann_2D": dict(mesh="circle_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("curved", [-0.35, 1.65])], penalty=1.0e30,
+                                         golden="poissonmod_test_ref_circle_neumann_2D.txt"),
+    "poissonmod_sphere_3D": dict(mesh="sphere_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], penalty=1.0e30, golden="poissonmod_test_ref_sphere_3D.txt"),
+    "poissonmod_sphere_neumann_3D": dict(mesh="sphere_cut.msh", f=5.5, dirichlet=[("horizontal", 0.5)], neumann=[("curved", [0.35, 1.65, 3.75])], penalty=1.0e30,
+                                         golden="poissonmod_test_ref_sphere_neumann_3D.txt"),
+})
+
 # Neumann flux cases of testlab (circle_cut.msh; modules/testlab/inputs/Test.circle.2D.trac*.arc): value = scalar flux,
 # valueX/valueY = flux vector q (q.n with the outward normal)
 NEUMANN_CASES = {

@@ -38,6 +38,11 @@ FILES = {
     "modules/poisson/check/poisson_test_ref_circle_2D_quad.txt": "poisson_test_ref_circle_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_circle_scalar_neumann_2D_quad.txt": "poisson_test_ref_circle_scalar_neumann_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_sphere_3D_hexa.txt": "poisson_test_ref_sphere_3D_hexa.txt",
+    # production poisson module on P1 cells
+    "modules/poisson/check/poisson_test_ref_circle_2D.txt": "poissonmod_test_ref_circle_2D.txt",
+    "modules/poisson/check/poisson_test_ref_circle_neumann_2D.txt": "poissonmod_test_ref_circle_neumann_2D.txt",
+    "modules/poisson/check/poisson_test_ref_sphere_3D.txt": "poissonmod_test_ref_sphere_3D.txt",
+    "modules/poisson/check/poisson_test_ref_sphere_neumann_3D.txt": "poissonmod_test_ref_sphere_neumann_3D.txt",
     # Laplace module (Quad4, Hexa8, Tet4 through the BSR back-ends)
     "meshes/msh/ring.quad.msh": "ring.quad.msh",
     "modules/laplace/check/test_ring_quad.txt": "laplace_test_ring_quad.txt",
