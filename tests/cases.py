@@ -107,6 +107,9 @@ Q1_ELASTICITY_CASES = {
     "truncated_cube_hexa_traction": dict(mesh="truncated_cube.hexa.msh", E=200e9, nu=0.3, f=[-9.8e1, -7.5e1, 5.9e1], dirichlet=[("top", [0.0, 0.0, 0.0])],
                                          traction=[("bottom", [12.9e11, -14.5e11, -18.8e11])], penalty=1.0e30,
                                          golden="elasticity_3D.dirichlet.traction.bodyforce.hexa.txt"),
+    # inputs/bar.2D.traction.bodyforce.arc (Tri3: traction and body force together)
+    "bar_2D_traction_bodyforce": dict(mesh="bar.msh", E=21.0e5, nu=0.28, f=[3.33, -6.66], dirichlet=[("left", [0.0, 0.0])], traction=[("right", [1.33, 2.13])],
+                                      penalty=1.0e30, golden="elasticity_bar.2D.traction.bodyforce.txt"),
     "truncated_cube_hexa": dict(mesh="truncated_cube.hexa.msh", E=200e9, nu=0.3, f=[-9.8e12, -7.5e12, 5.9e12],
                                 dirichlet=[("top", [1.0, 2.0, 8.0]), ("bottom", [12.9, -14.5, -18.8])], penalty=1.0e30,
                                 golden="elasticity_3D.dirichlet.bodyforce.hexa.txt"),

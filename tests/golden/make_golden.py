@@ -55,6 +55,7 @@ FILES = {
     "modules/elasticity/check/2D.dirichlet.bodyforce.quad.txt": "elasticity_2D.dirichlet.bodyforce.quad.txt",
     "modules/elasticity/check/bar.2D.Dirichlet.bodyForce.quad.txt": "elasticity_bar.2D.Dirichlet.bodyForce.quad.txt",
     "modules/elasticity/check/3D.dirichlet.bodyforce.hexa.txt": "elasticity_3D.dirichlet.bodyforce.hexa.txt",
+    "modules/elasticity/check/bar.2D.traction.bodyforce.txt": "elasticity_bar.2D.traction.bodyforce.txt",
     "modules/elasticity/check/2D.dirichlet.traction.bodyforce.quad.txt": "elasticity_2D.dirichlet.traction.bodyforce.quad.txt",
     "modules/elasticity/check/bar.2D.traction.bodyforce.quad.txt": "elasticity_bar.2D.traction.bodyforce.quad.txt",
     "modules/elasticity/check/3D.dirichlet.traction.bodyforce.hexa.txt": "elasticity_3D.dirichlet.traction.bodyforce.hexa.txt",
