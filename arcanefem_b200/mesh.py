@@ -168,6 +168,15 @@ def read_msh(path: str) -> Mesh:
         fl = np.concatenate(lst, axis=0)
         faces[name] = fl
         groups[name] = np.unique(fl.ravel()).astype(np.int32)
+    # named points (physical groups of dimension 0: the <dirichlet-point> targets of the reference's .arc files)
+    for ed, et, ty, a in blocks:
+        if ed != 0:
+            continue
+        for ptag in ent_phys.get((0, et), []):
+            name = phys_names.get((0, ptag))
+            if name is not None and name not in faces:
+                pts = tag2lid(a[:, 1:]).astype(np.int32).ravel()
+                groups[name] = np.unique(np.concatenate([groups.get(name, np.empty(0, np.int32)), pts])).astype(np.int32)
     return Mesh(dim=dim, coords=coords, cells=np.ascontiguousarray(cells), node_uid=uid.astype(np.int64), groups=groups, faces=faces)
 
 

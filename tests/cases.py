@@ -65,6 +65,16 @@ Q1_CASES.update({
                                          golden="poissonmod_test_ref_sphere_neumann_3D.txt"),
 })
 
+# <dirichlet-point> on named nodes (modules/poisson/inputs/perforatedSquare.pointDirichlet.2D.arc; the laplace module's
+# PointDirichlet.arc is the same problem with its own golden file)
+Q1_CASES.update({
+    # (these two golden files carry their solver's residual: Dirichlet nodes read 20.0000000000118; compared at 5e-5, upstream's bar is 1e-4)
+    "poissonmod_point_dirichlet_2D": dict(mesh="plancher.msh", f=0.0, penalty=1.0e30, golden="poissonmod_test_point_dirichlet_2D.txt", tol=5.0e-5,
+                                          dirichlet=[("topLeftCorner", 50.0), ("topRightCorner", 20.0), ("botLeftCorner", 20.0), ("botRightCorner", 50.0)]),
+    "laplace_point_dirichlet_2D": dict(mesh="plancher.msh", f=0.0, penalty=1.0e30, golden="laplace_test3_results.txt", tol=5.0e-5,
+                                       dirichlet=[("topLeftCorner", 50.0), ("topRightCorner", 20.0), ("botLeftCorner", 20.0), ("botRightCorner", 50.0)]),
+})
+
 # Neumann flux cases of testlab (circle_cut.msh; modules/testlab/inputs/Test.circle.2D.trac*.arc): value = scalar flux,
 # valueX/valueY = flux vector q (q.n with the outward normal)
 NEUMANN_CASES = {
@@ -110,6 +120,9 @@ Q1_ELASTICITY_CASES = {
     # inputs/bar.2D.traction.bodyforce.arc (Tri3: traction and body force together)
     "bar_2D_traction_bodyforce": dict(mesh="bar.msh", E=21.0e5, nu=0.28, f=[3.33, -6.66], dirichlet=[("left", [0.0, 0.0])], traction=[("right", [1.33, 2.13])],
                                       penalty=1.0e30, golden="elasticity_bar.2D.traction.bodyforce.txt"),
+    # inputs/bar.2D.PointDirichlet.Dirichlet.bodyForce.arc (component-wise Dirichlet on faces and on named nodes)
+    "bar_2D_point_dirichlet": dict(mesh="bar.msh", E=21.0e5, nu=0.28, f=[0.0, -1.0], penalty=1.0e30, golden="elasticity_bar.2D.PointDirichlet.Dirichlet.bodyForce.txt",
+                                   dirichlet=[("left", [0.0, None]), ("right", [1.0, None]), ("botLeft", [0.0, 0.0]), ("botRight", [None, 0.0])]),
     "truncated_cube_hexa": dict(mesh="truncated_cube.hexa.msh", E=200e9, nu=0.3, f=[-9.8e12, -7.5e12, 5.9e12],
                                 dirichlet=[("top", [1.0, 2.0, 8.0]), ("bottom", [12.9, -14.5, -18.8])], penalty=1.0e30,
                                 golden="elasticity_3D.dirichlet.bodyforce.hexa.txt"),

@@ -43,6 +43,11 @@ FILES = {
     "modules/poisson/check/poisson_test_ref_circle_neumann_2D.txt": "poissonmod_test_ref_circle_neumann_2D.txt",
     "modules/poisson/check/poisson_test_ref_sphere_3D.txt": "poissonmod_test_ref_sphere_3D.txt",
     "modules/poisson/check/poisson_test_ref_sphere_neumann_3D.txt": "poissonmod_test_ref_sphere_neumann_3D.txt",
+    # point Dirichlet conditions
+    "meshes/msh/plancher.msh": "plancher.msh",
+    "modules/poisson/check/poisson_test_point_dirichlet_2D.txt": "poissonmod_test_point_dirichlet_2D.txt",
+    "modules/laplace/check/test3_results.txt": "laplace_test3_results.txt",
+    "modules/elasticity/check/bar.2D.PointDirichlet.Dirichlet.bodyForce.txt": "elasticity_bar.2D.PointDirichlet.Dirichlet.bodyForce.txt",
     # Laplace module (Quad4, Hexa8, Tet4 through the BSR back-ends)
     "meshes/msh/ring.quad.msh": "ring.quad.msh",
     "modules/laplace/check/test_ring_quad.txt": "laplace_test_ring_quad.txt",
