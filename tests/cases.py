@@ -75,6 +75,25 @@ Q1_CASES.update({
                                        dirichlet=[("topLeftCorner", 50.0), ("topRightCorner", 20.0), ("botLeftCorner", 20.0), ("botRightCorner", 50.0)]),
 })
 
+# more of the same operator on other meshes and boundary data: modules/poisson/inputs/cube.3D.hexa.arc (source + flux over Quad4
+# faces), modules/laplace/inputs/truncated-cube.3D.arc (face and point Dirichlet on Tet4), the electrostatics module (rho = 0,
+# epsilon = 1: the same stiffness matrix; inputs/box-rods.arc, box-rods.quad.arc, rod-circle.arc, truncated_cube.hexa.arc)
+Q1_CASES.update({
+    "poissonmod_cube_3D_hexa8": dict(mesh="3x3x3_cube_hexa8.msh", f=9.8, dirichlet=[("left", 0.5)], neumann=[("right", [13.9])], penalty=1.0e30,
+                                     golden="poissonmod_test_ref_cube_3D_hexa8.txt"),
+    "laplace_truncated_cube_point": dict(mesh="truncated_cube.msh", f=0.0, dirichlet=[("center", 18.8), ("left", 0.8)], penalty=1.0e30,
+                                         golden="laplace_test_3D_truncated-cube.txt"),
+    "electrostatics_box_rods": dict(mesh="box-rods.msh", f=0.0, dirichlet=[("rod1", -1.0), ("rod2", 1.0), ("external", 0.0)], penalty=1.0e30,
+                                    golden="electrostatics_test_1.txt"),
+    "electrostatics_box_rods_quad": dict(mesh="box-rods.quad.msh", f=0.0, dirichlet=[("rod1", -1.0), ("rod2", 1.0), ("external", 0.0)], penalty=1.0e30,
+                                         golden="electrostatics_box-rods.quad.txt"),
+    "electrostatics_rod_circle": dict(mesh="box-rod-circle.msh", f=0.0, dirichlet=[("rod1", -1.0), ("circle", 1.0), ("external", 0.0)], penalty=1.0e30,
+                                      golden="electrostatics_test_2.txt"),
+    "electrostatics_truncated_cube_hexa": dict(mesh="truncated_cube.hexa.msh", f=0.0, neumann=[("verticalYZ", [-1.0])],
+                                               dirichlet=[("verticalYZ", -1.0), ("horizontal", 0.0)], penalty=1.0e30,
+                                               golden="electrostatics_truncated-cube.hexa.txt"),
+})
+
 # Neumann flux cases of testlab (circle_cut.msh; modules/testlab/inputs/Test.circle.2D.trac*.arc): value = scalar flux,
 # valueX/valueY = flux vector q (q.n with the outward normal)
 NEUMANN_CASES = {

@@ -48,6 +48,18 @@ FILES = {
     "modules/poisson/check/poisson_test_point_dirichlet_2D.txt": "poissonmod_test_point_dirichlet_2D.txt",
     "modules/laplace/check/test3_results.txt": "laplace_test3_results.txt",
     "modules/elasticity/check/bar.2D.PointDirichlet.Dirichlet.bodyForce.txt": "elasticity_bar.2D.PointDirichlet.Dirichlet.bodyForce.txt",
+    # the same operator on other meshes / boundary data (poisson cube, laplace truncated cube, electrostatics module)
+    "meshes/msh/3x3x3_cube_hexa8.msh": "3x3x3_cube_hexa8.msh",
+    "meshes/msh/truncated_cube.msh": "truncated_cube.msh",
+    "meshes/msh/box-rods.msh": "box-rods.msh",
+    "meshes/msh/box-rods.quad.msh": "box-rods.quad.msh",
+    "meshes/msh/box-rod-circle.msh": "box-rod-circle.msh",
+    "modules/poisson/check/poisson_test_ref_cube_3D_hexa8.txt": "poissonmod_test_ref_cube_3D_hexa8.txt",
+    "modules/laplace/check/test_3D_truncated-cube.txt": "laplace_test_3D_truncated-cube.txt",
+    "modules/electrostatics/check/test_1.txt": "electrostatics_test_1.txt",
+    "modules/electrostatics/check/test_2.txt": "electrostatics_test_2.txt",
+    "modules/electrostatics/check/box-rods.quad.txt": "electrostatics_box-rods.quad.txt",
+    "modules/electrostatics/check/truncated-cube.hexa.txt": "electrostatics_truncated-cube.hexa.txt",
     # Laplace module (Quad4, Hexa8, Tet4 through the BSR back-ends)
     "meshes/msh/ring.quad.msh": "ring.quad.msh",
     "modules/laplace/check/test_ring_quad.txt": "laplace_test_ring_quad.txt",
