@@ -36,7 +36,7 @@ _ARRAY_DTYPE = {ARRAY_ROWS: np.int32, ARRAY_COLUMNS: np.int32, ARRAY_VALUES: np.
                 ARRAY_COORDS: np.float64, ARRAY_CELL_NODES: np.int32, ARRAY_NODE_CELL_PTR: np.int32, ARRAY_NODE_CELL_LIST: np.int32}
 
 EXPORTS = [
-    "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_update_coordinates", "afb_set_own_cell_count", "afb_get_own_cell_count", "afb_renumber_columns", "afb_get_ij_arrays", "afb_memcpy_to_host", "afb_mesh_generate_box",
+    "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_update_coordinates", "afb_set_own_cell_count", "afb_set_cell_coefficient", "afb_get_own_cell_count", "afb_renumber_columns", "afb_get_ij_arrays", "afb_memcpy_to_host", "afb_mesh_generate_box",
     "afb_build_pattern", "afb_set_sparsity_algorithm", "afb_set_tiled_executor", "afb_set_vector_executor", "afb_set_tiled_stage_limit", "afb_options_from_name", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_assemble_rhs_neumann", "afb_set_dirichlet_nodes",
     "afb_dirichlet_penalty", "afb_set_elimination", "afb_set_forced_values", "afb_clear_dirichlet", "afb_apply_matrix_transformation",
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
@@ -180,6 +180,14 @@ class Context:
     def set_sparsity_algorithm(self, algorithm):
         """SPARSITY_FROM_CELLS = computeSparsityAtomic, SPARSITY_FROM_CONNECTIVITY = computeSparsityAtomicFree (re-builds on an unchanged mesh)."""
         _check(lib().afb_set_sparsity_algorithm(self._h, int(algorithm)))
+
+    def set_cell_coefficient(self, coefficient):
+        """per-cell multiplier of the Poisson element matrix ([nb_cell] doubles, or a scalar for all cells); None switches it off"""
+        if coefficient is None:
+            _check(lib().afb_set_cell_coefficient(self._h, None, MEM_HOST))
+            return
+        c = np.ascontiguousarray(np.broadcast_to(np.asarray(coefficient, dtype=np.float64), (self.nb_cell,)))
+        _check(lib().afb_set_cell_coefficient(self._h, _ptr(c), MEM_HOST))
 
     def set_vector_executor(self, executor):
         """VEC_EXEC_AUTO (default: rows on Tet4, units on Tri3), VEC_EXEC_ROWS, VEC_EXEC_UNITS: how VARIANT_TILED_GATHER runs for elasticity."""

@@ -294,6 +294,7 @@ int afb_set_mesh(afb_ctx* ctx, int dim, int npc, int32_t nb_node, int64_t nb_cel
               "afb_set_mesh(AFB_MEM_DEVICE): cell_nodes must be 16-byte aligned and xyz 8-byte aligned (pass a copy, or use AFB_MEM_HOST)");
   invalidate_pattern(ctx);
   ctx->has_mesh = false;
+  ctx->has_cell_coef = false; // per-cell data of the previous mesh
   ctx->dim = dim;
   ctx->npc = npc;
   ctx->nb_node = nb_node;
@@ -336,6 +337,20 @@ int afb_update_coordinates(afb_ctx* ctx, const double* xyz, int mem_space)
     }
     AFB_CUDA(cudaMemcpyAsync(ctx->coords.p, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
+  return AFB_OK;
+}
+
+int afb_set_cell_coefficient(afb_ctx* ctx, const double* coefficient, int mem_space)
+{
+  AFB_TRY(check_ctx(ctx));
+  AFB_REQUIRE(ctx->has_mesh, AFB_ERR_INVALID, "afb_set_cell_coefficient: no mesh set");
+  if (!coefficient) {
+    ctx->has_cell_coef = false;
+    return AFB_OK;
+  }
+  AFB_REQUIRE(mem_space == AFB_MEM_HOST || mem_space == AFB_MEM_DEVICE, AFB_ERR_INVALID, "afb_set_cell_coefficient: unknown memory space %d", mem_space);
+  AFB_TRY(upload(ctx, ctx->cell_coef, coefficient, sizeof(double) * (size_t)ctx->nb_cell, mem_space));
+  ctx->has_cell_coef = true;
   return AFB_OK;
 }
 

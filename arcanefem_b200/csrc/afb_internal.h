@@ -140,6 +140,8 @@ struct afb_ctx {
   int64_t nb_own_cell = 0;      // cells [0, nb_own_cell) belong to this sub-domain, the rest are ghost cells
   bool has_mesh = false;
   afb::DevBuf coords, conn, is_own; // double[nb_node*3], int32[nb_cell*npc], uint8[nb_node] (may be null => all owned)
+  afb::DevBuf cell_coef;            // double[nb_cell]: per-cell multiplier of the Poisson element matrix (afb_set_cell_coefficient)
+  bool has_cell_coef = false;
   bool all_own = true;
   afb::DevBuf nc_ptr, nc_list;      // node -> cells (int32[nb_node+1], int32[nb_cell*npc]), ascending cell ids
   int max_valence = 0;

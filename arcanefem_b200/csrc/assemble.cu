@@ -48,6 +48,7 @@ k_assemble_cellwise(const double* __restrict__ coords, const int32_t* __restrict
   int32_t nd[NPC];
   load_cell_nodes<NPC>(conn, cell, nd);
   E e;
+  if (prm.cell_coef) prm.scale = __ldg(prm.cell_coef + cell);
   e.init(coords, nd, prm);
 #pragma unroll(NPC <= 4 ? NPC : 1)
   for (int a = 0; a < NPC; ++a) {
@@ -137,6 +138,7 @@ k_assemble_nodewise(const double* __restrict__ coords, const int32_t* __restrict
     for (int i = 1; i < NPC; ++i)
       if (nd[i] == r) a = i;
     E e;
+    if (prm.cell_coef) prm.scale = __ldg(prm.cell_coef + cell);
     e.init(coords, nd, prm);
     if constexpr (NPC <= 4) {
       // compile-time row index: keeps the cofactors in registers (no dynamic indexing)
@@ -209,6 +211,11 @@ int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, in
   prm.p1 = params ? params[1] : 0.0;
   prm.flags = flags;
   const int npc = ctx->npc, dim = ctx->dim;
+  if (ctx->has_cell_coef) {
+    AFB_REQUIRE(op == AFB_OP_POISSON && (npc == dim + 1 || npc == (1 << dim)), AFB_ERR_UNSUPPORTED,
+                "a per-cell coefficient (afb_set_cell_coefficient) applies to the Poisson operator on Tri3 / Tet4 / Quad4 / Hexa8 cells");
+    prm.cell_coef = ctx->cell_coef.as<double>();
+  }
   if (op == AFB_OP_POISSON) {
     if (npc == 4 && dim == 3) return launch<Tet4Poisson>(ctx, format, variant, layout, prm);
     if (npc == 3 && dim == 2) return launch<Tri3Poisson>(ctx, format, variant, layout, prm);

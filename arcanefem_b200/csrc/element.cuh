@@ -32,6 +32,8 @@ namespace afb {
 struct ElemParams {
   double p0, p1;  // elasticity: lambda, mu
   int flags;      // AFB_FLAG_*
+  const double* cell_coef = nullptr; // per-cell multiplier of the Poisson element matrix (afb_set_cell_coefficient) or null
+  double scale = 1.0;                // the current cell's multiplier (set by the cell-wise / node-wise kernels)
 };
 
 __device__ __forceinline__ void load3(const double* __restrict__ coords, int32_t n, double& x, double& y, double& z)
@@ -111,7 +113,11 @@ struct Tri3Geom {
 struct Tet4Poisson {
   static constexpr int NPC = 4, B = 1, DIM = 3;
   Tet4Geom g;
-  __device__ __forceinline__ void init(const double* __restrict__ coords, const int32_t (&nd)[4], const ElemParams&) { g.init(coords, nd); }
+  __device__ __forceinline__ void init(const double* __restrict__ coords, const int32_t (&nd)[4], const ElemParams& p)
+  {
+    g.init(coords, nd);
+    g.s *= p.scale;
+  }
   __device__ __forceinline__ void block(int a, int b, double (&o)[1]) const { o[0] = g.dot(a, b) * g.s; }
   __device__ __forceinline__ double measure() const { return g.vol; }
 };
@@ -119,7 +125,11 @@ struct Tet4Poisson {
 struct Tri3Poisson {
   static constexpr int NPC = 3, B = 1, DIM = 2;
   Tri3Geom g;
-  __device__ __forceinline__ void init(const double* __restrict__ coords, const int32_t (&nd)[3], const ElemParams& p) { g.init(coords, nd, (p.flags & AFB_FLAG_SIGNED_TRI_AREA) != 0); }
+  __device__ __forceinline__ void init(const double* __restrict__ coords, const int32_t (&nd)[3], const ElemParams& p)
+  {
+    g.init(coords, nd, (p.flags & AFB_FLAG_SIGNED_TRI_AREA) != 0);
+    g.s *= p.scale;
+  }
   __device__ __forceinline__ void block(int a, int b, double (&o)[1]) const { o[0] = g.dot(a, b) * g.s; }
   __device__ __forceinline__ double measure() const { return g.area; }
 };
@@ -287,7 +297,7 @@ struct Quad4Poisson {
   static constexpr int NPC = 4, B = 1, DIM = 2;
   double K[4][4];
   double area;
-  __device__ void init(const double* __restrict__ coords, const int32_t (&nd)[4], const ElemParams&)
+  __device__ void init(const double* __restrict__ coords, const int32_t (&nd)[4], const ElemParams& prm)
   {
     double x[4], y[4];
 #pragma unroll
@@ -312,7 +322,7 @@ struct Quad4Poisson {
           J10 += det_[a] * x[a]; J11 += det_[a] * y[a];
         }
         const double det = J00 * J11 - J01 * J10;
-        const double inv = 1.0 / det;
+        const double inv = prm.scale / det;
         double ax[4], ay[4]; // det * physical gradients
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -338,7 +348,7 @@ struct Hexa8Poisson {
   static constexpr int NPC = 8, B = 1, DIM = 3;
   double K[8][8];
   double vol;
-  __device__ void init(const double* __restrict__ coords, const int32_t (&nd)[8], const ElemParams&)
+  __device__ void init(const double* __restrict__ coords, const int32_t (&nd)[8], const ElemParams& prm)
   {
     double x[8], y[8], z[8];
 #pragma unroll
@@ -372,7 +382,7 @@ struct Hexa8Poisson {
       const double c10 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c11 = J[0][0] * J[2][2] - J[0][2] * J[2][0], c12 = J[0][2] * J[1][0] - J[0][0] * J[1][2];
       const double c20 = J[1][0] * J[2][1] - J[1][1] * J[2][0], c21 = J[0][1] * J[2][0] - J[0][0] * J[2][1], c22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
       const double det = J[0][0] * c00 + J[0][1] * c10 + J[0][2] * c20;
-      const double inv = 1.0 / det;
+      const double inv = prm.scale / det;
       double ax[8], ay[8], az[8];
 #pragma unroll
       for (int a = 0; a < 8; ++a) {

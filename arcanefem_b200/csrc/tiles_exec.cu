@@ -916,6 +916,7 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   AFB_REQUIRE(ctx->npc == ctx->dim + 1 && ((op == AFB_OP_POISSON && !vec) || (op == AFB_OP_ELASTICITY && vec) || (op == AFB_OP_BILAPLACIAN && vec && ctx->npc == 3)),
               AFB_ERR_UNSUPPORTED,
               "AFB_VARIANT_TILED_GATHER is not available for operator %d on %d-node cells (P1 Poisson, P1 elasticity, Tri3 bilaplacian only); use AFB_VARIANT_NODEWISE", op, ctx->npc);
+  AFB_REQUIRE(!ctx->has_cell_coef, AFB_ERR_UNSUPPORTED, "AFB_VARIANT_TILED_GATHER does not take a per-cell coefficient (afb_set_cell_coefficient); use AFB_VARIANT_NODEWISE");
   TilePlan& P = ctx->plan;
   const int mode = flags & (AFB_FLAG_ALL_ROWS | AFB_FLAG_OWN_CELLS_ONLY);
   // scalar operators: the chained-slice executors when selected (afb_set_tiled_executor; chain_exec.cu, chain_flow.cu)

@@ -30,6 +30,8 @@ class Mesh:
     node_uid: np.ndarray          # int64 [nb_node] (gmsh tag; box meshes: = local id)
     # physical name -> int32 node ids (sorted unique) of its (dim-1) elements
     groups: dict = field(default_factory=dict)
+    # physical name -> int32 cell ids of a named volume (material regions)
+    cell_groups: dict = field(default_factory=dict)
     # physical name -> int32 [nb_face, nodes_per_face] boundary elements
     faces: dict = field(default_factory=dict)
 
@@ -153,6 +155,14 @@ def read_msh(path: str) -> Mesh:
     allc = np.concatenate([a for _, _, _, a in cell_blocks], axis=0)
     allc = allc[np.argsort(allc[:, 0], kind="stable")]
     cells = tag2lid(allc[:, 1:]).astype(np.int32)
+    cell_of_tag = {int(t): i for i, t in enumerate(allc[:, 0])}
+    cell_groups = {}
+    for ed, et, ty, a in cell_blocks:  # named volumes: <material-property><volume> of the reference's .arc files
+        for ptag in ent_phys.get((ed, et), []):
+            name = phys_names.get((ed, ptag))
+            if name is not None:
+                ids = np.array([cell_of_tag[int(t)] for t in a[:, 0]], dtype=np.int32)
+                cell_groups[name] = np.unique(np.concatenate([cell_groups.get(name, np.empty(0, np.int32)), ids])).astype(np.int32)
 
     groups, faces = {}, {}
     for ed, et, ty, a in blocks:
@@ -177,7 +187,7 @@ def read_msh(path: str) -> Mesh:
             if name is not None and name not in faces:
                 pts = tag2lid(a[:, 1:]).astype(np.int32).ravel()
                 groups[name] = np.unique(np.concatenate([groups.get(name, np.empty(0, np.int32)), pts])).astype(np.int32)
-    return Mesh(dim=dim, coords=coords, cells=np.ascontiguousarray(cells), node_uid=uid.astype(np.int64), groups=groups, faces=faces)
+    return Mesh(dim=dim, coords=coords, cells=np.ascontiguousarray(cells), node_uid=uid.astype(np.int64), groups=groups, faces=faces, cell_groups=cell_groups)
 
 
 def orient_boundary_faces(mesh: Mesh, faces: np.ndarray) -> np.ndarray:

@@ -162,6 +162,15 @@ AFB_API int afb_set_mesh(afb_ctx* ctx, int dim, int nodes_per_cell, int32_t nb_n
  */
 AFB_API int afb_update_coordinates(afb_ctx* ctx, const double* xyz, int mem_space);
 
+/*
+ * Per-cell coefficient of the Poisson operator: the element matrix of cell c is multiplied by coefficient[c] -- the
+ * conductivity m_cell_lambda of the reference's fourier / heat modules (modules/fourier/ElementMatrix.h:11-57,
+ * `area * lambda * (dxU ^ dxU) + ...`; multi-material cases set it per cell group), the permittivity of electrostatics.
+ * [nb_cell] doubles, copied; NULL switches it off; a new mesh drops it.  Cell-wise and node-wise variants on Tri3 / Tet4 /
+ * Quad4 / Hexa8; the tiled gather refuses (AFB_ERR_UNSUPPORTED).
+ */
+AFB_API int afb_set_cell_coefficient(afb_ctx* ctx, const double* coefficient, int mem_space);
+
 /* Cells [0, nb_own_cell) belong to this sub-domain, cells [nb_own_cell, nb_cell) are ghost cells
  * (Arcane's one-layer ghost cells; Cell::isOwn()).  Default after afb_set_mesh: all cells own. */
 AFB_API int afb_set_own_cell_count(afb_ctx* ctx, int64_t nb_own_cell);

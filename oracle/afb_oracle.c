@@ -778,6 +778,17 @@ ORC_API int64_t orc_value_index(const int32_t* rows, const int32_t* cols, int b,
  * The device back-ends add with atomics in arbitrary order; this sequential order
  * is one valid order, so device results are compared at 1e-12 (tests).
  */
+/* Per-cell coefficient of the stiffness operator (m_cell_lambda of the fourier / heat modules: modules/fourier/ElementMatrix.h:11,
+ * 22,45,57 `area * lambda * (dxU ^ dxU) + ...`; electrostatics epsilon): K_e of cell c is multiplied by coef[c].  Set before an
+ * orc_assemble_* call, NULL switches it off (test infrastructure: a process-wide pointer). */
+static const double* g_cell_coef = 0;
+ORC_API void orc_set_cell_coefficient(const double* coef) { g_cell_coef = coef; }
+static void scale_ke(double* K, int n, int64_t cell)
+{
+  if (!g_cell_coef) return;
+  for (int i = 0; i < n * n; ++i) K[i] *= g_cell_coef[cell];
+}
+
 ORC_API int orc_assemble_cellwise(int npc, int dim, int op, int form, const double* params,
                                   int32_t nb_node, int64_t nb_cell, const double* coords, const int32_t* conn, const uint8_t* is_own,
                                   const int32_t* rows, const int32_t* cols, int layout, int skip_zero, double* values)
@@ -789,6 +800,7 @@ ORC_API int orc_assemble_cellwise(int npc, int dim, int op, int form, const doub
   for (int64_t c = 0; c < nb_cell; ++c) {
     const int32_t* cn = conn + c * npc;
     if (element_matrix(npc, dim, op, form, params, coords, cn, K)) return -1;
+    scale_ke(K, n, c);
     for (int a1 = 0; a1 < npc; ++a1) {
       int32_t r = cn[a1];
       if (is_own && !is_own[r]) continue;
@@ -854,6 +866,7 @@ ORC_API int orc_assemble_nodewise(int npc, int dim, int op, int form, const doub
       for (int i = 0; i < npc; ++i) if (cn[i] == r) { a1 = i; break; }
       if (a1 < 0) continue;
       if (element_matrix(npc, dim, op, form, params, coords, cn, K)) { rc = -1; break; }
+      scale_ke(K, n, list[q]);
       for (int a2 = 0; a2 < npc; ++a2) {
         int32_t p = find_block(rows, cols, r, cn[a2]);
         if (p < 0) { rc = -2; break; }

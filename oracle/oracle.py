@@ -99,8 +99,19 @@ def build_pattern_host(npc, nb_node, cells, capacity):
 
 
 def assemble(mesh_dim, coords, cells, rows, cols, op=OP_POISSON, form=FORM_COMPACT, params=None,
-             layout=LAYOUT_PER_BLOCK, nodewise=False, is_own=None, skip_zero=False):
+             layout=LAYOUT_PER_BLOCK, nodewise=False, is_own=None, skip_zero=False, cell_coef=None):
+    """cell_coef: per-cell multiplier of the element matrix (conductivity of the fourier / heat modules)"""
     coords, cells, rows, cols = _f64(coords), _i32(cells), _i32(rows), _i32(cols)
+    if cell_coef is not None:
+        cell_coef = _f64(np.broadcast_to(np.asarray(cell_coef, dtype=np.float64), (cells.shape[0],)))
+        lib().orc_set_cell_coefficient(_p(cell_coef))
+    try:
+        return _assemble(mesh_dim, coords, cells, rows, cols, op, form, params, layout, nodewise, is_own, skip_zero)
+    finally:
+        lib().orc_set_cell_coefficient(None)
+
+
+def _assemble(mesh_dim, coords, cells, rows, cols, op, form, params, layout, nodewise, is_own, skip_zero):
     npc = cells.shape[1]
     b = block_size(op, mesh_dim)
     vals = np.zeros(int(cols.shape[0]) * b * b)

@@ -94,6 +94,41 @@ Q1_CASES.update({
                                                golden="electrostatics_truncated-cube.hexa.txt"),
 })
 
+# Fourier module (heat conduction: the stiffness operator times a per-cell conductivity, modules/fourier/ElementMatrix.h;
+# inputs/conduction.arc, conduction.quad.arc, conduction.3D.arc, conduction.sphere-cut.hexa.arc and the two-material
+# conduction.heterogeneous{,.quad}.arc; CMakeLists.txt:91-124).  `conductivity`: a number or {volume name: value}.
+Q1_CASES.update({
+    # (test1_results / test2_results predate the present inputs: their Dirichlet nodes read 5.0004 where the penalty gives 5 to 1e-12;
+    # they hold at upstream's own bar of 1e-4, the four other files to 5e-15)
+    "fourier_conduction_2D": dict(mesh="plancher.msh", f=1.0e5, conductivity=1.75, penalty=1.0e12, golden="fourier_test1_results.txt", tol=1.0e-4,
+                                  dirichlet=[("Cercle", 50.0), ("Bas", 5.0), ("Haut", 21.0)], neumann=[("Droite", [15.0]), ("Gauche", [0.0])]),
+    "fourier_conduction_quad": dict(mesh="plancher.quad4.msh", f=1.0e5, conductivity=1.75, penalty=1.0e12, golden="fourier_conduction_quad.txt",
+                                    dirichlet=[("Cercle", 50.0), ("Bas", 5.0), ("Haut", 21.0)], neumann=[("Droite", [15.0]), ("Gauche", [0.0])]),
+    "fourier_conduction_3D": dict(mesh="bar_dynamic_3D.msh", f=1.123e-2, conductivity=0.023, penalty=1.0e30, golden="fourier_test_conduction_3D.txt",
+                                  dirichlet=[("surfaceleft", 55.0), ("surfaceright", 12.0)]),
+    "fourier_conduction_hexa": dict(mesh="sphere_cut.hexa.msh", f=1.123e-2, conductivity=23.5, penalty=1.0e30, golden="fourier_conduction_hexa.txt",
+                                    dirichlet=[("horizontal", 55.0)], neumann=[("curved", [1003.67])]),
+    "fourier_two_materials": dict(mesh="multi-material.msh", f=15.0, conductivity={"Mat1": 100.0, "Mat2": 1.0}, penalty=1.0e30,
+                                  golden="fourier_test2_results.txt", tol=1.0e-4, dirichlet=[("Left", 50.0), ("Right", 5.0)]),
+    "fourier_two_materials_quad": dict(mesh="multi-material.quad.msh", f=15.0, conductivity={"Mat1": 100.0, "Mat2": 1.0}, penalty=1.0e30,
+                                       golden="fourier_conduction_multi-mat_quad.txt", dirichlet=[("Left", 50.0), ("Right", 5.0)]),
+})
+
+
+def cell_coefficient(mesh, case):
+    """per-cell conductivity of a case ([nb_cell]) or None"""
+    k = case.get("conductivity")
+    if k is None:
+        return None
+    out = np.zeros(mesh.cells.shape[0])
+    if isinstance(k, dict):
+        for name, v in k.items():
+            out[mesh.cell_groups[name]] = v
+    else:
+        out[:] = k
+    return out
+
+
 # Neumann flux cases of testlab (circle_cut.msh; modules/testlab/inputs/Test.circle.2D.trac*.arc): value = scalar flux,
 # valueX/valueY = flux vector q (q.n with the outward normal)
 NEUMANN_CASES = {

@@ -60,6 +60,16 @@ FILES = {
     "modules/electrostatics/check/test_2.txt": "electrostatics_test_2.txt",
     "modules/electrostatics/check/box-rods.quad.txt": "electrostatics_box-rods.quad.txt",
     "modules/electrostatics/check/truncated-cube.hexa.txt": "electrostatics_truncated-cube.hexa.txt",
+    # fourier module (conductivity per cell)
+    "meshes/msh/plancher.quad4.msh": "plancher.quad4.msh",
+    "meshes/msh/multi-material.msh": "multi-material.msh",
+    "meshes/msh/multi-material.quad.msh": "multi-material.quad.msh",
+    "modules/fourier/check/test1_results.txt": "fourier_test1_results.txt",
+    "modules/fourier/check/test2_results.txt": "fourier_test2_results.txt",
+    "modules/fourier/check/conduction_quad.txt": "fourier_conduction_quad.txt",
+    "modules/fourier/check/conduction_multi-mat_quad.txt": "fourier_conduction_multi-mat_quad.txt",
+    "modules/fourier/check/test_conduction_3D.txt": "fourier_test_conduction_3D.txt",
+    "modules/fourier/check/conduction_hexa.txt": "fourier_conduction_hexa.txt",
     # Laplace module (Quad4, Hexa8, Tet4 through the BSR back-ends)
     "meshes/msh/ring.quad.msh": "ring.quad.msh",
     "modules/laplace/check/test_ring_quad.txt": "laplace_test_ring_quad.txt",

@@ -1177,7 +1177,13 @@ def test_q1_poisson_golden_solution(exec_ctx, name, fmt, variant):
     ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
     c.set_mesh(m.dim, m.coords, m.cells)
     c.build_pattern(1)
+    coef = CS.cell_coefficient(m, case)
+    c.set_cell_coefficient(coef)  # (None: off)
+    if coef is not None and m.npc == m.dim + 1:
+        with pytest.raises(A.AfbError, match="per-cell coefficient"):
+            c.assemble(A.OP_POISSON, fmt=fmt, variant=A.VARIANT_TILED_GATHER)
     c.assemble(A.OP_POISSON, fmt=fmt, variant=variant)
+    c.set_cell_coefficient(None)
     c.rhs_reset()
     c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
     for group, q in case.get("neumann", []):

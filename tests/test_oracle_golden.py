@@ -87,7 +87,7 @@ def test_q1_poisson_golden(name, nodewise):
     case = CS.Q1_CASES[name]
     m = _load(case)
     rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
-    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=O.FORM_BSR, nodewise=nodewise)
+    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=O.FORM_BSR, nodewise=nodewise, cell_coef=CS.cell_coefficient(m, case))
     ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
     rhs = O.rhs_source_cellwise(m.dim, m.coords, m.cells, case["f"])
     for group, q in case.get("neumann", []):  # edges of the Quad4 mesh / Quad4 faces of the Hexa8 mesh, outward
