@@ -212,8 +212,8 @@ int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, in
   prm.flags = flags;
   const int npc = ctx->npc, dim = ctx->dim;
   if (ctx->has_cell_coef) {
-    AFB_REQUIRE(op == AFB_OP_POISSON && (npc == dim + 1 || npc == (1 << dim)), AFB_ERR_UNSUPPORTED,
-                "a per-cell coefficient (afb_set_cell_coefficient) applies to the Poisson operator on Tri3 / Tet4 / Quad4 / Hexa8 cells");
+    AFB_REQUIRE((op == AFB_OP_POISSON || op == AFB_OP_DIFFUSION_REACTION) && (npc == dim + 1 || npc == (1 << dim)), AFB_ERR_UNSUPPORTED,
+                "a per-cell coefficient (afb_set_cell_coefficient) applies to the Poisson / diffusion-reaction operators on Tri3 / Tet4 / Quad4 / Hexa8 cells");
     prm.cell_coef = ctx->cell_coef.as<double>();
   }
   if (op == AFB_OP_POISSON) {
@@ -232,6 +232,12 @@ int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, in
   }
   else if (op == AFB_OP_BILAPLACIAN) {
     if (npc == 3 && dim == 2) return launch<Tri3Bilaplacian>(ctx, format, variant, layout, prm);
+  }
+  else if (op == AFB_OP_DIFFUSION_REACTION) {
+    if (npc == 4 && dim == 3) return launch<Tet4DiffReact>(ctx, format, variant, layout, prm);
+    if (npc == 3 && dim == 2) return launch<Tri3DiffReact>(ctx, format, variant, layout, prm);
+    if (npc == 4 && dim == 2) return launch<Quad4DiffReact>(ctx, format, variant, layout, prm);
+    if (npc == 8 && dim == 3) return launch<Hexa8DiffReact>(ctx, format, variant, layout, prm);
   }
   // mirrors BSRFormat::computeNbColumns returning 0 / testlab _checkCellType FATAL for
   // unsupported cell types (femutils/BSRFormat.cc:339-341, modules/testlab/FemModule.cc:688-699)

@@ -134,6 +134,37 @@ struct Tri3Poisson {
   __device__ __forceinline__ double measure() const { return g.area; }
 };
 
+// alpha * stiffness + beta * consistent mass on P1 simplices (acoustics: modules/acoustics/ElementMatrix.h:14,29 with alpha = -1,
+// beta = kc2; heat: modules/heat/ElementMatrix.h with alpha = lambda, beta = 1/dt): mass = meas / ((d+1)(d+2)) * (1 + delta_ab)
+// (massMatrix(U,U) with U = 1, femutils/FemUtils.h:583-597).  A per-cell coefficient multiplies the stiffness part.
+struct Tet4DiffReact {
+  static constexpr int NPC = 4, B = 1, DIM = 3;
+  Tet4Geom g;
+  double mm;
+  __device__ __forceinline__ void init(const double* __restrict__ coords, const int32_t (&nd)[4], const ElemParams& p)
+  {
+    g.init(coords, nd);
+    g.s *= p.p0 * p.scale;
+    mm = p.p1 * g.vol * (1 / 20.);
+  }
+  __device__ __forceinline__ void block(int a, int b, double (&o)[1]) const { o[0] = g.dot(a, b) * g.s + (a == b ? 2.0 * mm : mm); }
+  __device__ __forceinline__ double measure() const { return g.vol; }
+};
+
+struct Tri3DiffReact {
+  static constexpr int NPC = 3, B = 1, DIM = 2;
+  Tri3Geom g;
+  double mm;
+  __device__ __forceinline__ void init(const double* __restrict__ coords, const int32_t (&nd)[3], const ElemParams& p)
+  {
+    g.init(coords, nd, false);
+    g.s *= p.p0 * p.scale;
+    mm = p.p1 * g.area * (1 / 12.);
+  }
+  __device__ __forceinline__ void block(int a, int b, double (&o)[1]) const { o[0] = g.dot(a, b) * g.s + (a == b ? 2.0 * mm : mm); }
+  __device__ __forceinline__ double measure() const { return g.area; }
+};
+
 struct Tet4Elasticity {
   static constexpr int NPC = 4, B = 3, DIM = 3;
   Tet4Geom g;
@@ -293,7 +324,9 @@ struct Tet10Poisson {
 // 2x2 (2x2x2) Gauss points at +-1/sqrt(3), weight 1: K_ab = sum_g detJ_g grad N_a . grad N_b.  The inverse Jacobian is applied
 // as adjugate / det: G_a = adj(J)^T dN_a / det, so K_ab = sum_g (A_a . A_b) / det_g with A_a = adj-transformed reference gradient.
 // ---------------------------------------------------------------------------------------------
-struct Quad4Poisson {
+// MASS: alpha * stiffness + beta * sum_gp N_a N_b detJ (modules/acoustics/ElementMatrixHexQuad.h), alpha = p0, beta = p1
+template <bool MASS>
+struct Quad4Op {
   static constexpr int NPC = 4, B = 1, DIM = 2;
   double K[4][4];
   double area;
@@ -322,7 +355,7 @@ struct Quad4Poisson {
           J10 += det_[a] * x[a]; J11 += det_[a] * y[a];
         }
         const double det = J00 * J11 - J01 * J10;
-        const double inv = prm.scale / det;
+        const double inv = (MASS ? prm.p0 * prm.scale : prm.scale) / det;
         double ax[4], ay[4]; // det * physical gradients
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -333,6 +366,13 @@ struct Quad4Poisson {
         for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int b = a; b < 4; ++b) K[a][b] += (ax[a] * ax[b] + ay[a] * ay[b]) * inv;
+        if constexpr (MASS) {
+          const double N[4] = { 0.25 * (1.0 - xi) * (1.0 - eta), 0.25 * (1.0 + xi) * (1.0 - eta), 0.25 * (1.0 + xi) * (1.0 + eta), 0.25 * (1.0 - xi) * (1.0 + eta) };
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b < 4; ++b) K[a][b] += N[a] * N[b] * (prm.p1 * det);
+        }
         area += det;
       }
 #pragma unroll
@@ -343,8 +383,11 @@ struct Quad4Poisson {
   __device__ __forceinline__ void block(int a, int b, double (&o)[1]) const { o[0] = K[a][b]; }
   __device__ __forceinline__ double measure() const { return area; }
 };
+using Quad4Poisson = Quad4Op<false>;
+using Quad4DiffReact = Quad4Op<true>;
 
-struct Hexa8Poisson {
+template <bool MASS>
+struct Hexa8Op {
   static constexpr int NPC = 8, B = 1, DIM = 3;
   double K[8][8];
   double vol;
@@ -382,7 +425,7 @@ struct Hexa8Poisson {
       const double c10 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c11 = J[0][0] * J[2][2] - J[0][2] * J[2][0], c12 = J[0][2] * J[1][0] - J[0][0] * J[1][2];
       const double c20 = J[1][0] * J[2][1] - J[1][1] * J[2][0], c21 = J[0][1] * J[2][0] - J[0][0] * J[2][1], c22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
       const double det = J[0][0] * c00 + J[0][1] * c10 + J[0][2] * c20;
-      const double inv = prm.scale / det;
+      const double inv = (MASS ? prm.p0 * prm.scale : prm.scale) / det;
       double ax[8], ay[8], az[8];
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
@@ -394,6 +437,15 @@ struct Hexa8Poisson {
       for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = a; b < 8; ++b) K[a][b] += (ax[a] * ax[b] + ay[a] * ay[b] + az[a] * az[b]) * inv;
+      if constexpr (MASS) {
+        double N[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) N[a] = 0.125 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta) * (1.0 + sz[a] * zeta);
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = a; b < 8; ++b) K[a][b] += N[a] * N[b] * (prm.p1 * det);
+      }
       vol += det;
     }
 #pragma unroll
@@ -404,6 +456,8 @@ struct Hexa8Poisson {
   __device__ __forceinline__ void block(int a, int b, double (&o)[1]) const { o[0] = K[a][b]; }
   __device__ __forceinline__ double measure() const { return vol; }
 };
+using Hexa8Poisson = Hexa8Op<false>;
+using Hexa8DiffReact = Hexa8Op<true>;
 
 // Quad4 / Hexa8 isotropic elasticity (modules/elasticity/ElementMatrixHexQuad.h:computeElementMatrix{Quad4,Hexa8}Base summed
 // over the 2x2 / 2x2x2 Gauss rule): per Gauss point the block of nodes (a, b) is w [lambda g_a g_b^T + mu g_b g_a^T + mu (g_a.g_b) I]

@@ -56,7 +56,12 @@ enum {
 enum {
   AFB_OP_POISSON = 0,    /* modules/testlab/FemModule.h:342-538, FemModule.cc:267-315, modules/poisson/ElementMatrix.h:28-118 */
   AFB_OP_ELASTICITY = 1, /* modules/elasticity/ElementMatrix.h:41-301; params = {lambda, mu}                               */
-  AFB_OP_BILAPLACIAN = 2 /* modules/bilaplacian/ElementMatrix.h:30-47 (Tri3, 2 DoF/node)                                   */
+  AFB_OP_BILAPLACIAN = 2, /* modules/bilaplacian/ElementMatrix.h:30-47 (Tri3, 2 DoF/node)                                   */
+  /* params = { alpha, beta }: alpha * stiffness + beta * consistent mass, 1 DoF/node -- the acoustics module (modules/acoustics/
+   * ElementMatrix.h:14,29: alpha = -1, beta = kc2; ElementMatrixHexQuad.h: alpha = +1) and the heat module's matrix (modules/heat/
+   * ElementMatrix.h: alpha = lambda, beta = 1/dt).  Tri3 / Tet4 / Quad4 / Hexa8, cell-wise and node-wise variants; a per-cell
+   * coefficient (afb_set_cell_coefficient) multiplies the stiffness part. */
+  AFB_OP_DIFFUSION_REACTION = 3
 };
 
 /* matrix format = how entries are located during the scatter and which view is native

@@ -39,7 +39,7 @@
 /* ------------------------------------------------------------------------- */
 /* enums shared with include/afb200.h (same numeric values)                   */
 /* ------------------------------------------------------------------------- */
-enum { ORC_OP_POISSON = 0, ORC_OP_ELASTICITY = 1, ORC_OP_BILAPLACIAN = 2 };
+enum { ORC_OP_POISSON = 0, ORC_OP_ELASTICITY = 1, ORC_OP_BILAPLACIAN = 2, ORC_OP_DIFFUSION_REACTION = 3 };
 /* which reference formulation of the element matrix to follow */
 enum {
   ORC_FORM_COMPACT = 0, /* modules/testlab/FemModule.h:342-463 (CSR/COO GPU back-ends)   */
@@ -597,7 +597,8 @@ static void ke_hexa8_poisson(const r3* m, double* K)
 /* Element-matrix dispatcher: K is (npc*b) x (npc*b), row-major.              */
 /* params: ELASTICITY -> {lambda, mu}                                         */
 /* ------------------------------------------------------------------------- */
-static int op_block_size(int op, int dim) { return op == ORC_OP_POISSON ? 1 : (op == ORC_OP_ELASTICITY ? dim : 2); }
+static int op_block_size(int op, int dim) { return (op == ORC_OP_POISSON || op == ORC_OP_DIFFUSION_REACTION) ? 1 : (op == ORC_OP_ELASTICITY ? dim : 2); }
+static double g_stiffness_scale = 1.0; /* per-cell coefficient of the stiffness part of ORC_OP_DIFFUSION_REACTION (set by the assembly loops) */
 
 static int element_matrix(int npc, int dim, int op, int form, const double* params, const double* coords, const int32_t* cn, double* K)
 {
@@ -640,6 +641,46 @@ static int element_matrix(int npc, int dim, int op, int form, const double* para
     if (npc == 8 && dim == 3) { ke_hexa8_poisson(m, K); return 0; }
     if (npc == 6 && dim == 2) { ke_tri6_poisson(m, K); return 0; }
     if (npc == 10 && dim == 3) { ke_tet10_poisson(m, K); return 0; }
+    return -1;
+  }
+  if (op == ORC_OP_DIFFUSION_REACTION) {
+    /* alpha * stiffness + beta * consistent mass: the acoustics module (modules/acoustics/ElementMatrix.h:14,29:
+     * -area (dxU^dxU) - area (dyU^dyU) + kc2 area (1/12) massMatrix(U,U); ElementMatrixHexQuad.h: (dxU^dxU) w + (dyU^dyU) w + (N^N) kc2 w
+     * per Gauss point) and the heat module (modules/heat/ElementMatrix.h: lambda (area (dxU^dxU) + area (dyU^dyU)) + (1/12) massMatrix(U,U) area / dt);
+     * massMatrix(U,U) with U = 1: ones with a doubled diagonal (femutils/FemUtils.h:583-597).  A per-cell coefficient multiplies alpha. */
+    const double alpha = params[0] * g_stiffness_scale, beta = params[1];
+    const int n = npc;
+    if (npc == dim + 1) {
+      double S[16];
+      double meas;
+      if (dim == 2) { ke_tri3_poisson_bsr(m[0], m[1], m[2], S); meas = area_tri3_unsigned(m[0], m[1], m[2]); }
+      else { ke_tet4_poisson_bsr(m[0], m[1], m[2], m[3], S); meas = volume_tet4(m[0], m[1], m[2], m[3]); }
+      const double mc = dim == 2 ? (1 / 12.) : (1 / 20.);
+      for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) K[a * n + b] = alpha * S[a * n + b] + beta * meas * mc * (a == b ? 2.0 : 1.0);
+      return 0;
+    }
+    if (npc == (1 << dim)) {
+      const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+      static const double sx[8] = { -1, 1, 1, -1, -1, 1, 1, -1 }, sy[8] = { -1, -1, 1, 1, -1, -1, 1, 1 }, sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+      for (int i = 0; i < n * n; ++i) K[i] = 0.0;
+      for (int ixi = 0; ixi < 2; ++ixi)
+        for (int ieta = 0; ieta < 2; ++ieta)
+          for (int izeta = 0; izeta < (dim == 3 ? 2 : 1); ++izeta) {
+            const double xi = gp[ixi], eta = gp[ieta], zeta = dim == 3 ? gp[izeta] : 0.0;
+            double dx[8], dy[8], dz[8], N[8];
+            const double w = q1_gradients(dim, m, xi, eta, zeta, dx, dy, dz);
+            for (int a = 0; a < n; ++a)
+              N[a] = dim == 2 ? 0.25 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta) : 0.125 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta) * (1.0 + sz[a] * zeta);
+            for (int a = 0; a < n; ++a)
+              for (int b = 0; b < n; ++b) {
+                double st = (dx[a] * dx[b]) * w + (dy[a] * dy[b]) * w;
+                if (dim == 3) st += (dz[a] * dz[b]) * w;
+                K[a * n + b] += alpha * st + (N[a] * N[b]) * beta * w;
+              }
+          }
+      return 0;
+    }
     return -1;
   }
   if (op == ORC_OP_ELASTICITY) {
@@ -783,9 +824,9 @@ ORC_API int64_t orc_value_index(const int32_t* rows, const int32_t* cols, int b,
  * orc_assemble_* call, NULL switches it off (test infrastructure: a process-wide pointer). */
 static const double* g_cell_coef = 0;
 ORC_API void orc_set_cell_coefficient(const double* coef) { g_cell_coef = coef; }
-static void scale_ke(double* K, int n, int64_t cell)
+static void scale_ke(double* K, int n, int64_t cell, int op)
 {
-  if (!g_cell_coef) return;
+  if (!g_cell_coef || op != ORC_OP_POISSON) return; /* (ORC_OP_DIFFUSION_REACTION took it inside, on the stiffness part) */
   for (int i = 0; i < n * n; ++i) K[i] *= g_cell_coef[cell];
 }
 
@@ -799,8 +840,9 @@ ORC_API int orc_assemble_cellwise(int npc, int dim, int op, int form, const doub
   double K[576];
   for (int64_t c = 0; c < nb_cell; ++c) {
     const int32_t* cn = conn + c * npc;
+    g_stiffness_scale = g_cell_coef ? g_cell_coef[c] : 1.0;
     if (element_matrix(npc, dim, op, form, params, coords, cn, K)) return -1;
-    scale_ke(K, n, c);
+    scale_ke(K, n, c, op);
     for (int a1 = 0; a1 < npc; ++a1) {
       int32_t r = cn[a1];
       if (is_own && !is_own[r]) continue;
@@ -865,8 +907,9 @@ ORC_API int orc_assemble_nodewise(int npc, int dim, int op, int form, const doub
       int a1 = -1;
       for (int i = 0; i < npc; ++i) if (cn[i] == r) { a1 = i; break; }
       if (a1 < 0) continue;
+      g_stiffness_scale = g_cell_coef ? g_cell_coef[list[q]] : 1.0;
       if (element_matrix(npc, dim, op, form, params, coords, cn, K)) { rc = -1; break; }
-      scale_ke(K, n, list[q]);
+      scale_ke(K, n, list[q], op);
       for (int a2 = 0; a2 < npc; ++a2) {
         int32_t p = find_block(rows, cols, r, cn[a2]);
         if (p < 0) { rc = -2; break; }

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libafb_oracle.so")
 
-OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN = 0, 1, 2
+OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN, OP_DIFFUSION_REACTION = 0, 1, 2, 3
 FORM_COMPACT, FORM_HOST, FORM_BSR, FORM_NODEWISE = 0, 1, 2, 3
 LAYOUT_PER_BLOCK, LAYOUT_PER_ROW = 0, 1
 
@@ -59,7 +59,7 @@ def _u8(a):
 
 
 def block_size(op: int, dim: int) -> int:
-    return 1 if op == OP_POISSON else (dim if op == OP_ELASTICITY else 2)
+    return 1 if op in (OP_POISSON, OP_DIFFUSION_REACTION) else (dim if op == OP_ELASTICITY else 2)
 
 
 def lame(E: float, nu: float):

@@ -115,6 +115,18 @@ Q1_CASES.update({
 })
 
 
+# Acoustics module (Helmholtz: alpha * stiffness + kc2 * consistent mass, no Dirichlet condition, scalar flux; modules/acoustics/
+# ElementMatrix.h:14,29 uses alpha = -1 on Tri3 / Tet4, ElementMatrixHexQuad.h alpha = +1 on Quad4 / Hexa8; inputs/sub.arc, sub.quad.arc,
+# 3d_sub.arc, 3d_sphere_in_sphere.hexa.arc)
+ACOUSTICS_CASES = {
+    "sub_2D": dict(mesh="sub.msh", alpha=-1.0, kc2=1.1, neumann=[("inner1", [1.0])], golden="acoustics_sub_2D.txt"),
+    "sub_2D_quad": dict(mesh="sub.quad.msh", alpha=1.0, kc2=1.1, neumann=[("inner1", [1.0])], golden="acoustics_sub_2D.quad.txt"),
+    "sub_3D": dict(mesh="sub_3d.msh", alpha=-1.0, kc2=18.0e5, neumann=[("inner", [11.0e2])], golden="acoustics_sphere_3d.txt"),
+    "sphere_in_sphere_hexa": dict(mesh="sphere_in_sphere.hexa.msh", alpha=1.0, kc2=18.0e5, neumann=[("inner", [11.0e2])], golden="acoustics_sphere_3d.hexa.txt",
+                                  tol=1.0e-6),  # (indefinite system with kc2 = 1.8e6: 4e-7 between two direct solves)
+}
+
+
 def cell_coefficient(mesh, case):
     """per-cell conductivity of a case ([nb_cell]) or None"""
     k = case.get("conductivity")

@@ -60,6 +60,15 @@ FILES = {
     "modules/electrostatics/check/test_2.txt": "electrostatics_test_2.txt",
     "modules/electrostatics/check/box-rods.quad.txt": "electrostatics_box-rods.quad.txt",
     "modules/electrostatics/check/truncated-cube.hexa.txt": "electrostatics_truncated-cube.hexa.txt",
+    # acoustics module (stiffness + mass)
+    "meshes/msh/sub.msh": "sub.msh",
+    "meshes/msh/sub.quad.msh": "sub.quad.msh",
+    "meshes/msh/sub_3d.msh": "sub_3d.msh",
+    "meshes/msh/sphere_in_sphere.hexa.msh": "sphere_in_sphere.hexa.msh",
+    "modules/acoustics/check/sub_2D.txt": "acoustics_sub_2D.txt",
+    "modules/acoustics/check/sub_2D.quad.txt": "acoustics_sub_2D.quad.txt",
+    "modules/acoustics/check/sphere_3d.txt": "acoustics_sphere_3d.txt",
+    "modules/acoustics/check/sphere_3d.hexa.txt": "acoustics_sphere_3d.hexa.txt",
     # fourier module (conductivity per cell)
     "meshes/msh/plancher.quad4.msh": "plancher.quad4.msh",
     "meshes/msh/multi-material.msh": "multi-material.msh",

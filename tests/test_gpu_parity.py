@@ -1165,6 +1165,48 @@ def test_q1_elasticity_golden_solution(exec_ctx, name, variant):
     assert CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-3, min_value=1.0e-10, subset=True) < 1.0e-4
 
 
+@pytest.mark.parametrize("mesh", ["L-shape_2D", "sphere_3D", "quad4", "hexa8"])
+@pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_COO, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
+                         ids=["csr-gpu", "coo-gpu", "af-bsr"])
+def test_diffusion_reaction_values(exec_ctx, mesh, fmt, variant):
+    """alpha * stiffness + beta * mass (acoustics / heat matrices), uniform and per-cell alpha, against the oracle"""
+    c = exec_ctx
+    m = M.box_mesh_q1(2, 11) if mesh == "quad4" else M.box_mesh_q1(3, 5) if mesh == "hexa8" else get_mesh(mesh)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(1)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    coef = 0.5 + np.arange(m.nb_cell) % 7
+    for params, cc in (([-1.0, 1.1], None), ([2.5, 40.0], coef)):
+        ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_DIFFUSION_REACTION, form=O.FORM_BSR, params=params, nodewise=variant == A.VARIANT_NODEWISE, cell_coef=cc)
+        c.set_cell_coefficient(cc)
+        c.reset_values()
+        c.assemble(A.OP_DIFFUSION_REACTION, params=params, fmt=fmt, variant=variant)
+        row_scaled_close(c.to_host(A.ARRAY_VALUES), ref, rows)
+    c.set_cell_coefficient(None)
+    with pytest.raises(A.AfbError):
+        c.assemble(A.OP_DIFFUSION_REACTION, params=[1.0, 1.0], fmt=fmt, variant=A.VARIANT_TILED_GATHER)
+    with pytest.raises(A.AfbError, match="alpha"):
+        c.assemble(A.OP_DIFFUSION_REACTION, fmt=fmt, variant=variant)
+
+
+@pytest.mark.parametrize("name", list(CS.ACOUSTICS_CASES))
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+def test_acoustics_golden_solution(exec_ctx, name, variant):
+    """the acoustics module's golden solution files (Helmholtz matrix = OP_DIFFUSION_REACTION, flux on the inner boundary)"""
+    c = exec_ctx
+    case = CS.ACOUSTICS_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(1)
+    c.assemble(A.OP_DIFFUSION_REACTION, params=[case["alpha"], case["kc2"]], fmt=A.FORMAT_BSR, variant=variant)
+    c.rhs_reset()
+    for group, q in case["neumann"]:
+        c.rhs_neumann(m.faces[group], q, kind=A.NEUMANN_FLUX)
+    rows, cols, vals, rhs = (c.to_host(w) for w in (A.ARRAY_ROWS, A.ARRAY_COLUMNS, A.ARRAY_VALUES, A.ARRAY_RHS))
+    u = spla.spsolve(sp.csr_matrix((vals, cols, rows)).tocsc(), rhs)
+    assert CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True) < case.get("tol", 1.0e-7)
+
+
 @pytest.mark.parametrize("name", list(CS.Q1_CASES))
 @pytest.mark.parametrize("fmt,variant", [(A.FORMAT_CSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_CELLWISE_ATOMIC), (A.FORMAT_BSR, A.VARIANT_NODEWISE)],
                          ids=["csr-gpu", "bsr", "af-bsr"])

@@ -98,6 +98,22 @@ def test_q1_poisson_golden(name, nodewise):
     assert worst < case.get("tol", 1.0e-7)
 
 
+@pytest.mark.parametrize("name", list(CS.ACOUSTICS_CASES))
+@pytest.mark.parametrize("nodewise", [False, True], ids=["bsr", "af-bsr"])
+def test_acoustics_golden(name, nodewise):
+    """alpha * stiffness + beta * mass (OP_DIFFUSION_REACTION) against the acoustics module's golden solution files"""
+    case = CS.ACOUSTICS_CASES[name]
+    m = _load(case)
+    rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_DIFFUSION_REACTION, form=O.FORM_BSR, params=[case["alpha"], case["kc2"]], nodewise=nodewise)
+    rhs = np.zeros(m.nb_node)
+    for group, q in case["neumann"]:
+        O.rhs_neumann(m.dim, 1, m.coords, m.faces[group], q, rhs, kind=O.NEUMANN_FLUX)
+    u = spla.spsolve(_csr(rows, cols, vals).tocsc(), rhs)
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True)
+    assert worst < case.get("tol", 1.0e-7)
+
+
 @pytest.mark.parametrize("name", list(CS.NEUMANN_CASES))
 def test_poisson_neumann_golden(name):
     """Constant flux term (modules/testlab/FemModule.cc:1534-1706): scalar value and q.n with the outward normal."""
