@@ -9,6 +9,11 @@
 #include "afb_internal.h"
 
 namespace afb {
+bool pdl_enabled()
+{
+  static const bool on = [] { const char* e = getenv("AFB_NO_PDL"); return !(e && *e && *e != '0'); }();
+  return on;
+}
 
 static thread_local char g_err[1024] = "";
 

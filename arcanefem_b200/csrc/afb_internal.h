@@ -273,6 +273,35 @@ int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int
 
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
+// Programmatic dependent launch for the kernels of the steady-state step (scan -> column placement -> assembly):
+// the grid may be scheduled while the kernel before it on the stream drains, which hides the launch latency between
+// dependent kernels (a few microseconds per boundary; 3 boundaries per step).  A kernel launched this way calls
+// pdl_enter() before its first global memory access: griddepcontrol.wait returns once the previous grid has completed
+// and its writes are visible, so the ordering seen by the kernel body is the stream order.  AFB_NO_PDL=1 launches normally.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
 #define AFB_LAUNCH_CHECK(ctx)                                                                 \
   do {                                                                                        \
     (ctx)->launches++;                                                                        \

@@ -160,6 +160,7 @@ k_pattern_nn_place(const TileDesc* __restrict__ desc, const int32_t* __restrict_
                    int32_t nb_node, int32_t* __restrict__ check /* device-mapped host words: rows[nb_node], stale flag */)
 {
   __shared__ int32_t s_dbase[TG_EMAX];
+  pdl_enter();
   const int32_t t = blockIdx.x;
   const TileDesc d = desc[t];
   const int R = d.nb_row, E = d.nb_entry;
@@ -328,9 +329,8 @@ int pattern_nn_place(afb_ctx* ctx, int32_t* check)
 {
   const TilePlan& P = ctx->plan;
   if (P.nb_tile == 0) return AFB_OK;
-  k_pattern_nn_place<<<P.nb_tile, pattern_threads(P), 0, ctx->stream>>>(P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), ctx->rows.as<int32_t>(),
-                                                                        P.nn_local.as<uint16_t>(), P.nn_e0.as<uint16_t>(), P.foot.as<int32_t>(), ctx->cols.as<int32_t>(),
-                                                                        ctx->nz_per_row.as<int32_t>(), ctx->nb_node, check);
+  AFB_CUDA(launch_pdl(k_pattern_nn_place, P.nb_tile, pattern_threads(P), 0, ctx->stream, P.tile_desc.as<TileDesc>(), P.tile_nodes.as<int32_t>(), ctx->rows.as<int32_t>(),
+                      P.nn_local.as<uint16_t>(), P.nn_e0.as<uint16_t>(), P.foot.as<int32_t>(), ctx->cols.as<int32_t>(), ctx->nz_per_row.as<int32_t>(), ctx->nb_node, check));
   AFB_LAUNCH_CHECK(ctx);
   return AFB_OK;
 }

@@ -112,6 +112,7 @@ k_scan_chained(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_
   __shared__ int total;
   __shared__ unsigned s_tile;
   __shared__ int s_prefix;
+  pdl_enter();
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
   __syncthreads();
   const int tile = (int)s_tile;
@@ -209,7 +210,7 @@ int exclusive_scan_i32(afb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n)
     unsigned long long* state = ctx->scan_state.as<unsigned long long>() + 1;
     unsigned* ticket = ctx->scan_state.as<unsigned>();
     ctx->scan_epoch = ctx->scan_epoch % 0x3FFFFFFFu + 1u;
-    k_scan_chained<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, state, ticket, ctx->scan_tickets, ctx->scan_epoch, nblk);
+    AFB_CUDA(launch_pdl(k_scan_chained, nblk, SCAN_THREADS, 0, ctx->stream, in, out, n, state, ticket, ctx->scan_tickets, ctx->scan_epoch, nblk));
     AFB_LAUNCH_CHECK(ctx);
     ctx->scan_tickets += (unsigned)nblk;
     return AFB_OK;

@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
 {
   extern __shared__ __align__(16) unsigned char ex_raw[];
   ExecSmem& S = *reinterpret_cast<ExecSmem*>(ex_raw);
+  pdl_enter();
   OutTables& O = *reinterpret_cast<OutTables*>(S.lists);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = TG_THREADS / 32;
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_vec(Exec
   static_assert(OP == 0 || NPC == 3, "the bilaplacian executor is for Tri3");
   extern __shared__ __align__(16) unsigned char ex_raw[];
   VecSmem<DIM>& S = *reinterpret_cast<VecSmem<DIM>*>(ex_raw);
+  pdl_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = TG_THREADS / 32;
   constexpr int DW = sizeof(TileDesc) / 4;
@@ -645,6 +647,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_rows_vec(ExecA
   constexpr int DIM = NPC - 1, B = DIM, BB = B * B, BS = RowsSmem<DIM>::BS;
   extern __shared__ __align__(16) unsigned char ex_raw[];
   RowsSmem<DIM>& S = *reinterpret_cast<RowsSmem<DIM>*>(ex_raw);
+  pdl_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = TG_THREADS / 32;
   constexpr int DW = sizeof(TileDesc) / 4;
@@ -966,8 +969,8 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   auto go = [&](auto kernel, size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, TG_THREADS, smem, ctx->stream>>>(A, prm);
-    return cudaGetLastError();
+    e = launch_pdl(kernel, grid, TG_THREADS, smem, ctx->stream, A, prm);
+    return e != cudaSuccess ? e : cudaGetLastError();
   };
   cudaError_t e;
   if (!vec) e = ctx->npc == 4 ? go(k_assemble_tiled<4>, sizeof(ExecSmem)) : go(k_assemble_tiled<3>, sizeof(ExecSmem));
