@@ -595,12 +595,15 @@ def run_b200(args):
     if not inner:
         # phase split (BuildMatrix / AddAndCompute): the same steps again with an event between the phases, outside the
         # timed region (an event record between two kernels costs a few microseconds of idle stream per boundary)
+        barrier()  # all ranks enter together: a late rank would show up as exchange wait in its neighbours' phases
         for k in range(args.steps):
             step(evs[k])
         if da is not None:
             da.wait()
         evs[-1][2].synchronize()
         barrier()
+        if world > 1 and mode == "exchange" and transport == "p2p" and ctx.p2p_status() != 0:
+            raise SystemExit(f"bench.py: ghost-row exchange timed out on rank {rank} (phase pass)")
     pattern_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     values_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
     exch_bytes = da.plan.bytes_per_exchange() if (da is not None and da.plan is not None) else (0, 0)
