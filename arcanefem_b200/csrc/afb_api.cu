@@ -135,8 +135,9 @@ int afb_destroy(afb_ctx* ctx)
                      &ctx->rhs, &ctx->csr_rows, &ctx->csr_cols, &ctx->csr_nbcol, &ctx->ij_rows, &ctx->ij_cols, &ctx->dir_node, &ctx->elim_info, &ctx->elim_value, &ctx->forced_info,
                      &ctx->forced_value, &ctx->saved_values, &ctx->tmp_i32a, &ctx->tmp_i32b, &ctx->tmp_scan, &ctx->tmp_ids, &ctx->tmp_vals, &ctx->tmp_flag, &ctx->tmp_lookback, &ctx->scan_state, &ctx->solver_work,
                      &ctx->plan.tile_desc, &ctx->plan.tile_nodes, &ctx->plan.tile_cells, &ctx->plan.unit_base, &ctx->plan.unit_len, &ctx->plan.emap, &ctx->plan.rowinfo, &ctx->plan.foot, &ctx->plan.lconn, &ctx->plan.lists,
-                     &ctx->plan.rowf, &ctx->plan.inc, &ctx->plan.inc_grp, &ctx->plan.col_scratch, &ctx->plan.nn_deg, &ctx->plan.nn_local, &ctx->plan.nn_e0, &ctx->plan.emap_rows,
-                     &ctx->plan.node_tile, &ctx->plan.node_lrow, &ctx->plan.scratch_a, &ctx->plan.scratch_b, &ctx->plan.scratch_c, &ctx->plan.stats };
+                     &ctx->plan.rowf, &ctx->plan.inc, &ctx->plan.inc_grp, &ctx->plan.col_scratch, &ctx->plan.nn_deg, &ctx->plan.nn_local, &ctx->plan.nn_e0, &ctx->plan.emap_rows, &ctx->plan.vr_units,
+                     &ctx->plan.node_tile, &ctx->plan.node_lrow, &ctx->plan.scratch_a, &ctx->plan.scratch_b, &ctx->plan.scratch_c, &ctx->plan.stats,
+                     &ctx->plan.arena_nodes, &ctx->plan.arena_desc, &ctx->plan.arena_tiles, &ctx->plan.arena_nn, &ctx->plan.arena_lists };
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

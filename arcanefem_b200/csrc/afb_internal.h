@@ -2,6 +2,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <initializer_list>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -76,6 +78,27 @@ struct DevBuf {
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// Several buffers that are (re)built together share one allocation: a cudaMalloc costs ~0.3 ms whatever its size, and the
+// inspector needs about twenty buffers per mesh.  The members become non-owning views into `arena` (256-byte aligned).
+struct GroupItem {
+  DevBuf* buf;
+  size_t bytes;
+};
+inline int reserve_group(DevBuf& arena, std::initializer_list<GroupItem> items)
+{
+  size_t total = 0;
+  for (const GroupItem& it : items) total += (std::max<size_t>(it.bytes, 16) + 255) & ~(size_t)255;
+  int rc = arena.reserve(total);
+  if (rc != AFB_OK) return rc;
+  size_t off = 0;
+  for (const GroupItem& it : items) {
+    const size_t sz = (std::max<size_t>(it.bytes, 16) + 255) & ~(size_t)255;
+    it.buf->alias(static_cast<char*>(arena.p) + off, sz);
+    off += sz;
+  }
+  return AFB_OK;
+}
+
 // Plan of the tiled path (inspector output, tiles_plan.cu).  The mesh tiling is a pure function
 // of the mesh topology and coordinates; the value plan additionally depends on the pattern, the
 // block size and the ownership mode.  Both survive pattern re-builds on the same mesh.
@@ -119,6 +142,7 @@ struct TilePlan {
   DevBuf lists;       // uint16: cache indices, per unit [len/2][32 lanes][2]; one contiguous region per tile (TMA bulk copy)
   DevBuf col_scratch; // int32[nb_entry]: columns in tile order between the two BuildMatrix passes (pattern_tiled.cu)
   DevBuf scratch_a, scratch_b, scratch_c, stats; // builder scratch
+  DevBuf arena_nodes, arena_desc, arena_tiles, arena_nn, arena_lists; // shared allocations of the buffers above (reserve_group)
 };
 
 } // namespace afb
@@ -250,6 +274,7 @@ int p2p_wait_stats(afb_ctx* ctx, double* ready_wait_us, double* pulled_wait_us, 
 int p2p_disconnect(afb_ctx* ctx);
 bool pattern_nn_ready(const afb_ctx* ctx);
 int pattern_nn_build(afb_ctx* ctx);
+int pattern_nn_reserve(afb_ctx* ctx);
 int pattern_nn_place(afb_ctx* ctx, int32_t* check);
 int pattern_tiled_extract(afb_ctx* ctx, int32_t* deg, int* stale);
 int pattern_tiled_place(afb_ctx* ctx);

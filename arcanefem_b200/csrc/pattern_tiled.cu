@@ -24,6 +24,7 @@
 // mode): per node its degree, per tile row its neighbours (self included) as ascending 16-bit
 // footprint indices.  A re-build is then: scan of the degrees -> row_index; k_pattern_nn_place
 // translates the footprint indices to node ids and stores them to their rows (coalesced runs).
+#include <chrono>
 #include <algorithm>
 
 #include "tiles.cuh"
@@ -295,14 +296,25 @@ int pattern_tiled_extract(afb_ctx* ctx, int32_t* deg, int* stale)
   return AFB_OK;
 }
 
+// the three arrays of the tile-local node-node connectivity, one allocation (sizes: nb_node and the tiling's nb_entry)
+int pattern_nn_reserve(afb_ctx* ctx)
+{
+  TilePlan& P = ctx->plan;
+  return reserve_group(P.arena_nn, { { &P.nn_deg, sizeof(int32_t) * ((size_t)ctx->nb_node + 1) },
+                                     { &P.nn_local, sizeof(uint16_t) * (size_t)std::max<int64_t>(P.nb_entry, 1) },
+                                     { &P.nn_e0, sizeof(uint16_t) * ((size_t)ctx->nb_node + 1) } });
+}
+
 // inspector: the tile-local node-node connectivity (once per mesh tiling)
 int pattern_nn_build(afb_ctx* ctx)
 {
   TilePlan& P = ctx->plan;
   P.nn_valid = false;
-  AFB_TRY(P.nn_deg.reserve(sizeof(int32_t) * ((size_t)ctx->nb_node + 1)));
-  AFB_TRY(P.nn_local.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(P.nb_entry, 1)));
-  AFB_TRY(P.nn_e0.reserve(sizeof(uint16_t) * ((size_t)ctx->nb_node + 1)));
+  const bool trace = getenv("AFB_INSPECTOR_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char* w) { if (trace) fprintf(stderr, "[inspector]     nn %8.1f us  %s\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), w); };
+  AFB_TRY(pattern_nn_reserve(ctx));
+  mark("reserved");
   AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
   AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), ctx->stream));
   AFB_CUDA(cudaMemsetAsync(P.nn_deg.p, 0, sizeof(int32_t) * ((size_t)ctx->nb_node + 1), ctx->stream));
@@ -316,9 +328,11 @@ int pattern_nn_build(afb_ctx* ctx)
                                                                               nullptr, P.nn_local.as<uint16_t>(), P.nn_e0.as<uint16_t>(), ctx->tmp_flag.as<int>());
     AFB_LAUNCH_CHECK(ctx);
   }
+  mark("launched");
   int stale = 0;
   AFB_CUDA(cudaMemcpyAsync(&stale, ctx->tmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   AFB_CUDA(cudaStreamSynchronize(ctx->stream));
+  mark("synchronised");
   AFB_REQUIRE(stale == 0, AFB_ERR_CUDA, "tile inspector: node-node connectivity does not fit the tiling");
   P.nn_mesh_gen = ctx->mesh_gen;
   P.nn_valid = true;

@@ -16,6 +16,7 @@
 //                 sums (Poisson) the diagonal is not listed at all: the executor derives it from
 //                 the row's off-diagonals.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -1115,8 +1116,40 @@ template <class F> static int launch_by_npc(int npc, F f)
   return f(std::integral_constant<int, 3>());
 }
 
+// list slots of a tile's value plan: contributions + per-unit padding up to the unit's longest list (<= valence + 1, even)
+static inline int64_t value_plan_tile_slots(const TileDesc& d, int npc, bool vec)
+{
+  const int64_t cap = (int64_t)(vec ? npc * npc : npc * (npc - 1)) * d.nb_cell + 32ll * (d.max_val + 2) + 32ll * ((d.nb_entry + 31) / 32) * 2 + 8;
+  return (cap + 7) & ~7ll; // a tile whose lists exceed the executor's staging buffer (TG_LMAX) is read from global memory
+}
+// the arrays of the value plan (entries-by-length plans: scalar executor and the "units" vector executor) in one allocation
+static int reserve_value_plan(TilePlan& P, int32_t nb_node, bool vec, int64_t units, int64_t slots)
+{
+  return reserve_group(P.arena_lists, { { &P.rowinfo, sizeof(uint32_t) * (size_t)nb_node },
+                                        { &P.unit_base, sizeof(uint32_t) * (size_t)std::max<int64_t>(units, 1) },
+                                        { &P.unit_len, sizeof(uint16_t) * (size_t)std::max<int64_t>(units, 1) },
+                                        { &P.emap, sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(units, 1) },
+                                        { &P.emap_rows, vec ? sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(units, 1) : 16 },
+                                        { &P.lists, sizeof(uint16_t) * (size_t)std::max<int64_t>(slots, 8) } });
+}
+
+// AFB_INSPECTOR_TRACE=1: host-side timeline of the inspector on stderr (microseconds since the call started)
+struct InspectorTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit InspectorTrace(const char* what) : on(getenv("AFB_INSPECTOR_TRACE") != nullptr), t0(std::chrono::steady_clock::now())
+  {
+    if (on) fprintf(stderr, "[inspector] %s\n", what);
+  }
+  void mark(const char* label) const
+  {
+    if (on) fprintf(stderr, "[inspector]   %8.1f us  %s\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), label);
+  }
+};
+
 int build_tile_mesh(afb_ctx* ctx, int cls)
 {
+  InspectorTrace tr("mesh tiling");
   AFB_REQUIRE(tiled_cells_supported(ctx), AFB_ERR_UNSUPPORTED, "the tiled path is not available for %d-node cells (P1 simplices only); use AFB_VARIANT_NODEWISE", ctx->npc);
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "tile inspector: build the pattern first");
   TilePlan& P = ctx->plan;
@@ -1141,17 +1174,17 @@ int build_tile_mesh(afb_ctx* ctx, int cls)
   AFB_LAUNCH_CHECK(ctx);
   AFB_CUDA(cudaMemcpyAsync(got, P.stats.p, sizeof(got), cudaMemcpyDeviceToHost, st));
   AFB_CUDA(cudaStreamSynchronize(st));
+  tr.mark("bounding box (sync)");
   double lo[3], ext[3];
   for (int a = 0; a < 3; ++a) {
     lo[a] = unorder_f64(got[a]);
     ext[a] = unorder_f64(got[3 + a]) - lo[a];
     if (!(ext[a] > 0.0) || a >= dim) ext[a] = 0.0;
   }
-  AFB_TRY(P.node_tile.reserve(sizeof(int32_t) * (size_t)nb_node));
-  AFB_TRY(P.node_lrow.reserve(sizeof(int32_t) * (size_t)nb_node));
-  AFB_TRY(P.tile_nodes.reserve(sizeof(int32_t) * (size_t)nb_node));
-  AFB_TRY(P.scratch_c.reserve(sizeof(int32_t) * (size_t)nb_node)); // brick_of
+  AFB_TRY(reserve_group(P.arena_nodes, { { &P.node_tile, sizeof(int32_t) * (size_t)nb_node }, { &P.node_lrow, sizeof(int32_t) * (size_t)nb_node },
+                                         { &P.tile_nodes, sizeof(int32_t) * (size_t)nb_node }, { &P.scratch_c, sizeof(int32_t) * (size_t)nb_node } })); // scratch_c: brick_of
   int32_t* brick_of = P.scratch_c.as<int32_t>();
+  tr.mark("node arrays reserved");
 
   // bricks holding ~rtarget nodes on a uniform mesh
   const int rtarget = dim == 3 ? (cls == 2 ? VR_RT3 : cls == 1 ? TV_RT3 : TG_RT3) : (cls == 2 ? VR_RT2 : cls == 1 ? TV_RT2 : TG_RT2);
@@ -1187,6 +1220,7 @@ int build_tile_mesh(afb_ctx* ctx, int cls)
   std::vector<int32_t> hptr((size_t)nb_brick + 1), hnt((size_t)nb_brick), hfirst((size_t)nb_brick + 1);
   AFB_CUDA(cudaMemcpyAsync(hptr.data(), bptr, sizeof(int32_t) * ((size_t)nb_brick + 1), cudaMemcpyDeviceToHost, st));
   AFB_CUDA(cudaStreamSynchronize(st));
+  tr.mark("bricks (sync)");
   // pieces per brick: start from the row limit, then refine the bricks whose tiles do not fit
   const int rmax0 = std::min(TG_RMAX, rtarget + rtarget / 2);
   for (int32_t b = 0; b < nb_brick; ++b) {
@@ -1208,8 +1242,7 @@ int build_tile_mesh(afb_ctx* ctx, int cls)
     nb_tile = (int32_t)run;
     AFB_CUDA(cudaMemcpyAsync(bntile, hnt.data(), sizeof(int32_t) * (size_t)nb_brick, cudaMemcpyHostToDevice, st));
     AFB_CUDA(cudaMemcpyAsync(bfirst, hfirst.data(), sizeof(int32_t) * ((size_t)nb_brick + 1), cudaMemcpyHostToDevice, st));
-    AFB_TRY(P.tile_desc.reserve(sizeof(TileDesc) * (size_t)std::max(nb_tile, 1)));
-    AFB_TRY(P.scratch_b.reserve(sizeof(int32_t) * 4 * (size_t)std::max(nb_tile, 1)));
+    AFB_TRY(reserve_group(P.arena_desc, { { &P.tile_desc, sizeof(TileDesc) * (size_t)std::max(nb_tile, 1) }, { &P.scratch_b, sizeof(int32_t) * 4 * (size_t)std::max(nb_tile, 1) } }));
     AFB_CUDA(cudaMemsetAsync(P.tile_desc.p, 0, sizeof(TileDesc) * (size_t)std::max(nb_tile, 1), st));
     k_tile_nodes<<<grid_for(nb_node, 256), 256, 0, st>>>(brick_of, bptr, bfirst, bntile, P.tile_nodes.as<int32_t>(), nb_node, P.node_tile.as<int32_t>(),
                                                           P.node_lrow.as<int32_t>(), P.tile_desc.as<TileDesc>());
@@ -1227,6 +1260,7 @@ int build_tile_mesh(afb_ctx* ctx, int cls)
     AFB_CUDA(cudaMemcpyAsync(hdesc.data(), P.tile_desc.p, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyDeviceToHost, st));
     AFB_CUDA(cudaMemcpyAsync(hstats.data(), stats, sizeof(int32_t) * 4 * (size_t)nb_tile, cudaMemcpyDeviceToHost, st));
     AFB_CUDA(cudaStreamSynchronize(st));
+    tr.mark("tile statistics (sync)");
     bool ok = true;
     for (int32_t b = 0; b < nb_brick; ++b) {
       bool bad = false;
@@ -1275,12 +1309,14 @@ int build_tile_mesh(afb_ctx* ctx, int cls)
   P.nb_foot = foot_off;
   P.nb_inc = inc_off;
   P.nb_entry = ent_off;
-  AFB_TRY(P.tile_cells.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(cell_off, 1)));
-  AFB_TRY(P.lconn.reserve(sizeof(ushort4) * (size_t)std::max<int64_t>(cell_off, 1)));
-  AFB_TRY(P.foot.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(foot_off, 1)));
-  AFB_TRY(P.rowf.reserve(sizeof(uint16_t) * (size_t)nb_node));
-  AFB_TRY(P.inc.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(inc_off, 1)));
-  AFB_TRY(P.inc_grp.reserve(sizeof(uint2) * (size_t)TG_GMAX * (size_t)std::max(nb_tile, 1)));
+  tr.mark("offsets (host)");
+  AFB_TRY(reserve_group(P.arena_tiles, { { &P.tile_cells, sizeof(int32_t) * (size_t)std::max<int64_t>(cell_off, 1) },
+                                         { &P.lconn, sizeof(ushort4) * (size_t)std::max<int64_t>(cell_off, 1) },
+                                         { &P.foot, sizeof(int32_t) * (size_t)std::max<int64_t>(foot_off, 1) },
+                                         { &P.rowf, sizeof(uint16_t) * (size_t)nb_node },
+                                         { &P.inc, sizeof(uint32_t) * (size_t)std::max<int64_t>(inc_off, 1) },
+                                         { &P.inc_grp, sizeof(uint2) * (size_t)TG_GMAX * (size_t)std::max(nb_tile, 1) } }));
+  tr.mark("tile arrays reserved");
   AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc.data(), sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
   AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
   AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), st));
@@ -1300,6 +1336,7 @@ int build_tile_mesh(afb_ctx* ctx, int cls)
   AFB_CUDA(cudaEventRecord(e1, st));
   AFB_CUDA(cudaEventSynchronize(e1));
   AFB_CUDA(cudaEventElapsedTime(&P.mesh_ms, e0, e1));
+  tr.mark("k_tile_mesh (sync)");
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   AFB_REQUIRE(err == 0, AFB_ERR_CUDA, "tile inspector: mesh tiling inconsistency (code %d)", err);
@@ -1308,6 +1345,7 @@ int build_tile_mesh(afb_ctx* ctx, int cls)
   P.mesh_b_class = cls;
   P.mesh_valid = true;
   AFB_TRY(pattern_nn_build(ctx)); // tile-local node-node connectivity of the connectivity-based BuildMatrix
+  tr.mark("node-node connectivity (queued)");
   return AFB_OK;
 }
 
@@ -1316,6 +1354,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
   TilePlan& P = ctx->plan;
   AFB_REQUIRE(P.mesh_valid, AFB_ERR_INVALID, "tile inspector: no mesh tiling");
   P.lists_valid = false;
+  InspectorTrace tr("value plan");
   cudaStream_t st = ctx->stream;
   const int npc = ctx->npc;
   const bool vec = ctx->b > 1;
@@ -1333,20 +1372,13 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
     d.list_off = (uint32_t)list_off;
     d.list_len = 0;
     unit_off += d.nb_unit;
-    // list slots: contributions + per-unit padding up to the unit's longest list (<= valence + 1, even)
-    int64_t cap = (int64_t)(vec ? npc * npc : npc * (npc - 1)) * d.nb_cell + 32ll * (d.max_val + 2) + 32ll * d.nb_unit * 2 + 8;
-    cap = (cap + 7) & ~7ll; // a tile whose lists exceed the executor's staging buffer (TG_LMAX) is read from global memory
-    list_off += cap;
+    list_off += value_plan_tile_slots(d, npc, vec);
     AFB_REQUIRE(list_off < (1ll << 32) && unit_off < (1ll << 26), AFB_ERR_OVERFLOW, "tile inspector: value plan exceeds 32-bit offsets");
   }
   P.nb_unit = unit_off;
   P.nb_list = list_off;
-  AFB_TRY(P.rowinfo.reserve(sizeof(uint32_t) * (size_t)ctx->nb_node));
-  AFB_TRY(P.unit_base.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(unit_off, 1)));
-  AFB_TRY(P.unit_len.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(unit_off, 1)));
-  AFB_TRY(P.emap.reserve(sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(unit_off, 1)));
-  if (vec) AFB_TRY(P.emap_rows.reserve(sizeof(uint32_t) * 32 * (size_t)std::max<int64_t>(unit_off, 1)));
-  AFB_TRY(P.lists.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(list_off, 8)));
+  AFB_TRY(reserve_value_plan(P, ctx->nb_node, vec, unit_off, list_off));
+  tr.mark("list arrays reserved");
   AFB_CUDA(cudaMemcpyAsync(P.tile_desc.p, hdesc, sizeof(TileDesc) * (size_t)nb_tile, cudaMemcpyHostToDevice, st));
   AFB_TRY(ctx->tmp_flag.reserve(2 * sizeof(int)));
   AFB_CUDA(cudaMemsetAsync(ctx->tmp_flag.p, 0, 2 * sizeof(int), st));
@@ -1379,6 +1411,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
   AFB_CUDA(cudaEventRecord(e1, st));
   AFB_CUDA(cudaEventSynchronize(e1));
   AFB_CUDA(cudaEventElapsedTime(&P.lists_ms, e0, e1));
+  tr.mark("k_tile_lists + k_bank_order (sync)");
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   AFB_REQUIRE(err == 0, AFB_ERR_CUDA, "tile inspector: value plan inconsistency (code %d)", err);
