@@ -3,7 +3,8 @@
 // The classes keep the names, method names, argument meaning and error behaviour of the ArcaneFEM
 // containers they stand in for (paths relative to the ArcaneFEM source root):
 //
-//   CsrFormatMatrixView  femutils/CsrFormatMatrixView.h:135-210
+//   CsrFormatMatrixView  femutils/CsrFormatMatrixView.h:135-210 (+ CsrRowColumnIndex / CsrRowColumnIterator / CsrRow :39-126)
+//   Real4, RealMatrix<N,M>, RealVector<N>   femutils/FemUtils.h:35-598  (in FemTypes.h)
 //   CsrFormat            femutils/CsrFormatMatrix.h:37-142, CsrFormatMatrix.cc:35-121
 //   CooFormat            femutils/CooFormatMatrix.h:38-306
 //   BSRMatrix, BSRFormat femutils/BSRFormat.h:77-249, BSRFormat.cc:48-106,350-395
@@ -33,13 +34,14 @@
 #include <vector>
 
 #include "afb200.h"
+#include "arcanefem_b200/FemTypes.h"
 
 namespace arcanefem_b200 {
 
 using Int8 = std::int8_t;
 using Int32 = std::int32_t;
 using Int64 = std::int64_t;
-using Real = double;
+// Real is declared in FemTypes.h
 
 //! ARCANE_FATAL / ARCANE_THROW equivalent
 class FatalError : public std::runtime_error {
@@ -107,8 +109,53 @@ class Context {
 template <class T> struct DeviceSpan {
   T* ptr = nullptr;
   Int64 n = 0;
-  T* data() const { return ptr; }
-  Int64 size() const { return n; }
+  AFB_HOST_DEVICE T* data() const { return ptr; }
+  AFB_HOST_DEVICE Int64 size() const { return n; }
+  AFB_HOST_DEVICE T& operator[](Int64 i) const { return ptr[i]; } // dereferences DEVICE memory: for kernels over the view
+};
+
+/*---------------------------------------------------------------------------*/
+//! Position of one stored entry in the columns / values arrays (femutils/CsrFormatMatrixView.h:39-62); -1 = none
+class CsrRowColumnIndex {
+ public:
+  using IndexType = Int32;
+  CsrRowColumnIndex() = default;
+  AFB_HOST_DEVICE explicit constexpr CsrRowColumnIndex(IndexType index) : m_index(index) {}
+  AFB_HOST_DEVICE constexpr IndexType value() const { return m_index; }
+  AFB_HOST_DEVICE constexpr operator IndexType() const { return m_index; }
+  AFB_HOST_DEVICE constexpr bool isNull() const { return m_index < 0; }
+
+ private:
+  IndexType m_index = -1;
+};
+//! Walks the entries of one row (femutils/CsrFormatMatrixView.h:67-96)
+class CsrRowColumnIterator {
+ public:
+  CsrRowColumnIterator() = default;
+  AFB_HOST_DEVICE explicit constexpr CsrRowColumnIterator(Int32 index) : m_index(index) {}
+  AFB_HOST_DEVICE constexpr CsrRowColumnIndex operator*() const { return CsrRowColumnIndex(m_index); }
+  AFB_HOST_DEVICE constexpr CsrRowColumnIterator& operator++()
+  {
+    ++m_index;
+    return *this;
+  }
+  friend AFB_HOST_DEVICE constexpr bool operator!=(const CsrRowColumnIterator& a, const CsrRowColumnIterator& b) { return a.m_index != b.m_index; }
+  AFB_HOST_DEVICE constexpr bool isValid() const { return m_index != -1; }
+
+ private:
+  Int32 m_index = -1;
+};
+//! The entries [begin, end) of one row, for range-based for (femutils/CsrFormatMatrixView.h:101-126)
+class CsrRow {
+ public:
+  CsrRow() = default;
+  AFB_HOST_DEVICE constexpr CsrRow(Int32 begin, Int32 end) : m_begin(begin), m_end(end) {}
+  AFB_HOST_DEVICE constexpr CsrRowColumnIterator begin() const { return CsrRowColumnIterator(m_begin); }
+  AFB_HOST_DEVICE constexpr CsrRowColumnIterator end() const { return CsrRowColumnIterator(m_end); }
+  AFB_HOST_DEVICE constexpr Int32 size() const { return m_end - m_begin; }
+
+ private:
+  Int32 m_begin = -1, m_end = -1;
 };
 
 /*---------------------------------------------------------------------------*/
@@ -122,9 +169,24 @@ class CsrFormatMatrixView {
   DeviceSpan<const Int32> rowsNbColumn() const { return m_matrix_rows_nb_column; }
   DeviceSpan<const Int32> columns() const { return m_matrix_columns; }
   DeviceSpan<Real> values() const { return m_values; }
-  Int32 nbRow() const { return (Int32)m_matrix_rows.size(); }
-  Int32 nbColumn() const { return (Int32)m_matrix_columns.size(); }
-  Int32 nbValue() const { return (Int32)m_values.size(); }
+  AFB_HOST_DEVICE Int32 nbRow() const { return (Int32)m_matrix_rows.size(); }
+  AFB_HOST_DEVICE Int32 nbColumn() const { return (Int32)m_matrix_columns.size(); }
+  AFB_HOST_DEVICE Int32 nbValue() const { return (Int32)m_values.size(); }
+  // Element access as in the reference (femutils/CsrFormatMatrixView.h:171-215).  The spans point into HBM: these are for
+  // kernels that receive the view by value (or for a view built over host copies, as tests/cpp/types_driver.cpp does).
+  AFB_HOST_DEVICE Int32 row(Int32 index) const { return m_matrix_rows[index]; }
+  AFB_HOST_DEVICE Int32 nbColumnForRow(Int32 row) const { return m_matrix_rows_nb_column[row]; }
+  AFB_HOST_DEVICE Int32 column(CsrRowColumnIndex rc) const { return m_matrix_columns[rc.value()]; }
+  AFB_HOST_DEVICE Real& value(CsrRowColumnIndex rc) const { return m_values[rc.value()]; }
+  //! entries of `row`: rows() has no sentinel, the last row ends at nbColumn()
+  AFB_HOST_DEVICE CsrRow rowRange(Int32 row) const { return CsrRow(m_matrix_rows[row], row + 1 == nbRow() ? nbColumn() : m_matrix_rows[row + 1]); }
+  //! linear search of `column_id` in `row`; null index when absent
+  AFB_HOST_DEVICE CsrRowColumnIndex tryFindColumnInRow(Int32 row, Int32 column_id) const
+  {
+    for (CsrRowColumnIndex rc : rowRange(row))
+      if (column(rc) == column_id) return rc;
+    return CsrRowColumnIndex();
+  }
 
  private:
   DeviceSpan<const Int32> m_matrix_rows, m_matrix_rows_nb_column, m_matrix_columns;
@@ -146,6 +208,16 @@ class DoFLinearSystem {
     m_has_view = false;
     m_view = CSRFormatView();
     check(afb_clear_dirichlet(m_ctx.handle()));
+  }
+  //! DoFLinearSystem::matrixAddValue / matrixSetValue (femutils/DoFLinearSystem.h:186-194): one entry of the assembled matrix,
+  //! DoF ids; an entry outside the pattern is an error (the reference's CSR implementation has no slot for it either)
+  void matrixAddValue(Int32 row, Int32 column, Real value) { check(afb_matrix_set_value(m_ctx.handle(), row, column, value, 1)); }
+  void matrixSetValue(Int32 row, Int32 column, Real value) { check(afb_matrix_set_value(m_ctx.handle(), row, column, value, 0)); }
+  Real matrixGetValue(Int32 row, Int32 column)
+  {
+    Real v = 0.0;
+    check(afb_matrix_get_value(m_ctx.handle(), row, column, &v));
+    return v;
   }
   void eliminateRow(Int32 dof, Real value) { check(afb_set_elimination(m_ctx.handle(), AFB_ELIMINATE_ROW, 1, &dof, &value, AFB_MEM_HOST)); }
   void eliminateRowColumn(Int32 dof, Real value) { check(afb_set_elimination(m_ctx.handle(), AFB_ELIMINATE_ROW_COLUMN, 1, &dof, &value, AFB_MEM_HOST)); }

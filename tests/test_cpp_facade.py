@@ -264,3 +264,40 @@ def test_handoff_arrays_as_hypre_and_petsc_receive_them(handoff_driver, tmp_path
     # MatSetPreallocationCOOLocal(nnz, coo_rows, coo_cols) + MatSetValuesCOO(values, INSERT_VALUES) + MatAssemblyBegin/End
     assert pmeta.tolist() == [cols.size, 1, 2]
     assert np.array_equal(coo_i, np.repeat(np.arange(n), np.diff(rows))) and np.array_equal(coo_j, cols) and np.array_equal(coo_v, hvals)
+
+
+# ---- value types and CSR row iteration (include/arcanefem_b200/FemTypes.h, CsrRow / CsrRowColumnIndex) ------------------------
+
+def test_value_types_and_row_iteration_on_the_host(tmp_path):
+    """CPU: Real4 / RealMatrix / RealVector algebra and the CsrFormatMatrixView accessors (view over host arrays), -Wall -Werror."""
+    if not os.path.exists(os.path.join(LIBDIR, "libafb200.so")):
+        pytest.skip("libafb200.so not built")
+    out = str(tmp_path / "types_driver")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "types_driver.cpp"), "-o", out,
+                    "-L" + LIBDIR, "-lafb200", "-Wl,-rpath," + LIBDIR], check=True)
+    r = subprocess.run([out], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "types ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.fixture(scope="module")
+def view_kernel(tmp_path_factory):
+    if not os.path.exists(os.path.join(LIBDIR, "libafb200.so")):
+        pytest.skip("libafb200.so not built")
+    out = str(tmp_path_factory.mktemp("cpp") / "view_kernel")
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-Xcompiler", "-Wall,-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "view_kernel.cu"), "-o", out, "-L" + LIBDIR, "-lafb200", "-Xlinker", "-rpath," + LIBDIR], check=True)
+    return out
+
+
+def test_user_kernel_over_the_device_view_compiles(view_kernel):
+    """CPU: a user kernel written against the reference's view interface and value types compiles for sm_100a (__host__ __device__ members)."""
+    assert os.path.exists(view_kernel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [6, 24])
+def test_user_kernel_over_the_device_view(view_kernel, n):
+    """rowRange / value / tryFindColumnInRow on the device view of an assembled Poisson matrix: zero row sums, positive diagonals,
+    every entry walked once; DoFLinearSystem::matrixGetValue / matrixAddValue / matrixSetValue agree with what the kernel read."""
+    r = subprocess.run([view_kernel, str(n)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "view ok" in r.stdout, r.stdout + r.stderr
