@@ -397,6 +397,7 @@ int afb_mesh_generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t 
 
 int afb_build_pattern(afb_ctx* ctx, int nb_dof_per_node, int32_t* nb_block_row, int64_t* nb_block_nnz)
 {
+  afb::NvtxRange nvtx_range("BuildMatrix");
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_mesh, AFB_ERR_INVALID, "afb_build_pattern: no mesh set");
   // BSRMatrix::initialize argument checks (femutils/BSRFormat.cc:51-55)
@@ -434,6 +435,7 @@ int afb_reset_values(afb_ctx* ctx)
 
 int afb_assemble_bilinear(afb_ctx* ctx, int op, const double* params, int nb_params, int format, int variant, int value_layout, int flags)
 {
+  afb::NvtxRange nvtx_range("AddAndCompute");
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_assemble_bilinear: build the pattern first");
   AFB_REQUIRE(format == AFB_FORMAT_CSR || format == AFB_FORMAT_COO || format == AFB_FORMAT_BSR, AFB_ERR_INVALID, "unknown matrix format %d", format);
@@ -467,6 +469,7 @@ int afb_rhs_reset(afb_ctx* ctx)
 
 int afb_assemble_rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewise, int signed_tri_area)
 {
+  afb::NvtxRange nvtx_range("AssembleLinearOperator(source)");
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern && f, AFB_ERR_INVALID, "afb_assemble_rhs_source: no pattern / null source");
   return rhs_source(ctx, f, nb_f, nodewise, signed_tri_area);
@@ -474,6 +477,7 @@ int afb_assemble_rhs_source(afb_ctx* ctx, const double* f, int nb_f, int nodewis
 
 int afb_assemble_rhs_neumann(afb_ctx* ctx, int64_t nb_face, const int32_t* face_nodes, int kind, int nb_value, const double* values, int skip_dirichlet, int mem_space)
 {
+  afb::NvtxRange nvtx_range("AssembleLinearOperator(boundary)");
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern && (nb_face == 0 || face_nodes) && values, AFB_ERR_INVALID, "afb_assemble_rhs_neumann: no pattern / null argument");
   // faces: 2-node edges (any 2-D mesh with straight edges: Tri3, Quad4), 3-node triangles (Tet4), 4-node quadrilaterals (Hexa8)
@@ -851,6 +855,7 @@ int afb_memcpy_to_host(afb_ctx* ctx, void* dst_host, const void* src_device, siz
 
 int afb_solve_pcg(afb_ctx* ctx, double rtol, double atol, int max_iter, double* x, int mem_space, int* iterations, double* residual)
 {
+  afb::NvtxRange nvtx_range("StationarySolve");
   AFB_TRY(check_ctx(ctx));
   AFB_REQUIRE(ctx->has_pattern && ctx->assembled, AFB_ERR_INVALID, "afb_solve_pcg: assemble the matrix first");
   AFB_REQUIRE(rtol >= 0.0 && atol >= 0.0 && max_iter >= 0, AFB_ERR_INVALID, "afb_solve_pcg: negative tolerance / iteration count");

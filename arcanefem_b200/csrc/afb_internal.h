@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <initializer_list>
 #include <stdint.h>
@@ -297,6 +298,15 @@ int scatter_flags(afb_ctx* ctx, uint8_t* flags, double* vals, uint8_t flag, int3
 int generate_box(afb_ctx* ctx, int dim, int n, double jitter, uint32_t seed, int k_lo, int k_hi, int ghost_cell_layer);
 
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// NVTX range over an API phase, named after the reference's time-stats scopes / ProfileRegion labels (BuildMatrix, AddAndCompute:
+// modules/testlab/CsrGpuBiliAssembly.cc:313-338).  Header-only NVTX: a no-op unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Programmatic dependent launch for the kernels of the steady-state step (scan -> column placement -> assembly):
 // the grid may be scheduled while the kernel before it on the stream drains, which hides the launch latency between

@@ -582,6 +582,7 @@ int afb_xplan_create(afb_ctx* ctx, const afb_transport* t, const int64_t* node_g
 
 int afb_xplan_exchange(afb_xplan* x)
 {
+  afb::NvtxRange nvtx_range("GhostRowExchange");
   AFB_REQUIRE(x, AFB_ERR_INVALID, "afb_xplan_exchange: null plan");
   AFB_REQUIRE(x->ctx, AFB_ERR_INVALID, "afb_xplan_exchange: the plan's context was destroyed");
   afb_ctx* ctx = x->ctx;

@@ -1149,6 +1149,7 @@ struct InspectorTrace {
 
 int build_tile_mesh(afb_ctx* ctx, int cls)
 {
+  afb::NvtxRange nvtx_range("TileInspector(mesh)");
   InspectorTrace tr("mesh tiling");
   AFB_REQUIRE(tiled_cells_supported(ctx), AFB_ERR_UNSUPPORTED, "the tiled path is not available for %d-node cells (P1 simplices only); use AFB_VARIANT_NODEWISE", ctx->npc);
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "tile inspector: build the pattern first");
@@ -1351,6 +1352,7 @@ int build_tile_mesh(afb_ctx* ctx, int cls)
 
 int build_tile_lists(afb_ctx* ctx, int mode_flags)
 {
+  afb::NvtxRange nvtx_range("TileInspector(values)");
   TilePlan& P = ctx->plan;
   AFB_REQUIRE(P.mesh_valid, AFB_ERR_INVALID, "tile inspector: no mesh tiling");
   P.lists_valid = false;
@@ -1425,6 +1427,7 @@ int build_tile_lists(afb_ctx* ctx, int mode_flags)
 
 int build_tile_rowlists(afb_ctx* ctx, int mode_flags)
 {
+  afb::NvtxRange nvtx_range("TileInspector(values)");
   TilePlan& P = ctx->plan;
   AFB_REQUIRE(P.mesh_valid && P.mesh_b_class == 2, AFB_ERR_INVALID, "tile inspector: no mesh tiling for the row-ordered executor");
   P.lists_valid = false;
