@@ -370,6 +370,88 @@ def to_p2(mesh: Mesh) -> Mesh:
     return Mesh(dim=mesh.dim, coords=np.ascontiguousarray(coords), cells=np.ascontiguousarray(cells), node_uid=uid, groups=dict(mesh.groups))
 
 
+def subdivide(mesh: Mesh, times: int = 1) -> Mesh:
+    """Uniform refinement of a P1 simplex mesh, the stand-in for Arcane's `<subdivider><nb-subdivision>` mesh option
+    (e.g. modules/elasticity/inputs/bar.3D.Dirichlet.bodyForce.arc:18-20): every edge gets a midpoint node (ids appended after the
+    existing nodes in ascending (min,max) vertex-pair order, as `to_p2`), a triangle becomes 4 triangles, a tetrahedron 8
+    (4 corner tetrahedra + the inner octahedron cut along its shortest diagonal), all with the parent's orientation.  Children of cell c are cells [k*c, k*c+k) (k = 4 or 8); boundary faces, node groups and cell groups follow.
+    The node and cell numbering is this repo's, not Arcane's (the subdivider is not part of the reference's sources)."""
+    for _ in range(times):
+        npc = mesh.npc
+        if npc not in (3, 4) or npc != mesh.dim + 1:
+            raise ValueError("subdivide: P1 simplex cells only")
+        p2 = to_p2(mesh)
+        c = p2.cells.astype(np.int64)
+        if npc == 3:
+            # Tri6 local order: 3=(0,1) 4=(1,2) 5=(2,0)
+            kids = [(0, 3, 5), (3, 1, 4), (5, 4, 2), (3, 4, 5)]
+        else:
+            # Tet10 local order: 4=(0,1) 5=(1,2) 6=(0,2) 7=(0,3) 8=(1,3) 9=(2,3); inner octahedron: see below
+            kids = [(0, 4, 6, 7), (4, 1, 5, 8), (6, 5, 2, 9), (7, 8, 9, 3),
+                    (4, 6, 7, 8), (4, 5, 6, 8), (6, 5, 9, 8), (6, 9, 7, 8)]
+        cells = np.stack([c[:, list(k)] for k in kids], axis=1)
+        coords = p2.coords
+        if npc == 4:
+            # the octahedron is cut along its shortest diagonal (ties: 6-8, then 4-9, then 7-5), which keeps the children's shape
+            # bounded under repeated refinement (a Kuhn box refined once this way is the Kuhn box of twice the resolution)
+            inner = [[(4, 6, 7, 8), (4, 5, 6, 8), (6, 5, 9, 8), (6, 9, 7, 8)],
+                     [(4, 9, 5, 6), (4, 9, 6, 7), (4, 9, 7, 8), (4, 9, 8, 5)],
+                     [(7, 5, 4, 6), (7, 5, 6, 9), (7, 5, 9, 8), (7, 5, 8, 4)]]
+            diag = [(6, 8), (4, 9), (7, 5)]
+            length = np.stack([np.linalg.norm(coords[c[:, a]] - coords[c[:, b]], axis=1) for a, b in diag], axis=1)
+            best = length.min(axis=1, keepdims=True)
+            choice = np.argmax(length <= best * (1.0 + 1e-12), axis=1)  # first diagonal within rounding of the shortest
+            for d in (1, 2):
+                sel = choice == d
+                for q in range(4):
+                    cells[sel, 4 + q] = c[sel][:, list(inner[d][q])]
+        cells = cells.reshape(-1, npc)
+        # keep the parent's orientation (sign of the signed measure) in every child
+        def signed(cc):
+            x = coords[cc]
+            if npc == 3:
+                e1, e2 = x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]
+                return e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+            return np.einsum("ij,ij->i", np.cross(x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]), x[:, 3] - x[:, 0])
+        flip = np.sign(signed(cells)) != np.repeat(np.sign(signed(mesh.cells.astype(np.int64))), len(kids))
+        cells[flip, -2], cells[flip, -1] = cells[flip, -1].copy(), cells[flip, -2].copy()
+        # mid-edge id of a vertex pair: the sorted unique keys of to_p2
+        pairs = [(0, 1), (1, 2), (2, 0)] if npc == 3 else [(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]
+        mc = mesh.cells.astype(np.int64)
+        keys = np.unique(np.concatenate([(np.minimum(mc[:, a], mc[:, b]) << 32) | np.maximum(mc[:, a], mc[:, b]) for a, b in pairs]))
+        def mid(a, b):
+            k = (np.minimum(a, b).astype(np.int64) << 32) | np.maximum(a, b).astype(np.int64)
+            pos = np.searchsorted(keys, k)
+            if np.any(pos >= keys.size) or np.any(keys[np.minimum(pos, keys.size - 1)] != k):
+                raise ValueError("subdivide: a boundary face has an edge that is not an edge of the mesh")
+            return mesh.nb_node + pos
+        faces = {}
+        for name, f in mesh.faces.items():
+            f = np.asarray(f, dtype=np.int64)
+            if f.ndim != 2 or f.shape[0] == 0:
+                faces[name] = f.astype(np.int32)
+            elif f.shape[1] == 2:  # edge -> 2 edges, same direction
+                m01 = mid(f[:, 0], f[:, 1])
+                faces[name] = np.stack([np.stack([f[:, 0], m01], 1), np.stack([m01, f[:, 1]], 1)], 1).reshape(-1, 2).astype(np.int32)
+            elif f.shape[1] == 3:  # triangle -> 4 triangles, same normal
+                a, b, cc = f[:, 0], f[:, 1], f[:, 2]
+                ab, bc, ca = mid(a, b), mid(b, cc), mid(cc, a)
+                faces[name] = np.stack([np.stack([a, ab, ca], 1), np.stack([ab, b, bc], 1), np.stack([ca, bc, cc], 1), np.stack([ab, bc, ca], 1)], 1).reshape(-1, 3).astype(np.int32)
+            else:
+                faces[name] = f.astype(np.int32)  # points
+        groups = {}
+        for name, ids in mesh.groups.items():
+            if name in faces and faces[name].ndim == 2 and faces[name].shape[1] >= 2:
+                groups[name] = np.unique(faces[name]).astype(np.int32)
+            else:
+                groups[name] = np.asarray(ids, dtype=np.int32)
+        k = len(kids)
+        cell_groups = {name: (np.asarray(ids, dtype=np.int64)[:, None] * k + np.arange(k)[None, :]).reshape(-1).astype(np.int32) for name, ids in mesh.cell_groups.items()}
+        mesh = Mesh(dim=mesh.dim, coords=np.ascontiguousarray(coords), cells=np.ascontiguousarray(cells.astype(np.int32)), node_uid=p2.node_uid,
+                    groups=groups, cell_groups=cell_groups, faces=faces)
+    return mesh
+
+
 def box_counts(dim: int, n: int):
     """(nb_cell, nb_node, nb_edge, nnz) of the P1 box."""
     if dim == 3:
