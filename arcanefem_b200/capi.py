@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AFB200_LIB") or os.path.join(_HERE, "libafb200.so")  # AFB200_LIB: tuning builds (scratch/build_variants.sh)
 
 # enums of afb200.h
-OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN, OP_DIFFUSION_REACTION = 0, 1, 2, 3
+OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN, OP_DIFFUSION_REACTION, OP_ELASTODYNAMICS = 0, 1, 2, 3, 4
 FORMAT_CSR, FORMAT_COO, FORMAT_BSR = 0, 1, 2
 VARIANT_CELLWISE_ATOMIC, VARIANT_NODEWISE, VARIANT_TILED_GATHER = 0, 1, 2
 LAYOUT_PER_BLOCK, LAYOUT_PER_ROW = 0, 1

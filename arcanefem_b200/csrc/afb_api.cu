@@ -440,11 +440,12 @@ int afb_assemble_bilinear(afb_ctx* ctx, int op, const double* params, int nb_par
   AFB_REQUIRE(ctx->has_pattern, AFB_ERR_INVALID, "afb_assemble_bilinear: build the pattern first");
   AFB_REQUIRE(format == AFB_FORMAT_CSR || format == AFB_FORMAT_COO || format == AFB_FORMAT_BSR, AFB_ERR_INVALID, "unknown matrix format %d", format);
   AFB_REQUIRE(value_layout == AFB_LAYOUT_PER_BLOCK || value_layout == AFB_LAYOUT_PER_ROW, AFB_ERR_INVALID, "unknown value layout %d", value_layout);
-  const int need_b = (op == AFB_OP_POISSON || op == AFB_OP_DIFFUSION_REACTION) ? 1 : (op == AFB_OP_ELASTICITY ? ctx->dim : (op == AFB_OP_BILAPLACIAN ? 2 : -1));
+  const int need_b = (op == AFB_OP_POISSON || op == AFB_OP_DIFFUSION_REACTION) ? 1 : ((op == AFB_OP_ELASTICITY || op == AFB_OP_ELASTODYNAMICS) ? ctx->dim : (op == AFB_OP_BILAPLACIAN ? 2 : -1));
   AFB_REQUIRE(need_b > 0, AFB_ERR_INVALID, "unknown operator %d", op);
   AFB_REQUIRE(need_b == ctx->b, AFB_ERR_INVALID, "operator %d needs %d dof per node, pattern was built with %d", op, need_b, ctx->b);
   AFB_REQUIRE(op != AFB_OP_ELASTICITY || (params && nb_params >= 2), AFB_ERR_INVALID, "elasticity needs params = {lambda, mu}");
   AFB_REQUIRE(op != AFB_OP_DIFFUSION_REACTION || (params && nb_params >= 2), AFB_ERR_INVALID, "diffusion-reaction needs params = {alpha, beta}");
+  AFB_REQUIRE(op != AFB_OP_ELASTODYNAMICS || (params && nb_params >= 3), AFB_ERR_INVALID, "elastodynamics needs params = {c0, c1, c2}");
   AFB_REQUIRE(!(ctx->b > 1 && format != AFB_FORMAT_BSR), AFB_ERR_INVALID, "CSR/COO back-ends hold one dof per node; use AFB_FORMAT_BSR for b=%d", ctx->b);
   AFB_REQUIRE(!(ctx->assembled && ctx->layout != value_layout), AFB_ERR_INVALID, "values already hold the other layout; afb_reset_values first");
   ctx->layout = value_layout;

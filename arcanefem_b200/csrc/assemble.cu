@@ -209,6 +209,7 @@ int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, in
   ElemParams prm;
   prm.p0 = params ? params[0] : 0.0;
   prm.p1 = params ? params[1] : 0.0;
+  prm.p2 = (params && op == AFB_OP_ELASTODYNAMICS) ? params[2] : 0.0;
   prm.flags = flags;
   const int npc = ctx->npc, dim = ctx->dim;
   if (ctx->has_cell_coef) {
@@ -238,6 +239,10 @@ int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, in
     if (npc == 3 && dim == 2) return launch<Tri3DiffReact>(ctx, format, variant, layout, prm);
     if (npc == 4 && dim == 2) return launch<Quad4DiffReact>(ctx, format, variant, layout, prm);
     if (npc == 8 && dim == 3) return launch<Hexa8DiffReact>(ctx, format, variant, layout, prm);
+  }
+  else if (op == AFB_OP_ELASTODYNAMICS) {
+    if (npc == 4 && dim == 3) return launch<Tet4Elastodynamics>(ctx, format, variant, layout, prm);
+    if (npc == 3 && dim == 2) return launch<Tri3Elastodynamics>(ctx, format, variant, layout, prm);
   }
   // mirrors BSRFormat::computeNbColumns returning 0 / testlab _checkCellType FATAL for
   // unsupported cell types (femutils/BSRFormat.cc:339-341, modules/testlab/FemModule.cc:688-699)

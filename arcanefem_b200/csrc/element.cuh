@@ -31,6 +31,7 @@ namespace afb {
 
 struct ElemParams {
   double p0, p1;  // elasticity: lambda, mu
+  double p2 = 0.0; // elastodynamics: {p0, p1, p2} = {c0, c1, c2}
   int flags;      // AFB_FLAG_*
   const double* cell_coef = nullptr; // per-cell multiplier of the Poisson element matrix (afb_set_cell_coefficient) or null
   double scale = 1.0;                // the current cell's multiplier (set by the cell-wise / node-wise kernels)
@@ -186,6 +187,29 @@ struct Tet4Elasticity {
   }
 };
 
+// elastodynamics (modules/elastodynamics/ElementMatrix.h): elasticity with (lambda, mu) = (c1, c2) + c0 * consistent mass on each component
+struct Tet4Elastodynamics {
+  static constexpr int NPC = 4, B = 3, DIM = 3;
+  Tet4Elasticity e;
+  double mm;
+  __device__ __forceinline__ void init(const double* __restrict__ coords, const int32_t (&nd)[4], const ElemParams& p)
+  {
+    ElemParams q = p;
+    q.p0 = p.p1;
+    q.p1 = p.p2;
+    e.init(coords, nd, q);
+    mm = p.p0 * e.g.vol * (1 / 20.);
+  }
+  __device__ __forceinline__ void block(int a, int b, double (&o)[9]) const
+  {
+    e.block(a, b, o);
+    const double m = a == b ? 2.0 * mm : mm;
+    o[0] += m;
+    o[4] += m;
+    o[8] += m;
+  }
+};
+
 struct Tri3Elasticity {
   static constexpr int NPC = 3, B = 2, DIM = 2;
   Tri3Geom g;
@@ -204,6 +228,27 @@ struct Tri3Elasticity {
 #pragma unroll
       for (int j = 0; j < 2; ++j)
         o[i * 2 + j] = ls * g.c[a][i] * g.c[b][j] + ms * g.c[a][j] * g.c[b][i] + (i == j ? dd : 0.0);
+  }
+};
+
+struct Tri3Elastodynamics {
+  static constexpr int NPC = 3, B = 2, DIM = 2;
+  Tri3Elasticity e;
+  double mm;
+  __device__ __forceinline__ void init(const double* __restrict__ coords, const int32_t (&nd)[3], const ElemParams& p)
+  {
+    ElemParams q = p;
+    q.p0 = p.p1;
+    q.p1 = p.p2;
+    e.init(coords, nd, q);
+    mm = p.p0 * e.g.area * (1 / 12.);
+  }
+  __device__ __forceinline__ void block(int a, int b, double (&o)[4]) const
+  {
+    e.block(a, b, o);
+    const double m = a == b ? 2.0 * mm : mm;
+    o[0] += m;
+    o[3] += m;
   }
 };
 

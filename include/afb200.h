@@ -61,7 +61,11 @@ enum {
    * ElementMatrix.h:14,29: alpha = -1, beta = kc2; ElementMatrixHexQuad.h: alpha = +1) and the heat module's matrix (modules/heat/
    * ElementMatrix.h: alpha = lambda, beta = 1/dt).  Tri3 / Tet4 / Quad4 / Hexa8, cell-wise and node-wise variants; a per-cell
    * coefficient (afb_set_cell_coefficient) multiplies the stiffness part. */
-  AFB_OP_DIFFUSION_REACTION = 3
+  AFB_OP_DIFFUSION_REACTION = 3,
+  /* params = { c0, c1, c2 }: the Newmark-beta / generalised-alpha matrix of the elastodynamics module (modules/elastodynamics/
+   * ElementMatrix.h:41-60 Tria3, :150-196 Tetra4; coefficients FemModule.cc:197-225): the elasticity matrix with lambda = c1,
+   * mu = c2 plus c0 times the consistent mass on every component.  dim DoF/node, BSR; Tri3 / Tet4, cell-wise and node-wise variants. */
+  AFB_OP_ELASTODYNAMICS = 4
 };
 
 /* matrix format = how entries are located during the scatter and which view is native

@@ -59,7 +59,8 @@ inline void check(int rc)
 }
 
 //! replaces the device lambda handed to BSRFormat::assembleBilinear*
-enum class Operator { Poisson = AFB_OP_POISSON, Elasticity = AFB_OP_ELASTICITY, Bilaplacian = AFB_OP_BILAPLACIAN };
+enum class Operator { Poisson = AFB_OP_POISSON, Elasticity = AFB_OP_ELASTICITY, Bilaplacian = AFB_OP_BILAPLACIAN, DiffusionReaction = AFB_OP_DIFFUSION_REACTION,
+                      Elastodynamics = AFB_OP_ELASTODYNAMICS };
 
 //! femutils/FemUtilsGlobal.h:51-62
 enum class eMatrixEliminationType { None = AFB_ELIMINATE_NONE, Row = AFB_ELIMINATE_ROW, RowColumn = AFB_ELIMINATE_ROW_COLUMN };

@@ -39,7 +39,7 @@
 /* ------------------------------------------------------------------------- */
 /* enums shared with include/afb200.h (same numeric values)                   */
 /* ------------------------------------------------------------------------- */
-enum { ORC_OP_POISSON = 0, ORC_OP_ELASTICITY = 1, ORC_OP_BILAPLACIAN = 2, ORC_OP_DIFFUSION_REACTION = 3 };
+enum { ORC_OP_POISSON = 0, ORC_OP_ELASTICITY = 1, ORC_OP_BILAPLACIAN = 2, ORC_OP_DIFFUSION_REACTION = 3, ORC_OP_ELASTODYNAMICS = 4 };
 /* which reference formulation of the element matrix to follow */
 enum {
   ORC_FORM_COMPACT = 0, /* modules/testlab/FemModule.h:342-463 (CSR/COO GPU back-ends)   */
@@ -597,7 +597,7 @@ static void ke_hexa8_poisson(const r3* m, double* K)
 /* Element-matrix dispatcher: K is (npc*b) x (npc*b), row-major.              */
 /* params: ELASTICITY -> {lambda, mu}                                         */
 /* ------------------------------------------------------------------------- */
-static int op_block_size(int op, int dim) { return (op == ORC_OP_POISSON || op == ORC_OP_DIFFUSION_REACTION) ? 1 : (op == ORC_OP_ELASTICITY ? dim : 2); }
+static int op_block_size(int op, int dim) { return (op == ORC_OP_POISSON || op == ORC_OP_DIFFUSION_REACTION) ? 1 : ((op == ORC_OP_ELASTICITY || op == ORC_OP_ELASTODYNAMICS) ? dim : 2); }
 static double g_stiffness_scale = 1.0; /* per-cell coefficient of the stiffness part of ORC_OP_DIFFUSION_REACTION (set by the assembly loops) */
 
 static int element_matrix(int npc, int dim, int op, int form, const double* params, const double* coords, const int32_t* cn, double* K)
@@ -691,6 +691,41 @@ static int element_matrix(int npc, int dim, int op, int form, const double* para
   }
   if (op == ORC_OP_BILAPLACIAN) {
     if (npc == 3 && dim == 2) { ke_tri3_bilaplacian(m[0], m[1], m[2], K); return 0; }
+    return -1;
+  }
+  if (op == ORC_OP_ELASTODYNAMICS) {
+    /* Newmark-beta / generalised-alpha matrix of the elastodynamics module, params = {c0, c1, c2}
+     * (modules/elastodynamics/ElementMatrix.h:41-60 Tria3, :150-196 Tetra4; coefficients FemModule.cc:203-205):
+     *   (c0/12) (massMatrix(Ux,Ux) + massMatrix(Uy,Uy)) area + c1 (cross terms) area + (2 c2 + c1) (normal terms) area + c2 (shear terms) area
+     * = the elasticity element matrix with lambda = c1, mu = c2, plus c0 times the consistent mass on every component
+     * ((1 + delta_ab)/12 area, /20 volume: massMatrix femutils/FemUtils.h:583-597). */
+    const double c0 = params[0], c1 = params[1], c2 = params[2];
+    if (npc == 3 && dim == 2) {
+      double M[36];
+      const double area = area_tri3_unsigned(m[0], m[1], m[2]);
+      const double Ux[6] = { 1., 0., 1., 0., 1., 0. }, Uy[6] = { 0., 1., 0., 1., 0., 1. };
+      ke_tri3_elasticity(m[0], m[1], m[2], c1, c2, K);
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+          const double dbl = i == j ? 2. : 1.;
+          M[i * 6 + j] = (c0 / 12.) * ((Ux[i] * Ux[j]) * dbl + (Uy[i] * Uy[j]) * dbl) * area;
+        }
+      for (int i = 0; i < 36; ++i) K[i] = M[i] + K[i];
+      return 0;
+    }
+    if (npc == 4 && dim == 3) {
+      double M[144];
+      const double volume = volume_tet4(m[0], m[1], m[2], m[3]);
+      ke_tet4_elasticity(m[0], m[1], m[2], m[3], c1, c2, K);
+      for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 12; ++j) {
+          const double dbl = i == j ? 2. : 1.;
+          const double same = (i % 3) == (j % 3) ? 1. : 0.; /* Ux^Ux + Uy^Uy + Uz^Uz */
+          M[i * 12 + j] = (c0 / 20.) * (same * dbl) * volume;
+        }
+      for (int i = 0; i < 144; ++i) K[i] = M[i] + K[i];
+      return 0;
+    }
     return -1;
   }
   return -1;

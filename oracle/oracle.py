@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libafb_oracle.so")
 
-OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN, OP_DIFFUSION_REACTION = 0, 1, 2, 3
+OP_POISSON, OP_ELASTICITY, OP_BILAPLACIAN, OP_DIFFUSION_REACTION, OP_ELASTODYNAMICS = 0, 1, 2, 3, 4
 FORM_COMPACT, FORM_HOST, FORM_BSR, FORM_NODEWISE = 0, 1, 2, 3
 LAYOUT_PER_BLOCK, LAYOUT_PER_ROW = 0, 1
 
@@ -59,7 +59,7 @@ def _u8(a):
 
 
 def block_size(op: int, dim: int) -> int:
-    return 1 if op in (OP_POISSON, OP_DIFFUSION_REACTION) else (dim if op == OP_ELASTICITY else 2)
+    return 1 if op in (OP_POISSON, OP_DIFFUSION_REACTION) else (dim if op in (OP_ELASTICITY, OP_ELASTODYNAMICS) else 2)
 
 
 def lame(E: float, nu: float):
@@ -73,7 +73,7 @@ def element_matrix(npc, dim, op, form, coords, cell_nodes, params=None):
     K = np.zeros((npc * b, npc * b))
     coords = _f64(coords)
     cn = _i32(cell_nodes)
-    prm = _f64(params if params is not None else [0.0, 0.0])
+    prm = _f64(params if params is not None else [0.0, 0.0, 0.0])
     rc = lib().orc_element_matrix(npc, dim, op, form, _p(prm), _p(coords), _p(cn), _p(K))
     assert rc == 0
     return K

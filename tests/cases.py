@@ -194,6 +194,52 @@ Q1_ELASTICITY_CASES = {
                                 golden="elasticity_3D.dirichlet.bodyforce.hexa.txt"),
 }
 
+# modules/elastodynamics/inputs/bar.arc, bar.3D.arc: Newmark-beta time loop (gamma = 1/2, beta = 1/4, no damping) on the
+# stiffness + mass operator; the golden files hold the displacement of the last step
+ELASTODYNAMICS_CASES = {
+    "bar_2D": dict(mesh="bar_dynamic.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 0.0],
+                   dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[("surfaceright", [0.0, 0.01])], penalty=1.0e30, golden="elastodynamics_2D_bar.txt"),
+    "bar_3D": dict(mesh="bar_dynamic_3D.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=0.5, f=[131.0e2, 113.8e6, 567.0e8],
+                   dirichlet=[("surfaceleft", [0.0, 0.0, 0.0])], traction=[("surfaceright", [0.0, 1869.1e2, 0.0])], penalty=1.0e30,
+                   golden="elastodynamics_bar_3d.txt"),
+}
+
+
+def newmark_coefficients(case):
+    """modules/elastodynamics/FemModule.cc:197-215 with etam = etak = 0: c0 (mass), c1 (lambda-like), c2 (mu-like), c3, c4 (right-hand side)"""
+    gamma = 0.5
+    beta = (1. / 4.) * (gamma + 0.5) * (gamma + 0.5)
+    rho, dt = case["rho"], case["dt"]
+    c0 = rho / (beta * dt * dt)
+    c3 = rho / beta / dt
+    c4 = rho * ((1. - 2. * beta) / 2. / beta)
+    return gamma, beta, c0, case["lam"], case["mu"], c3, c4
+
+
+def newmark_time_loop(case, nb_dof, solve_step, mass_times):
+    """The module's time loop (FemModule.cc:29-131, 277-330): t starts at dt, the loop ends after the step that starts with
+    t >= tmax - dt.  solve_step(rhs_dynamic) -> displacement of the step (the caller adds the static loads and the Dirichlet rows);
+    mass_times(x) = consistent mass matrix (rho = 1 per component) times x.  Returns the last displacement."""
+    gamma, beta, c0, _, _, c3, c4 = newmark_coefficients(case)
+    dt = case["dt"]
+    t, tmax = dt, case["tmax"] - dt
+    U = np.zeros(nb_dof)
+    V = np.zeros(nb_dof)
+    A = np.zeros(nb_dof)
+    dU = U
+    while True:
+        last = t >= tmax
+        dU = solve_step(mass_times(c0 * U + c3 * V + c4 * A))
+        a_new = (dU - U - dt * V) / (beta * dt * dt) - (1. - 2. * beta) / (2. * beta) * A
+        V = V + dt * ((1. - gamma) * A + gamma * a_new)
+        A = a_new
+        U = dU
+        t += dt
+        if last:
+            break
+    return dU
+
+
 # modules/bilaplacian/inputs/direct.arc
 BILAPLACIAN_CASE = dict(mesh="bilap.msh", f=-786.25, dirichlet=[("boundary", [145.5, None])], penalty=1.0e30,
                         golden="bilaplacian_2d_test.txt")

@@ -98,6 +98,10 @@ FILES = {
     "modules/poisson/check/poisson_test_ref_circle_neumann_2D_quad.txt": "poisson_test_ref_circle_neumann_2D_quad.txt",
     "modules/poisson/check/poisson_test_ref_sphere_neumann_3D_hexa.txt": "poisson_test_ref_sphere_neumann_3D_hexa.txt",
     "modules/poisson/check/poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt": "poisson_test_ref_sphere_scalar_neumann_3D_hexa.txt",
+    # elastodynamics module (Newmark-beta time loop on the stiffness + mass operator): inputs/bar.arc, inputs/bar.3D.arc
+    "meshes/msh/bar_dynamic.msh": "bar_dynamic.msh",
+    "modules/elastodynamics/check/2D_elastodynamics_bar.txt": "elastodynamics_2D_bar.txt",
+    "modules/elastodynamics/check/bar_3d.txt": "elastodynamics_bar_3d.txt",
 }
 
 if __name__ == "__main__":

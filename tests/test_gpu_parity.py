@@ -1189,6 +1189,66 @@ def test_diffusion_reaction_values(exec_ctx, mesh, fmt, variant):
         c.assemble(A.OP_DIFFUSION_REACTION, fmt=fmt, variant=variant)
 
 
+@pytest.mark.parametrize("mesh", ["L-shape_2D", "sphere_3D", "box3"])
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+@pytest.mark.parametrize("layout", [A.LAYOUT_PER_BLOCK, A.LAYOUT_PER_ROW], ids=["per-block", "per-row"])
+def test_elastodynamics_values(exec_ctx, mesh, variant, layout):
+    """stiffness + mass matrix of the elastodynamics module (c0, c1, c2 of a Newmark step) against the oracle"""
+    c = exec_ctx
+    m = M.box_mesh(3, 6) if mesh == "box3" else get_mesh(mesh)
+    b = m.dim
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(b)
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    for params in ([625.0, 576.9230769, 384.6153846], [0.0, 1.0e6, 8.0e5], [3.0, 0.0, 0.0]):
+        ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTODYNAMICS, form=O.FORM_BSR, params=params, layout=layout, nodewise=variant == A.VARIANT_NODEWISE)
+        c.reset_values()
+        c.assemble(A.OP_ELASTODYNAMICS, params=params, fmt=A.FORMAT_BSR, variant=variant, layout=layout)
+        got = c.to_host(A.ARRAY_VALUES)
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 1e-12 * scale
+    with pytest.raises(A.AfbError):
+        c.assemble(A.OP_ELASTODYNAMICS, params=[1.0, 1.0, 1.0], fmt=A.FORMAT_BSR, variant=A.VARIANT_TILED_GATHER, layout=layout)
+    with pytest.raises(A.AfbError, match="c0"):
+        c.assemble(A.OP_ELASTODYNAMICS, params=[1.0, 1.0], fmt=A.FORMAT_BSR, variant=variant, layout=layout)
+
+
+@pytest.mark.parametrize("name", list(CS.ELASTODYNAMICS_CASES))
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+def test_elastodynamics_golden_solution(exec_ctx, name, variant):
+    """the elastodynamics module's golden displacement files through its Newmark-beta time loop: operator, mass matrix, body force and
+    traction assembled on the GPU, penalty Dirichlet rows on the GPU, the per-step solves on the host"""
+    c = exec_ctx
+    case = CS.ELASTODYNAMICS_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    b = m.dim
+    _, _, c0, c1, c2, _, _ = CS.newmark_coefficients(case)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    # consistent mass (one DoF per node), then the block system
+    c.build_pattern(1)
+    c.assemble(A.OP_DIFFUSION_REACTION, params=[0.0, 1.0], fmt=A.FORMAT_BSR, variant=variant)
+    mass = sp.csr_matrix((c.to_host(A.ARRAY_VALUES), c.to_host(A.ARRAY_COLUMNS), c.to_host(A.ARRAY_ROWS)))
+    c.build_pattern(b)
+    c.assemble(A.OP_ELASTODYNAMICS, params=[c0, c1, c2], fmt=A.FORMAT_BSR, variant=variant, layout=A.LAYOUT_PER_ROW)
+    c.rhs_reset()
+    c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
+    for group, t in case["traction"]:
+        c.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), t, kind=A.NEUMANN_TRACTION)
+    static = c.to_host(A.ARRAY_RHS).copy()
+    c.dirichlet_penalty(ids, g, case["penalty"])
+    crow, ccol, vals = (c.to_host(w) for w in (A.ARRAY_CSR_ROWS, A.ARRAY_CSR_COLUMNS, A.ARRAY_VALUES))
+    lu = spla.splu(sp.csr_matrix((vals, ccol, crow)).tocsc())
+
+    def solve_step(dynamic):
+        rhs = static + dynamic
+        rhs[ids] = case["penalty"] * np.asarray(g)
+        return lu.solve(rhs)
+
+    u = CS.newmark_time_loop(case, m.nb_node * b, solve_step, lambda x: (mass @ x.reshape(m.nb_node, b)).reshape(-1))
+    assert CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-4, min_value=1.0e-14) < 1.0e-5
+
+
 @pytest.mark.parametrize("name", list(CS.ACOUSTICS_CASES))
 @pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
 def test_acoustics_golden_solution(exec_ctx, name, variant):

@@ -225,6 +225,45 @@ def test_q1_elasticity_golden(name, nodewise):
     assert worst < 1.0e-4
 
 
+@pytest.mark.parametrize("name", list(CS.ELASTODYNAMICS_CASES))
+@pytest.mark.parametrize("nodewise", [False, True], ids=["bsr", "af-bsr"])
+def test_elastodynamics_golden(name, nodewise):
+    """Stiffness + mass operator of the elastodynamics module (modules/elastodynamics/ElementMatrix.h) through the module's Newmark-beta
+    time loop, against its own golden displacement files (epsilon 1e-4, FemModule.cc:536-540)."""
+    case = CS.ELASTODYNAMICS_CASES[name]
+    m = _load(case)
+    b = m.dim
+    _, _, c0, c1, c2, _, _ = CS.newmark_coefficients(case)
+    rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTODYNAMICS, form=O.FORM_BSR, params=[c0, c1, c2], layout=O.LAYOUT_PER_ROW, nodewise=nodewise)
+    mass = _csr(rows, cols, O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_DIFFUSION_REACTION, form=O.FORM_BSR, params=[0.0, 1.0]))
+    static = O.rhs_source_cellwise(m.dim, m.coords, m.cells, case["f"], signed_area=False)
+    for group, t in case["traction"]:
+        O.rhs_neumann(m.dim, b, m.coords, M.orient_boundary_faces(m, m.faces[group]), t, static, kind=O.NEUMANN_TRACTION)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    crow, ccol, _ = O.bsr_to_csr(b, rows, cols)
+    lhs = vals.copy()
+    O.dirichlet_penalty(crow, ccol, lhs, np.zeros(m.nb_node * b), ids, g, case["penalty"])
+    lu = spla.splu(_csr(crow, ccol, lhs).tocsc())
+
+    def mass_times(x):
+        return (mass @ x.reshape(m.nb_node, b)).reshape(-1)
+
+    def solve_step(dynamic):
+        rhs = static + dynamic
+        rhs[ids] = case["penalty"] * np.asarray(g)
+        return lu.solve(rhs)
+
+    u = CS.newmark_time_loop(case, m.nb_node * b, solve_step, mass_times)
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], b), b, eps=1.0e-4, min_value=1.0e-14)
+    assert worst < 1.0e-5
+    # composition: the operator is the elasticity matrix with (lambda, mu) = (c1, c2) plus c0 times the mass on every component
+    ke = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[c1, c2], layout=O.LAYOUT_PER_ROW, nodewise=nodewise)
+    A = _csr(crow, ccol, ke) + c0 * sp.kron(mass, sp.identity(b), format="csr")
+    d = abs(A - _csr(crow, ccol, vals))
+    assert d.max() <= 1e-12 * abs(A).max()
+
+
 def test_elasticity_per_block_layout_equals_per_row():
     case = CS.ELASTICITY_CASES["bar_3D"]
     m, b, rows, cols, v_row, *_ = _elasticity_system(case, O.LAYOUT_PER_ROW, False)
