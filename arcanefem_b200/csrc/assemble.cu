@@ -243,6 +243,8 @@ int assemble_bilinear(afb_ctx* ctx, int op, const double* params, int format, in
   else if (op == AFB_OP_ELASTODYNAMICS) {
     if (npc == 4 && dim == 3) return launch<Tet4Elastodynamics>(ctx, format, variant, layout, prm);
     if (npc == 3 && dim == 2) return launch<Tri3Elastodynamics>(ctx, format, variant, layout, prm);
+    if (npc == 4 && dim == 2) return launch<Quad4Elastodynamics>(ctx, format, variant, layout, prm);
+    if (npc == 8 && dim == 3) return launch<Hexa8Elastodynamics>(ctx, format, variant, layout, prm);
   }
   // mirrors BSRFormat::computeNbColumns returning 0 / testlab _checkCellType FATAL for
   // unsupported cell types (femutils/BSRFormat.cc:339-341, modules/testlab/FemModule.cc:688-699)

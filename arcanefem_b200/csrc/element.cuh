@@ -595,6 +595,44 @@ struct Q1Elasticity {
 using Quad4Elasticity = Q1Elasticity<2>;
 using Hexa8Elasticity = Q1Elasticity<3>;
 
+// elastodynamics on Quad4 / Hexa8 (modules/elastodynamics/ElementMatrixHexQuad.h): Q1 elasticity with (lambda, mu) = (c1, c2) plus
+// c0 * sum over the Gauss points of N_a N_b detJ on every component
+template <int DIM_>
+struct Q1Elastodynamics {
+  static constexpr int DIM = DIM_, NPC = DIM_ == 2 ? 4 : 8, B = DIM_, NG = 1 << DIM_;
+  Q1Elasticity<DIM_> e;
+  double c0;
+  __device__ void init(const double* __restrict__ coords, const int32_t (&nd)[NPC], const ElemParams& p)
+  {
+    ElemParams q = p;
+    q.p0 = p.p1;
+    q.p1 = p.p2;
+    e.init(coords, nd, q);
+    c0 = p.p0;
+  }
+  // shape function a at Gauss point g (same point order as Q1Elasticity::init)
+  __device__ __forceinline__ static double shape(int g, int a)
+  {
+    const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+    const double xi = gp[(g >> (DIM - 1)) & 1], eta = gp[(g >> (DIM - 2)) & 1], zeta = DIM == 3 ? gp[g & 1] : 0.0;
+    const double sx = ((a & 3) == 1 || (a & 3) == 2) ? 1.0 : -1.0, sy = (a & 2) ? 1.0 : -1.0, sz = (a & 4) ? 1.0 : -1.0;
+    return (DIM == 3 ? 0.125 * (1.0 + sz * zeta) : 0.25) * (1.0 + sx * xi) * (1.0 + sy * eta);
+  }
+  __device__ void block(int a, int b, double (&o)[DIM_ * DIM_]) const
+  {
+    e.block(a, b, o);
+    double m = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) m += shape(g, a) * shape(g, b) * e.w[g];
+    m *= c0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) o[i * DIM + i] += m;
+  }
+  __device__ __forceinline__ double measure() const { return e.meas; }
+};
+using Quad4Elastodynamics = Q1Elastodynamics<2>;
+using Hexa8Elastodynamics = Q1Elastodynamics<3>;
+
 // ---------------------------------------------------------------------------------------------
 // position of `col` in the ascending segment cols[lo,hi) (present by construction)
 __device__ __forceinline__ int find_col(const int32_t* __restrict__ cols, int lo, int hi, int32_t col)

@@ -64,7 +64,8 @@ enum {
   AFB_OP_DIFFUSION_REACTION = 3,
   /* params = { c0, c1, c2 }: the Newmark-beta / generalised-alpha matrix of the elastodynamics module (modules/elastodynamics/
    * ElementMatrix.h:41-60 Tria3, :150-196 Tetra4; coefficients FemModule.cc:197-225): the elasticity matrix with lambda = c1,
-   * mu = c2 plus c0 times the consistent mass on every component.  dim DoF/node, BSR; Tri3 / Tet4, cell-wise and node-wise variants. */
+   * mu = c2 plus c0 times the consistent mass on every component (ElementMatrixHexQuad.h for Quad4 / Hexa8: the same, per Gauss point).
+   * dim DoF/node, BSR; Tri3 / Tet4 / Quad4 / Hexa8, cell-wise and node-wise variants. */
   AFB_OP_ELASTODYNAMICS = 4
 };
 

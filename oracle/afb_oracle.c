@@ -726,6 +726,30 @@ static int element_matrix(int npc, int dim, int op, int form, const double* para
       for (int i = 0; i < 144; ++i) K[i] = M[i] + K[i];
       return 0;
     }
+    if ((npc == 4 && dim == 2) || (npc == 8 && dim == 3)) {
+      /* modules/elastodynamics/ElementMatrixHexQuad.h: per Gauss point c0 ((Nx^Nx) + (Ny^Ny) [+ (Nz^Nz)]) weight + the elasticity terms
+       * with (c1, c2); the elasticity part is ke_q1_elasticity, the mass part is summed here over the same 2x2(x2) rule */
+      const int n = npc, nd = n * dim;
+      const double gp[2] = { -0.57735026918962576451, 0.57735026918962576451 };
+      static const double sx[8] = { -1, 1, 1, -1, -1, 1, 1, -1 }, sy[8] = { -1, -1, 1, 1, -1, -1, 1, 1 }, sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+      double Mq[576];
+      for (int i = 0; i < nd * nd; ++i) Mq[i] = 0.0;
+      for (int ixi = 0; ixi < 2; ++ixi)
+        for (int ieta = 0; ieta < 2; ++ieta)
+          for (int izeta = 0; izeta < (dim == 3 ? 2 : 1); ++izeta) {
+            const double xi = gp[ixi], eta = gp[ieta], zeta = dim == 3 ? gp[izeta] : 0.0;
+            double dx[8], dy[8], dz[8], N[8];
+            const double w = q1_gradients(dim, m, xi, eta, zeta, dx, dy, dz);
+            for (int a = 0; a < n; ++a)
+              N[a] = dim == 2 ? 0.25 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta) : 0.125 * (1.0 + sx[a] * xi) * (1.0 + sy[a] * eta) * (1.0 + sz[a] * zeta);
+            for (int a = 0; a < n; ++a)
+              for (int b = 0; b < n; ++b)
+                for (int k = 0; k < dim; ++k) Mq[(a * dim + k) * nd + (b * dim + k)] += (c0 * (N[a] * N[b])) * w;
+          }
+      ke_q1_elasticity(dim, m, c1, c2, K);
+      for (int i = 0; i < nd * nd; ++i) K[i] = Mq[i] + K[i];
+      return 0;
+    }
     return -1;
   }
   return -1;

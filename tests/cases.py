@@ -202,7 +202,20 @@ ELASTODYNAMICS_CASES = {
     "bar_3D": dict(mesh="bar_dynamic_3D.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=0.5, f=[131.0e2, 113.8e6, 567.0e8],
                    dirichlet=[("surfaceleft", [0.0, 0.0, 0.0])], traction=[("surfaceright", [0.0, 1869.1e2, 0.0])], penalty=1.0e30,
                    golden="elastodynamics_bar_3d.txt"),
+    # Quad4 / Hexa8 (modules/elastodynamics/ElementMatrixHexQuad.h): inputs/bar.quad.arc, bar.3D.hexa.arc
+    "bar_quad": dict(mesh="bar_dynamic_quad.msh", rho=12.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 13.5e2],
+                     dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[], penalty=1.0e30, golden="elastodynamics_bar.quad.txt",
+                     min_rel=1.0e-8),  # one x-displacement on the symmetry line is 7e-9 against 15 elsewhere: pure cancellation, skipped
+    "bar_3D_hexa": dict(mesh="bar_dynamic_3Dhexa.msh", rho=1232434.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=0.5, f=[131.0e2, 113.8e6, 567.0e8],
+                        dirichlet=[("left", [0.0, 0.0, 0.0])], traction=[], penalty=1.0e30, golden="elastodynamics_bar_3d.hexa.txt", min_rel=1.0e-8),
 }
+
+
+def golden_floor(case, golden):
+    """smallest golden value compared: upstream's 1e-14, or `min_rel` times the largest golden value where a case has entries that are
+    zero up to cancellation"""
+    gmax = max(abs(v) for vals in golden.values() for v in vals)
+    return max(1.0e-14, case.get("min_rel", 0.0) * gmax)
 
 
 def newmark_coefficients(case):

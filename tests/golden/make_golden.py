@@ -102,6 +102,11 @@ FILES = {
     "meshes/msh/bar_dynamic.msh": "bar_dynamic.msh",
     "modules/elastodynamics/check/2D_elastodynamics_bar.txt": "elastodynamics_2D_bar.txt",
     "modules/elastodynamics/check/bar_3d.txt": "elastodynamics_bar_3d.txt",
+    # the same on Quad4 / Hexa8: inputs/bar.quad.arc, bar.3D.hexa.arc
+    "meshes/msh/bar_dynamic_quad.msh": "bar_dynamic_quad.msh",
+    "meshes/msh/bar_dynamic_3Dhexa.msh": "bar_dynamic_3Dhexa.msh",
+    "modules/elastodynamics/check/bar.quad.txt": "elastodynamics_bar.quad.txt",
+    "modules/elastodynamics/check/bar_3d.hexa.txt": "elastodynamics_bar_3d.hexa.txt",
 }
 
 if __name__ == "__main__":
