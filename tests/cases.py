@@ -253,6 +253,35 @@ def newmark_time_loop(case, nb_dof, solve_step, mass_times):
     return dU
 
 
+# Heat module (implicit Euler on lambda * stiffness + mass / dt; modules/heat/ElementMatrix.h:36, :107, ElementMatrixHexQuad.h;
+# inputs/conduction.arc, conduction.quad.arc, 3d_conduction.arc).  The golden files hold the temperature of the last step.
+HEAT_CASES = {
+    "plate_2D": dict(mesh="plate.msh", lam=1.75, dt=0.4, tmax=20.0, Tinit=30.0, dirichlet=[("left", 10.0)], penalty=1.0e31,
+                     golden="heat_2d_conduction.txt"),
+    "plate_2D_quad": dict(mesh="plate.quad.msh", lam=1.75, dt=0.4, tmax=20.0, Tinit=30.0, dirichlet=[("left", 10.0)], penalty=1.0e31,
+                          golden="heat_2d_conduction.quad.txt"),
+    "truncated_cube_3D": dict(mesh="truncated_cube.msh", lam=1.75, dt=0.1, tmax=1.0, Tinit=30.0,
+                              dirichlet=[("top", 100.6), ("bottom", 1.6)], penalty=1.0e30, golden="heat_3d_conduction.txt"),
+}
+
+
+def heat_time_loop(case, nb_node, solve_step, mass_times):
+    """The module's time loop (modules/heat/FemModule.cc:74-135, 232-245, 350-363): t starts at 0 and grows by dt after every solve; the
+    loop ends with the first step that starts at t >= tmax (that step is still solved, and checked against the golden file).
+    solve_step(rhs) -> temperature of the step (the caller sets the Dirichlet rows); mass_times(x) = consistent mass matrix times x.
+    The right-hand side of a step is the mass matrix applied to (previous temperature / dt)."""
+    dt, tmax = case["dt"], case["tmax"]
+    t = 0.0
+    T = np.full(nb_node, case["Tinit"])
+    while True:
+        last = t >= tmax
+        T = solve_step(mass_times(T * (1.0 / dt)))
+        t += dt
+        if last:
+            break
+    return T
+
+
 # modules/bilaplacian/inputs/direct.arc
 BILAPLACIAN_CASE = dict(mesh="bilap.msh", f=-786.25, dirichlet=[("boundary", [145.5, None])], penalty=1.0e30,
                         golden="bilaplacian_2d_test.txt")

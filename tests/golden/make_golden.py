@@ -102,6 +102,11 @@ FILES = {
     "meshes/msh/bar_dynamic.msh": "bar_dynamic.msh",
     "modules/elastodynamics/check/2D_elastodynamics_bar.txt": "elastodynamics_2D_bar.txt",
     "modules/elastodynamics/check/bar_3d.txt": "elastodynamics_bar_3d.txt",
+    # heat module (implicit Euler on lambda * stiffness + mass / dt): inputs/conduction.arc, 3d_conduction.arc, conduction.quad.arc
+    "meshes/msh/plate.msh": "plate.msh",
+    "modules/heat/check/2d_conduction.txt": "heat_2d_conduction.txt",
+    "modules/heat/check/3d_conduction.txt": "heat_3d_conduction.txt",
+    "modules/heat/check/2d_conduction.quad.txt": "heat_2d_conduction.quad.txt",
     # the same on Quad4 / Hexa8: inputs/bar.quad.arc, bar.3D.hexa.arc
     "meshes/msh/bar_dynamic_quad.msh": "bar_dynamic_quad.msh",
     "meshes/msh/bar_dynamic_3Dhexa.msh": "bar_dynamic_3Dhexa.msh",

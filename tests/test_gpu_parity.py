@@ -1250,6 +1250,35 @@ def test_elastodynamics_golden_solution(exec_ctx, name, variant):
     assert CS.compare_to_golden(m, u, golden, b, eps=1.0e-4, min_value=CS.golden_floor(case, golden), subset=True) < case.get("tol", 1.0e-5)
 
 
+@pytest.mark.parametrize("name", list(CS.HEAT_CASES))
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+def test_heat_golden_solution(exec_ctx, name, variant):
+    """the heat module's golden temperature files through its implicit Euler time loop: lambda * stiffness + mass / dt
+    (OP_DIFFUSION_REACTION) and the mass matrix of the right-hand side assembled on the GPU, penalty rows on the GPU, the per-step
+    solves on the host"""
+    c = exec_ctx
+    case = CS.HEAT_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(1)
+    c.assemble(A.OP_DIFFUSION_REACTION, params=[0.0, 1.0], fmt=A.FORMAT_BSR, variant=variant)
+    mass = sp.csr_matrix((c.to_host(A.ARRAY_VALUES).copy(), c.to_host(A.ARRAY_COLUMNS).copy(), c.to_host(A.ARRAY_ROWS).copy()))
+    c.reset_values()
+    c.assemble(A.OP_DIFFUSION_REACTION, params=[case["lam"], 1.0 / case["dt"]], fmt=A.FORMAT_BSR, variant=variant)
+    c.rhs_reset()
+    c.dirichlet_penalty(ids, g, case["penalty"])
+    rows, cols, vals = (c.to_host(w) for w in (A.ARRAY_ROWS, A.ARRAY_COLUMNS, A.ARRAY_VALUES))
+    lu = spla.splu(sp.csr_matrix((vals, cols, rows)).tocsc())
+
+    def solve_step(rhs):
+        rhs[ids] = case["penalty"] * np.asarray(g)
+        return lu.solve(rhs)
+
+    T = CS.heat_time_loop(case, m.nb_node, solve_step, lambda x: mass @ x)
+    assert CS.compare_to_golden(m, T, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True) < case.get("tol", 1.0e-7)
+
+
 @pytest.mark.parametrize("name", list(CS.ACOUSTICS_CASES))
 @pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
 def test_acoustics_golden_solution(exec_ctx, name, variant):

@@ -265,6 +265,30 @@ def test_elastodynamics_golden(name, nodewise):
     assert d.max() <= 1e-12 * abs(A).max()
 
 
+@pytest.mark.parametrize("name", list(CS.HEAT_CASES))
+@pytest.mark.parametrize("nodewise", [False, True], ids=["bsr", "af-bsr"])
+def test_heat_golden(name, nodewise):
+    """lambda * stiffness + mass / dt (OP_DIFFUSION_REACTION) through the heat module's implicit Euler time loop, against its own golden
+    temperature files (modules/heat/check/2d_conduction.txt, 2d_conduction.quad.txt, 3d_conduction.txt)"""
+    case = CS.HEAT_CASES[name]
+    m = _load(case)
+    rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_DIFFUSION_REACTION, form=O.FORM_BSR, params=[case["lam"], 1.0 / case["dt"]], nodewise=nodewise)
+    mass = _csr(rows, cols, O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_DIFFUSION_REACTION, form=O.FORM_BSR, params=[0.0, 1.0]))
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    lhs = vals.copy()
+    O.dirichlet_penalty(rows, cols, lhs, np.zeros(m.nb_node), ids, g, case["penalty"])
+    lu = spla.splu(_csr(rows, cols, lhs).tocsc())
+
+    def solve_step(rhs):
+        rhs[ids] = case["penalty"] * np.asarray(g)
+        return lu.solve(rhs)
+
+    T = CS.heat_time_loop(case, m.nb_node, solve_step, lambda x: mass @ x)
+    worst = CS.compare_to_golden(m, T, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True)
+    assert worst < case.get("tol", 1.0e-7)
+
+
 def test_elasticity_per_block_layout_equals_per_row():
     case = CS.ELASTICITY_CASES["bar_3D"]
     m, b, rows, cols, v_row, *_ = _elasticity_system(case, O.LAYOUT_PER_ROW, False)
