@@ -35,6 +35,8 @@ _ARRAY_DTYPE = {ARRAY_ROWS: np.int32, ARRAY_COLUMNS: np.int32, ARRAY_VALUES: np.
                 ARRAY_COO_ROWS: np.int32, ARRAY_CSR_ROWS: np.int32, ARRAY_CSR_COLUMNS: np.int32, ARRAY_CSR_NB_COLUMN: np.int32,
                 ARRAY_COORDS: np.float64, ARRAY_CELL_NODES: np.int32, ARRAY_NODE_CELL_PTR: np.int32, ARRAY_NODE_CELL_LIST: np.int32}
 
+MSH_GROUP_POINTS, MSH_GROUP_FACES, MSH_GROUP_CELLS = 0, 1, 2   # afb_msh_group kinds
+
 EXPORTS = [
     "afb_create", "afb_destroy", "afb_last_error", "afb_version", "afb_set_stream", "afb_synchronize", "afb_set_mesh", "afb_update_coordinates", "afb_set_own_cell_count", "afb_set_cell_coefficient", "afb_get_own_cell_count", "afb_renumber_columns", "afb_get_ij_arrays", "afb_memcpy_to_host", "afb_mesh_generate_box",
     "afb_build_pattern", "afb_set_sparsity_algorithm", "afb_set_tiled_executor", "afb_set_vector_executor", "afb_set_tiled_stage_limit", "afb_options_from_name", "afb_reset_values", "afb_assemble_bilinear", "afb_rhs_reset", "afb_assemble_rhs_source", "afb_assemble_rhs_neumann", "afb_set_dirichlet_nodes",
@@ -42,6 +44,7 @@ EXPORTS = [
     "afb_apply_rhs_transformation", "afb_matrix_get_value", "afb_matrix_set_value", "afb_get_csr_view", "afb_get_bsr", "afb_get_coo", "afb_get_rhs", "afb_get_mesh", "afb_copy_to_host",
     "afb_lookup_value_slots", "afb_add_values_at", "afb_values_tail",
     "afb_p2p_export", "afb_p2p_connect", "afb_p2p_exchange", "afb_p2p_exchange_async", "afb_p2p_wait", "afb_p2p_status", "afb_p2p_wait_stats", "afb_p2p_disconnect", "afb_partition_create", "afb_partition_destroy", "afb_partition_sizes", "afb_partition_get",
+    "afb_msh_read", "afb_msh_destroy", "afb_msh_sizes", "afb_msh_get", "afb_msh_group", "afb_msh_group_get",
     "afb_xplan_host_create", "afb_xplan_host_destroy", "afb_xplan_host_peers", "afb_xplan_host_pairs", "afb_xplan_host_numbering",
     "afb_xplan_create", "afb_xplan_destroy", "afb_xplan_exchange", "afb_xplan_wait", "afb_xplan_numbering", "afb_xplan_info", "afb_solve_pcg", "afb_last_timings", "afb_inspector_timings", "afb_launch_count",
 ]

@@ -12,6 +12,7 @@ entity carries that physical name (modules/testlab/FemModule.cc:657-663).
 """
 from __future__ import annotations
 
+import os
 import struct
 from dataclasses import dataclass, field
 
@@ -188,6 +189,43 @@ def read_msh(path: str) -> Mesh:
                 pts = tag2lid(a[:, 1:]).astype(np.int32).ravel()
                 groups[name] = np.unique(np.concatenate([groups.get(name, np.empty(0, np.int32)), pts])).astype(np.int32)
     return Mesh(dim=dim, coords=coords, cells=np.ascontiguousarray(cells), node_uid=uid.astype(np.int64), groups=groups, faces=faces, cell_groups=cell_groups)
+
+
+def read_msh_native(path: str) -> Mesh:
+    """The same mesh through the C ABI's reader (`afb_msh_*`, csrc/mesh_io.cu: Gmsh 4.1 binary and ASCII) -- what a C++ host links."""
+    import ctypes as C
+
+    from . import capi as A
+    lib = A.lib()
+    h = C.c_void_p()
+    A._check(lib.afb_msh_read(os.fsencode(path), C.byref(h)))
+    try:
+        dim, npc, nn, ng = C.c_int(), C.c_int(), C.c_int32(), C.c_int32()
+        nc = C.c_int64()
+        A._check(lib.afb_msh_sizes(h, C.byref(dim), C.byref(npc), C.byref(nn), C.byref(nc), C.byref(ng)))
+        coords = np.empty((nn.value, 3), dtype=np.float64)
+        cells = np.empty((nc.value, npc.value), dtype=np.int32)
+        uid = np.empty(nn.value, dtype=np.int64)
+        A._check(lib.afb_msh_get(h, A._ptr(coords), A._ptr(cells), A._ptr(uid)))
+        groups, faces, cell_groups = {}, {}, {}
+        for g in range(ng.value):
+            name, kind, npi = C.c_char_p(), C.c_int(), C.c_int()
+            n_item, n_node = C.c_int64(), C.c_int64()
+            A._check(lib.afb_msh_group(h, g, C.byref(name), C.byref(kind), C.byref(n_item), C.byref(npi), C.byref(n_node)))
+            items = np.empty((n_item.value, npi.value), dtype=np.int32)
+            nodes = np.empty(n_node.value, dtype=np.int32)
+            A._check(lib.afb_msh_group_get(h, g, A._ptr(items), A._ptr(nodes)))
+            key = name.value.decode()
+            if kind.value == A.MSH_GROUP_CELLS:
+                cell_groups[key] = items.ravel()
+            elif kind.value == A.MSH_GROUP_FACES:
+                faces[key] = items
+                groups[key] = nodes
+            else:
+                groups[key] = nodes
+    finally:
+        lib.afb_msh_destroy(h)
+    return Mesh(dim=dim.value, coords=coords, cells=cells, node_uid=uid, groups=groups, faces=faces, cell_groups=cell_groups)
 
 
 def orient_boundary_faces(mesh: Mesh, faces: np.ndarray) -> np.ndarray:

@@ -510,6 +510,28 @@ typedef struct afb_transport {
 } afb_transport;
 
 /*
+ * Mesh ingestion: Gmsh 4.1 files, binary or ASCII (host only, no context needed).  Stands in for Arcane's MshMeshReader, which every
+ * .arc file of the reference selects through `<filename>meshes/....msh</filename>` (e.g. modules/testlab/inputs/Test.L-shape.2D.arc:17-21),
+ * with the conventions the assembly path and the golden solution files rely on: node uniqueId = gmsh node tag, local id = rank of
+ * the tag; cells = the elements of the highest dimension (one type per mesh), ordered by element tag; groups by physical name:
+ * surfaces (`<surface>`: (dim-1) elements, plus their node group as modules/testlab/FemModule.cc:657-663 takes it), volumes
+ * (`<material-property><volume>`) and points (`<dirichlet-point><node>`).  AFB_ERR_INVALID with the byte offset in afb_last_error
+ * for anything malformed or truncated.
+ */
+enum { AFB_MSH_GROUP_POINTS = 0, AFB_MSH_GROUP_FACES = 1, AFB_MSH_GROUP_CELLS = 2 };
+typedef struct afb_msh afb_msh;
+AFB_API int afb_msh_read(const char* path, afb_msh** out);
+AFB_API int afb_msh_destroy(afb_msh* m);
+AFB_API int afb_msh_sizes(const afb_msh* m, int* dim, int* nodes_per_cell, int32_t* nb_node, int64_t* nb_cell, int32_t* nb_group);
+/* arrays in afb_set_mesh's layout (any pointer may be NULL): xyz [nb_node*3], cell_nodes [nb_cell*nodes_per_cell] local ids, node_uid [nb_node] */
+AFB_API int afb_msh_get(const afb_msh* m, double* xyz, int32_t* cell_nodes, int64_t* node_uid);
+/* group g: name (owned by the mesh), kind (AFB_MSH_GROUP_*), items (faces / cells / points), nodes per item (faces), size of its node group (0 for cells) */
+AFB_API int afb_msh_group(const afb_msh* m, int32_t g, const char** name, int* kind, int64_t* nb_item, int* nodes_per_item, int64_t* nb_group_node);
+/* items: faces [nb_item*nodes_per_item] node ids in file order (afb_assemble_rhs_neumann's input), cells / points [nb_item] ascending ids;
+ * nodes: the group's nodes, ascending (afb_set_dirichlet_nodes' input) */
+AFB_API int afb_msh_group_get(const afb_msh* m, int32_t g, int32_t* items, int32_t* nodes);
+
+/*
  * Partition of a global mesh into `world` sub-domains by recursive coordinate bisection of the cell centroids (what the
  * reference asks of Arcane's partitioner; structured boxes come out as slabs / bricks).  Semantics of an Arcane sub-domain
  * as ArcaneFEM sees it: own cells + one layer of ghost cells, every node has exactly one owner (the lowest rank among the

@@ -301,3 +301,39 @@ def test_user_kernel_over_the_device_view(view_kernel, n):
     every entry walked once; DoFLinearSystem::matrixGetValue / matrixAddValue / matrixSetValue agree with what the kernel read."""
     r = subprocess.run([view_kernel, str(n)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "view ok" in r.stdout, r.stdout + r.stderr
+
+
+# ---- a host without Arcane and without Python: mesh file -> golden solution (tests/cpp/msh_driver.cpp over afb_msh_*) ------------
+
+@pytest.fixture(scope="module")
+def msh_driver(tmp_path_factory):
+    if not os.path.exists(os.path.join(LIBDIR, "libafb200.so")):
+        pytest.skip("libafb200.so not built")
+    out = str(tmp_path_factory.mktemp("cpp") / "msh_driver")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "msh_driver.cpp"), "-o", out,
+                    "-L" + LIBDIR, "-lafb200", "-Wl,-rpath," + LIBDIR], check=True)
+    return out
+
+
+def test_msh_driver_reads_the_reference_meshes_on_the_host(msh_driver):
+    """CPU: the reader needs neither a GPU nor a context"""
+    from tests import cases as CS
+    r = subprocess.run([msh_driver, "info", os.path.join(CS.GOLDEN, "L-shape.msh")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mesh dim=2 npc=3 nodes=151 cells=254" in r.stdout and "group boundary kind=1" in r.stdout
+    r = subprocess.run([msh_driver, "info", os.path.join(CS.GOLDEN, "missing.msh")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "cannot open" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["L-shape_2D", "L-shape_3D", "sphere_3D"])
+def test_msh_driver_file_to_golden_solution(msh_driver, name):
+    """the testlab Poisson cases from the mesh file alone, in C++: afb_msh_* -> afb_set_mesh -> tiled assembly -> penalty -> PCG,
+    compared inside the driver with the reference's golden solution file"""
+    from tests import cases as CS
+    case = CS.POISSON_CASES[name]
+    args = [msh_driver, "solve", os.path.join(CS.GOLDEN, case["mesh"]), repr(case["f"]), repr(case["penalty"]), os.path.join(CS.GOLDEN, case["golden"])]
+    for group, value in case["dirichlet"]:
+        args += [group, repr(value)]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "golden ok" in r.stdout, r.stdout + r.stderr

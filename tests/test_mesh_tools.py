@@ -151,3 +151,110 @@ def test_refined_fixture_through_the_cuda_path(name):
             got = ctx.to_host(A.ARRAY_VALUES)
             err = np.abs(got - ref) / np.maximum(np.maximum(np.abs(got), np.abs(ref)), rowmax)
             assert err.max() <= 1e-12, (variant, err.max())
+
+
+# ---- the C ABI's Gmsh reader (afb_msh_*, csrc/mesh_io.cu): host-only, so checked on the CPU -------------------------------------
+
+ALL_MSH = sorted(f for f in os.listdir(CS.GOLDEN) if f.endswith(".msh"))
+
+
+def _same_mesh(a, b):
+    assert a.dim == b.dim
+    assert np.array_equal(a.node_uid, b.node_uid)
+    assert np.array_equal(a.coords, b.coords)          # bit-exact: the same doubles, reordered the same way
+    assert np.array_equal(a.cells, b.cells) and a.cells.dtype == b.cells.dtype
+    for attr in ("groups", "faces", "cell_groups"):
+        da, db = getattr(a, attr), getattr(b, attr)
+        assert sorted(da) == sorted(db), attr
+        for k in da:
+            assert np.array_equal(da[k], db[k]), (attr, k)
+
+
+@pytest.mark.parametrize("name", ALL_MSH)
+def test_native_msh_reader_matches_on_every_reference_fixture(name):
+    """every mesh file of the reference this repo carries (binary msh 4.1; Tri3, Quad4, Tet4, Hexa8; surfaces, volumes, named points):
+    nodes, cells and all groups identical to the Python reader the golden-solution tests are pinned with"""
+    path = os.path.join(CS.GOLDEN, name)
+    _same_mesh(M.read_msh_native(path), M.read_msh(path))
+
+
+_ASCII_MSH = """$MeshFormat
+4.1 0 8
+$EndMeshFormat
+$PhysicalNames
+3
+0 7 "corner"
+1 5 "left"
+2 9 "plate"
+$EndPhysicalNames
+$Entities
+1 1 1 0
+1 0 0 0 1 7
+1 0 0 0 0 1 0 1 5 2 1 -1
+1 0 0 0 1 1 0 1 9 1 1
+$EndEntities
+$Comment
+a section the path does not use, with a $ in it
+$EndComment
+$Nodes
+2 4 1 40
+0 1 0 1
+30
+0 0 0
+2 1 0 3
+40
+10
+20
+1 1 0
+1 0 0
+0 1 0
+$EndNodes
+$Elements
+3 4 1 4
+0 1 15 1
+1 30
+1 1 1 1
+2 30 20
+2 1 2 2
+4 10 20 40
+3 30 10 20
+$EndElements
+"""
+
+
+def test_native_msh_reader_ascii(tmp_path):
+    """the ASCII flavour of msh 4.1, node tags out of order, cells out of tag order, an unknown section in between"""
+    p = tmp_path / "tiny.msh"
+    p.write_text(_ASCII_MSH)
+    m = M.read_msh_native(str(p))
+    assert (m.dim, m.nb_node, m.nb_cell, m.npc) == (2, 4, 2, 3)
+    assert m.node_uid.tolist() == [10, 20, 30, 40]
+    assert m.coords.tolist() == [[1, 0, 0], [0, 1, 0], [0, 0, 0], [1, 1, 0]]
+    assert m.cells.tolist() == [[2, 0, 1], [0, 1, 3]]                   # element tags 3, 4 -> local node ids
+    assert m.faces["left"].tolist() == [[2, 1]] and m.groups["left"].tolist() == [1, 2]
+    assert m.groups["corner"].tolist() == [2]
+    assert m.cell_groups["plate"].tolist() == [0, 1]
+
+
+def test_native_msh_reader_rejects_bad_files(tmp_path):
+    from arcanefem_b200 import capi as A
+    with pytest.raises(A.AfbError, match="cannot open"):
+        M.read_msh_native(str(tmp_path / "missing.msh"))
+    data = open(os.path.join(CS.GOLDEN, "L-shape.msh"), "rb").read()
+    for cut in (len(data) // 3, len(data) // 2, len(data) - 20):        # truncated inside a binary section / before the end tag
+        p = tmp_path / f"cut{cut}.msh"
+        p.write_bytes(data[:cut])
+        with pytest.raises(A.AfbError, match="afb_msh_read"):
+            M.read_msh_native(str(p))
+    p = tmp_path / "v2.msh"
+    p.write_text("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n")
+    with pytest.raises(A.AfbError, match="4.1"):
+        M.read_msh_native(str(p))
+    p = tmp_path / "dangling.msh"
+    p.write_text(_ASCII_MSH.replace("4 10 20 40", "4 10 20 99"))
+    with pytest.raises(A.AfbError, match="node tag 99"):
+        M.read_msh_native(str(p))
+    p = tmp_path / "text.msh"
+    p.write_text("hello\n")
+    with pytest.raises(A.AfbError, match="not a msh file"):
+        M.read_msh_native(str(p))
