@@ -75,6 +75,24 @@ Q1_CASES.update({
                                        dirichlet=[("topLeftCorner", 50.0), ("topRightCorner", 20.0), ("botLeftCorner", 20.0), ("botRightCorner", 50.0)]),
 })
 
+# Aerodynamics module (potential flow around an airfoil / an airplane: the Poisson matrix, no source; Dirichlet rows by penalty first,
+# then the far-field condition psi = y - angle * x (2-D) / z - angle * x (3-D) on the outer boundary, which overwrites them where the
+# groups meet: modules/aerodynamics/FemModule.cc:225-252; inputs/Joukowski.arc, Joukowski.quad.arc, Joukowski_3d.arc, Joukowski_3d.hexa.arc)
+def _farfield(dim, angle=0.1):
+    return lambda x: x[dim - 1] - angle * x[0]
+
+
+Q1_CASES.update({
+    "aerodynamics_2D": dict(mesh="NACA0012.msh", f=0.0, penalty=1.0e30, golden="aerodynamics_test_2d.txt",
+                            dirichlet=[("upperAirfoil", 0.0), ("lowerAirfoil", 0.0), ("FarField", _farfield(2))]),
+    "aerodynamics_2D_quad": dict(mesh="NACA0012.quad.msh", f=0.0, penalty=1.0e30, golden="aerodynamics_test_2d.quad.txt",
+                                 dirichlet=[("upperAirfoil", 0.0), ("lowerAirfoil", 0.0), ("FarField", _farfield(2))]),
+    "aerodynamics_3D": dict(mesh="aerodynamics_3d_coarse.msh", f=0.0, penalty=1.0e30, golden="aerodynamics_test_3d.txt",
+                            dirichlet=[("airplane", 0.0), ("outer", _farfield(3))]),
+    "aerodynamics_3D_hexa": dict(mesh="aerodynamics_3d_coarse.hexa.msh", f=0.0, penalty=1.0e30, golden="aerodynamics_test_3d.hexa.txt",
+                                 dirichlet=[("inner", 0.0), ("outer", _farfield(3))]),
+})
+
 # more of the same operator on other meshes and boundary data: modules/poisson/inputs/cube.3D.hexa.arc (source + flux over Quad4
 # faces), modules/laplace/inputs/truncated-cube.3D.arc (face and point Dirichlet on Tet4), the electrostatics module (rho = 0,
 # epsilon = 1: the same stiffness matrix; inputs/box-rods.arc, box-rods.quad.arc, rod-circle.arc, truncated_cube.hexa.arc)
@@ -312,6 +330,10 @@ def dirichlet_dofs(mesh, dirichlet, b):
     modules/testlab/FemModule.cc:647-677).  Returns (dof_ids, values) sorted by dof."""
     val = {}
     for name, v in dirichlet:
+        if callable(v):  # a value per node (far-field condition of the aerodynamics module)
+            for node in mesh.groups[name]:
+                val[int(node) * b] = float(v(mesh.coords[node]))
+            continue
         vs = [v] if b == 1 and not isinstance(v, (list, tuple)) else list(v)
         for node in mesh.groups[name]:
             for k, x in enumerate(vs):

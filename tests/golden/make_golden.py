@@ -102,6 +102,16 @@ FILES = {
     "meshes/msh/bar_dynamic.msh": "bar_dynamic.msh",
     "modules/elastodynamics/check/2D_elastodynamics_bar.txt": "elastodynamics_2D_bar.txt",
     "modules/elastodynamics/check/bar_3d.txt": "elastodynamics_bar_3d.txt",
+    # aerodynamics module (potential flow: the Poisson matrix with a far-field penalty condition psi = y - angle * x (z - angle * x in 3-D),
+    # modules/aerodynamics/FemModule.cc:236-252; inputs/Joukowski.arc, Joukowski.quad.arc, Joukowski_3d.arc, Joukowski_3d.hexa.arc)
+    "meshes/msh/NACA0012.msh": "NACA0012.msh",
+    "meshes/msh/NACA0012.quad.msh": "NACA0012.quad.msh",
+    "meshes/msh/aerodynamics_3d_coarse.msh": "aerodynamics_3d_coarse.msh",
+    "meshes/msh/aerodynamics_3d_coarse.hexa.msh": "aerodynamics_3d_coarse.hexa.msh",
+    "modules/aerodynamics/check/test_2d.txt": "aerodynamics_test_2d.txt",
+    "modules/aerodynamics/check/test_2d.quad.txt": "aerodynamics_test_2d.quad.txt",
+    "modules/aerodynamics/check/test_3d.txt": "aerodynamics_test_3d.txt",
+    "modules/aerodynamics/check/test_3d.hexa.txt": "aerodynamics_test_3d.hexa.txt",
     # heat module (implicit Euler on lambda * stiffness + mass / dt): inputs/conduction.arc, 3d_conduction.arc, conduction.quad.arc
     "meshes/msh/plate.msh": "plate.msh",
     "modules/heat/check/2d_conduction.txt": "heat_2d_conduction.txt",
