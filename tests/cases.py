@@ -300,6 +300,32 @@ def heat_time_loop(case, nb_node, solve_step, mass_times):
     return T
 
 
+# FourierNL module: -div(lambda(u) grad u) = 0 with lambda(u) = (1 + u)^m, solved by Picard iterations; on Tri3 / Tet4 the conductivity of a
+# cell is lambda at the mean of its nodal values of the previous iterate (modules/fouriernl/ElementMatrix.h:29-41, ConductivityCoefficient.h:16),
+# i.e. the Poisson operator with a per-cell coefficient re-assembled every iteration (inputs/Test.nonlinear.conduction.arc,
+# Test.3d.nonlinear.conduction.arc; defaults of Fem.axl: m = 2, nlin-rtol 1e-5, at most 30 iterations).  The module's Quad4 / Hexa8 matrices take
+# lambda at the Gauss points from a nodal field -- a different operator, not covered.
+FOURIERNL_CASES = {
+    "unit_square_tria": dict(mesh="unit_square.msh", m=2.0, rtol=1.0e-5, max_iters=30, dirichlet=[("left", 0.0), ("right", 1.0)], penalty=1.0e30,
+                             golden="fouriernl_conduction_tria.txt"),
+    "unit_cube_tetra": dict(mesh="unit_cube.msh", m=2.0, rtol=1.0e-5, max_iters=30, dirichlet=[("left", 0.0), ("right", 1.0)], penalty=1.0e30,
+                            golden="fouriernl_conduction_tetra.txt"),
+}
+
+
+def picard_loop(case, mesh, solve_with_conductivity):
+    """modules/fouriernl/FemModule.cc:155-210, 466-492: u_k starts at zero; every iteration assembles with lambda((mean of u_k over the cell)),
+    solves, and stops when max |u - u_k| < nlin-rtol.  solve_with_conductivity(lambda_per_cell) -> u.  Returns (u, iterations)."""
+    uk = np.zeros(mesh.nb_node)
+    for it in range(1, case["max_iters"] + 1):
+        lam = (1.0 + uk[mesh.cells.astype(np.int64)].sum(axis=1) / mesh.npc) ** case["m"]
+        u = solve_with_conductivity(lam)
+        if np.abs(u - uk).max() < case["rtol"]:
+            return u, it
+        uk = u
+    raise AssertionError("Picard iterations did not converge")
+
+
 # modules/bilaplacian/inputs/direct.arc
 BILAPLACIAN_CASE = dict(mesh="bilap.msh", f=-786.25, dirichlet=[("boundary", [145.5, None])], penalty=1.0e30,
                         golden="bilaplacian_2d_test.txt")

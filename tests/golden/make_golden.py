@@ -112,6 +112,12 @@ FILES = {
     "modules/aerodynamics/check/test_2d.quad.txt": "aerodynamics_test_2d.quad.txt",
     "modules/aerodynamics/check/test_3d.txt": "aerodynamics_test_3d.txt",
     "modules/aerodynamics/check/test_3d.hexa.txt": "aerodynamics_test_3d.hexa.txt",
+    # fouriernl module (Picard iterations on lambda(u) = (1 + u)^m, lambda taken at the cell mean on Tri3 / Tet4: modules/fouriernl/ElementMatrix.h:29-41;
+    # inputs/Test.nonlinear.conduction.arc, Test.3d.nonlinear.conduction.arc)
+    "meshes/msh/unit_square.msh": "unit_square.msh",
+    "meshes/msh/unit_cube.msh": "unit_cube.msh",
+    "modules/fouriernl/check/conduction_tria.txt": "fouriernl_conduction_tria.txt",
+    "modules/fouriernl/check/conduction_tetra.txt": "fouriernl_conduction_tetra.txt",
     # heat module (implicit Euler on lambda * stiffness + mass / dt): inputs/conduction.arc, 3d_conduction.arc, conduction.quad.arc
     "meshes/msh/plate.msh": "plate.msh",
     "modules/heat/check/2d_conduction.txt": "heat_2d_conduction.txt",

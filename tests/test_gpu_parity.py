@@ -1279,6 +1279,38 @@ def test_heat_golden_solution(exec_ctx, name, variant):
     assert CS.compare_to_golden(m, T, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True) < case.get("tol", 1.0e-7)
 
 
+@pytest.mark.parametrize("name", list(CS.FOURIERNL_CASES))
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+def test_fouriernl_golden_solution(exec_ctx, name, variant):
+    """the FourierNL module's Picard loop with everything but the update of the conductivity on the device: per iteration the values are
+    reset, the Poisson operator is re-assembled with the new per-cell conductivity on the unchanged pattern, the penalty rows are set and
+    the system is solved by the PCG stand-in; the converged temperature against the module's golden files"""
+    c = exec_ctx
+    case = CS.FOURIERNL_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(1)
+    launches = []
+
+    def solve(lam):
+        n0 = c.launch_count()
+        c.reset_values()
+        c.set_cell_coefficient(lam)
+        c.assemble(A.OP_POISSON, fmt=A.FORMAT_BSR, variant=variant)
+        c.rhs_reset()
+        c.dirichlet_penalty(ids, g, case["penalty"])
+        u, it, _ = c.solve_pcg(rtol=1e-13, max_iter=20000)
+        assert 0 < it < 20000
+        launches.append(c.launch_count() - n0)
+        return u.copy()
+
+    u, iters = CS.picard_loop(case, m, solve)
+    c.set_cell_coefficient(None)
+    assert 2 < iters < case["max_iters"] and min(launches) > 0
+    assert CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True) < 1.0e-4
+
+
 @pytest.mark.parametrize("name", list(CS.ACOUSTICS_CASES))
 @pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
 def test_acoustics_golden_solution(exec_ctx, name, variant):

@@ -289,6 +289,27 @@ def test_heat_golden(name, nodewise):
     assert worst < case.get("tol", 1.0e-7)
 
 
+@pytest.mark.parametrize("name", list(CS.FOURIERNL_CASES))
+@pytest.mark.parametrize("nodewise", [False, True], ids=["bsr", "af-bsr"])
+def test_fouriernl_golden(name, nodewise):
+    """Poisson operator with a per-cell conductivity re-assembled in every Picard iteration of the FourierNL module, against its golden files"""
+    case = CS.FOURIERNL_CASES[name]
+    m = _load(case)
+    rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
+
+    def solve(lam):
+        vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=O.FORM_BSR, nodewise=nodewise, cell_coef=lam)
+        rhs = np.zeros(m.nb_node)
+        O.dirichlet_penalty(rows, cols, vals, rhs, ids, g, case["penalty"])
+        return spla.spsolve(_csr(rows, cols, vals).tocsc(), rhs)
+
+    u, iters = CS.picard_loop(case, m, solve)
+    assert 2 < iters < case["max_iters"]
+    worst = CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True)
+    assert worst < 1.0e-4   # (the golden file is a converged Picard iterate at nlin-rtol 1e-5, not an exact solve)
+
+
 def test_elasticity_per_block_layout_equals_per_row():
     case = CS.ELASTICITY_CASES["bar_3D"]
     m, b, rows, cols, v_row, *_ = _elasticity_system(case, O.LAYOUT_PER_ROW, False)
