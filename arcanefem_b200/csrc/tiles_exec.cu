@@ -35,7 +35,7 @@ namespace afb {
 template <int NPC> struct OffDiagK;
 template <> struct OffDiagK<4> {
   static constexpr int N = 6;
-  __device__ static __forceinline__ void compute(const double* __restrict__ cx, uint2 ln, const ElemParams&, double (&K)[6])
+  template <bool COEF = false> __device__ static __forceinline__ void compute(const double* __restrict__ cx, uint2 ln, const ElemParams&, double (&K)[6], double coef = 1.0)
   {
     const double* p0 = cx + 3 * (ln.x & 0xFFFFu);
     const double* p1 = cx + 3 * (ln.x >> 16);
@@ -43,19 +43,21 @@ template <> struct OffDiagK<4> {
     const double* p3 = cx + 3 * (ln.y >> 16);
     Tet4Geom g;
     g.init_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+    if (COEF) g.s *= coef; // as the cell-wise kernel scales it (element.cuh: g.s *= p.scale)
     K[0] = g.dot(0, 1) * g.s; K[1] = g.dot(0, 2) * g.s; K[2] = g.dot(0, 3) * g.s;
     K[3] = g.dot(1, 2) * g.s; K[4] = g.dot(1, 3) * g.s; K[5] = g.dot(2, 3) * g.s;
   }
 };
 template <> struct OffDiagK<3> {
   static constexpr int N = 3;
-  __device__ static __forceinline__ void compute(const double* __restrict__ cx, uint2 ln, const ElemParams& prm, double (&K)[6])
+  template <bool COEF = false> __device__ static __forceinline__ void compute(const double* __restrict__ cx, uint2 ln, const ElemParams& prm, double (&K)[6], double coef = 1.0)
   {
     const double* p0 = cx + 3 * (ln.x & 0xFFFFu);
     const double* p1 = cx + 3 * (ln.x >> 16);
     const double* p2 = cx + 3 * (ln.y & 0xFFFFu);
     Tri3Geom g;
     g.init_xy(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], (prm.flags & AFB_FLAG_SIGNED_TRI_AREA) != 0);
+    if (COEF) g.s *= coef;
     K[0] = g.dot(0, 1) * g.s; K[1] = g.dot(0, 2) * g.s; K[2] = g.dot(1, 2) * g.s;
     K[3] = K[4] = K[5] = 0.0;
   }
@@ -97,6 +99,7 @@ struct TilePrefetch {
   int32_t fidx, node;     // level-1 indices (footprint node, row node) of the tile after that
   uint32_t em[TG_UPW];    // entry map words of this warp's units (scalar executor)
   uint2 unit;             // unit record `threadIdx.x` (row-ordered vector executor)
+  int32_t cid[TG_PF_ROUNDS]; // global ids of this thread's cells (scalar executor with a per-cell coefficient)
 };
 
 struct ExecArgs {
@@ -117,6 +120,8 @@ struct ExecArgs {
   double* values;
   int accumulate;
   int list_stage_max; // tiles with more 16-bit list slots read their lists from global memory (<= the staging buffer)
+  const int32_t* tile_cells; // global ids of the tiles' cells and the per-cell multiplier they index (afb_set_cell_coefficient):
+  const double* cell_coef;   // read by the _coef instantiation of the scalar executor only
 };
 
 // The next tiles' inputs travel in two waves so that no warp ever waits on a dependent load:
@@ -129,7 +134,7 @@ __device__ __forceinline__ void prefetch_level1(const TileDesc& d, const ExecArg
   if ((int)threadIdx.x < d.nb_row) pf.node = __ldg(A.tile_nodes + d.node_off + threadIdx.x);
 }
 
-template <int ROUNDS, int THREADS, bool EMAP = false>
+template <int ROUNDS, int THREADS, bool EMAP = false, bool COEF = false>
 __device__ __forceinline__ void prefetch_level2(const TileDesc& d, const ExecArgs& A, TilePrefetch& pf)
 {
   if constexpr (EMAP) {
@@ -150,6 +155,8 @@ __device__ __forceinline__ void prefetch_level2(const TileDesc& d, const ExecArg
   for (int r = 0; r < ROUNDS; ++r) {
     const int lc = min(r * THREADS + (int)threadIdx.x, d.nb_cell - 1);
     if (d.nb_cell > 0) pf.ln[r] = __ldg(reinterpret_cast<const uint2*>(A.lconn) + d.cell_off + lc);
+    if constexpr (COEF)
+      if (d.nb_cell > 0) pf.cid[r] = __ldg(A.tile_cells + d.cell_off + lc);
   }
   if ((int)threadIdx.x < d.nb_unit) {
     pf.ubase = __ldg(A.unit_base + d.unit_off + threadIdx.x);
@@ -198,8 +205,8 @@ __device__ __forceinline__ void stage_rows(SM& S, const TileDesc& d, const TileP
   else if ((int)threadIdx.x == d.nb_row) S.rowinfo[threadIdx.x] = pack_rowinfo(d.nb_entry, 0, false);
 }
 
-template <int NPC>
-__global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs A, ElemParams prm)
+template <int NPC, bool COEF>
+__device__ __forceinline__ void assemble_tiled_body(const ExecArgs& A, const ElemParams& prm)
 {
   extern __shared__ __align__(16) unsigned char ex_raw[];
   ExecSmem& S = *reinterpret_cast<ExecSmem*>(ex_raw);
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
 #endif
   if (t < A.nb_tile) {
     prefetch_level1(S.desc[0], A, pf);
-    prefetch_level2<TG_ROUNDS, TG_THREADS, true>(S.desc[0], A, pf); // the only exposed dependent load of the kernel
+    prefetch_level2<TG_ROUNDS, TG_THREADS, true, COEF>(S.desc[0], A, pf); // the only exposed dependent load of the kernel
     if ((int64_t)t + gridDim.x < A.nb_tile) prefetch_level1(S.desc[1], A, pf);
     stage_early(S, S.desc[0], pf);
   }
@@ -252,6 +259,11 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
                    : "memory");
     }
     // ---- phase A: off-diagonal element-matrix values of the tile's cells, once each ----
+    double cf[COEF ? TG_ROUNDS : 1]; // (the cells' ids came with the level-2 wave: one exposed load per tile, all rounds in flight together)
+    if constexpr (COEF) {
+#pragma unroll
+      for (int r = 0; r < TG_ROUNDS; ++r) cf[r] = r * TG_THREADS + (int)threadIdx.x < d.nb_cell ? __ldg(A.cell_coef + pf.cid[r]) : 1.0;
+    }
 #pragma unroll
     for (int r = 0; r < TG_ROUNDS; ++r) {
       const int lc = r * TG_THREADS + threadIdx.x;
@@ -261,7 +273,8 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
       if (lc < d.nb_cell) {
 #endif
         double K[6];
-        OffDiagK<NPC>::compute(S.cx, pf.ln[r], prm, K);
+        if (COEF) OffDiagK<NPC>::template compute<true>(S.cx, pf.ln[r], prm, K, cf[r]);
+        else OffDiagK<NPC>::compute(S.cx, pf.ln[r], prm, K);
 #pragma unroll
         for (int p = 0; p < OffDiagK<NPC>::N; ++p) S.Kc[p * TG_CS + lc] = K[p];
       }
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
     uint32_t em[TG_UPW];
 #pragma unroll
     for (int q = 0; q < TG_UPW; ++q) em[q] = pf.em[q];
-    if (tn < A.nb_tile) prefetch_level2<TG_ROUNDS, TG_THREADS, true>(S.desc[nslot], A, pf);
+    if (tn < A.nb_tile) prefetch_level2<TG_ROUNDS, TG_THREADS, true, COEF>(S.desc[nslot], A, pf);
     if (tnn < A.nb_tile) prefetch_level1(S.desc[nnslot], A, pf);
     int32_t desc_word = 0;
     if (threadIdx.x < DW && tnnn < A.nb_tile) desc_word = __ldg(reinterpret_cast<const int32_t*>(A.desc + tnnn) + threadIdx.x);
@@ -386,6 +399,20 @@ __global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs
     t = (int32_t)tn;
     slot = nslot;
   }
+}
+
+template <int NPC>
+__global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled(ExecArgs A, ElemParams prm)
+{
+  assemble_tiled_body<NPC, false>(A, prm);
+}
+
+// the same executor with a per-cell multiplier of the element matrix (afb_set_cell_coefficient: conductivity of the fourier /
+// electrostatics / FourierNL modules); its own kernel so that the plain one keeps its registers and its instruction stream
+template <int NPC>
+__global__ void __launch_bounds__(TG_THREADS, TG_MINB) k_assemble_tiled_coef(ExecArgs A, ElemParams prm)
+{
+  assemble_tiled_body<NPC, true>(A, prm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -919,7 +946,8 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   AFB_REQUIRE(ctx->npc == ctx->dim + 1 && ((op == AFB_OP_POISSON && !vec) || (op == AFB_OP_ELASTICITY && vec) || (op == AFB_OP_BILAPLACIAN && vec && ctx->npc == 3)),
               AFB_ERR_UNSUPPORTED,
               "AFB_VARIANT_TILED_GATHER is not available for operator %d on %d-node cells (P1 Poisson, P1 elasticity, Tri3 bilaplacian only); use AFB_VARIANT_NODEWISE", op, ctx->npc);
-  AFB_REQUIRE(!ctx->has_cell_coef, AFB_ERR_UNSUPPORTED, "AFB_VARIANT_TILED_GATHER does not take a per-cell coefficient (afb_set_cell_coefficient); use AFB_VARIANT_NODEWISE");
+  AFB_REQUIRE(!ctx->has_cell_coef || (!vec && ctx->tiled_exec == AFB_TILED_EXEC_BRICKS), AFB_ERR_UNSUPPORTED,
+              "AFB_VARIANT_TILED_GATHER takes a per-cell coefficient (afb_set_cell_coefficient) for the Poisson operator with the brick executor only; use AFB_VARIANT_NODEWISE");
   TilePlan& P = ctx->plan;
   const int mode = flags & (AFB_FLAG_ALL_ROWS | AFB_FLAG_OWN_CELLS_ONLY);
   // scalar operators: the chained-slice executors when selected (afb_set_tiled_executor; chain_exec.cu, chain_flow.cu)
@@ -965,6 +993,8 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   A.values = ctx->values.as<double>();
   A.accumulate = accumulate;
   A.list_stage_max = (int)std::min<int64_t>(vec ? TV_LMAX : TG_LMAX, ctx->tiled_stage_limit / 2);
+  A.tile_cells = P.tile_cells.as<int32_t>();
+  A.cell_coef = ctx->has_cell_coef ? ctx->cell_coef.as<double>() : nullptr;
   const int grid = std::min<int>(P.nb_tile, TG_MINB * ctx->sm_count);
   auto go = [&](auto kernel, size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -973,7 +1003,8 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
     return e != cudaSuccess ? e : cudaGetLastError();
   };
   cudaError_t e;
-  if (!vec) e = ctx->npc == 4 ? go(k_assemble_tiled<4>, sizeof(ExecSmem)) : go(k_assemble_tiled<3>, sizeof(ExecSmem));
+  if (!vec && ctx->has_cell_coef) e = ctx->npc == 4 ? go(k_assemble_tiled_coef<4>, sizeof(ExecSmem)) : go(k_assemble_tiled_coef<3>, sizeof(ExecSmem));
+  else if (!vec) e = ctx->npc == 4 ? go(k_assemble_tiled<4>, sizeof(ExecSmem)) : go(k_assemble_tiled<3>, sizeof(ExecSmem));
   else if (rows_exec && ctx->npc == 4)
     e = layout == AFB_LAYOUT_PER_BLOCK ? go(k_assemble_rows_vec<4, AFB_LAYOUT_PER_BLOCK>, sizeof(RowsSmem<3>)) : go(k_assemble_rows_vec<4, AFB_LAYOUT_PER_ROW>, sizeof(RowsSmem<3>));
   else if (rows_exec)

@@ -176,8 +176,11 @@ AFB_API int afb_update_coordinates(afb_ctx* ctx, const double* xyz, int mem_spac
  * Per-cell coefficient of the Poisson operator: the element matrix of cell c is multiplied by coefficient[c] -- the
  * conductivity m_cell_lambda of the reference's fourier / heat modules (modules/fourier/ElementMatrix.h:11-57,
  * `area * lambda * (dxU ^ dxU) + ...`; multi-material cases set it per cell group), the permittivity of electrostatics.
+ * The FourierNL module's Picard loop re-assembles with a new one every iteration (modules/fouriernl/ElementMatrix.h:29-41: lambda at
+ * the mean of the previous iterate over the cell).
  * [nb_cell] doubles, copied; NULL switches it off; a new mesh drops it.  Cell-wise and node-wise variants on Tri3 / Tet4 /
- * Quad4 / Hexa8; the tiled gather refuses (AFB_ERR_UNSUPPORTED).
+ * Quad4 / Hexa8; the tiled gather takes it for AFB_OP_POISSON on Tri3 / Tet4 with the brick executor (its plan does not depend on
+ * the coefficient: a new coefficient costs no inspector run), AFB_ERR_UNSUPPORTED for the chained-slice executors.
  */
 AFB_API int afb_set_cell_coefficient(afb_ctx* ctx, const double* coefficient, int mem_space);
 

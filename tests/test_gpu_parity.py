@@ -289,6 +289,77 @@ def test_poisson_values(ctx, name, fmt, variant):
     row_scaled_close(ctx.to_host(A.ARRAY_VALUES), v1, rows)
 
 
+@pytest.mark.parametrize("name", P1_POISSON)
+@pytest.mark.parametrize("fmt", [A.FORMAT_CSR, A.FORMAT_BSR], ids=["tiled-csr", "tiled-bsr"])
+def test_poisson_values_with_cell_coefficient_tiled(ctx, name, fmt):
+    """per-cell conductivity (afb_set_cell_coefficient: fourier, electrostatics, FourierNL modules) through the tiled executor
+    (k_assemble_tiled_coef) against the oracle; a new coefficient on the same plan, then none again"""
+    m = get_mesh(name)
+    ctx.set_mesh(m.dim, m.coords, m.cells)
+    ctx.build_pattern(1)
+    rows, cols = ctx.to_host(A.ARRAY_ROWS), ctx.to_host(A.ARRAY_COLUMNS)
+    form = O.FORM_NODEWISE if fmt == A.FORMAT_CSR else O.FORM_BSR
+    flags = A.FLAG_SIGNED_TRI_AREA if fmt != A.FORMAT_BSR else 0
+    rng = np.random.default_rng(7)
+    for trial in range(2):
+        cc = 10.0 ** rng.uniform(-2.0, 2.0, m.nb_cell)
+        ctx.set_cell_coefficient(cc)
+        ctx.reset_values()
+        ctx.assemble(A.OP_POISSON, fmt=fmt, variant=A.VARIANT_TILED_GATHER, flags=flags)
+        ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=form, nodewise=True, cell_coef=cc)
+        row_scaled_close(ctx.to_host(A.ARRAY_VALUES), ref, rows)
+    ctx.set_cell_coefficient(None)
+    ctx.reset_values()
+    ctx.assemble(A.OP_POISSON, fmt=fmt, variant=A.VARIANT_TILED_GATHER, flags=flags)
+    row_scaled_close(ctx.to_host(A.ARRAY_VALUES), O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_POISSON, form=form, nodewise=True), rows)
+    # the chained-slice executors and the vector executors do not take it: a clear error, no silent fallback
+    ctx.set_cell_coefficient(1.5)
+    ctx.set_tiled_executor(A.TILED_EXEC_CHAIN)
+    with pytest.raises(A.AfbError, match="per-cell coefficient"):
+        ctx.assemble(A.OP_POISSON, fmt=fmt, variant=A.VARIANT_TILED_GATHER, flags=flags)
+    ctx.set_tiled_executor(A.TILED_EXEC_BRICKS)
+    ctx.set_cell_coefficient(None)
+
+
+def test_full_size_cell_coefficient_tiled_against_cellwise(ctx):
+    """C2-size box: the tiled executor with a per-cell coefficient equals the atomic cell-wise variant entry by entry (1e-12 of the row),
+    is bit-reproducible, and a uniform coefficient c equals c times the plain matrix"""
+    import torch
+    n = 120
+    ctx.generate_box(3, n)
+    nbc, nbn, nbe, nnz = M.box_counts(3, n)
+    ctx.build_pattern(1)
+    v = ctx.csr_view()
+    rows = A.as_torch(v["rows"], nbn + 1, np.int32, 0).long()
+    vals = A.as_torch(v["values"], nnz, np.float64, 0)
+    cc = 10.0 ** np.random.default_rng(11).uniform(-1.0, 1.0, nbc)
+    ctx.set_cell_coefficient(cc)
+    out = {}
+    for variant in (A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_TILED_GATHER, A.VARIANT_TILED_GATHER):
+        ctx.reset_values()
+        ctx.assemble(A.OP_POISSON, variant=variant)
+        ctx.synchronize()
+        x = vals.clone()
+        torch.cuda.synchronize()
+        if variant in out:
+            assert bool(torch.equal(x, out[variant]))
+        out[variant] = x
+    rid = torch.repeat_interleave(torch.arange(nbn, device="cuda"), rows[1:] - rows[:-1])
+    scale = torch.zeros(nbn, dtype=torch.float64, device="cuda").scatter_reduce_(0, rid, out[A.VARIANT_CELLWISE_ATOMIC].abs(), "amax")
+    assert float(((out[A.VARIANT_TILED_GATHER] - out[A.VARIANT_CELLWISE_ATOMIC]).abs() / scale[rid]).max()) < 1e-12
+    ctx.set_cell_coefficient(2.5)
+    ctx.reset_values()
+    ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+    ctx.synchronize()
+    scaled = vals.clone()
+    torch.cuda.synchronize()
+    ctx.set_cell_coefficient(None)
+    ctx.reset_values()
+    ctx.assemble(A.OP_POISSON, variant=A.VARIANT_TILED_GATHER)
+    ctx.synchronize()
+    assert float(((scaled - 2.5 * vals).abs() / scale[rid]).max()) < 1e-12
+
+
 def test_signed_area_of_clockwise_triangles(ctx):
     """the testlab compact path gives a negative-definite K_e for a
     clockwise triangle, the BSR path does not."""
@@ -1280,7 +1351,7 @@ def test_heat_golden_solution(exec_ctx, name, variant):
 
 
 @pytest.mark.parametrize("name", list(CS.FOURIERNL_CASES))
-@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
+@pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE, A.VARIANT_TILED_GATHER], ids=["bsr", "af-bsr", "tiled"])
 def test_fouriernl_golden_solution(exec_ctx, name, variant):
     """the FourierNL module's Picard loop with everything but the update of the conductivity on the device: per iteration the values are
     reset, the Poisson operator is re-assembled with the new per-cell conductivity on the unchanged pattern, the penalty rows are set and
@@ -1343,10 +1414,14 @@ def test_q1_poisson_golden_solution(exec_ctx, name, fmt, variant):
     c.build_pattern(1)
     coef = CS.cell_coefficient(m, case)
     c.set_cell_coefficient(coef)  # (None: off)
-    if coef is not None and m.npc == m.dim + 1:
-        with pytest.raises(A.AfbError, match="per-cell coefficient"):
-            c.assemble(A.OP_POISSON, fmt=fmt, variant=A.VARIANT_TILED_GATHER)
+    tiled = None
+    if coef is not None and m.npc == m.dim + 1 and fmt != A.FORMAT_COO:  # the B200 executor takes the conductivity too
+        c.assemble(A.OP_POISSON, fmt=fmt, variant=A.VARIANT_TILED_GATHER)
+        tiled = c.to_host(A.ARRAY_VALUES).copy()
+        c.reset_values()
     c.assemble(A.OP_POISSON, fmt=fmt, variant=variant)
+    if tiled is not None:
+        row_scaled_close(tiled, c.to_host(A.ARRAY_VALUES), c.to_host(A.ARRAY_ROWS))
     c.set_cell_coefficient(None)
     c.rhs_reset()
     c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
