@@ -114,14 +114,15 @@ struct ExecArgs {
   const uint32_t* unit_base;
   const uint16_t* unit_len;
   const uint32_t* emap;
-  const uint32_t* emap_rows; // vector plans only
+  union {                      // (one slot: a larger argument block costs the plain scalar executor two registers)
+    const uint32_t* emap_rows; // vector plans only
+    const int32_t* tile_cells; // scalar executor with a per-cell coefficient (ElemParams::cell_coef): global ids of the tiles' cells
+  };
   const uint16_t* lists;
   const uint2* vr_units;     // row-ordered vector plans only
   double* values;
   int accumulate;
   int list_stage_max; // tiles with more 16-bit list slots read their lists from global memory (<= the staging buffer)
-  const int32_t* tile_cells; // global ids of the tiles' cells and the per-cell multiplier they index (afb_set_cell_coefficient):
-  const double* cell_coef;   // read by the _coef instantiation of the scalar executor only
 };
 
 // The next tiles' inputs travel in two waves so that no warp ever waits on a dependent load:
@@ -262,7 +263,7 @@ __device__ __forceinline__ void assemble_tiled_body(const ExecArgs& A, const Ele
     double cf[COEF ? TG_ROUNDS : 1]; // (the cells' ids came with the level-2 wave: one exposed load per tile, all rounds in flight together)
     if constexpr (COEF) {
 #pragma unroll
-      for (int r = 0; r < TG_ROUNDS; ++r) cf[r] = r * TG_THREADS + (int)threadIdx.x < d.nb_cell ? __ldg(A.cell_coef + pf.cid[r]) : 1.0;
+      for (int r = 0; r < TG_ROUNDS; ++r) cf[r] = r * TG_THREADS + (int)threadIdx.x < d.nb_cell ? __ldg(prm.cell_coef + pf.cid[r]) : 1.0;
     }
 #pragma unroll
     for (int r = 0; r < TG_ROUNDS; ++r) {
@@ -987,14 +988,14 @@ int assemble_tiled(afb_ctx* ctx, int op, const double* params, int layout, int f
   A.unit_base = P.unit_base.as<uint32_t>();
   A.unit_len = P.unit_len.as<uint16_t>();
   A.emap = P.emap.as<uint32_t>();
-  A.emap_rows = vec ? P.emap_rows.as<uint32_t>() : nullptr;
+  if (vec) A.emap_rows = P.emap_rows.as<uint32_t>();
+  else A.tile_cells = P.tile_cells.as<int32_t>();
   A.lists = P.lists.as<uint16_t>();
   A.vr_units = rows_exec ? P.vr_units.as<uint2>() : nullptr;
   A.values = ctx->values.as<double>();
   A.accumulate = accumulate;
   A.list_stage_max = (int)std::min<int64_t>(vec ? TV_LMAX : TG_LMAX, ctx->tiled_stage_limit / 2);
-  A.tile_cells = P.tile_cells.as<int32_t>();
-  A.cell_coef = ctx->has_cell_coef ? ctx->cell_coef.as<double>() : nullptr;
+  if (ctx->has_cell_coef) prm.cell_coef = ctx->cell_coef.as<double>();
   const int grid = std::min<int>(P.nb_tile, TG_MINB * ctx->sm_count);
   auto go = [&](auto kernel, size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
