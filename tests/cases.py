@@ -326,6 +326,79 @@ def picard_loop(case, mesh, solve_with_conductivity):
     raise AssertionError("Picard iterations did not converge")
 
 
+# Soildynamics module, 2-D Tri3 cases: the elastodynamics matrix (same element matrix, modules/soildynamics/ElementMatrix.h) plus the paraxial
+# (absorbing) boundary of modules/soildynamics/Paraxial.h on the surface `lower`: every boundary edge adds c7 * length * P to the matrix and
+# length * (c7 U - c8 V + c9 A) . P to the right-hand side of each step (inputs/constant-traction.arc, constant-traction.pointbc.arc)
+SOILDYNAMICS_CASES = {
+    "semi_circle_constant_traction": dict(mesh="semi-circle-soil.msh", E=6.62e6, nu=0.45, rho=2500.0, dt=0.01, tmax=0.08, f=[0.0, 0.0],
+                                          traction=[("input", [0.01, 0.01])], paraxial=["lower"], dirichlet=[], penalty=1.0e30,
+                                          golden="soildynamics_test_2D_constant_traction.txt"),
+    "semi_circle_constant_traction_pointbc": dict(mesh="semi-circle-soil.msh", E=6.62e6, nu=0.45, rho=2500.0, dt=0.01, tmax=0.08, f=[3359.6, 3452.3],
+                                                  traction=[("input", [0.01, 0.01])], paraxial=["lower"], dirichlet=[("source", [0.0, 0.0003])],
+                                                  penalty=1.0e30, golden="soildynamics_test_2D_constant_traction_pointbc.txt"),
+}
+
+
+def soildynamics_coefficients(case):
+    """modules/soildynamics/FemModule.cc:156-196: Lame constants and wave speeds from (E, nu, rho), Newmark-beta constants c0..c9"""
+    E, nu, rho, dt = case["E"], case["nu"], case["rho"], case["dt"]
+    mu = E / (2 * (1 + nu))
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    cs = np.sqrt(mu / rho)
+    cp = np.sqrt((lam + 2. * mu) / rho)
+    gamma = 0.5
+    beta = (1. / 4.) * (gamma + 0.5) * (gamma + 0.5)
+    return dict(lam=lam, mu=mu, cs=cs, cp=cp, gamma=gamma, beta=beta, c0=rho / (beta * dt * dt), c3=rho / (beta * dt), c4=rho * (1. / 2. / beta - 1.),
+                c7=rho * gamma / beta / dt, c8=rho * (1. - gamma / beta), c9=rho * dt * (1. - gamma / (2. * beta)))
+
+
+def _mass_matrix(u, v):
+    """femutils/FemUtils.h:583-597 massMatrix(lhs, rhs): outer product with a doubled diagonal"""
+    m = np.outer(u, v)
+    m[np.diag_indices_from(m)] *= 2.
+    return m
+
+
+def paraxial_boundary_matrix(mesh, faces, cp, cs):
+    """sum over the boundary edges of length * P_edge as a scipy CSR matrix over the 2 * nb_node DoFs
+    (modules/soildynamics/Paraxial.h:27-41 `_computeParaxialElementMatrixEdge2`, scatter as :137-190)"""
+    import scipy.sparse as sp
+    ux, uy = np.array([1., 0., 1., 0.]), np.array([0., 1., 0., 1.])
+    rows, cols, vals = [], [], []
+    for n0, n1 in np.asarray(faces, dtype=np.int64):
+        dx, dy = mesh.coords[n1, 0] - mesh.coords[n0, 0], mesh.coords[n1, 1] - mesh.coords[n0, 1]
+        length = np.sqrt(dx * dx + dy * dy)
+        nx, ny = dy / length, -dx / length
+        P = ((nx * nx * cp + ny * ny * cs) * _mass_matrix(ux, ux) + (ny * ny * cp + nx * nx * cs) * _mass_matrix(uy, uy)
+             + (nx * ny * (cp - cs)) * _mass_matrix(ux, uy) + (nx * ny * (cp - cs)) * _mass_matrix(uy, ux)) / 6.
+        dofs = np.array([2 * n0, 2 * n0 + 1, 2 * n1, 2 * n1 + 1])
+        rows.append(np.repeat(dofs, 4))
+        cols.append(np.tile(dofs, 4))
+        vals.append((length * P).ravel())
+    B = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(2 * mesh.nb_node, 2 * mesh.nb_node)).tocsr()
+    B.sum_duplicates()
+    return B
+
+
+def soildynamics_time_loop(case, nb_dof, step):
+    """modules/soildynamics/FemModule.cc:28-62, 75-78, 262-290: t starts at dt, the step that starts with t >= tmax is the last (and the one
+    compared with the golden file).  step(U, V, A) -> displacement of the step."""
+    k = soildynamics_coefficients(case)
+    gamma, beta, dt = k["gamma"], k["beta"], case["dt"]
+    t = dt
+    U, V, A = np.zeros(nb_dof), np.zeros(nb_dof), np.zeros(nb_dof)
+    while True:
+        last = t >= case["tmax"]
+        dU = step(U, V, A)
+        a_new = (dU - U - dt * V) / (beta * dt * dt) - (1. - 2. * beta) / (2. * beta) * A
+        V = V + dt * ((1. - gamma) * A + gamma * a_new)
+        A = a_new
+        U = dU
+        t += dt
+        if last:
+            return dU
+
+
 # modules/bilaplacian/inputs/direct.arc
 BILAPLACIAN_CASE = dict(mesh="bilap.msh", f=-786.25, dirichlet=[("boundary", [145.5, None])], penalty=1.0e30,
                         golden="bilaplacian_2d_test.txt")

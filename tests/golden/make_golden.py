@@ -118,6 +118,11 @@ FILES = {
     "meshes/msh/unit_cube.msh": "unit_cube.msh",
     "modules/fouriernl/check/conduction_tria.txt": "fouriernl_conduction_tria.txt",
     "modules/fouriernl/check/conduction_tetra.txt": "fouriernl_conduction_tetra.txt",
+    # soildynamics module (the elastodynamics matrix + the paraxial absorbing boundary, modules/soildynamics/Paraxial.h; inputs/constant-traction.arc,
+    # constant-traction.pointbc.arc)
+    "meshes/msh/semi-circle-soil.msh": "semi-circle-soil.msh",
+    "modules/soildynamics/check/test_2D_constant_traction.txt": "soildynamics_test_2D_constant_traction.txt",
+    "modules/soildynamics/check/test_2D_constant_traction_pointbc.txt": "soildynamics_test_2D_constant_traction_pointbc.txt",
     # heat module (implicit Euler on lambda * stiffness + mass / dt): inputs/conduction.arc, 3d_conduction.arc, conduction.quad.arc
     "meshes/msh/plate.msh": "plate.msh",
     "modules/heat/check/2d_conduction.txt": "heat_2d_conduction.txt",

@@ -1382,6 +1382,75 @@ def test_fouriernl_golden_solution(exec_ctx, name, variant):
     assert CS.compare_to_golden(m, u, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True) < 1.0e-4
 
 
+def _values_per_row(b, rows, values, layout):
+    """block values in the order of the expanded scalar CSR (= the per-row layout): [block row][i][entry][j]"""
+    if layout == A.LAYOUT_PER_ROW:
+        return np.array(values, copy=True)
+    out = np.empty_like(values)
+    bb = b * b
+    for n in range(rows.size - 1):
+        lo, cnt = int(rows[n]), int(rows[n + 1] - rows[n])
+        blk = np.asarray(values[lo * bb:(lo + cnt) * bb]).reshape(cnt, b, b)          # [entry][i][j]
+        out[lo * bb:(lo + cnt) * bb] = blk.transpose(1, 0, 2).reshape(-1)             # [i][entry][j]
+    return out
+
+
+@pytest.mark.parametrize("name", list(CS.SOILDYNAMICS_CASES))
+@pytest.mark.parametrize("variant,layout", [(A.VARIANT_CELLWISE_ATOMIC, A.LAYOUT_PER_BLOCK), (A.VARIANT_NODEWISE, A.LAYOUT_PER_ROW)], ids=["bsr", "af-bsr"])
+def test_soildynamics_golden_solution(exec_ctx, name, variant, layout):
+    """the soildynamics module's golden displacement files (Tri3): Newmark matrix, mass, body force, traction and penalty rows on the GPU;
+    the paraxial boundary entries are added to the assembled device matrix the way the module calls BSRMatrix::addValue
+    (modules/soildynamics/Paraxial.h:153-186) -- one afb_lookup_value_slots + one afb_add_values_at over the boundary's (row, column) pairs"""
+    import torch
+    c = exec_ctx
+    case = CS.SOILDYNAMICS_CASES[name]
+    m = _fixture_mesh(case["mesh"])
+    b = 2
+    k = CS.soildynamics_coefficients(case)
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    c.set_mesh(m.dim, m.coords, m.cells)
+    c.build_pattern(1)
+    c.assemble(A.OP_DIFFUSION_REACTION, params=[0.0, 1.0], fmt=A.FORMAT_BSR, variant=variant)
+    mass = sp.csr_matrix((c.to_host(A.ARRAY_VALUES).copy(), c.to_host(A.ARRAY_COLUMNS).copy(), c.to_host(A.ARRAY_ROWS).copy()))
+    c.build_pattern(b)
+    c.assemble(A.OP_ELASTODYNAMICS, params=[k["c0"], k["lam"], k["mu"]], fmt=A.FORMAT_BSR, variant=variant, layout=layout)
+    B = sum(CS.paraxial_boundary_matrix(m, m.faces[grp], k["cp"], k["cs"]) for grp in case["paraxial"]).tocoo()
+    n = B.nnz
+    slots = torch.empty(n, dtype=torch.int64, device="cuda:0")
+    c.lookup_value_slots(n, torch.from_numpy(B.row.astype(np.int32)).cuda(), torch.from_numpy(B.col.astype(np.int32)).cuda(), slots)
+    assert bool((slots >= 0).all()) and int(torch.unique(slots).numel()) == n
+    c.add_values_at(n, slots, torch.from_numpy(np.ascontiguousarray(k["c7"] * B.data)).cuda())
+    c.synchronize()
+    # what the device matrix holds now, entry by entry, against the oracle's matrix plus the same boundary terms
+    rows, cols = c.to_host(A.ARRAY_ROWS), c.to_host(A.ARRAY_COLUMNS)
+    crow, ccol = c.to_host(A.ARRAY_CSR_ROWS).copy(), c.to_host(A.ARRAY_CSR_COLUMNS).copy()
+    got = _values_per_row(b, rows, c.to_host(A.ARRAY_VALUES), layout)
+    ref = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTODYNAMICS, form=O.FORM_BSR, params=[k["c0"], k["lam"], k["mu"]], layout=O.LAYOUT_PER_ROW,
+                     nodewise=variant == A.VARIANT_NODEWISE)
+    want = (sp.csr_matrix((ref, ccol, crow)) + k["c7"] * B.tocsr()).tocsr()
+    want.sort_indices()
+    d = abs(sp.csr_matrix((got, ccol, crow)) - want)
+    assert d.max() <= 1e-12 * abs(want).max()
+    c.rhs_reset()
+    c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
+    for group, t in case["traction"]:
+        c.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), t, kind=A.NEUMANN_TRACTION)
+    static = c.to_host(A.ARRAY_RHS).copy()
+    c.dirichlet_penalty(ids, g, case["penalty"])
+    vals = _values_per_row(b, rows, c.to_host(A.ARRAY_VALUES), layout)
+    lu = spla.splu(sp.csr_matrix((vals, ccol, crow)).tocsc())
+    Bc = B.tocsr()
+
+    def step(U, V, Acc):
+        rhs = static + (mass @ (k["c0"] * U + k["c3"] * V + k["c4"] * Acc).reshape(m.nb_node, b)).reshape(-1) + Bc @ (k["c7"] * U - k["c8"] * V + k["c9"] * Acc)
+        rhs[ids] = case["penalty"] * np.asarray(g)
+        return lu.solve(rhs)
+
+    u = CS.soildynamics_time_loop(case, m.nb_node * b, step)
+    golden = CS.load_golden(case["golden"], b)
+    assert CS.compare_to_golden(m, u, golden, b, eps=1.0e-4, min_value=CS.golden_floor(case, golden), subset=True) < case.get("tol", 1.0e-5)
+
+
 @pytest.mark.parametrize("name", list(CS.ACOUSTICS_CASES))
 @pytest.mark.parametrize("variant", [A.VARIANT_CELLWISE_ATOMIC, A.VARIANT_NODEWISE], ids=["bsr", "af-bsr"])
 def test_acoustics_golden_solution(exec_ctx, name, variant):

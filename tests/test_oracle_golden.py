@@ -310,6 +310,42 @@ def test_fouriernl_golden(name, nodewise):
     assert worst < 1.0e-4   # (the golden file is a converged Picard iterate at nlin-rtol 1e-5, not an exact solve)
 
 
+@pytest.mark.parametrize("name", list(CS.SOILDYNAMICS_CASES))
+@pytest.mark.parametrize("nodewise", [False, True], ids=["bsr", "af-bsr"])
+def test_soildynamics_golden(name, nodewise):
+    """The soildynamics module on Tri3: elastodynamics operator + paraxial boundary entries added to the assembled matrix
+    (BSRMatrix::addValue in modules/soildynamics/Paraxial.h:153-186), Newmark-beta loop, against the module's golden displacement files."""
+    case = CS.SOILDYNAMICS_CASES[name]
+    m = _load(case)
+    b = 2
+    k = CS.soildynamics_coefficients(case)
+    rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
+    vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTODYNAMICS, form=O.FORM_BSR, params=[k["c0"], k["lam"], k["mu"]], layout=O.LAYOUT_PER_ROW, nodewise=nodewise)
+    mass = _csr(rows, cols, O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_DIFFUSION_REACTION, form=O.FORM_BSR, params=[0.0, 1.0]))
+    static = O.rhs_source_cellwise(m.dim, m.coords, m.cells, case["f"], signed_area=False)
+    for group, t in case["traction"]:
+        O.rhs_neumann(m.dim, b, m.coords, M.orient_boundary_faces(m, m.faces[group]), t, static, kind=O.NEUMANN_TRACTION)
+    B = sum(CS.paraxial_boundary_matrix(m, m.faces[g], k["cp"], k["cs"]) for g in case["paraxial"])
+    crow, ccol, _ = O.bsr_to_csr(b, rows, cols)
+    lhs = (_csr(crow, ccol, vals) + k["c7"] * B).tocsr()
+    lhs.sort_indices()
+    assert lhs.nnz == crow[-1]  # the boundary entries fall inside the cell pattern
+    ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
+    lv = lhs.data.copy()
+    O.dirichlet_penalty(lhs.indptr.astype(np.int32), lhs.indices.astype(np.int32), lv, np.zeros(m.nb_node * b), ids, g, case["penalty"])
+    lu = spla.splu(sp.csr_matrix((lv, lhs.indices, lhs.indptr)).tocsc())
+
+    def step(U, V, A):
+        rhs = static + (mass @ (k["c0"] * U + k["c3"] * V + k["c4"] * A).reshape(m.nb_node, b)).reshape(-1) + B @ (k["c7"] * U - k["c8"] * V + k["c9"] * A)
+        rhs[ids] = case["penalty"] * np.asarray(g)
+        return lu.solve(rhs)
+
+    u = CS.soildynamics_time_loop(case, m.nb_node * b, step)
+    golden = CS.load_golden(case["golden"], b)
+    worst = CS.compare_to_golden(m, u, golden, b, eps=1.0e-4, min_value=CS.golden_floor(case, golden), subset=True)
+    assert worst < case.get("tol", 1.0e-5)
+
+
 def test_elasticity_per_block_layout_equals_per_row():
     case = CS.ELASTICITY_CASES["bar_3D"]
     m, b, rows, cols, v_row, *_ = _elasticity_system(case, O.LAYOUT_PER_ROW, False)
