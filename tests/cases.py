@@ -280,20 +280,68 @@ HEAT_CASES = {
                           golden="heat_2d_conduction.quad.txt"),
     "truncated_cube_3D": dict(mesh="truncated_cube.msh", lam=1.75, dt=0.1, tmax=1.0, Tinit=30.0,
                               dirichlet=[("top", 100.6), ("bottom", 1.6)], penalty=1.0e30, golden="heat_3d_conduction.txt"),
+    # convection (Robin) boundaries: (surface, h, T_ext) -- h * face mass matrix into the matrix, h * T_ext * measure / nodes into the right-hand side
+    # (modules/heat/FemModule.cc:305-348); flux boundaries (scalar <neumann>) and <dirichlet-point> conditions
+    "plate_2D_convection": dict(mesh="plate.msh", lam=1.75, dt=0.4, tmax=20.0, Tinit=30.0, dirichlet=[("left", 10.0)], penalty=1.0e31,
+                                convection=[("right", 1.0, 20.0), ("top", 1.0, 20.0), ("bottom", 1.0, 20.0)], golden="heat_2d_conduction_convection.txt"),
+    "plate_2D_convection_quad": dict(mesh="plate.quad.msh", lam=1.75, dt=0.4, tmax=20.0, Tinit=30.0, dirichlet=[("left", 10.0)], penalty=1.0e31,
+                                     convection=[("right", 5.0, 15.0)], golden="heat_2d_conduction_convection.quad.txt"),
+    "plate_2D_neumann_points": dict(mesh="plate.msh", lam=1.75, dt=0.4, tmax=20.0, Tinit=30.0, dirichlet=[("topLeft", 1.8), ("botRight", 31.0)], penalty=1.0e31,
+                                    neumann=[("left", [9.6])], golden="heat_2d_conduction_neumann_pointBC.txt"),
+    "plate_2D_neumann_points_quad": dict(mesh="plate.quad.msh", lam=1.75, dt=0.4, tmax=20.0, Tinit=30.0, dirichlet=[("topLeft", 1.8), ("botRight", 31.0)],
+                                         penalty=1.0e31, neumann=[("left", [9.6])], golden="heat_2d_conduction_neumann_pointBC.quad.txt"),
+    "truncated_cube_3D_convection_point": dict(mesh="truncated_cube.msh", lam=1.75, dt=0.1, tmax=1.0, Tinit=30.0, dirichlet=[("bottom", 2.6), ("center", 100.6)],
+                                               penalty=1.0e30, convection=[("top", 1.9, 30.0)], golden="heat_3d_conduction_convection_pointBC.txt"),
+    "truncated_cube_3D_convection_hexa": dict(mesh="truncated_cube.hexa.msh", lam=1.75, dt=0.4, tmax=20.0, Tinit=30.0, dirichlet=[("left", 10.0)], penalty=1.0e30,
+                                              convection=[("right", 5.0, 15.0)], golden="heat_3d_conduction_convection.hexa.txt"),
+    "truncated_cube_3D_neumann_hexa": dict(mesh="truncated_cube.hexa.msh", lam=1.75, dt=0.4, tmax=20.0, Tinit=30.0, dirichlet=[("top", 10.6)], penalty=1.0e30,
+                                           neumann=[("bottom", [1.2])], golden="heat_3d_conduction_neumann.hexa.txt"),
 }
 
 
-def heat_time_loop(case, nb_node, solve_step, mass_times):
+def face_measure(mesh, face):
+    """femutils/ArcaneFemFunctions.h:172-215: edge length, triangle area, quadrilateral area as two triangles (n1: n2-n1 x n0-n1, n3: n0-n3 x n2-n3)"""
+    x = mesh.coords[np.asarray(face, dtype=np.int64)]
+    if len(face) == 2:
+        return float(np.linalg.norm(x[1] - x[0]))
+    if len(face) == 3:
+        return float(np.linalg.norm(np.cross(x[1] - x[0], x[2] - x[0]))) / 2.0
+    return 0.5 * float(np.linalg.norm(np.cross(x[2] - x[1], x[0] - x[1])) + np.linalg.norm(np.cross(x[0] - x[3], x[2] - x[3])))
+
+
+def convection_boundary_terms(mesh, case):
+    """modules/heat/FemModule.cc:305-348: per face of a convection surface h * factor * massMatrix(1, 1) * measure into the matrix (factor 1/6 on
+    edges, 1/12 on triangles, 1/20 on quadrilaterals) and h * T_ext * measure / nodes into the right-hand side.  Returns (scipy CSR, vector)."""
+    import scipy.sparse as sp
+    n = mesh.nb_node
+    rows, cols, vals = [np.empty(0, np.int64)], [np.empty(0, np.int64)], [np.empty(0)]
+    rhs = np.zeros(n)
+    for group, h, text in case.get("convection", []):
+        for face in mesh.faces[group]:
+            k = len(face)
+            measure = face_measure(mesh, face)
+            Ke = h * {2: 1 / 6., 3: 1 / 12., 4: 1 / 20.}[k] * _mass_matrix(np.ones(k), np.ones(k)) * measure
+            f = np.asarray(face, dtype=np.int64)
+            rows.append(np.repeat(f, k))
+            cols.append(np.tile(f, k))
+            vals.append(Ke.ravel())
+            rhs[f] += (h * text) * measure / k
+    B = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+    B.sum_duplicates()
+    return B, rhs
+
+
+def heat_time_loop(case, nb_node, solve_step, mass_times, static=None):
     """The module's time loop (modules/heat/FemModule.cc:74-135, 232-245, 350-363): t starts at 0 and grows by dt after every solve; the
     loop ends with the first step that starts at t >= tmax (that step is still solved, and checked against the golden file).
     solve_step(rhs) -> temperature of the step (the caller sets the Dirichlet rows); mass_times(x) = consistent mass matrix times x.
-    The right-hand side of a step is the mass matrix applied to (previous temperature / dt)."""
+    The right-hand side of a step is the mass matrix applied to (previous temperature / dt), plus `static` (convection and flux terms)."""
     dt, tmax = case["dt"], case["tmax"]
     t = 0.0
     T = np.full(nb_node, case["Tinit"])
     while True:
         last = t >= tmax
-        T = solve_step(mass_times(T * (1.0 / dt)))
+        T = solve_step(mass_times(T * (1.0 / dt)) + (0.0 if static is None else static))
         t += dt
         if last:
             break

@@ -128,6 +128,16 @@ FILES = {
     "modules/heat/check/2d_conduction.txt": "heat_2d_conduction.txt",
     "modules/heat/check/3d_conduction.txt": "heat_3d_conduction.txt",
     "modules/heat/check/2d_conduction.quad.txt": "heat_2d_conduction.quad.txt",
+    # ... with convection (Robin) boundaries, flux boundaries and point conditions: inputs/conduction.convection.arc, conduction.convection.quad.arc,
+    # conduction.neumann.point-dirichlet.arc, conduction.neumann.point-dirichlet.quad.arc, 3d_conduction.pointBc.convection.arc,
+    # 3d_conduction.convection.hexa.arc, 3d_conduction.neumann.hexa.arc
+    "modules/heat/check/2d_conduction_convection.txt": "heat_2d_conduction_convection.txt",
+    "modules/heat/check/2d_conduction_convection.quad.txt": "heat_2d_conduction_convection.quad.txt",
+    "modules/heat/check/2d_conduction_neumann_pointBC.txt": "heat_2d_conduction_neumann_pointBC.txt",
+    "modules/heat/check/2d_conduction_neumann_pointBC.quad.txt": "heat_2d_conduction_neumann_pointBC.quad.txt",
+    "modules/heat/check/3d_conduction_convection_pointBC.txt": "heat_3d_conduction_convection_pointBC.txt",
+    "modules/heat/check/3d_conduction_convection.hexa.txt": "heat_3d_conduction_convection.hexa.txt",
+    "modules/heat/check/3d_conduction_neumann.hexa.txt": "heat_3d_conduction_neumann.hexa.txt",
     # the same on Quad4 / Hexa8: inputs/bar.quad.arc, bar.3D.hexa.arc
     "meshes/msh/bar_dynamic_quad.msh": "bar_dynamic_quad.msh",
     "meshes/msh/bar_dynamic_3Dhexa.msh": "bar_dynamic_3Dhexa.msh",

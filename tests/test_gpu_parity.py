@@ -1337,7 +1337,20 @@ def test_heat_golden_solution(exec_ctx, name, variant):
     mass = sp.csr_matrix((c.to_host(A.ARRAY_VALUES).copy(), c.to_host(A.ARRAY_COLUMNS).copy(), c.to_host(A.ARRAY_ROWS).copy()))
     c.reset_values()
     c.assemble(A.OP_DIFFUSION_REACTION, params=[case["lam"], 1.0 / case["dt"]], fmt=A.FORMAT_BSR, variant=variant)
+    # convection surfaces: their face mass matrices go into the device matrix as the module's matrixAddValue calls do (modules/heat/FemModule.cc:317-331)
+    B, static = CS.convection_boundary_terms(m, case)
+    if B.nnz:
+        import torch
+        Bc = B.tocoo()
+        slots = torch.empty(Bc.nnz, dtype=torch.int64, device="cuda:0")
+        c.lookup_value_slots(Bc.nnz, torch.from_numpy(Bc.row.astype(np.int32)).cuda(), torch.from_numpy(Bc.col.astype(np.int32)).cuda(), slots)
+        assert bool((slots >= 0).all())
+        c.add_values_at(Bc.nnz, slots, torch.from_numpy(np.ascontiguousarray(Bc.data)).cuda())
+        c.synchronize()
     c.rhs_reset()
+    for group, q in case.get("neumann", []):
+        c.rhs_neumann(m.faces[group], q, kind=A.NEUMANN_FLUX)
+    static = static + c.to_host(A.ARRAY_RHS)
     c.dirichlet_penalty(ids, g, case["penalty"])
     rows, cols, vals = (c.to_host(w) for w in (A.ARRAY_ROWS, A.ARRAY_COLUMNS, A.ARRAY_VALUES))
     lu = spla.splu(sp.csr_matrix((vals, cols, rows)).tocsc())
@@ -1346,7 +1359,7 @@ def test_heat_golden_solution(exec_ctx, name, variant):
         rhs[ids] = case["penalty"] * np.asarray(g)
         return lu.solve(rhs)
 
-    T = CS.heat_time_loop(case, m.nb_node, solve_step, lambda x: mass @ x)
+    T = CS.heat_time_loop(case, m.nb_node, solve_step, lambda x: mass @ x, static)
     assert CS.compare_to_golden(m, T, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True) < case.get("tol", 1.0e-7)
 
 

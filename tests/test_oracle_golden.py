@@ -276,7 +276,13 @@ def test_heat_golden(name, nodewise):
     vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_DIFFUSION_REACTION, form=O.FORM_BSR, params=[case["lam"], 1.0 / case["dt"]], nodewise=nodewise)
     mass = _csr(rows, cols, O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_DIFFUSION_REACTION, form=O.FORM_BSR, params=[0.0, 1.0]))
     ids, g = CS.dirichlet_dofs(m, case["dirichlet"], 1)
-    lhs = vals.copy()
+    B, static = CS.convection_boundary_terms(m, case)   # (empty without convection surfaces)
+    for group, q in case.get("neumann", []):
+        O.rhs_neumann(m.dim, 1, m.coords, m.faces[group], q, static, kind=O.NEUMANN_FLUX)
+    A_ = (_csr(rows, cols, vals) + B).tocsr()
+    A_.sort_indices()
+    assert A_.nnz == rows[-1]
+    lhs = A_.data.copy()
     O.dirichlet_penalty(rows, cols, lhs, np.zeros(m.nb_node), ids, g, case["penalty"])
     lu = spla.splu(_csr(rows, cols, lhs).tocsc())
 
@@ -284,7 +290,7 @@ def test_heat_golden(name, nodewise):
         rhs[ids] = case["penalty"] * np.asarray(g)
         return lu.solve(rhs)
 
-    T = CS.heat_time_loop(case, m.nb_node, solve_step, lambda x: mass @ x)
+    T = CS.heat_time_loop(case, m.nb_node, solve_step, lambda x: mass @ x, static)
     worst = CS.compare_to_golden(m, T, CS.load_golden(case["golden"], 1), 1, eps=1.0e-4, min_value=1.0e-16, subset=True)
     assert worst < case.get("tol", 1.0e-7)
 
