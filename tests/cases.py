@@ -226,6 +226,23 @@ ELASTODYNAMICS_CASES = {
                      min_rel=1.0e-8),  # one x-displacement on the symmetry line is 7e-9 against 15 elsewhere: pure cancellation, skipped
     "bar_3D_hexa": dict(mesh="bar_dynamic_3Dhexa.msh", rho=1232434.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=0.5, f=[131.0e2, 113.8e6, 567.0e8],
                         dirichlet=[("left", [0.0, 0.0, 0.0])], traction=[], penalty=1.0e30, golden="elastodynamics_bar_3d.hexa.txt", min_rel=1.0e-8),
+    # traction over Quad4 edges / Hexa8 faces, body force + traction, <dirichlet-point> conditions (inputs/bar.dirichlet-traction.quad.arc,
+    # bar.3D.dirichlet-traction.hexa.arc, bar.dirichlet.traction.bodyforce.quad.arc, semi-circle.pointBC.arc, truncated-cube.pointBC.arc)
+    "bar_quad_traction": dict(mesh="bar_dynamic_quad.msh", rho=12.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 13.5e2],
+                              dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[("surfaceright", [1.7e6, 2.7e6])], penalty=1.0e30,
+                              golden="elastodynamics_bar_2d_dirichlet-traction.quad.txt", min_rel=1.0e-8),
+    "bar_3D_hexa_traction": dict(mesh="bar_dynamic_3Dhexa.msh", rho=1232434.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=0.5, f=[0.0, 0.0, 0.0],
+                                 dirichlet=[("left", [0.0, 0.0, 0.0])], traction=[("right", [1.7e6, 2.7e6, 2.4e7])], penalty=1.0e30,
+                                 golden="elastodynamics_bar_3d_dirichlet-traction.hexa.txt", min_rel=1.0e-8),
+    "bar_quad_traction_bodyforce": dict(mesh="bar_dynamic_quad.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=1.0, f=[0.0, -2000.0],
+                                        dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[("surfaceright", [0.0, -1.0])], penalty=1.0e30,
+                                        golden="elastodynamics_bar_dirichlet_traction_bodyforce.quad.txt", min_rel=1.0e-8),
+    "semi_circle_point": dict(mesh="semi-circle.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=1.0, f=[0.0, 0.0],
+                              dirichlet=[("boderCircle", [0.0, 0.0]), ("source", [10.0, 10.0])], traction=[], penalty=1.0e30,
+                              golden="elastodynamics_semi-ciricle_point-bc.txt", min_rel=1.0e-8),
+    "truncated_cube_point": dict(mesh="truncated_cube.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=1.0, f=[145.5e5, 56456.5e6, 87842.5e5],
+                                 dirichlet=[("bottom", [0.0, 0.0, 0.0]), ("center", [18.0, 13.0, 14.0])], traction=[], penalty=1.0e30,
+                                 golden="elastodynamics_truncated-cube_point-bc.txt", min_rel=1.0e-8),
 }
 
 

@@ -123,6 +123,14 @@ FILES = {
     "meshes/msh/semi-circle-soil.msh": "semi-circle-soil.msh",
     "modules/soildynamics/check/test_2D_constant_traction.txt": "soildynamics_test_2D_constant_traction.txt",
     "modules/soildynamics/check/test_2D_constant_traction_pointbc.txt": "soildynamics_test_2D_constant_traction_pointbc.txt",
+    # elastodynamics module, more boundary data on the same operator: inputs/bar.dirichlet-traction.quad.arc, bar.3D.dirichlet-traction.hexa.arc,
+    # bar.dirichlet.traction.bodyforce.quad.arc, semi-circle.pointBC.arc, truncated-cube.pointBC.arc
+    "meshes/msh/semi-circle.msh": "semi-circle.msh",
+    "modules/elastodynamics/check/bar_2d_dirichlet-traction.quad.txt": "elastodynamics_bar_2d_dirichlet-traction.quad.txt",
+    "modules/elastodynamics/check/bar_3d_dirichlet-traction.hexa.txt": "elastodynamics_bar_3d_dirichlet-traction.hexa.txt",
+    "modules/elastodynamics/check/bar_dirichlet_traction_bodyforce.quad.txt": "elastodynamics_bar_dirichlet_traction_bodyforce.quad.txt",
+    "modules/elastodynamics/check/semi-ciricle_point-bc.txt": "elastodynamics_semi-ciricle_point-bc.txt",
+    "modules/elastodynamics/check/truncated-cube_point-bc.txt": "elastodynamics_truncated-cube_point-bc.txt",
     # heat module (implicit Euler on lambda * stiffness + mass / dt): inputs/conduction.arc, 3d_conduction.arc, conduction.quad.arc
     "meshes/msh/plate.msh": "plate.msh",
     "modules/heat/check/2d_conduction.txt": "heat_2d_conduction.txt",
