@@ -316,6 +316,19 @@ HEAT_CASES = {
 }
 
 
+def add_in_pattern(rows, cols, vals, B):
+    """vals + the entries of the scipy matrix B, inside the CSR pattern (rows, cols) with ascending columns per row (what a sequence of
+    matrixAddValue calls does); every entry of B has to exist in the pattern"""
+    out = np.array(vals, dtype=np.float64, copy=True)
+    Bc = B.tocoo()
+    for r, c, v in zip(Bc.row, Bc.col, Bc.data):
+        lo, hi = int(rows[r]), int(rows[r + 1])
+        k = lo + int(np.searchsorted(cols[lo:hi], c))
+        assert k < hi and cols[k] == c, (r, c)
+        out[k] += v
+    return out
+
+
 def face_measure(mesh, face):
     """femutils/ArcaneFemFunctions.h:172-215: edge length, triangle area, quadrilateral area as two triangles (n1: n2-n1 x n0-n1, n3: n0-n3 x n2-n3)"""
     x = mesh.coords[np.asarray(face, dtype=np.int64)]
@@ -401,16 +414,50 @@ SOILDYNAMICS_CASES = {
     "semi_circle_constant_traction_pointbc": dict(mesh="semi-circle-soil.msh", E=6.62e6, nu=0.45, rho=2500.0, dt=0.01, tmax=0.08, f=[3359.6, 3452.3],
                                                   traction=[("input", [0.01, 0.01])], paraxial=["lower"], dirichlet=[("source", [0.0, 0.0003])],
                                                   penalty=1.0e30, golden="soildynamics_test_2D_constant_traction_pointbc.txt"),
+    # double-couple source (modules/soildynamics/DoubleCouple.h: the force of a time table overwrites the right-hand side at four named nodes --
+    # x-DoF of north (+) / south (-), y-DoF of east (-) / west (+)) in a square with paraxial boundaries all around; material given by wave speeds
+    "square_double_couple": dict(mesh="square_double-couple.msh", cs=2.0, cp=4.0, rho=1.0, dt=0.01, tmax=0.2, f=[0.0, 0.0], traction=[],
+                                 paraxial=["left", "top", "right", "bottom"], dirichlet=[], penalty=1.0e30,
+                                 double_couple=dict(north="sourceT", south="sourceB", east="sourceR", west="sourceL", table="soildynamics_force_loading_dc.txt"),
+                                 golden="soildynamics_test_paraxial_results.txt"),
+    "square_double_couple_bodyforce": dict(mesh="square_double-couple.msh", cs=2.0, cp=4.0, rho=1.0, dt=0.01, tmax=0.2, f=[1255.1, 32289.5], traction=[],
+                                           paraxial=["left", "top", "right", "bottom"], dirichlet=[], penalty=1.0e30,
+                                           double_couple=dict(north="sourceT", south="sourceB", east="sourceR", west="sourceL", table="soildynamics_force_loading_dc.txt"),
+                                           golden="soildynamics_test_paraxial_body-force_results.txt"),
 }
+
+
+def double_couple_rhs(case, mesh):
+    """modules/soildynamics/DoubleCouple.h:20-63 (2-D): returns apply(rhs, t), which overwrites the four source DoFs with the table's force at
+    time t (linear interpolation between the rows of the table, femutils/FemUtils.cc:182-212), or None for a case without such a source"""
+    dc = case.get("double_couple")
+    if dc is None:
+        return None
+    table = np.loadtxt(os.path.join(GOLDEN, dc["table"]))
+    dofs = [(2 * int(n), +1.0) for n in mesh.groups[dc["north"]]] + [(2 * int(n), -1.0) for n in mesh.groups[dc["south"]]] \
+        + [(2 * int(n) + 1, -1.0) for n in mesh.groups[dc["east"]]] + [(2 * int(n) + 1, +1.0) for n in mesh.groups[dc["west"]]]
+
+    def apply(rhs, t):
+        force = float(np.interp(t, table[:, 0], table[:, 1]))
+        for dof, sign in dofs:
+            rhs[dof] = sign * force
+        return rhs
+    return apply
 
 
 def soildynamics_coefficients(case):
     """modules/soildynamics/FemModule.cc:156-196: Lame constants and wave speeds from (E, nu, rho), Newmark-beta constants c0..c9"""
-    E, nu, rho, dt = case["E"], case["nu"], case["rho"], case["dt"]
-    mu = E / (2 * (1 + nu))
-    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
-    cs = np.sqrt(mu / rho)
-    cp = np.sqrt((lam + 2. * mu) / rho)
+    rho, dt = case["rho"], case["dt"]
+    if "E" in case:
+        E, nu = case["E"], case["nu"]
+        mu = E / (2 * (1 + nu))
+        lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+        cs = np.sqrt(mu / rho)
+        cp = np.sqrt((lam + 2. * mu) / rho)
+    else:  # wave speeds given
+        cs, cp = case["cs"], case["cp"]
+        mu = cs * cs * rho
+        lam = cp * cp * rho - 2 * mu
     gamma = 0.5
     beta = (1. / 4.) * (gamma + 0.5) * (gamma + 0.5)
     return dict(lam=lam, mu=mu, cs=cs, cp=cp, gamma=gamma, beta=beta, c0=rho / (beta * dt * dt), c3=rho / (beta * dt), c4=rho * (1. / 2. / beta - 1.),
@@ -447,14 +494,14 @@ def paraxial_boundary_matrix(mesh, faces, cp, cs):
 
 def soildynamics_time_loop(case, nb_dof, step):
     """modules/soildynamics/FemModule.cc:28-62, 75-78, 262-290: t starts at dt, the step that starts with t >= tmax is the last (and the one
-    compared with the golden file).  step(U, V, A) -> displacement of the step."""
+    compared with the golden file).  step(U, V, A, t) -> displacement of the step."""
     k = soildynamics_coefficients(case)
     gamma, beta, dt = k["gamma"], k["beta"], case["dt"]
     t = dt
     U, V, A = np.zeros(nb_dof), np.zeros(nb_dof), np.zeros(nb_dof)
     while True:
         last = t >= case["tmax"]
-        dU = step(U, V, A)
+        dU = step(U, V, A, t)
         a_new = (dU - U - dt * V) / (beta * dt * dt) - (1. - 2. * beta) / (2. * beta) * A
         V = V + dt * ((1. - gamma) * A + gamma * a_new)
         A = a_new

@@ -123,6 +123,12 @@ FILES = {
     "meshes/msh/semi-circle-soil.msh": "semi-circle-soil.msh",
     "modules/soildynamics/check/test_2D_constant_traction.txt": "soildynamics_test_2D_constant_traction.txt",
     "modules/soildynamics/check/test_2D_constant_traction_pointbc.txt": "soildynamics_test_2D_constant_traction_pointbc.txt",
+    # ... and its double-couple source (a force table in time applied at four named nodes, modules/soildynamics/DoubleCouple.h) inside a box of
+    # paraxial boundaries: inputs/double-couple.paraxial.arc, double-couple.paraxial.body-force.arc
+    "meshes/msh/square_double-couple.msh": "square_double-couple.msh",
+    "modules/soildynamics/data/force_loading_dc.txt": "soildynamics_force_loading_dc.txt",
+    "modules/soildynamics/check/test_paraxial_results.txt": "soildynamics_test_paraxial_results.txt",
+    "modules/soildynamics/check/test_paraxial_body-force_results.txt": "soildynamics_test_paraxial_body-force_results.txt",
     # elastodynamics module, more boundary data on the same operator: inputs/bar.dirichlet-traction.quad.arc, bar.3D.dirichlet-traction.hexa.arc,
     # bar.dirichlet.traction.bodyforce.quad.arc, semi-circle.pointBC.arc, truncated-cube.pointBC.arc
     "meshes/msh/semi-circle.msh": "semi-circle.msh",

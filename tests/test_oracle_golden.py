@@ -279,10 +279,7 @@ def test_heat_golden(name, nodewise):
     B, static = CS.convection_boundary_terms(m, case)   # (empty without convection surfaces)
     for group, q in case.get("neumann", []):
         O.rhs_neumann(m.dim, 1, m.coords, m.faces[group], q, static, kind=O.NEUMANN_FLUX)
-    A_ = (_csr(rows, cols, vals) + B).tocsr()
-    A_.sort_indices()
-    assert A_.nnz == rows[-1]
-    lhs = A_.data.copy()
+    lhs = CS.add_in_pattern(rows, cols, vals, B)
     O.dirichlet_penalty(rows, cols, lhs, np.zeros(m.nb_node), ids, g, case["penalty"])
     lu = spla.splu(_csr(rows, cols, lhs).tocsc())
 
@@ -333,16 +330,17 @@ def test_soildynamics_golden(name, nodewise):
         O.rhs_neumann(m.dim, b, m.coords, M.orient_boundary_faces(m, m.faces[group]), t, static, kind=O.NEUMANN_TRACTION)
     B = sum(CS.paraxial_boundary_matrix(m, m.faces[g], k["cp"], k["cs"]) for g in case["paraxial"])
     crow, ccol, _ = O.bsr_to_csr(b, rows, cols)
-    lhs = (_csr(crow, ccol, vals) + k["c7"] * B).tocsr()
-    lhs.sort_indices()
-    assert lhs.nnz == crow[-1]  # the boundary entries fall inside the cell pattern
+    lv = CS.add_in_pattern(crow, ccol, vals, k["c7"] * B)  # (the boundary entries fall inside the cell pattern)
     ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
-    lv = lhs.data.copy()
-    O.dirichlet_penalty(lhs.indptr.astype(np.int32), lhs.indices.astype(np.int32), lv, np.zeros(m.nb_node * b), ids, g, case["penalty"])
-    lu = spla.splu(sp.csr_matrix((lv, lhs.indices, lhs.indptr)).tocsc())
+    O.dirichlet_penalty(crow, ccol, lv, np.zeros(m.nb_node * b), ids, g, case["penalty"])
+    lu = spla.splu(_csr(crow, ccol, lv).tocsc())
 
-    def step(U, V, A):
+    source = CS.double_couple_rhs(case, m)
+
+    def step(U, V, A, t):
         rhs = static + (mass @ (k["c0"] * U + k["c3"] * V + k["c4"] * A).reshape(m.nb_node, b)).reshape(-1) + B @ (k["c7"] * U - k["c8"] * V + k["c9"] * A)
+        if source is not None:
+            source(rhs, t)
         rhs[ids] = case["penalty"] * np.asarray(g)
         return lu.solve(rhs)
 
