@@ -243,7 +243,38 @@ ELASTODYNAMICS_CASES = {
     "truncated_cube_point": dict(mesh="truncated_cube.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=1.0, f=[145.5e5, 56456.5e6, 87842.5e5],
                                  dirichlet=[("bottom", [0.0, 0.0, 0.0]), ("center", [18.0, 13.0, 14.0])], traction=[], penalty=1.0e30,
                                  golden="elastodynamics_truncated-cube_point-bc.txt", min_rel=1.0e-8),
+    # traction from a table in time (traction_table: surface -> file of `t tx ty tz` rows, linear in between): inputs/bar.transient-traction.arc,
+    # bar.transient-traction.quad.arc, bar.3D.transient-traction.arc, bar.3D.transient-traction.hexa.arc
+    "bar_2D_transient": dict(mesh="bar_dynamic.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 0.0],
+                             dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[], traction_table=[("surfaceright", "elastodynamics_traction_bar_test_1.txt")],
+                             penalty=1.0e30, golden="elastodynamics_2D_bar_transient_traction.txt", min_rel=1.0e-8),
+    "bar_quad_transient": dict(mesh="bar_dynamic_quad.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 0.0],
+                               dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[], traction_table=[("surfaceright", "elastodynamics_traction_bar_test_1.txt")],
+                               penalty=1.0e30, golden="elastodynamics_bar_transient-traction.quad.txt", min_rel=1.0e-8),
+    "bar_3D_transient": dict(mesh="bar_dynamic_3D.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.1, tmax=0.5, f=[0.0, 0.0, 0.0],
+                             dirichlet=[("surfaceleft", [0.0, 0.0, 0.0])], traction=[], traction_table=[("surfaceright", "elastodynamics_traction_bar_test_1.txt")],
+                             penalty=1.0e30, golden="elastodynamics_bar_3d_transient-traction.txt", min_rel=1.0e-8),
+    "bar_3D_hexa_transient": dict(mesh="bar_dynamic_3Dhexa.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.1, tmax=0.5, f=[0.0, 0.0, 0.0],
+                                  dirichlet=[("left", [0.0, 0.0, 0.0])], traction=[], traction_table=[("right", "elastodynamics_traction_bar_test_1.txt")],
+                                  penalty=1.0e30, golden="elastodynamics_bar_3d_transient-traction.hexa.txt", min_rel=1.0e-8),
 }
+
+
+def transient_traction(case, b, unit_rhs):
+    """traction tables of a case: unit_rhs(group, k) -> right-hand side of a unit traction in direction k on the surface (the term is linear in the
+    traction vector, femutils/ArcaneFemFunctions.h:2987-2996).  Returns rhs(t), the sum over the surfaces of table(t)[k] * unit_rhs(group, k)."""
+    terms = []
+    for group, fname in case.get("traction_table", []):
+        table = np.loadtxt(os.path.join(GOLDEN, fname))
+        terms.append((table, [unit_rhs(group, k) for k in range(b)]))
+
+    def rhs(t):
+        out = 0.0
+        for table, units in terms:
+            for k, u in enumerate(units):
+                out = out + float(np.interp(t, table[:, 0], table[:, 1 + k])) * u
+        return out
+    return rhs
 
 
 def golden_floor(case, golden):
@@ -266,7 +297,7 @@ def newmark_coefficients(case):
 
 def newmark_time_loop(case, nb_dof, solve_step, mass_times):
     """The module's time loop (FemModule.cc:29-131, 277-330): t starts at dt, the loop ends after the step that starts with
-    t >= tmax - dt.  solve_step(rhs_dynamic) -> displacement of the step (the caller adds the static loads and the Dirichlet rows);
+    t >= tmax - dt.  solve_step(rhs_dynamic, t) -> displacement of the step (the caller adds the static loads and the Dirichlet rows);
     mass_times(x) = consistent mass matrix (rho = 1 per component) times x.  Returns the last displacement."""
     gamma, beta, c0, _, _, c3, c4 = newmark_coefficients(case)
     dt = case["dt"]
@@ -277,7 +308,7 @@ def newmark_time_loop(case, nb_dof, solve_step, mass_times):
     dU = U
     while True:
         last = t >= tmax
-        dU = solve_step(mass_times(c0 * U + c3 * V + c4 * A))
+        dU = solve_step(mass_times(c0 * U + c3 * V + c4 * A), t)
         a_new = (dU - U - dt * V) / (beta * dt * dt) - (1. - 2. * beta) / (2. * beta) * A
         V = V + dt * ((1. - gamma) * A + gamma * a_new)
         A = a_new

@@ -137,6 +137,13 @@ FILES = {
     "modules/elastodynamics/check/bar_dirichlet_traction_bodyforce.quad.txt": "elastodynamics_bar_dirichlet_traction_bodyforce.quad.txt",
     "modules/elastodynamics/check/semi-ciricle_point-bc.txt": "elastodynamics_semi-ciricle_point-bc.txt",
     "modules/elastodynamics/check/truncated-cube_point-bc.txt": "elastodynamics_truncated-cube_point-bc.txt",
+    # ... and a traction read from a table in time (femutils/ArcaneFemFunctions.h:2959-2997): inputs/bar.transient-traction.arc, bar.transient-traction.quad.arc,
+    # bar.3D.transient-traction.arc, bar.3D.transient-traction.hexa.arc
+    "modules/elastodynamics/data/traction_bar_test_1.txt": "elastodynamics_traction_bar_test_1.txt",
+    "modules/elastodynamics/check/2D_elastodynamics_bar_transient_traction.txt": "elastodynamics_2D_bar_transient_traction.txt",
+    "modules/elastodynamics/check/bar_transient-traction.quad.txt": "elastodynamics_bar_transient-traction.quad.txt",
+    "modules/elastodynamics/check/bar_3d_transient-traction.txt": "elastodynamics_bar_3d_transient-traction.txt",
+    "modules/elastodynamics/check/bar_3d_transient-traction.hexa.txt": "elastodynamics_bar_3d_transient-traction.hexa.txt",
     # heat module (implicit Euler on lambda * stiffness + mass / dt): inputs/conduction.arc, 3d_conduction.arc, conduction.quad.arc
     "meshes/msh/plate.msh": "plate.msh",
     "modules/heat/check/2d_conduction.txt": "heat_2d_conduction.txt",

@@ -1307,12 +1307,19 @@ def test_elastodynamics_golden_solution(exec_ctx, name, variant):
     for group, t in case["traction"]:
         c.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), t, kind=A.NEUMANN_TRACTION)
     static = c.to_host(A.ARRAY_RHS).copy()
+
+    def unit_rhs(group, comp):  # a unit traction on the surface, assembled on the GPU
+        c.rhs_reset()
+        c.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), [1.0 if i == comp else 0.0 for i in range(b)], kind=A.NEUMANN_TRACTION)
+        return c.to_host(A.ARRAY_RHS).copy()
+
+    table_rhs = CS.transient_traction(case, b, unit_rhs)
     c.dirichlet_penalty(ids, g, case["penalty"])
     crow, ccol, vals = (c.to_host(w) for w in (A.ARRAY_CSR_ROWS, A.ARRAY_CSR_COLUMNS, A.ARRAY_VALUES))
     lu = spla.splu(sp.csr_matrix((vals, ccol, crow)).tocsc())
 
-    def solve_step(dynamic):
-        rhs = static + dynamic
+    def solve_step(dynamic, t):
+        rhs = static + dynamic + table_rhs(t)
         rhs[ids] = case["penalty"] * np.asarray(g)
         return lu.solve(rhs)
 

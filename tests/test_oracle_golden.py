@@ -249,8 +249,15 @@ def test_elastodynamics_golden(name, nodewise):
     def mass_times(x):
         return (mass @ x.reshape(m.nb_node, b)).reshape(-1)
 
-    def solve_step(dynamic):
-        rhs = static + dynamic
+    def unit_rhs(group, comp):
+        out = np.zeros(m.nb_node * b)
+        O.rhs_neumann(m.dim, b, m.coords, M.orient_boundary_faces(m, m.faces[group]), [1.0 if i == comp else 0.0 for i in range(b)], out, kind=O.NEUMANN_TRACTION)
+        return out
+
+    table_rhs = CS.transient_traction(case, b, unit_rhs)
+
+    def solve_step(dynamic, t):
+        rhs = static + dynamic + table_rhs(t)
         rhs[ids] = case["penalty"] * np.asarray(g)
         return lu.solve(rhs)
 
