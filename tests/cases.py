@@ -445,6 +445,10 @@ SOILDYNAMICS_CASES = {
     "semi_circle_constant_traction_pointbc": dict(mesh="semi-circle-soil.msh", E=6.62e6, nu=0.45, rho=2500.0, dt=0.01, tmax=0.08, f=[3359.6, 3452.3],
                                                   traction=[("input", [0.01, 0.01])], paraxial=["lower"], dirichlet=[("source", [0.0, 0.0003])],
                                                   penalty=1.0e30, golden="soildynamics_test_2D_constant_traction_pointbc.txt"),
+    # traction table in time + body force + paraxial boundary (inputs/transient-traction.arc)
+    "semi_circle_transient_traction": dict(mesh="semi-circle-soil.msh", E=6.62e6, nu=0.45, rho=2500.0, dt=0.01, tmax=0.08, f=[0.0, 315.9], traction=[],
+                                           traction_table=[("input", "soildynamics_semi-circle-soil-traction.txt")], paraxial=["lower"], dirichlet=[],
+                                           penalty=1.0e30, golden="soildynamics_test_2D_transient_traction.txt"),
     # double-couple source (modules/soildynamics/DoubleCouple.h: the force of a time table overwrites the right-hand side at four named nodes --
     # x-DoF of north (+) / south (-), y-DoF of east (-) / west (+)) in a square with paraxial boundaries all around; material given by wave speeds
     "square_double_couple": dict(mesh="square_double-couple.msh", cs=2.0, cp=4.0, rho=1.0, dt=0.01, tmax=0.2, f=[0.0, 0.0], traction=[],

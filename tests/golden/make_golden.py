@@ -129,6 +129,9 @@ FILES = {
     "modules/soildynamics/data/force_loading_dc.txt": "soildynamics_force_loading_dc.txt",
     "modules/soildynamics/check/test_paraxial_results.txt": "soildynamics_test_paraxial_results.txt",
     "modules/soildynamics/check/test_paraxial_body-force_results.txt": "soildynamics_test_paraxial_body-force_results.txt",
+    # ... and a traction table in time: inputs/transient-traction.arc
+    "modules/soildynamics/data/semi-circle-soil-traction.txt": "soildynamics_semi-circle-soil-traction.txt",
+    "modules/soildynamics/check/test_2D_transient_traction.txt": "soildynamics_test_2D_transient_traction.txt",
     # elastodynamics module, more boundary data on the same operator: inputs/bar.dirichlet-traction.quad.arc, bar.3D.dirichlet-traction.hexa.arc,
     # bar.dirichlet.traction.bodyforce.quad.arc, semi-circle.pointBC.arc, truncated-cube.pointBC.arc
     "meshes/msh/semi-circle.msh": "semi-circle.msh",

@@ -1454,6 +1454,13 @@ def test_soildynamics_golden_solution(exec_ctx, name, variant, layout):
     for group, t in case["traction"]:
         c.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), t, kind=A.NEUMANN_TRACTION)
     static = c.to_host(A.ARRAY_RHS).copy()
+
+    def unit_rhs(group, comp):  # a unit traction on the surface, assembled on the GPU
+        c.rhs_reset()
+        c.rhs_neumann(M.orient_boundary_faces(m, m.faces[group]), [1.0 if i == comp else 0.0 for i in range(b)], kind=A.NEUMANN_TRACTION)
+        return c.to_host(A.ARRAY_RHS).copy()
+
+    table_rhs = CS.transient_traction(case, b, unit_rhs)
     c.dirichlet_penalty(ids, g, case["penalty"])
     vals = _values_per_row(b, rows, c.to_host(A.ARRAY_VALUES), layout)
     lu = spla.splu(sp.csr_matrix((vals, ccol, crow)).tocsc())
@@ -1462,7 +1469,7 @@ def test_soildynamics_golden_solution(exec_ctx, name, variant, layout):
     source = CS.double_couple_rhs(case, m)
 
     def step(U, V, Acc, t):
-        rhs = static + (mass @ (k["c0"] * U + k["c3"] * V + k["c4"] * Acc).reshape(m.nb_node, b)).reshape(-1) + Bc @ (k["c7"] * U - k["c8"] * V + k["c9"] * Acc)
+        rhs = static + table_rhs(t) + (mass @ (k["c0"] * U + k["c3"] * V + k["c4"] * Acc).reshape(m.nb_node, b)).reshape(-1) + Bc @ (k["c7"] * U - k["c8"] * V + k["c9"] * Acc)
         if source is not None:
             source(rhs, t)
         rhs[ids] = case["penalty"] * np.asarray(g)

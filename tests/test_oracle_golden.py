@@ -344,8 +344,15 @@ def test_soildynamics_golden(name, nodewise):
 
     source = CS.double_couple_rhs(case, m)
 
+    def unit_rhs(group, comp):
+        out = np.zeros(m.nb_node * b)
+        O.rhs_neumann(m.dim, b, m.coords, M.orient_boundary_faces(m, m.faces[group]), [1.0 if i == comp else 0.0 for i in range(b)], out, kind=O.NEUMANN_TRACTION)
+        return out
+
+    table_rhs = CS.transient_traction(case, b, unit_rhs)
+
     def step(U, V, A, t):
-        rhs = static + (mass @ (k["c0"] * U + k["c3"] * V + k["c4"] * A).reshape(m.nb_node, b)).reshape(-1) + B @ (k["c7"] * U - k["c8"] * V + k["c9"] * A)
+        rhs = static + table_rhs(t) + (mass @ (k["c0"] * U + k["c3"] * V + k["c4"] * A).reshape(m.nb_node, b)).reshape(-1) + B @ (k["c7"] * U - k["c8"] * V + k["c9"] * A)
         if source is not None:
             source(rhs, t)
         rhs[ids] = case["penalty"] * np.asarray(g)
