@@ -251,6 +251,13 @@ ELASTODYNAMICS_CASES = {
     "bar_quad_transient": dict(mesh="bar_dynamic_quad.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 0.0],
                                dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[], traction_table=[("surfaceright", "elastodynamics_traction_bar_test_1.txt")],
                                penalty=1.0e30, golden="elastodynamics_bar_transient-traction.quad.txt", min_rel=1.0e-8),
+    # Rayleigh damping (inputs/bar.damping.arc): etam on the mass, etak on the stiffness
+    "bar_2D_damping": dict(mesh="bar_dynamic.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 0.0], etam=0.01, etak=0.01,
+                           dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[("surfaceright", [0.0, 0.01])], penalty=1.0e30,
+                           golden="elastodynamics_2D_bar_constant_traction_damping.txt", min_rel=1.0e-8),
+    "bar_quad_three_steps": dict(mesh="bar_dynamic_quad.msh", rho=12.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=0.25, f=[0.0, -13.5e5],
+                                 dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[], traction_table=[("surfaceright", "elastodynamics_traction_bar_three_steps.txt")],
+                                 penalty=1.0e30, golden="elastodynamics_2D_bar_transient_traction_three_steps.txt", min_rel=1.0e-8),  # (inputs/bar.dirichlet.three-step-traction.bodyforce.quad.arc)
     "bar_3D_transient": dict(mesh="bar_dynamic_3D.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.1, tmax=0.5, f=[0.0, 0.0, 0.0],
                              dirichlet=[("surfaceleft", [0.0, 0.0, 0.0])], traction=[], traction_table=[("surfaceright", "elastodynamics_traction_bar_test_1.txt")],
                              penalty=1.0e30, golden="elastodynamics_bar_3d_transient-traction.txt", min_rel=1.0e-8),
@@ -289,13 +296,35 @@ def newmark_coefficients(case):
     gamma = 0.5
     beta = (1. / 4.) * (gamma + 0.5) * (gamma + 0.5)
     rho, dt = case["rho"], case["dt"]
-    c0 = rho / (beta * dt * dt)
-    c3 = rho / beta / dt
-    c4 = rho * ((1. - 2. * beta) / 2. / beta)
-    return gamma, beta, c0, case["lam"], case["mu"], c3, c4
+    etam, etak = case.get("etam", 0.0), case.get("etak", 0.0)  # Rayleigh damping (zero in most cases)
+    c0 = rho / (beta * dt * dt) + etam * rho * gamma / beta / dt
+    c1 = case["lam"] + case["lam"] * etak * gamma / beta / dt
+    c2 = case["mu"] + case["mu"] * etak * gamma / beta / dt
+    c3 = rho / beta / dt - etam * rho * (1 - gamma / beta)
+    c4 = rho * ((1. - 2. * beta) / 2. / beta - etam * dt * (1. - gamma / 2 / beta))
+    return gamma, beta, c0, c1, c2, c3, c4
 
 
-def newmark_time_loop(case, nb_dof, solve_step, mass_times):
+def newmark_damping_terms(case, stiff_times):
+    """modules/elastodynamics/FemModule.cc:205-215 (c5 .. c10) and SourceTerm.h:79-84: the stiffness-type right-hand side terms of Rayleigh damping,
+    -K(c5, c6) U + K(c7, c9) V + K(c8, c10) A with K(lambda, mu) the elasticity matrix; stiff_times(lambda, mu, x) = K(lambda, mu) x.
+    Returns f(U, V, A) or None without stiffness damping."""
+    etak = case.get("etak", 0.0)
+    if etak == 0.0:
+        return None
+    gamma = 0.5
+    beta = (1. / 4.) * (gamma + 0.5) * (gamma + 0.5)
+    lam, mu, dt = case["lam"], case["mu"], case["dt"]
+    c5 = -lam * etak * gamma / beta / dt
+    c6 = -mu * etak * gamma / beta / dt
+    c7 = etak * lam * (gamma / beta - 1)
+    c8 = etak * lam * dt * ((1. - 2 * beta) / 2. / beta - (1. - gamma))
+    c9 = etak * mu * (gamma / beta - 1)
+    c10 = etak * mu * dt * ((1. - 2 * beta) / 2. / beta - (1. - gamma))
+    return lambda U, V, A: -stiff_times(c5, c6, U) + stiff_times(c7, c9, V) + stiff_times(c8, c10, A)
+
+
+def newmark_time_loop(case, nb_dof, solve_step, mass_times, damping=None):
     """The module's time loop (FemModule.cc:29-131, 277-330): t starts at dt, the loop ends after the step that starts with
     t >= tmax - dt.  solve_step(rhs_dynamic, t) -> displacement of the step (the caller adds the static loads and the Dirichlet rows);
     mass_times(x) = consistent mass matrix (rho = 1 per component) times x.  Returns the last displacement."""
@@ -308,7 +337,7 @@ def newmark_time_loop(case, nb_dof, solve_step, mass_times):
     dU = U
     while True:
         last = t >= tmax
-        dU = solve_step(mass_times(c0 * U + c3 * V + c4 * A), t)
+        dU = solve_step(mass_times(c0 * U + c3 * V + c4 * A) + (0.0 if damping is None else damping(U, V, A)), t)
         a_new = (dU - U - dt * V) / (beta * dt * dt) - (1. - 2. * beta) / (2. * beta) * A
         V = V + dt * ((1. - gamma) * A + gamma * a_new)
         A = a_new

@@ -143,6 +143,10 @@ FILES = {
     # ... and a traction read from a table in time (femutils/ArcaneFemFunctions.h:2959-2997): inputs/bar.transient-traction.arc, bar.transient-traction.quad.arc,
     # bar.3D.transient-traction.arc, bar.3D.transient-traction.hexa.arc
     "modules/elastodynamics/data/traction_bar_test_1.txt": "elastodynamics_traction_bar_test_1.txt",
+    "modules/elastodynamics/data/traction_bar_three_steps.txt": "elastodynamics_traction_bar_three_steps.txt",
+    # ... Rayleigh damping (etam, etak: stiffness-type terms on the right-hand side, modules/elastodynamics/SourceTerm.h:69-85): inputs/bar.damping.arc
+    "modules/elastodynamics/check/2D_elastodynamics_bar_constant_traction_damping.txt": "elastodynamics_2D_bar_constant_traction_damping.txt",
+    "modules/elastodynamics/check/2D_elastodynamics_bar_transient_traction_three_steps.txt": "elastodynamics_2D_bar_transient_traction_three_steps.txt",
     "modules/elastodynamics/check/2D_elastodynamics_bar_transient_traction.txt": "elastodynamics_2D_bar_transient_traction.txt",
     "modules/elastodynamics/check/bar_transient-traction.quad.txt": "elastodynamics_bar_transient-traction.quad.txt",
     "modules/elastodynamics/check/bar_3d_transient-traction.txt": "elastodynamics_bar_3d_transient-traction.txt",

@@ -1301,6 +1301,15 @@ def test_elastodynamics_golden_solution(exec_ctx, name, variant):
     c.assemble(A.OP_DIFFUSION_REACTION, params=[0.0, 1.0], fmt=A.FORMAT_BSR, variant=variant)
     mass = sp.csr_matrix((c.to_host(A.ARRAY_VALUES), c.to_host(A.ARRAY_COLUMNS), c.to_host(A.ARRAY_ROWS)))
     c.build_pattern(b)
+    damping = None
+    if case.get("etak", 0.0) != 0.0:  # Rayleigh damping: the elasticity matrices of the right-hand side terms, from the GPU too
+        parts = []
+        for prm in ([1.0, 0.0], [0.0, 1.0]):
+            c.reset_values()
+            c.assemble(A.OP_ELASTICITY, params=prm, fmt=A.FORMAT_BSR, variant=variant, layout=A.LAYOUT_PER_ROW)
+            parts.append(sp.csr_matrix((c.to_host(A.ARRAY_VALUES).copy(), c.to_host(A.ARRAY_CSR_COLUMNS).copy(), c.to_host(A.ARRAY_CSR_ROWS).copy())))
+        c.reset_values()
+        damping = CS.newmark_damping_terms(case, lambda lam, mu, x: lam * (parts[0] @ x) + mu * (parts[1] @ x))
     c.assemble(A.OP_ELASTODYNAMICS, params=[c0, c1, c2], fmt=A.FORMAT_BSR, variant=variant, layout=A.LAYOUT_PER_ROW)
     c.rhs_reset()
     c.rhs_source(case["f"], nodewise=variant == A.VARIANT_NODEWISE)
@@ -1323,7 +1332,7 @@ def test_elastodynamics_golden_solution(exec_ctx, name, variant):
         rhs[ids] = case["penalty"] * np.asarray(g)
         return lu.solve(rhs)
 
-    u = CS.newmark_time_loop(case, m.nb_node * b, solve_step, lambda x: (mass @ x.reshape(m.nb_node, b)).reshape(-1))
+    u = CS.newmark_time_loop(case, m.nb_node * b, solve_step, lambda x: (mass @ x.reshape(m.nb_node, b)).reshape(-1), damping)
     golden = CS.load_golden(case["golden"], b)
     assert CS.compare_to_golden(m, u, golden, b, eps=1.0e-4, min_value=CS.golden_floor(case, golden), subset=True) < case.get("tol", 1.0e-5)
 

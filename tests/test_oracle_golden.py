@@ -261,7 +261,10 @@ def test_elastodynamics_golden(name, nodewise):
         rhs[ids] = case["penalty"] * np.asarray(g)
         return lu.solve(rhs)
 
-    u = CS.newmark_time_loop(case, m.nb_node * b, solve_step, mass_times)
+    k_lam = _csr(crow, ccol, O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[1.0, 0.0], layout=O.LAYOUT_PER_ROW, nodewise=nodewise))
+    k_mu = _csr(crow, ccol, O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTICITY, form=O.FORM_BSR, params=[0.0, 1.0], layout=O.LAYOUT_PER_ROW, nodewise=nodewise))
+    damping = CS.newmark_damping_terms(case, lambda lam, mu, x: lam * (k_lam @ x) + mu * (k_mu @ x))
+    u = CS.newmark_time_loop(case, m.nb_node * b, solve_step, mass_times, damping)
     golden = CS.load_golden(case["golden"], b)
     worst = CS.compare_to_golden(m, u, golden, b, eps=1.0e-4, min_value=CS.golden_floor(case, golden), subset=True)
     assert worst < case.get("tol", 1.0e-5)
