@@ -255,6 +255,10 @@ ELASTODYNAMICS_CASES = {
     "bar_2D_damping": dict(mesh="bar_dynamic.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 0.0], etam=0.01, etak=0.01,
                            dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[("surfaceright", [0.0, 0.01])], penalty=1.0e30,
                            golden="elastodynamics_2D_bar_constant_traction_damping.txt", min_rel=1.0e-8),
+    # generalized-alpha time discretization (inputs/bar.Galpha.arc)
+    "bar_2D_galpha": dict(mesh="bar_dynamic.msh", rho=1.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=2.0, f=[0.0, 0.0], alpm=0.20, alpf=0.40,
+                          dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[("surfaceright", [0.0, 0.01])], penalty=1.0e30,
+                          golden="elastodynamics_2D_Galpha_time_discretization.txt", min_rel=1.0e-8),
     "bar_quad_three_steps": dict(mesh="bar_dynamic_quad.msh", rho=12.0, lam=576.9230769, mu=384.6153846, dt=0.08, tmax=0.25, f=[0.0, -13.5e5],
                                  dirichlet=[("surfaceleft", [0.0, 0.0])], traction=[], traction_table=[("surfaceright", "elastodynamics_traction_bar_three_steps.txt")],
                                  penalty=1.0e30, golden="elastodynamics_2D_bar_transient_traction_three_steps.txt", min_rel=1.0e-8),  # (inputs/bar.dirichlet.three-step-traction.bodyforce.quad.arc)
@@ -291,37 +295,43 @@ def golden_floor(case, golden):
     return max(1.0e-14, case.get("min_rel", 0.0) * gmax)
 
 
-def newmark_coefficients(case):
-    """modules/elastodynamics/FemModule.cc:197-215 with etam = etak = 0: c0 (mass), c1 (lambda-like), c2 (mu-like), c3, c4 (right-hand side)"""
-    gamma = 0.5
+def _time_constants(case):
+    """modules/elastodynamics/FemModule.cc:197-232: c0 .. c10 of the Newmark-beta scheme (alpm = alpf = 0) and of the generalized-alpha scheme
+    (a case with alpm / alpf), Rayleigh damping etam / etak included"""
+    rho, dt, lam, mu = case["rho"], case["dt"], case["lam"], case["mu"]
+    etam, etak = case.get("etam", 0.0), case.get("etak", 0.0)
+    alpm, alpf = case.get("alpm", 0.0), case.get("alpf", 0.0)
+    gamma = 0.5 + alpf - alpm
     beta = (1. / 4.) * (gamma + 0.5) * (gamma + 0.5)
-    rho, dt = case["rho"], case["dt"]
-    etam, etak = case.get("etam", 0.0), case.get("etak", 0.0)  # Rayleigh damping (zero in most cases)
-    c0 = rho / (beta * dt * dt) + etam * rho * gamma / beta / dt
-    c1 = case["lam"] + case["lam"] * etak * gamma / beta / dt
-    c2 = case["mu"] + case["mu"] * etak * gamma / beta / dt
-    c3 = rho / beta / dt - etam * rho * (1 - gamma / beta)
-    c4 = rho * ((1. - 2. * beta) / 2. / beta - etam * dt * (1. - gamma / 2 / beta))
-    return gamma, beta, c0, c1, c2, c3, c4
+    c = [0.0] * 11
+    c[0] = rho * (1. - alpm) / (beta * dt * dt) + etam * rho * gamma * (1 - alpf) / beta / dt
+    c[1] = lam * (1. - alpf) + lam * etak * gamma * (1. - alpf) / beta / dt
+    c[2] = mu * (1. - alpf) + mu * etak * gamma * (1. - alpf) / beta / dt
+    c[3] = rho * (1. - alpm) / beta / dt - etam * rho * (1 - gamma * (1 - alpf) / beta)
+    c[4] = rho * ((1. - alpm) * (1. - 2. * beta) / 2. / beta - alpm - etam * dt * (1. - alpf) * (1. - gamma / 2 / beta))
+    c[5] = lam * alpf - lam * etak * gamma * (1. - alpf) / beta / dt
+    c[6] = mu * alpf - mu * etak * gamma * (1. - alpf) / beta / dt
+    c[7] = etak * lam * (gamma * (1. - alpf) / beta - 1)
+    c[8] = etak * lam * dt * (1. - alpf) * ((1. - 2 * beta) / 2. / beta - (1. - gamma))
+    c[9] = etak * mu * (gamma * (1. - alpf) / beta - 1)
+    c[10] = etak * mu * dt * (1. - alpf) * ((1. - 2 * beta) / 2. / beta - (1. - gamma))
+    return gamma, beta, c
+
+
+def newmark_coefficients(case):
+    """gamma, beta, c0 (mass), c1 (lambda-like), c2 (mu-like), c3, c4 (mass terms of the right-hand side)"""
+    gamma, beta, c = _time_constants(case)
+    return gamma, beta, c[0], c[1], c[2], c[3], c[4]
 
 
 def newmark_damping_terms(case, stiff_times):
-    """modules/elastodynamics/FemModule.cc:205-215 (c5 .. c10) and SourceTerm.h:79-84: the stiffness-type right-hand side terms of Rayleigh damping,
+    """modules/elastodynamics/SourceTerm.h:79-84: the stiffness-type right-hand side terms (Rayleigh damping, generalized-alpha),
     -K(c5, c6) U + K(c7, c9) V + K(c8, c10) A with K(lambda, mu) the elasticity matrix; stiff_times(lambda, mu, x) = K(lambda, mu) x.
-    Returns f(U, V, A) or None without stiffness damping."""
-    etak = case.get("etak", 0.0)
-    if etak == 0.0:
+    Returns f(U, V, A), or None when c5 .. c10 are all zero."""
+    _, _, c = _time_constants(case)
+    if not any(c[5:]):
         return None
-    gamma = 0.5
-    beta = (1. / 4.) * (gamma + 0.5) * (gamma + 0.5)
-    lam, mu, dt = case["lam"], case["mu"], case["dt"]
-    c5 = -lam * etak * gamma / beta / dt
-    c6 = -mu * etak * gamma / beta / dt
-    c7 = etak * lam * (gamma / beta - 1)
-    c8 = etak * lam * dt * ((1. - 2 * beta) / 2. / beta - (1. - gamma))
-    c9 = etak * mu * (gamma / beta - 1)
-    c10 = etak * mu * dt * ((1. - 2 * beta) / 2. / beta - (1. - gamma))
-    return lambda U, V, A: -stiff_times(c5, c6, U) + stiff_times(c7, c9, V) + stiff_times(c8, c10, A)
+    return lambda U, V, A: -stiff_times(c[5], c[6], U) + stiff_times(c[7], c[9], V) + stiff_times(c[8], c[10], A)
 
 
 def newmark_time_loop(case, nb_dof, solve_step, mass_times, damping=None):

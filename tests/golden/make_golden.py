@@ -146,6 +146,8 @@ FILES = {
     "modules/elastodynamics/data/traction_bar_three_steps.txt": "elastodynamics_traction_bar_three_steps.txt",
     # ... Rayleigh damping (etam, etak: stiffness-type terms on the right-hand side, modules/elastodynamics/SourceTerm.h:69-85): inputs/bar.damping.arc
     "modules/elastodynamics/check/2D_elastodynamics_bar_constant_traction_damping.txt": "elastodynamics_2D_bar_constant_traction_damping.txt",
+    # ... generalized-alpha time discretization (inputs/bar.Galpha.arc)
+    "modules/elastodynamics/check/2D_elastodynamics_Galpha_time_discretization.txt": "elastodynamics_2D_Galpha_time_discretization.txt",
     "modules/elastodynamics/check/2D_elastodynamics_bar_transient_traction_three_steps.txt": "elastodynamics_2D_bar_transient_traction_three_steps.txt",
     "modules/elastodynamics/check/2D_elastodynamics_bar_transient_traction.txt": "elastodynamics_2D_bar_transient_traction.txt",
     "modules/elastodynamics/check/bar_transient-traction.quad.txt": "elastodynamics_bar_transient-traction.quad.txt",

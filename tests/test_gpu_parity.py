@@ -1302,7 +1302,7 @@ def test_elastodynamics_golden_solution(exec_ctx, name, variant):
     mass = sp.csr_matrix((c.to_host(A.ARRAY_VALUES), c.to_host(A.ARRAY_COLUMNS), c.to_host(A.ARRAY_ROWS)))
     c.build_pattern(b)
     damping = None
-    if case.get("etak", 0.0) != 0.0:  # Rayleigh damping: the elasticity matrices of the right-hand side terms, from the GPU too
+    if CS.newmark_damping_terms(case, None) is not None:  # Rayleigh damping, generalized-alpha: the elasticity matrices of the right-hand side terms, from the GPU too
         parts = []
         for prm in ([1.0, 0.0], [0.0, 1.0]):
             c.reset_values()
