@@ -494,6 +494,12 @@ SOILDYNAMICS_CASES = {
                                  paraxial=["left", "top", "right", "bottom"], dirichlet=[], penalty=1.0e30,
                                  double_couple=dict(north="sourceT", south="sourceB", east="sourceR", west="sourceL", table="soildynamics_force_loading_dc.txt"),
                                  golden="soildynamics_test_paraxial_results.txt"),
+    # 3-D: paraxial triangles of a Tet4 mesh, the double couple acts on the x- and z-DoFs (inputs/3d.double-couple.paraxial.soil.arc; the Hexa8
+    # twin's mesh file carries its source points as isolated nodes without physical groups -- not reproduced)
+    "cube_double_couple_3D": dict(mesh="cube_double_couple_3d.msh", cs=21.5, cp=40.0, rho=9.0, dt=0.01, tmax=0.1, f=[0.0, 0.0, 0.0], traction=[],
+                                  paraxial=["leftsur"], dirichlet=[], penalty=1.0e30,
+                                  double_couple=dict(north="dcNorth", south="dcSouth", east="dcEast", west="dcWest", table="soildynamics_force_loading_dc.txt"),
+                                  golden="soildynamics_3d_test_paraxial_double_couple.txt"),
     "square_double_couple_bodyforce": dict(mesh="square_double-couple.msh", cs=2.0, cp=4.0, rho=1.0, dt=0.01, tmax=0.2, f=[1255.1, 32289.5], traction=[],
                                            paraxial=["left", "top", "right", "bottom"], dirichlet=[], penalty=1.0e30,
                                            double_couple=dict(north="sourceT", south="sourceB", east="sourceR", west="sourceL", table="soildynamics_force_loading_dc.txt"),
@@ -502,14 +508,15 @@ SOILDYNAMICS_CASES = {
 
 
 def double_couple_rhs(case, mesh):
-    """modules/soildynamics/DoubleCouple.h:20-63 (2-D): returns apply(rhs, t), which overwrites the four source DoFs with the table's force at
+    """modules/soildynamics/DoubleCouple.h:20-63: returns apply(rhs, t), which overwrites the four source DoFs with the table's force at
     time t (linear interpolation between the rows of the table, femutils/FemUtils.cc:182-212), or None for a case without such a source"""
     dc = case.get("double_couple")
     if dc is None:
         return None
     table = np.loadtxt(os.path.join(GOLDEN, dc["table"]))
-    dofs = [(2 * int(n), +1.0) for n in mesh.groups[dc["north"]]] + [(2 * int(n), -1.0) for n in mesh.groups[dc["south"]]] \
-        + [(2 * int(n) + 1, -1.0) for n in mesh.groups[dc["east"]]] + [(2 * int(n) + 1, +1.0) for n in mesh.groups[dc["west"]]]
+    b, ew = mesh.dim, mesh.dim - 1  # north / south act on the x-DoF, east / west on the y-DoF in 2-D and on the z-DoF in 3-D
+    dofs = [(b * int(n), +1.0) for n in mesh.groups[dc["north"]]] + [(b * int(n), -1.0) for n in mesh.groups[dc["south"]]] \
+        + [(b * int(n) + ew, -1.0) for n in mesh.groups[dc["east"]]] + [(b * int(n) + ew, +1.0) for n in mesh.groups[dc["west"]]]
 
     def apply(rhs, t):
         force = float(np.interp(t, table[:, 0], table[:, 1]))
@@ -546,22 +553,40 @@ def _mass_matrix(u, v):
 
 
 def paraxial_boundary_matrix(mesh, faces, cp, cs):
-    """sum over the boundary edges of length * P_edge as a scipy CSR matrix over the 2 * nb_node DoFs
-    (modules/soildynamics/Paraxial.h:27-41 `_computeParaxialElementMatrixEdge2`, scatter as :137-190)"""
+    """sum over the boundary faces of measure * P_face as a scipy CSR matrix over the dim * nb_node DoFs: edges in 2-D, triangles / quadrilaterals
+    in 3-D (modules/soildynamics/Paraxial.h:27-90 `_computeParaxialElementMatrix{Edge2,Tria3,Quad4}`, scatter as :137-190).  With n the unit
+    normal (its sign does not matter): P = sum_a (n_a^2 cp + (1 - n_a^2) cs) M(U_a, U_a) + sum_{a != b} n_a n_b (cp - cs) M(U_a, U_b), divided by
+    6 / 12 / 20, U_a = 1 on the a-th DoF of every node of the face."""
     import scipy.sparse as sp
-    ux, uy = np.array([1., 0., 1., 0.]), np.array([0., 1., 0., 1.])
+    b = mesh.dim
     rows, cols, vals = [], [], []
-    for n0, n1 in np.asarray(faces, dtype=np.int64):
-        dx, dy = mesh.coords[n1, 0] - mesh.coords[n0, 0], mesh.coords[n1, 1] - mesh.coords[n0, 1]
-        length = np.sqrt(dx * dx + dy * dy)
-        nx, ny = dy / length, -dx / length
-        P = ((nx * nx * cp + ny * ny * cs) * _mass_matrix(ux, ux) + (ny * ny * cp + nx * nx * cs) * _mass_matrix(uy, uy)
-             + (nx * ny * (cp - cs)) * _mass_matrix(ux, uy) + (nx * ny * (cp - cs)) * _mass_matrix(uy, ux)) / 6.
-        dofs = np.array([2 * n0, 2 * n0 + 1, 2 * n1, 2 * n1 + 1])
-        rows.append(np.repeat(dofs, 4))
-        cols.append(np.tile(dofs, 4))
-        vals.append((length * P).ravel())
-    B = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(2 * mesh.nb_node, 2 * mesh.nb_node)).tocsr()
+    for face in np.asarray(faces, dtype=np.int64):
+        k = len(face)
+        x = mesh.coords[face]
+        if k == 2:
+            d = x[1] - x[0]
+            nrm = np.array([d[1], -d[0]]) / np.sqrt(d[0] * d[0] + d[1] * d[1])
+        elif k == 3:
+            nrm = np.cross(x[1] - x[0], x[2] - x[0])
+            nrm = nrm / np.linalg.norm(nrm)
+        else:  # Newell's formula (femutils/ArcaneFemFunctions.h:493-512)
+            nxt = np.roll(x, -1, axis=0)
+            nrm = np.array([np.sum((x[:, 1] - nxt[:, 1]) * (x[:, 2] + nxt[:, 2])), np.sum((x[:, 2] - nxt[:, 2]) * (x[:, 0] + nxt[:, 0])),
+                            np.sum((x[:, 0] - nxt[:, 0]) * (x[:, 1] + nxt[:, 1]))])
+            nrm = nrm / np.linalg.norm(nrm)
+        U = [np.tile(np.eye(b)[a], k) for a in range(b)]
+        P = np.zeros((b * k, b * k))
+        for a in range(b):
+            P += (nrm[a] * nrm[a] * cp + (1. - nrm[a] * nrm[a]) * cs) * _mass_matrix(U[a], U[a])
+            for c in range(b):
+                if c != a:
+                    P += (nrm[a] * nrm[c] * (cp - cs)) * _mass_matrix(U[a], U[c])
+        P /= {2: 6., 3: 12., 4: 20.}[k]
+        dofs = (b * face[:, None] + np.arange(b)[None, :]).ravel()
+        rows.append(np.repeat(dofs, b * k))
+        cols.append(np.tile(dofs, b * k))
+        vals.append((face_measure(mesh, face) * P).ravel())
+    B = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(b * mesh.nb_node, b * mesh.nb_node)).tocsr()
     B.sum_duplicates()
     return B
 

@@ -129,6 +129,9 @@ FILES = {
     "modules/soildynamics/data/force_loading_dc.txt": "soildynamics_force_loading_dc.txt",
     "modules/soildynamics/check/test_paraxial_results.txt": "soildynamics_test_paraxial_results.txt",
     "modules/soildynamics/check/test_paraxial_body-force_results.txt": "soildynamics_test_paraxial_body-force_results.txt",
+    # ... in 3-D (paraxial triangles / quadrilaterals, modules/soildynamics/Paraxial.h:43-90): inputs/3d.double-couple.paraxial.soil.arc
+    "meshes/msh/cube_double_couple_3d.msh": "cube_double_couple_3d.msh",
+    "modules/soildynamics/check/3d_test_paraxial_double_couple.txt": "soildynamics_3d_test_paraxial_double_couple.txt",
     # ... and a traction table in time: inputs/transient-traction.arc
     "modules/soildynamics/data/semi-circle-soil-traction.txt": "soildynamics_semi-circle-soil-traction.txt",
     "modules/soildynamics/check/test_2D_transient_traction.txt": "soildynamics_test_2D_transient_traction.txt",

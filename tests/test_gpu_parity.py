@@ -1434,7 +1434,7 @@ def test_soildynamics_golden_solution(exec_ctx, name, variant, layout):
     c = exec_ctx
     case = CS.SOILDYNAMICS_CASES[name]
     m = _fixture_mesh(case["mesh"])
-    b = 2
+    b = m.dim
     k = CS.soildynamics_coefficients(case)
     ids, g = CS.dirichlet_dofs(m, case["dirichlet"], b)
     c.set_mesh(m.dim, m.coords, m.cells)

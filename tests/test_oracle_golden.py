@@ -330,7 +330,7 @@ def test_soildynamics_golden(name, nodewise):
     (BSRMatrix::addValue in modules/soildynamics/Paraxial.h:153-186), Newmark-beta loop, against the module's golden displacement files."""
     case = CS.SOILDYNAMICS_CASES[name]
     m = _load(case)
-    b = 2
+    b = m.dim
     k = CS.soildynamics_coefficients(case)
     rows, cols = O.build_pattern(m.npc, m.nb_node, m.cells)
     vals = O.assemble(m.dim, m.coords, m.cells, rows, cols, op=O.OP_ELASTODYNAMICS, form=O.FORM_BSR, params=[k["c0"], k["lam"], k["mu"]], layout=O.LAYOUT_PER_ROW, nodewise=nodewise)
