@@ -363,15 +363,20 @@ def timed_steps(ev, stream, fn_build, fn_values, reps):
     return statistics.mean(e[0].elapsed_time(e[1]) for e in evs), statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
 
 
-def side_config(torch, A, device, stream, ev, name, n, op, b, layouts, peak):
+def side_config(torch, A, device, stream, ev, name, n, op, b, layouts, peak, coefficient=None):
     """One entry of the `configs` block: another BASELINE configuration on the same GPU, same protocol
-    (steady-state BuildMatrix + AddAndCompute, tiled gather), checked against the oracle's digest."""
+    (steady-state BuildMatrix + AddAndCompute, tiled gather), checked against the oracle's digest.
+    coefficient: a uniform per-cell conductivity (afb_set_cell_coefficient) -- the [nb_cell] array is read cell by cell all the same
+    (k_assemble_tiled_coef), and the digest has to be `coefficient` times the golden one."""
     out = []
     ctx = A.Context(device, stream=stream.cuda_stream)
     try:
         info = ctx.generate_box(3, n)
         nbr, nnz = ctx.build_pattern(b)
         bytes_values, bytes_pattern = algorithmic_bytes(info["nb_cell"], info["nb_node"], nnz, b=b)
+        if coefficient is not None:
+            ctx.set_cell_coefficient(float(coefficient))
+            bytes_values += 8 * info["nb_cell"]
         params = None
         if op == A.OP_ELASTICITY:
             lam = E_MOD * NU / ((1 + NU) * (1 - 2 * NU))
@@ -388,10 +393,15 @@ def side_config(torch, A, device, stream, ev, name, n, op, b, layouts, peak):
             bm, vm = timed_steps(ev, stream, lambda: ctx.build_pattern(b), asm, 5)
             key = ("poisson3d_n%d" if op == A.OP_POISSON else "elasticity3d_n%d") % n
             ga, gt, _ = matrix_digest(torch, A, ctx, device, nbr, b, layout)
+            if coefficient is not None:
+                ga, gt = ga / coefficient, gt / coefficient
             ach = bytes_values / (vm * 1e-3) / 1e9
             tkey = f"k_assemble_tiled<4>:3d:n={n}:b=1" if b == 1 else f"k_assemble_rows_vec<4, {layout}>:3d:n={n}:b={b}"
+            if coefficient is not None:
+                tkey = f"k_assemble_tiled_coef<4>:3d:n={n}:b=1"
             traffic, traffic_src = committed_traffic(None, n, exact_key=tkey)
-            out.append({"config": name, "workload": f"box n={n} ({info['nb_cell']} Tet4), " + ("Poisson b=1 CSR" if b == 1 else f"elasticity b={b} BSR, values {'per block (BSR)' if layout == 0 else 'per row (AF-BSR / CSR hand-off)'}"),
+            out.append({"config": name, "workload": f"box n={n} ({info['nb_cell']} Tet4), " + ("Poisson b=1 CSR" if b == 1 else f"elasticity b={b} BSR, values {'per block (BSR)' if layout == 0 else 'per row (AF-BSR / CSR hand-off)'}")
+                        + ("" if coefficient is None else f", per-cell conductivity array (uniform {coefficient}: fourier / FourierNL modules), digest / {coefficient} checked"),
                         "variant": VARIANT_NAMES[2], "build_matrix_ms": bm, "add_and_compute_ms": vm, "ms_per_step": bm + vm,
                         "elements_per_s": info["nb_cell"] / ((bm + vm) * 1e-3),
                         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": float(bytes_values),
@@ -858,6 +868,7 @@ def run_b200(args):
             if n != 120:
                 cfgs += side_config(torch, A, local_rank, stream, ev, "C2", 120, A.OP_POISSON, 1, [A.LAYOUT_PER_BLOCK], peak)
             cfgs += side_config(torch, A, local_rank, stream, ev, "C3", args.n_c3, A.OP_ELASTICITY, 3, [A.LAYOUT_PER_ROW, A.LAYOUT_PER_BLOCK], peak)
+            cfgs += side_config(torch, A, local_rank, stream, ev, "C2+conductivity", 120, A.OP_POISSON, 1, [A.LAYOUT_PER_BLOCK], peak, coefficient=2.5)
             line["configs"] = cfgs
         if cpus_at_start is not None:
             os.sched_setaffinity(0, cpus_at_start)  # the CPU baseline uses every host core again
