@@ -188,7 +188,56 @@ ELASTICITY_CASES = {
 
 # Quad4 / Hexa8 elasticity (modules/elasticity/ElementMatrixHexQuad.h): inputs/2D.dirichlet.bodyforce.quad.arc,
 # bar.2D.Dirichlet.bodyForce.quad.arc, 3D.dirichlet.bodyforce.hexa.arc
+def cartesian_mesh(n, length):
+    """Arcane's Cartesian2D / Cartesian3D mesh generator as the reference's .arc files use it (`<generator name="Cartesian2D">` with
+    `<x><n>..</n><length>..</length></x>` ..., origin 0, generate-sod-groups): Quad4 / Hexa8 cells, node uniqueId = i + j (nx+1) + k (nx+1)(ny+1),
+    face groups XMIN / XMAX / YMIN / ... as node groups (all the Dirichlet conditions need)."""
+    from arcanefem_b200 import mesh as M
+    dim = len(n)
+    npts = [k + 1 for k in n]
+    grids = np.meshgrid(*[np.arange(p) for p in npts], indexing="ij")
+    stride = [1, npts[0], npts[0] * npts[1]][:dim]
+    uid = sum(g * s for g, s in zip(grids, stride)).ravel()
+    order = np.argsort(uid)
+    ijk = np.stack([g.ravel() for g in grids], axis=1)[order]
+    coords = np.zeros((ijk.shape[0], 3))
+    for a in range(dim):
+        coords[:, a] = ijk[:, a] * (length[a] / n[a])
+    node = lambda *idx: sum(i * s for i, s in zip(idx, stride))
+    cells = []
+    if dim == 2:
+        for j in range(n[1]):
+            for i in range(n[0]):
+                cells.append([node(i, j), node(i + 1, j), node(i + 1, j + 1), node(i, j + 1)])
+    else:
+        for k in range(n[2]):
+            for j in range(n[1]):
+                for i in range(n[0]):
+                    cells.append([node(i, j, k), node(i + 1, j, k), node(i + 1, j + 1, k), node(i, j + 1, k),
+                                  node(i, j, k + 1), node(i + 1, j, k + 1), node(i + 1, j + 1, k + 1), node(i, j + 1, k + 1)])
+    groups = {}
+    for a, axis in enumerate("XYZ"[:dim]):
+        groups[axis + "MIN"] = np.flatnonzero(ijk[:, a] == 0).astype(np.int32)
+        groups[axis + "MAX"] = np.flatnonzero(ijk[:, a] == n[a]).astype(np.int32)
+    return M.Mesh(dim=dim, coords=coords, cells=np.array(cells, dtype=np.int32), node_uid=np.arange(ijk.shape[0], dtype=np.int64), groups=groups)
+
+
+def load_mesh(name):
+    """a reference mesh file of tests/golden/, or `cartesian:nx,ny[,nz]:lx,ly[,lz]` for Arcane's generated meshes"""
+    from arcanefem_b200 import mesh as M
+    if name.startswith("cartesian:"):
+        _, n, length = name.split(":")
+        return cartesian_mesh([int(v) for v in n.split(",")], [float(v) for v in length.split(",")])
+    return M.read_msh(os.path.join(GOLDEN, name))
+
+
 Q1_ELASTICITY_CASES = {
+    # Arcane's cartesian generator instead of a mesh file (inputs/bar.2D.cartesian.Dirichlet.bodyForce.arc, bar.3D.cartesian.Dirichlet.bodyForce.arc)
+    "cartesian_bar_2D": dict(mesh="cartesian:10,2:1.0,0.1", E=21.0e5, nu=0.28, f=[-1.0, 0.0], dirichlet=[("XMIN", [0.0, 0.0]), ("XMAX", [None, 1.0])],
+                             penalty=1.0e30, golden="elasticity_bar.2D.cartesian.Dirichlet.bodyForce.txt"),
+    "cartesian_bar_3D": dict(mesh="cartesian:10,2,2:1.0,0.1,0.04", E=21.0e5, nu=0.28, f=[-1.0, 0.0, 0.0],
+                             dirichlet=[("XMIN", [0.0, 0.0, 0.0]), ("XMAX", [None, 1.0, None])], penalty=1.0e30,
+                             golden="elasticity_bar.3D.cartesian.Dirichlet.bodyForce.txt", min_rel=1.0e-6),  # (mid-plane components are 1e-9 of the deflection: cancellation)
     "five_quads": dict(mesh="five_quads.msh", E=200e9, nu=0.3, f=[-9818949214245.0, -7818949234281.0],
                        dirichlet=[("bot", [0.0, 0.0]), ("top", [1.9, 14.5])], penalty=1.0e30, golden="elasticity_2D.dirichlet.bodyforce.quad.txt"),
     "plate_quad": dict(mesh="plate.quad.msh", E=21.0e5, nu=0.28, f=[0.0, -1.0], dirichlet=[("left", [0.0, 0.0])], penalty=1.0e30,

@@ -156,6 +156,10 @@ FILES = {
     "modules/elastodynamics/check/bar_transient-traction.quad.txt": "elastodynamics_bar_transient-traction.quad.txt",
     "modules/elastodynamics/check/bar_3d_transient-traction.txt": "elastodynamics_bar_3d_transient-traction.txt",
     "modules/elastodynamics/check/bar_3d_transient-traction.hexa.txt": "elastodynamics_bar_3d_transient-traction.hexa.txt",
+    # elasticity on Arcane's cartesian generator (Quad4 / Hexa8 bars built in tests/cases.py::cartesian_mesh): inputs/bar.2D.cartesian.Dirichlet.bodyForce.arc,
+    # bar.3D.cartesian.Dirichlet.bodyForce.arc
+    "modules/elasticity/check/bar.2D.cartesian.Dirichlet.bodyForce.txt": "elasticity_bar.2D.cartesian.Dirichlet.bodyForce.txt",
+    "modules/elasticity/check/bar.3D.cartesian.Dirichlet.bodyForce.txt": "elasticity_bar.3D.cartesian.Dirichlet.bodyForce.txt",
     # heat module (implicit Euler on lambda * stiffness + mass / dt): inputs/conduction.arc, 3d_conduction.arc, conduction.quad.arc
     "meshes/msh/plate.msh": "plate.msh",
     "modules/heat/check/2d_conduction.txt": "heat_2d_conduction.txt",
